@@ -1,0 +1,222 @@
+// Ghost-row exchange over NCCL (send/recv grouped into one all-to-all-v per exchange).
+// NCCL is bound at run time with dlopen so that the library loads on machines without NCCL and
+// shares the copy the host process (e.g. torch) has already loaded.
+#include "comm.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace dory {
+namespace {
+
+struct NcclApi {
+    void *handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    std::string error;
+};
+
+NcclApi &api() {
+    static NcclApi a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            a.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (a.handle) break;
+        }
+        if (!a.handle) {
+            a.error = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+            return;
+        }
+#define DORY_SYM(field, sym)                                                   \
+    a.field = reinterpret_cast<decltype(a.field)>(dlsym(a.handle, #sym));      \
+    if (!a.field) {                                                            \
+        a.error = "libnccl is missing symbol " #sym;                           \
+        return;                                                                \
+    }
+        DORY_SYM(GetUniqueId, ncclGetUniqueId)
+        DORY_SYM(CommInitRank, ncclCommInitRank)
+        DORY_SYM(CommDestroy, ncclCommDestroy)
+        DORY_SYM(GroupStart, ncclGroupStart)
+        DORY_SYM(GroupEnd, ncclGroupEnd)
+        DORY_SYM(Send, ncclSend)
+        DORY_SYM(Recv, ncclRecv)
+        DORY_SYM(AllReduce, ncclAllReduce)
+        DORY_SYM(GetErrorString, ncclGetErrorString)
+#undef DORY_SYM
+    });
+    return a;
+}
+
+#define NC(call)                                                                         \
+    do {                                                                                 \
+        ncclResult_t _r = (call);                                                        \
+        if (_r != ncclSuccess) return std::string(#call " failed: ") + api().GetErrorString(_r); \
+    } while (0)
+#define CUS(call)                                                                        \
+    do {                                                                                 \
+        cudaError_t _c = (call);                                                         \
+        if (_c != cudaSuccess) return std::string(#call " failed: ") + cudaGetErrorString(_c); \
+    } while (0)
+
+__global__ void scatter_rows_kernel(const float4 *__restrict__ src, const uint32_t *__restrict__ slots,
+                                    uint32_t n, float4 *__restrict__ dst, uint32_t ld4) {
+    const uint32_t r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n) return;
+    const float4 *s = src + (size_t)r * ld4;
+    float4 *d = dst + (size_t)slots[r] * ld4;
+    for (uint32_t c = threadIdx.x & 31; c < ld4; c += 32) d[c] = s[c];
+}
+
+static_assert(sizeof(ncclUniqueId) == 128, "DORY_UNIQUE_ID_BYTES must match ncclUniqueId");
+
+}  // namespace
+
+Comm::~Comm() {
+    for (Plan &p : plan_) {
+        if (p.dSendIds) cudaFree(p.dSendIds);
+        if (p.dRecvSlots) cudaFree(p.dRecvSlots);
+        if (p.sendStage) cudaFree(p.sendStage);
+        if (p.recvStage) cudaFree(p.recvStage);
+    }
+    if (nccl_ && api().CommDestroy) api().CommDestroy(static_cast<ncclComm_t>(nccl_));
+}
+
+std::string Comm::unique_id(void *id128) {
+    NcclApi &a = api();
+    if (!a.error.empty()) return a.error;
+    ncclUniqueId id;
+    NC(a.GetUniqueId(&id));
+    std::memcpy(id128, &id, sizeof id);
+    return "";
+}
+
+std::string Comm::init(const void *id128, int rank, int nranks, int device) {
+    NcclApi &a = api();
+    if (!a.error.empty()) return a.error;
+    rank_ = rank;
+    nranks_ = nranks;
+    device_ = device;
+    CUS(cudaSetDevice(device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof id);
+    ncclComm_t c;
+    NC(a.CommInitRank(&c, nranks, id, rank));
+    nccl_ = c;
+    for (Plan &p : plan_) {
+        p.sendCount.assign(nranks, 0);
+        p.sendOff.assign(nranks, 0);
+        p.recvCount.assign(nranks, 0);
+        p.recvOff.assign(nranks, 0);
+        p.recvSlots.assign(nranks, {});
+    }
+    return "";
+}
+
+std::string Comm::set_send_lists(int dir, const std::vector<std::vector<uint32_t>> &ids, uint32_t maxld,
+                                 cudaStream_t s) {
+    Plan &p = plan_[dir];
+    std::vector<uint32_t> flat;
+    for (int q = 0; q < nranks_; ++q) {
+        p.sendOff[q] = (uint32_t)flat.size();
+        p.sendCount[q] = q == rank_ ? 0 : (uint32_t)ids[q].size();
+        if (q != rank_) flat.insert(flat.end(), ids[q].begin(), ids[q].end());
+    }
+    p.sendTotal = (uint32_t)flat.size();
+    CUS(cudaMalloc(&p.dSendIds, std::max<size_t>(flat.size(), 1) * 4));
+    if (!flat.empty()) CUS(cudaMemcpyAsync(p.dSendIds, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, s));
+    p.sendStageFloats = (size_t)std::max<uint32_t>(p.sendTotal, 1) * maxld;
+    CUS(cudaMalloc(&p.sendStage, p.sendStageFloats * 4));
+    CUS(cudaStreamSynchronize(s));
+    return "";
+}
+
+std::string Comm::set_recv_slots(int dir, int peer, const uint32_t *slots, uint32_t n, uint32_t, cudaStream_t) {
+    Plan &p = plan_[dir];
+    if (peer == rank_ && n) return "a partition does not receive ghost rows from itself";
+    p.recvSlots[peer].assign(slots, slots + n);
+    p.recvDirty = true;
+    return "";
+}
+
+std::string Comm::finalize_recv(Plan &p, uint32_t maxld, cudaStream_t s) {
+    std::vector<uint32_t> flat;
+    for (int q = 0; q < nranks_; ++q) {
+        p.recvOff[q] = (uint32_t)flat.size();
+        p.recvCount[q] = (uint32_t)p.recvSlots[q].size();
+        flat.insert(flat.end(), p.recvSlots[q].begin(), p.recvSlots[q].end());
+    }
+    p.recvTotal = (uint32_t)flat.size();
+    p.recvIdentity = true;
+    for (uint32_t i = 0; i < flat.size(); ++i)
+        if (flat[i] != i) {
+            p.recvIdentity = false;
+            break;
+        }
+    if (p.dRecvSlots) cudaFree(p.dRecvSlots), p.dRecvSlots = nullptr;
+    if (p.recvStage) cudaFree(p.recvStage), p.recvStage = nullptr;
+    CUS(cudaMalloc(&p.dRecvSlots, std::max<size_t>(flat.size(), 1) * 4));
+    if (!flat.empty()) CUS(cudaMemcpyAsync(p.dRecvSlots, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, s));
+    if (!p.recvIdentity) {
+        p.recvStageFloats = (size_t)std::max<uint32_t>(p.recvTotal, 1) * maxld;
+        CUS(cudaMalloc(&p.recvStage, p.recvStageFloats * 4));
+    }
+    CUS(cudaStreamSynchronize(s));
+    p.recvDirty = false;
+    return "";
+}
+
+std::string Comm::exchange(int dir, const float *local, float *ghost, uint32_t ld, cudaStream_t s, int &launches) {
+    NcclApi &a = api();
+    Plan &p = plan_[dir];
+    if (p.recvDirty) {
+        // staging is sized for the widest layer the caller will ever exchange; ld of this call bounds it
+        std::string m = finalize_recv(p, (uint32_t)(p.sendStageFloats / std::max<uint32_t>(p.sendTotal, 1)), s);
+        if (!m.empty()) return m;
+    }
+    if ((size_t)p.sendTotal * ld > p.sendStageFloats) return "exchange: row pitch exceeds staging capacity";
+    launches = 0;
+    if (p.sendTotal) {  // pack: one launch for all peers
+        if (launch_gather_rows(local, p.dSendIds, p.sendTotal, p.sendStage, ld, s) < 0) return "pack kernel launch failed";
+        ++launches;
+    }
+    float *recvBase = p.recvIdentity ? ghost : p.recvStage;
+    ncclComm_t c = static_cast<ncclComm_t>(nccl_);
+    NC(a.GroupStart());
+    for (int q = 0; q < nranks_; ++q) {
+        if (q == rank_) continue;
+        if (p.sendCount[q])
+            NC(a.Send(p.sendStage + (size_t)p.sendOff[q] * ld, (size_t)p.sendCount[q] * ld, ncclFloat, q, c, s));
+        if (p.recvCount[q])
+            NC(a.Recv(recvBase + (size_t)p.recvOff[q] * ld, (size_t)p.recvCount[q] * ld, ncclFloat, q, c, s));
+    }
+    NC(a.GroupEnd());
+    if (!p.recvIdentity && p.recvTotal) {
+        scatter_rows_kernel<<<(p.recvTotal + 7) / 8, 256, 0, s>>>(reinterpret_cast<const float4 *>(p.recvStage),
+                                                                  p.dRecvSlots, p.recvTotal,
+                                                                  reinterpret_cast<float4 *>(ghost), ld / 4);
+        if (cudaGetLastError() != cudaSuccess) return "unpack kernel launch failed";
+        ++launches;
+    }
+    return "";
+}
+
+std::string Comm::allreduce_sum(float *buf, size_t n, cudaStream_t s) {
+    NcclApi &a = api();
+    NC(a.AllReduce(buf, buf, n, ncclFloat, ncclSum, static_cast<ncclComm_t>(nccl_), s));
+    return "";
+}
+
+}  // namespace dory

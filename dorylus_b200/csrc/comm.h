@@ -1,0 +1,56 @@
+// Ghost-row exchange between the partitions of one 8-GPU box (internal).
+//
+// Replaces the reference's ZeroMQ data channel (commmanager/commmanager.cpp:214-279), the per-row
+// (gvid, features) messages of Engine::verticesPushOut (engine/utils.cpp:623-650), the std::map
+// lookups of ghostReceiverGCN (engine/ops/gcn_ops.cpp:310-318), the per-message ACKs and the
+// scatter barrier (ops/pipeline.cpp:262-281) with one all-to-all-v over NVLink per (layer, dir).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace dory {
+
+class Comm {
+public:
+    Comm() = default;
+    ~Comm();
+    Comm(const Comm &) = delete;
+    Comm &operator=(const Comm &) = delete;
+
+    // All methods return "" on success or an error message.
+    static std::string unique_id(void *id128);
+    std::string init(const void *id128, int rank, int nranks, int device);
+    // Send side: per peer, the local row ids to ship (graph.<id>.bin send lists).
+    std::string set_send_lists(int dir, const std::vector<std::vector<uint32_t>> &ids, uint32_t maxld,
+                               cudaStream_t s);
+    // Receive side: per peer, the ghost slots its rows land in, in arrival order.
+    std::string set_recv_slots(int dir, int peer, const uint32_t *slots, uint32_t n, uint32_t maxld,
+                               cudaStream_t s);
+    // Ships rows of `local` ([V x ld]) to the peers and fills `ghost` ([G x ld]).
+    std::string exchange(int dir, const float *local, float *ghost, uint32_t ld, cudaStream_t s, int &launches);
+    std::string allreduce_sum(float *buf, size_t n, cudaStream_t s);
+
+private:
+    struct Plan {
+        std::vector<uint32_t> sendCount, sendOff;  // per peer, rows
+        std::vector<uint32_t> recvCount, recvOff;
+        std::vector<std::vector<uint32_t>> recvSlots;  // host copy per peer
+        uint32_t sendTotal = 0, recvTotal = 0;
+        uint32_t *dSendIds = nullptr;    // concatenated send ids, peer order
+        uint32_t *dRecvSlots = nullptr;  // concatenated recv slots, peer order
+        float *sendStage = nullptr, *recvStage = nullptr;
+        size_t sendStageFloats = 0, recvStageFloats = 0;
+        bool recvIdentity = false;  // concatenated slots == 0..G-1: receive straight into the ghost block
+        bool recvDirty = true;
+    };
+    std::string finalize_recv(Plan &p, uint32_t maxld, cudaStream_t s);
+
+    void *nccl_ = nullptr;  // ncclComm_t
+    int rank_ = 0, nranks_ = 1, device_ = 0;
+    Plan plan_[2];
+};
+
+}  // namespace dory

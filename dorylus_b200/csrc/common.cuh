@@ -1,0 +1,121 @@
+// Shared device/host declarations of the engine (internal; not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+namespace dory {
+
+// Row-major fp32 matrix resident in HBM.  `ld` (floats) is the padded row pitch: a multiple of 32
+// floats (one 128 B line) for widths > 16, a multiple of 4 otherwise, so that every row starts
+// 16 B-aligned for 128-bit loads and wide rows start on a cache-line boundary.  Padding columns are
+// kept at zero by every producer.
+struct DevMat {
+    float *p = nullptr;
+    uint64_t rows = 0;
+    uint32_t cols = 0;
+    uint32_t ld = 0;
+    __host__ __device__ float *row(uint64_t r) const { return p + r * ld; }
+    DevMat rows_from(uint64_t r0, uint64_t n) const {
+        DevMat m = *this;
+        m.p = p + r0 * ld;
+        m.rows = n;
+        return m;
+    }
+};
+
+inline uint32_t padded_ld(uint32_t cols) {
+    if (cols <= 16) return (cols + 3u) & ~3u;
+    return (cols + 31u) & ~31u;
+}
+
+// ---- aggregation (spmm.cu) ---------------------------------------------------------------
+enum SelfMode : int {
+    SELF_NORM = 0,   // out = selfw[v] * src[v] + sum      (GCN, vtxDataVec)
+    SELF_ONE = 1,    // out = src[v] + sum                 (GAT forward, unit self weight)
+    SELF_ZERO = 2,   // out = sum                          (GAT backward, first term)
+    SELF_ACCUM = 3   // out = out + sum                    (GAT backward, second term)
+};
+
+struct SpmmArgs {
+    const uint64_t *ptrs;   // [V+1] columnPtrs (CSC, forward) or rowPtrs (CSR, backward)
+    const uint32_t *idx;    // [E]   source row in `src` (local id, or V + ghost slot)
+    const float *vals;      // [E]
+    const float *selfw;     // [V]   vtxDataVec (SELF_NORM only)
+    const float *src;       // [(V+G) x ld] local rows then ghost rows
+    float *out;             // [V x ld]
+    uint32_t ld;            // common row pitch of src and out, in floats
+    uint32_t nvec;          // row width in float4 units to process (= ld / 4)
+    int self_mode;
+    const uint32_t *heavy;  // row ids with degree >= heavy threshold, degree-descending (may be null)
+    uint32_t n_heavy;
+    const uint32_t *light;  // remaining row ids, degree-descending; null => rows low..low+n_light-1
+    uint32_t n_light;
+    uint32_t low;           // first row when `light` is null
+};
+
+// Launches the aggregation; returns the number of kernels launched, or -1 on a launch error.
+int launch_spmm(const SpmmArgs &a, cudaStream_t s);
+// Tuning override read once from DORY_SPMM_CFG="LG,VEC" (lanes per row, float4 per lane).
+void spmm_set_config(int lg, int vec);
+
+// ---- dense apply (dense.cu) ----------------------------------------------------------------
+enum GemmEpilogue : int { EPI_NONE = 0, EPI_TANH = 1 };
+
+// C[M x N] = op(A) . op(B), fp32 SIMT.  transA: A stored [K x M]; transB: B stored [N x K].
+// EPI_TANH additionally writes C2 = tanh(C).  For transA (the dW = AH^T . G reduction over all
+// vertices) the K range is split over `ws` partial buffers and reduced in a fixed order.
+struct GemmArgs {
+    const float *A;
+    uint32_t lda;
+    const float *B;
+    uint32_t ldb;
+    float *C;
+    uint32_t ldc;
+    float *C2;  // EPI_TANH second output (same ldc), else null
+    uint64_t M;
+    uint32_t N;
+    uint64_t K;
+    bool transA, transB;
+    int epilogue;
+    float *ws;         // split-K workspace (transA only)
+    size_t ws_floats;  // capacity of ws
+};
+int launch_gemm(const GemmArgs &g, cudaStream_t s);
+
+// g = aTg (*) (1 - h^2)                              (CPU_comm.cpp:142-143)
+int launch_tanh_backward(const float *aTg, const float *h, float *g, uint64_t n, cudaStream_t s);
+
+// Last-layer fused softmax / validation statistics / maskout / gradient scale
+// (CPU_comm.cpp:108-121).  Writes d = (maskout(softmax(z)) - lab) / denom into `d`,
+// optionally the un-masked predictions into `pred`, and acc/loss sums into stats[0..1].
+struct SoftmaxCEArgs {
+    const float *z;    // [V x ld] logits
+    const float *lab;  // [V x ld] one-hot labels
+    float *d;          // [V x ld]
+    float *pred;       // [V x ld] or null
+    uint32_t ld, C;
+    uint32_t V;
+    uint32_t trainEnd;    // (unsigned)(V * TRAIN_PORTION)
+    uint32_t valEnd;      // trainEnd + (unsigned)(V * VAL_PORTION)
+    uint64_t maskFloats;  // quirk Q6: number of FLOATS after row trainEnd overwritten by labels
+    bool strictMask;      // DORY_FLAG_STRICT_MASK: overwrite whole rows >= trainEnd
+    float denom;          // (float)(globalVtxCnt * TRAIN_PORTION)
+    float *rowstat;       // [2 x V] scratch: per-row acc / loss contributions
+    float *stats;         // [2] device: acc sum, loss sum
+};
+int launch_softmax_ce(const SoftmaxCEArgs &a, cudaStream_t s);
+
+// Adam step on one weight matrix (AdamOptimizer.cpp:36-48); lr_t is computed on the host.
+int launch_adam(float *w, const float *grad, float *m, float *v, size_t n, float lr_t, float beta1,
+                float beta2, float eps, cudaStream_t s);
+
+int launch_fill(float *p, size_t n, float value, cudaStream_t s);
+
+// ---- ghost exchange (comm.cu) ---------------------------------------------------------------
+// Packs rows `ids[i]` of src into dst[i] (row pitch ld floats, nvec float4 per row).
+int launch_gather_rows(const float *src, const uint32_t *ids, uint32_t n, float *dst, uint32_t ld,
+                       cudaStream_t s);
+
+}  // namespace dory

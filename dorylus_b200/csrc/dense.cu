@@ -1,0 +1,365 @@
+// Dense apply on the fp32 CUDA-core path, plus the element-wise pieces of ApplyVertex.
+//
+// Stands in for CPUComm::vtxNNForwardGCN / vtxNNBackwardGCN and helpers (reference
+// commmanager/CPU_comm.cpp:98-159, 265-297, 424-471), i.e. for Matrix::dot -> cblas_sgemm
+// (common/matrix.cpp:263-315) and, on the reference GPU backend, cublasSgemm + cudnnActivation +
+// cudnnSoftmax + thrust (GPU-Computation/comp_server.cu:104-204).
+//
+// gemm_simt_kernel is the exact-fp32 path: it is used for the skinny products (N = #classes), the
+// transposed products (dW = AH^T . G with a deterministic split-K, grad = G . W^T) and as the
+// fallback when tensor cores are disabled; the large H.W contraction runs on tcgen05 (gemm_tc.cu).
+#include <cmath>
+
+#include "common.cuh"
+
+namespace dory {
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4;
+constexpr int kGemmThreads = (BM / TM) * (BN / TN);  // 256
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_simt_kernel(const float *__restrict__ A, uint32_t lda, const float *__restrict__ B, uint32_t ldb,
+                 float *__restrict__ C, uint32_t ldc, float *__restrict__ C2, uint64_t M, uint32_t N,
+                 uint64_t K, uint64_t kchunk, size_t split_stride, int epilogue) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const uint64_t m0 = (uint64_t)blockIdx.x * BM;
+    const uint32_t n0 = blockIdx.y * BN;
+    const uint64_t kbeg = (uint64_t)blockIdx.z * kchunk;
+    const uint64_t kend = min(K, kbeg + kchunk);
+    const int ty = tid / (BN / TN), tx = tid % (BN / TN);
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (uint64_t k0 = kbeg; k0 < kend; k0 += BK) {
+        // ---- A tile -> As[k][m]
+        if (!TA) {  // A is [M x K]: vector loads along k, transposed into smem
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = tid / 4 + 64 * i, k4 = (tid % 4) * 4;
+                const uint64_t m = m0 + r, k = k0 + k4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < M && k < kend) {  // K ranges are multiples of 4 here
+                    v = *reinterpret_cast<const float4 *>(A + m * lda + k);
+                }
+                As[k4 + 0][r] = v.x;
+                As[k4 + 1][r] = v.y;
+                As[k4 + 2][r] = v.z;
+                As[k4 + 3][r] = v.w;
+            }
+        } else {  // A is [K x M]: vector loads along m
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int kk = tid / 32 + 8 * i, m4 = (tid % 32) * 4;
+                const uint64_t k = k0 + kk, m = m0 + m4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < kend && m < M) v = *reinterpret_cast<const float4 *>(A + k * lda + m);
+                *reinterpret_cast<float4 *>(&As[kk][m4]) = v;
+            }
+        }
+        // ---- B tile -> Bs[k][n]
+        if (!TB) {  // B is [K x N]
+            const int kk = tid / 16, n4 = (tid % 16) * 4;
+            const uint64_t k = k0 + kk;
+            const uint32_t n = n0 + n4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < kend && n < N) v = *reinterpret_cast<const float4 *>(B + k * ldb + n);
+            *reinterpret_cast<float4 *>(&Bs[kk][n4]) = v;
+        } else {  // B is [N x K]
+            const int r = tid / 4, k4 = (tid % 4) * 4;
+            const uint32_t n = n0 + r;
+            const uint64_t k = k0 + k4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < N && k < kend) v = *reinterpret_cast<const float4 *>(B + (size_t)n * ldb + k);
+            Bs[k4 + 0][r] = v.x;
+            Bs[k4 + 1][r] = v.y;
+            Bs[k4 + 2][r] = v.z;
+            Bs[k4 + 3][r] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[kk][ty * TM]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[kk][ty * TM + 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][tx * TN]);
+            const float av[TM] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[TN] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    float *Cz = C + (size_t)blockIdx.z * split_stride;
+    const uint32_t n = n0 + tx * TN;
+    if (n < N) {
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const uint64_t m = m0 + ty * TM + i;
+            if (m >= M) continue;
+            const float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            *reinterpret_cast<float4 *>(Cz + m * ldc + n) = v;
+            if (epilogue == EPI_TANH) {
+                const float4 t = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
+                *reinterpret_cast<float4 *>(C2 + m * ldc + n) = t;
+            }
+        }
+    }
+}
+
+// C[i] = sum_z ws[z][i] in ascending z (fixed order => reproducible dW).
+__global__ void splitk_reduce_kernel(const float *__restrict__ ws, float *__restrict__ C, size_t n4,
+                                     size_t stride4, int nsplit) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 *w4 = reinterpret_cast<const float4 *>(ws);
+    float4 s = w4[i];
+    for (int z = 1; z < nsplit; ++z) {
+        const float4 v = w4[(size_t)z * stride4 + i];
+        s.x += v.x;
+        s.y += v.y;
+        s.z += v.z;
+        s.w += v.w;
+    }
+    reinterpret_cast<float4 *>(C)[i] = s;
+}
+
+__global__ void tanh_backward_kernel(const float4 *__restrict__ aTg, const float4 *__restrict__ h,
+                                     float4 *__restrict__ g, size_t n4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 a = aTg[i], t = h[i];
+    g[i] = make_float4(a.x * (1.f - t.x * t.x), a.y * (1.f - t.y * t.y), a.z * (1.f - t.z * t.z),
+                       a.w * (1.f - t.w * t.w));
+}
+
+// One warp per vertex row; C <= 32 * kMaxPerLane classes.
+constexpr int kMaxPerLane = 8;
+__global__ void __launch_bounds__(256) softmax_ce_kernel(const SoftmaxCEArgs a) {
+    const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= a.V) return;
+    const float *z = a.z + (size_t)row * a.ld;
+    const float *lab = a.lab + (size_t)row * a.ld;
+    float v[kMaxPerLane], lb[kMaxPerLane];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kMaxPerLane; ++j) {
+        const uint32_t c = lane + 32 * j;
+        v[j] = c < a.C ? z[c] : -INFINITY;
+        lb[j] = c < a.C ? lab[c] : 0.f;
+        mx = fmaxf(mx, v[j]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxPerLane; ++j) {
+        const uint32_t c = lane + 32 * j;
+        v[j] = c < a.C ? expf(v[j] - mx) : 0.f;
+        sum += v[j];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float denom = 1e-20f + sum;  // CPU_comm.cpp:285-290
+    // argmax of predictions / labels (first maximum, like the reference's argmax helper)
+    float pbest = -INFINITY, lbest = -INFINITY;
+    uint32_t pidx = 0, lidx = 0;
+#pragma unroll
+    for (int j = 0; j < kMaxPerLane; ++j) {
+        const uint32_t c = lane + 32 * j;
+        v[j] = v[j] / denom;
+        if (c < a.C) {
+            if (v[j] > pbest) pbest = v[j], pidx = c;
+            if (lb[j] > lbest) lbest = lb[j], lidx = c;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float pb = __shfl_xor_sync(0xffffffffu, pbest, o);
+        const uint32_t pi = __shfl_xor_sync(0xffffffffu, pidx, o);
+        if (pb > pbest || (pb == pbest && pi < pidx)) pbest = pb, pidx = pi;
+        const float lbv = __shfl_xor_sync(0xffffffffu, lbest, o);
+        const uint32_t li = __shfl_xor_sync(0xffffffffu, lidx, o);
+        if (lbv > lbest || (lbv == lbest && li < lidx)) lbest = lbv, lidx = li;
+    }
+    // getTrainStat over the validation slice (CPU_comm.cpp:448-462)
+    if (row >= a.trainEnd && row < a.valEnd) {
+        // acc += label[argmax(pred)];  loss -= log(pred[argmax(label)])
+        float accv = 0.f, lossv = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxPerLane; ++j) {
+            const uint32_t c = lane + 32 * j;
+            if (c == pidx) accv = lb[j];
+            if (c == lidx) lossv = -logf(v[j]);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            accv += __shfl_xor_sync(0xffffffffu, accv, o);
+            lossv += __shfl_xor_sync(0xffffffffu, lossv, o);
+        }
+        if (lane == 0) {
+            a.rowstat[row - a.trainEnd] = accv;
+            a.rowstat[(size_t)a.V + (row - a.trainEnd)] = lossv;
+        }
+    }
+    // maskout + hadamardSub + scale (CPU_comm.cpp:118-121, 464-471)
+    const uint64_t maskBeg = (uint64_t)a.trainEnd * a.C;
+#pragma unroll
+    for (int j = 0; j < kMaxPerLane; ++j) {
+        const uint32_t c = lane + 32 * j;
+        if (c >= a.C) continue;
+        if (a.pred) a.pred[(size_t)row * a.ld + c] = v[j];
+        float p = v[j];
+        const uint64_t flat = (uint64_t)row * a.C + c;  // index in the reference's dense V x C array
+        const bool masked = a.strictMask ? (row >= a.trainEnd)
+                                         : (flat >= maskBeg && flat < maskBeg + a.maskFloats);
+        if (masked) p = lb[j];
+        a.d[(size_t)row * a.ld + c] = (p - lb[j]) / a.denom;
+    }
+}
+
+// stats[0] = sum rowstat[0..n), stats[1] = sum rowstat[V..V+n); single block, fixed tree.
+__global__ void __launch_bounds__(1024) stat_reduce_kernel(const float *__restrict__ rowstat, uint32_t V,
+                                                           uint32_t n, float *__restrict__ stats) {
+    __shared__ float sa[1024], sl[1024];
+    float acc = 0.f, loss = 0.f;
+    for (uint32_t i = threadIdx.x; i < n; i += 1024) {
+        acc += rowstat[i];
+        loss += rowstat[(size_t)V + i];
+    }
+    sa[threadIdx.x] = acc;
+    sl[threadIdx.x] = loss;
+    __syncthreads();
+    for (int o = 512; o; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            sa[threadIdx.x] += sa[threadIdx.x + o];
+            sl[threadIdx.x] += sl[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        stats[0] = sa[0];
+        stats[1] = sl[0];
+    }
+}
+
+__global__ void adam_kernel(float *__restrict__ w, const float *__restrict__ grad, float *__restrict__ m,
+                            float *__restrict__ v, size_t n, float lr_t, float beta1, float beta2,
+                            float eps) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // AdamOptimizer.cpp:39-46; (1. - BETA) is evaluated in double in the reference.
+    const float gt = grad[i];
+    const float mi = (float)((double)(beta1 * m[i]) + (1. - (double)beta1) * (double)gt);
+    const float vi = (float)((double)(beta2 * v[i]) + (1. - (double)beta2) * (double)gt * (double)gt);
+    m[i] = mi;
+    v[i] = vi;
+    // `sqrt` resolves to the double overload in the reference (unqualified call, <cmath>)
+    const float delta = (float)((double)(lr_t * mi) / (sqrt((double)vi) + (double)eps));
+    w[i] -= delta;
+}
+
+__global__ void fill_kernel(float *__restrict__ p, size_t n, float value) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = value;
+}
+
+__global__ void gather_rows_kernel(const float4 *__restrict__ src, const uint32_t *__restrict__ ids,
+                                   uint32_t n, float4 *__restrict__ dst, uint32_t ld4) {
+    // one warp per row
+    const uint32_t r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n) return;
+    const float4 *s = src + (size_t)ids[r] * ld4;
+    float4 *d = dst + (size_t)r * ld4;
+    for (uint32_t c = threadIdx.x & 31; c < ld4; c += 32) d[c] = s[c];
+}
+
+}  // namespace
+
+int launch_gemm(const GemmArgs &g, cudaStream_t s) {
+    dim3 grid((unsigned)((g.M + BM - 1) / BM), (g.N + BN - 1) / BN, 1);
+    int launches = 0;
+    if (g.transA) {
+        // split the vertex dimension so that ~4 CTAs per SM are in flight; partials reduced in order
+        const size_t cfloats = (size_t)g.M * g.ldc;
+        int nsplit = (int)std::min<uint64_t>((g.K + 2047) / 2048, 592 / std::max(1u, grid.x * grid.y));
+        nsplit = std::max(1, std::min<int>(nsplit, (int)(g.ws_floats / std::max<size_t>(cfloats, 1))));
+        uint64_t kchunk = (g.K + nsplit - 1) / nsplit;
+        kchunk = (kchunk + BK - 1) / BK * BK;
+        nsplit = (int)((g.K + kchunk - 1) / kchunk);
+        if (nsplit <= 1) {
+            if (g.transB)
+                gemm_simt_kernel<true, true><<<grid, kGemmThreads, 0, s>>>(g.A, g.lda, g.B, g.ldb, g.C, g.ldc, nullptr, g.M, g.N, g.K, g.K, 0, EPI_NONE);
+            else
+                gemm_simt_kernel<true, false><<<grid, kGemmThreads, 0, s>>>(g.A, g.lda, g.B, g.ldb, g.C, g.ldc, nullptr, g.M, g.N, g.K, g.K, 0, EPI_NONE);
+            ++launches;
+        } else {
+            grid.z = nsplit;
+            if (g.transB)
+                gemm_simt_kernel<true, true><<<grid, kGemmThreads, 0, s>>>(g.A, g.lda, g.B, g.ldb, g.ws, g.ldc, nullptr, g.M, g.N, g.K, kchunk, cfloats, EPI_NONE);
+            else
+                gemm_simt_kernel<true, false><<<grid, kGemmThreads, 0, s>>>(g.A, g.lda, g.B, g.ldb, g.ws, g.ldc, nullptr, g.M, g.N, g.K, kchunk, cfloats, EPI_NONE);
+            const size_t n4 = cfloats / 4;
+            splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(g.ws, g.C, n4, n4, nsplit);
+            launches += 2;
+        }
+    } else {
+        if (g.transB)
+            gemm_simt_kernel<false, true><<<grid, kGemmThreads, 0, s>>>(g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.C2, g.M, g.N, g.K, g.K, 0, g.epilogue);
+        else
+            gemm_simt_kernel<false, false><<<grid, kGemmThreads, 0, s>>>(g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.C2, g.M, g.N, g.K, g.K, 0, g.epilogue);
+        ++launches;
+    }
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return launches;
+}
+
+int launch_tanh_backward(const float *aTg, const float *h, float *g, uint64_t n, cudaStream_t s) {
+    const size_t n4 = n / 4;
+    if (n4 == 0) return 0;
+    tanh_backward_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<const float4 *>(aTg), reinterpret_cast<const float4 *>(h),
+        reinterpret_cast<float4 *>(g), n4);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_softmax_ce(const SoftmaxCEArgs &a, cudaStream_t s) {
+    if (a.C > 32 * kMaxPerLane) return -1;
+    if (a.V == 0) return 0;
+    softmax_ce_kernel<<<(a.V + 7) / 8, 256, 0, s>>>(a);
+    stat_reduce_kernel<<<1, 1024, 0, s>>>(a.rowstat, a.V, a.valEnd - a.trainEnd, a.stats);
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
+
+int launch_adam(float *w, const float *grad, float *m, float *v, size_t n, float lr_t, float beta1,
+                float beta2, float eps, cudaStream_t s) {
+    if (n == 0) return 0;
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, grad, m, v, n, lr_t, beta1, beta2, eps);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_fill(float *p, size_t n, float value, cudaStream_t s) {
+    if (n == 0) return 0;
+    fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n, value);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_gather_rows(const float *src, const uint32_t *ids, uint32_t n, float *dst, uint32_t ld,
+                       cudaStream_t s) {
+    if (n == 0) return 0;
+    gather_rows_kernel<<<(n + 7) / 8, 256, 0, s>>>(reinterpret_cast<const float4 *>(src), ids, n,
+                                                   reinterpret_cast<float4 *>(dst), ld / 4);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace dory

@@ -1,0 +1,1215 @@
+// The engine behind include/dorylus_b200.h: partition state resident in HBM, the named-tensor
+// table, the SAGA operators and the per-epoch state machine.
+//
+// Reference counterparts: Engine (src/graph-server/engine/engine.{hpp,cpp}, engine/utils.cpp,
+// engine/ops/gcn_ops.cpp, gat_ops.cpp), ResourceComm / CPUComm (commmanager/resource_comm.cpp,
+// CPU_comm.cpp) and the weight-server pieces a synchronous run needs (weight-server/
+// weightserver.cpp:515-612, AdamOptimizer.cpp).  Design notes: DESIGN.md.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/dorylus_b200.h"
+#include "comm.h"
+#include "common.cuh"
+#include "gat.cuh"
+#include "gemm_tc.cuh"
+#include "loader.h"
+
+using namespace dory;
+
+namespace {
+
+constexpr double kTrainPortion = 0.66;  // src/common/utils.hpp:60
+constexpr double kValPortion = 0.1;     // src/common/utils.hpp:61
+constexpr uint32_t kHeavyDegree = 1024; // rows with more edges get a whole CTA (spmm.cu)
+constexpr int kNumEvents = 64;
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes) {
+        o.p = nullptr;
+        o.bytes = 0;
+    }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    cudaError_t alloc(size_t n) {
+        release();
+        if (n == 0) n = 16;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    template <class T>
+    T *as() const { return static_cast<T *>(p); }
+};
+
+struct Adjacency {
+    DevBuf ptrs, idx, vals, heavy, light;
+    uint64_t nnz = 0;
+    uint32_t n_heavy = 0, n_light = 0;
+};
+
+struct WeightSet {
+    DevBuf w, dw, m, v;
+    uint32_t rows = 0, cols = 0, ld = 0, prows = 0;  // prows: rows incl. zero padding (= ld of the input width)
+    size_t floats() const { return (size_t)prows * ld; }
+};
+
+}  // namespace
+
+struct dory_engine {
+    dory_config cfg{};
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t events[kNumEvents] = {};
+    bool loaded = false;
+
+    // graph (Graph, graph/graph.hpp:60-99)
+    uint32_t V = 0, gV = 0, Gs = 0, Gd = 0;
+    uint64_t Ein = 0, Eout = 0, Eglob = 0;
+    Adjacency fwd, bwd;  // forwardAdj (CSC), backwardAdj (CSR)
+    DevBuf norms;        // vtxDataVec
+    std::vector<uint32_t> l2g;
+    std::vector<std::vector<uint32_t>> sendIds[2];  // [dir][peer] local ids (host copy)
+
+    // tensors: backing allocations + (layer, name) -> view
+    std::vector<std::unique_ptr<DevBuf>> pool;
+    std::map<std::pair<uint32_t, std::string>, DevMat> tensors;
+    std::vector<WeightSet> W;    // "w" per layer
+    std::vector<WeightSet> Ai;   // GAT "a_i" per layer (F' x 1)
+    DevBuf scratchA, scratchB;   // V x max(ld) scratch (d / interGrad / pred)
+    DevBuf gemm_ws;              // split-K partials
+    DevBuf rowstat, stats_dev;   // softmax-CE reduction scratch
+    DevBuf flush;                // L2 flush target
+
+    // Adam (AdamOptimizer.hpp:69-84)
+    float beta1 = .9f, beta2 = .999f, eps = 1e-07f, lr_t = 0.f;
+    unsigned adam_epochs = 0;
+
+    dory_stats stats{};
+    std::unique_ptr<dory::Comm> comm;
+
+    uint32_t L() const { return cfg.n_layers; }
+    uint32_t dim(uint32_t i) const { return cfg.dims[i]; }
+};
+
+namespace {
+
+int fail(dory_engine *e, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t _c = (call);                                                              \
+        if (_c != cudaSuccess)                                                                \
+            return fail(e, DORY_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_c), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+#define LAUNCHED(expr)                                                                  \
+    do {                                                                                \
+        int _n = (expr);                                                                \
+        if (_n < 0)                                                                     \
+            return fail(e, DORY_ECUDA, "kernel launch failed: %s (%s:%d)",              \
+                        cudaGetErrorString(cudaGetLastError()), __FILE__, __LINE__);    \
+        e->stats.kernel_launches += (uint64_t)_n;                                       \
+    } while (0)
+
+DevMat new_tensor(dory_engine *e, uint64_t rows, uint32_t cols, cudaError_t &err) {
+    DevMat m;
+    m.rows = rows;
+    m.cols = cols;
+    m.ld = padded_ld(cols);
+    auto buf = std::make_unique<DevBuf>();
+    const size_t bytes = (size_t)std::max<uint64_t>(rows, 1) * m.ld * sizeof(float);
+    err = buf->alloc(bytes);
+    if (err != cudaSuccess) return m;
+    err = cudaMemsetAsync(buf->p, 0, bytes, e->stream);
+    m.p = buf->as<float>();
+    e->pool.push_back(std::move(buf));
+    return m;
+}
+
+const DevMat *find_tensor(const dory_engine *e, uint32_t layer, const char *name) {
+    auto it = e->tensors.find({layer, std::string(name)});
+    return it == e->tensors.end() ? nullptr : &it->second;
+}
+
+// Degree-descending row lists (longest-processing-time-first issue order for spmm.cu).
+void build_row_lists(const std::vector<uint64_t> &ptrs, std::vector<uint32_t> &heavy,
+                     std::vector<uint32_t> &light) {
+    const uint32_t V = (uint32_t)ptrs.size() - 1;
+    std::vector<uint32_t> order(V);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        return (ptrs[a + 1] - ptrs[a]) > (ptrs[b + 1] - ptrs[b]);
+    });
+    heavy.clear();
+    light.clear();
+    for (uint32_t v : order) ((ptrs[v + 1] - ptrs[v]) >= kHeavyDegree ? heavy : light).push_back(v);
+}
+
+int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const uint8_t *idx,
+                     const uint8_t *vals, uint64_t nnz, uint32_t V, uint32_t nSrcRows) {
+    adj.nnz = nnz;
+    std::vector<uint64_t> hp(V + 1);
+    std::memcpy(hp.data(), ptrs, 8 * ((size_t)V + 1));
+    for (uint32_t v = 0; v < V; ++v)
+        if (hp[v + 1] < hp[v]) return fail(e, DORY_EFORMAT, "adjacency offsets decrease at vertex %u", v);
+    CU(adj.ptrs.alloc(8 * ((size_t)V + 1)));
+    CU(adj.idx.alloc(4 * nnz));
+    CU(adj.vals.alloc(4 * nnz));
+    CU(cudaMemcpyAsync(adj.ptrs.p, hp.data(), 8 * ((size_t)V + 1), cudaMemcpyHostToDevice, e->stream));
+    if (nnz) {
+        // validate indices on the host: an out-of-range id would be an out-of-bounds gather
+        const uint8_t *p = idx;
+        for (uint64_t i = 0; i < nnz; ++i, p += 4) {
+            uint32_t s;
+            std::memcpy(&s, p, 4);
+            if (s >= nSrcRows) return fail(e, DORY_EFORMAT, "edge %llu references row %u >= %u",
+                                           (unsigned long long)i, s, nSrcRows);
+        }
+        CU(cudaMemcpyAsync(adj.idx.p, idx, 4 * nnz, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(adj.vals.p, vals, 4 * nnz, cudaMemcpyHostToDevice, e->stream));
+    }
+    std::vector<uint32_t> heavy, light;
+    build_row_lists(hp, heavy, light);
+    adj.n_heavy = (uint32_t)heavy.size();
+    adj.n_light = (uint32_t)light.size();
+    CU(adj.heavy.alloc(4 * heavy.size()));
+    CU(adj.light.alloc(4 * light.size()));
+    if (!heavy.empty())
+        CU(cudaMemcpyAsync(adj.heavy.p, heavy.data(), 4 * heavy.size(), cudaMemcpyHostToDevice, e->stream));
+    if (!light.empty())
+        CU(cudaMemcpyAsync(adj.light.p, light.data(), 4 * light.size(), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));  // host staging vectors die at scope exit
+    return DORY_OK;
+}
+
+int alloc_weight(dory_engine *e, WeightSet &w, uint32_t rows, uint32_t cols) {
+    w.rows = rows;
+    w.cols = cols;
+    w.ld = padded_ld(cols);
+    w.prows = padded_ld(rows);
+    const size_t bytes = w.floats() * sizeof(float);
+    for (DevBuf *b : {&w.w, &w.dw, &w.m, &w.v}) {
+        CU(b->alloc(bytes));
+        CU(cudaMemsetAsync(b->p, 0, bytes, e->stream));
+    }
+    return DORY_OK;
+}
+
+// Engine::preallocateGCN, gcn_ops.cpp:27-93.  Local rows and ghost rows of one logical source
+// tensor share ONE allocation ([V + G] rows) so that adjacency indices address it directly.
+int preallocate_gcn(dory_engine *e) {
+    const uint32_t L = e->L(), V = e->V;
+    cudaError_t ce = cudaSuccess;
+    auto T = [&](uint32_t layer, const char *name, const DevMat &m) { e->tensors[{layer, name}] = m; };
+    DevMat x = new_tensor(e, (uint64_t)V + e->Gs, e->dim(0), ce);
+    CU(ce);
+    T(0, "x", x.rows_from(0, V));
+    T(0, "fg", x.rows_from(V, e->Gs));
+    for (uint32_t l = 0; l < L; ++l) {
+        DevMat ah = new_tensor(e, V, e->dim(l), ce);
+        CU(ce);
+        T(l, "ah", ah);
+        if (l + 1 < L) {
+            DevMat z = new_tensor(e, V, e->dim(l + 1), ce);
+            CU(ce);
+            DevMat h = new_tensor(e, (uint64_t)V + e->Gs, e->dim(l + 1), ce);
+            CU(ce);
+            T(l, "z", z);
+            T(l, "h", h.rows_from(0, V));
+            T(l + 1, "fg", h.rows_from(V, e->Gs));
+        }
+    }
+    DevMat lab = new_tensor(e, V, e->dim(L), ce);
+    CU(ce);
+    T(L - 1, "lab", lab);
+    for (uint32_t l = L - 1; l > 0; --l) {
+        DevMat grad = new_tensor(e, (uint64_t)V + e->Gd, e->dim(l), ce);
+        CU(ce);
+        T(l, "grad", grad.rows_from(0, V));
+        T(l - 1, "bg", grad.rows_from(V, e->Gd));
+        DevMat aTg = new_tensor(e, V, e->dim(l), ce);
+        CU(ce);
+        T(l - 1, "aTg", aTg);
+    }
+    return DORY_OK;
+}
+
+// Engine::preallocateGAT, gat_ops.cpp:27-115.
+int preallocate_gat(dory_engine *e) {
+    const uint32_t L = e->L(), V = e->V;
+    cudaError_t ce = cudaSuccess;
+    auto T = [&](uint32_t layer, const char *name, const DevMat &m) { e->tensors[{layer, name}] = m; };
+    DevMat h0 = new_tensor(e, V, e->dim(0), ce);
+    CU(ce);
+    T(0, "h", h0);
+    for (uint32_t l = 0; l < L; ++l) {
+        const uint32_t nf = e->dim(l + 1);
+        DevMat z = new_tensor(e, (uint64_t)V + e->Gs, nf, ce);
+        CU(ce);
+        T(l, "z", z.rows_from(0, V));
+        T(l, "fg_z", z.rows_from(V, e->Gs));
+        // per-edge vectors (E x 1 in the reference) are stored densely: ld = 1
+        for (const char *nm : {"az", "dA"}) {
+            DevMat m;
+            auto buf = std::make_unique<DevBuf>();
+            CU(buf->alloc(4 * (size_t)std::max<uint64_t>(e->Ein, 1)));
+            CU(cudaMemsetAsync(buf->p, 0, buf->bytes, e->stream));
+            m.p = buf->as<float>();
+            m.rows = e->Ein;
+            m.cols = 1;
+            m.ld = 1;
+            e->pool.push_back(std::move(buf));
+            T(l, nm, m);
+        }
+        {   // "A" aliases forwardAdj.values for every layer (quirk Q12, gat_ops.cpp:61-64)
+            DevMat m;
+            m.p = e->fwd.vals.as<float>();
+            m.rows = e->Ein;
+            m.cols = 1;
+            m.ld = 1;
+            T(l, "A", m);
+        }
+        DevMat ah = new_tensor(e, V, nf, ce);
+        CU(ce);
+        T(l, "ah", ah);
+        DevMat grad = new_tensor(e, (uint64_t)V + e->Gd, nf, ce);
+        CU(ce);
+        T(l, "grad", grad.rows_from(0, V));
+        T(l, "bg_d", grad.rows_from(V, e->Gd));
+        DevMat aTg = new_tensor(e, V, nf, ce);
+        CU(ce);
+        T(l, "aTg", aTg);
+    }
+    DevMat lab = new_tensor(e, V, e->dim(L), ce);
+    CU(ce);
+    T(L - 1, "lab", lab);
+    return DORY_OK;
+}
+
+bool is_edge_vector(const DevMat &m) { return m.ld == 1 && m.cols == 1; }
+
+int copy_in(dory_engine *e, const DevMat &m, const float *host) {
+    if (m.rows == 0) return DORY_OK;
+    if (is_edge_vector(m)) {
+        CU(cudaMemcpyAsync(m.p, host, 4 * m.rows, cudaMemcpyHostToDevice, e->stream));
+    } else {
+        CU(cudaMemcpy2DAsync(m.p, (size_t)m.ld * 4, host, (size_t)m.cols * 4, (size_t)m.cols * 4, m.rows,
+                             cudaMemcpyHostToDevice, e->stream));
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    return DORY_OK;
+}
+
+int copy_out(dory_engine *e, const DevMat &m, float *host) {
+    if (m.rows == 0) return DORY_OK;
+    if (is_edge_vector(m)) {
+        CU(cudaMemcpyAsync(host, m.p, 4 * m.rows, cudaMemcpyDeviceToHost, e->stream));
+    } else {
+        CU(cudaMemcpy2DAsync(host, (size_t)m.cols * 4, m.p, (size_t)m.ld * 4, (size_t)m.cols * 4, m.rows,
+                             cudaMemcpyDeviceToHost, e->stream));
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    return DORY_OK;
+}
+
+// AdamOptimizer::nextIteration, AdamOptimizer.cpp:29-34 (float/double mix as in the reference:
+// pow and sqrt are the double overloads, the results are narrowed into float members).
+void adam_next_iteration(dory_engine *e) {
+    ++e->adam_epochs;
+    const float b1p = (float)std::pow((double)e->beta1, (double)e->adam_epochs);
+    const float b2p = (float)std::pow((double)e->beta2, (double)e->adam_epochs);
+    e->lr_t = (float)((double)e->cfg.learning_rate * std::sqrt((double)(1 - b2p)) / (double)(1 - b1p));
+}
+
+int check_loaded(dory_engine *e) {
+    if (!e) return DORY_EINVAL;
+    if (!e->loaded) return fail(e, DORY_ESTATE, "no partition loaded (call dory_load_partition first)");
+    return DORY_OK;
+}
+
+SpmmArgs spmm_args(const Adjacency &adj, const float *selfw, int mode, const DevMat &src, const DevMat &out,
+                   uint32_t low, uint32_t up, uint32_t V) {
+    SpmmArgs a{};
+    a.ptrs = adj.ptrs.as<uint64_t>();
+    a.idx = adj.idx.as<uint32_t>();
+    a.vals = adj.vals.as<float>();
+    a.selfw = selfw;
+    a.src = src.p;
+    a.out = out.p;
+    a.ld = src.ld;
+    a.nvec = src.ld / 4;
+    a.self_mode = mode;
+    if (low == 0 && up == V) {
+        a.heavy = adj.heavy.as<uint32_t>();
+        a.n_heavy = adj.n_heavy;
+        a.light = adj.light.as<uint32_t>();
+        a.n_light = adj.n_light;
+        a.low = 0;
+    } else {  // sub-range chunk (Lambda-style chunking): natural order, warp per row
+        a.heavy = nullptr;
+        a.n_heavy = 0;
+        a.light = nullptr;
+        a.n_light = up - low;
+        a.low = low;
+    }
+    return a;
+}
+
+uint64_t edges_in_range(dory_engine *e, const Adjacency &adj, uint32_t low, uint32_t up) {
+    if (low == 0 && up == e->V) return adj.nnz;
+    return 0;  // partial chunks are not counted (would need a device read)
+}
+
+// ------------------------------------------------------------------ GCN operators
+int aggregate_gcn(dory_engine *e, const dory_chunk *c) {
+    const uint32_t L = e->L();
+    if (c->upBound > e->V || c->lowBound > c->upBound) return fail(e, DORY_EINVAL, "chunk bounds out of range");
+    const DevMat *src, *out;
+    const Adjacency *adj;
+    if (c->dir == DORY_FORWARD) {
+        if (c->layer >= L) return fail(e, DORY_EINVAL, "aggregate: forward layer %u out of range", c->layer);
+        src = c->layer == 0 ? find_tensor(e, 0, "x") : find_tensor(e, c->layer - 1, "h");
+        out = find_tensor(e, c->layer, "ah");
+        adj = &e->fwd;
+    } else {
+        if (c->layer == 0 || c->layer >= L) return fail(e, DORY_EINVAL, "aggregate: backward layer %u out of range", c->layer);
+        src = find_tensor(e, c->layer, "grad");
+        out = find_tensor(e, c->layer - 1, "aTg");
+        adj = &e->bwd;
+    }
+    SpmmArgs a = spmm_args(*adj, e->norms.as<float>(), SELF_NORM, *src, *out, c->lowBound, c->upBound, e->V);
+    LAUNCHED(launch_spmm(a, e->stream));
+    e->stats.edges_aggregated += edges_in_range(e, *adj, c->lowBound, c->upBound);
+    return DORY_OK;
+}
+
+bool use_tensor_cores(const dory_engine *e) { return !(e->cfg.flags & DORY_FLAG_NO_TENSOR_CORES); }
+
+// Z = A . W (+ tanh): tcgen05 path when the shape qualifies, else fp32 SIMT.
+int gemm_nn(dory_engine *e, const DevMat &A, const WeightSet &W, const DevMat &C, const DevMat *C2) {
+    if (use_tensor_cores(e)) {
+        int n = launch_gemm_tc(A.p, A.ld, A.rows, W.w.as<float>(), W.ld, W.prows, C.p, C2 ? C2->p : nullptr, C.ld,
+                               C2 ? EPI_TANH : EPI_NONE, e->stream);
+        if (n > 0) {
+            e->stats.kernel_launches += n;
+            return DORY_OK;
+        }
+        if (n < 0) return fail(e, DORY_ECUDA, "tcgen05 GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        // n == 0: shape not supported by the tensor-core kernel -> SIMT path below
+    }
+    GemmArgs g{};
+    g.A = A.p; g.lda = A.ld; g.B = W.w.as<float>(); g.ldb = W.ld; g.C = C.p; g.ldc = C.ld;
+    g.C2 = C2 ? C2->p : nullptr;
+    g.M = A.rows; g.N = C.ld; g.K = A.ld;
+    g.transA = false; g.transB = false; g.epilogue = C2 ? EPI_TANH : EPI_NONE;
+    LAUNCHED(launch_gemm(g, e->stream));
+    return DORY_OK;
+}
+
+// C = G . W^T   (G: V x Fout, W: Fin x Fout -> C: V x Fin)
+int gemm_nt(dory_engine *e, const float *G, uint32_t ldg, uint64_t rows, const WeightSet &W, const DevMat &C) {
+    GemmArgs g{};
+    g.A = G; g.lda = ldg; g.B = W.w.as<float>(); g.ldb = W.ld; g.C = C.p; g.ldc = C.ld;
+    g.M = rows; g.N = C.ld; g.K = W.ld;
+    g.transA = false; g.transB = true; g.epilogue = EPI_NONE;
+    LAUNCHED(launch_gemm(g, e->stream));
+    return DORY_OK;
+}
+
+// dW = A^T . G   (A: V x Fin, G: V x Fout -> dW: Fin x Fout), deterministic split over vertices
+int gemm_tn(dory_engine *e, const DevMat &A, const float *G, uint32_t ldg, WeightSet &W, float *out) {
+    GemmArgs g{};
+    g.A = A.p; g.lda = A.ld; g.B = G; g.ldb = ldg; g.C = out; g.ldc = W.ld;
+    g.M = W.prows; g.N = W.ld; g.K = A.rows;
+    g.transA = true; g.transB = false; g.epilogue = EPI_NONE;
+    g.ws = e->gemm_ws.as<float>(); g.ws_floats = e->gemm_ws.bytes / 4;
+    LAUNCHED(launch_gemm(g, e->stream));
+    return DORY_OK;
+}
+
+// CPUComm::vtxNNForwardGCN, CPU_comm.cpp:98-135
+int vtx_forward_gcn(dory_engine *e, uint32_t layer) {
+    const uint32_t L = e->L();
+    if (layer >= L) return fail(e, DORY_EINVAL, "apply_vertex: layer %u out of range", layer);
+    const DevMat &ah = *find_tensor(e, layer, "ah");
+    WeightSet &W = e->W[layer];
+    if (layer + 1 < L) {
+        return gemm_nn(e, ah, W, *find_tensor(e, layer, "z"), find_tensor(e, layer, "h"));
+    }
+    // last layer: logits -> softmax / stats / maskout / scale -> grad, dW
+    const DevMat &lab = *find_tensor(e, layer, "lab");
+    DevMat logits = lab;  // same shape
+    logits.p = e->scratchA.as<float>();
+    DevMat d = lab;
+    d.p = e->scratchB.as<float>();
+    int rc = gemm_nn(e, ah, W, logits, nullptr);
+    if (rc) return rc;
+    SoftmaxCEArgs s{};
+    s.z = logits.p; s.lab = lab.p; s.d = d.p; s.pred = nullptr;
+    s.ld = lab.ld; s.C = lab.cols; s.V = e->V;
+    s.trainEnd = (unsigned)(e->V * kTrainPortion);
+    s.valEnd = s.trainEnd + (unsigned)(e->V * kValPortion);
+    s.maskFloats = e->V - s.trainEnd;  // CPU_comm.cpp:470: sizeof(FeatType) * (end - stt)
+    s.strictMask = (e->cfg.flags & DORY_FLAG_STRICT_MASK) != 0;
+    s.denom = (float)(e->gV * kTrainPortion);  // CPU_comm.cpp:121
+    s.rowstat = e->rowstat.as<float>();
+    s.stats = e->stats_dev.as<float>();
+    LAUNCHED(launch_softmax_ce(s, e->stream));
+    e->stats.val_rows = s.valEnd - s.trainEnd;
+    if (layer > 0) {
+        rc = gemm_nt(e, d.p, d.ld, e->V, W, *find_tensor(e, layer, "grad"));
+        if (rc) return rc;
+    }
+    return gemm_tn(e, ah, d.p, d.ld, W, W.dw.as<float>());
+}
+
+// CPUComm::vtxNNBackwardGCN, CPU_comm.cpp:137-159
+int vtx_backward_gcn(dory_engine *e, uint32_t layer) {
+    const uint32_t L = e->L();
+    if (layer + 1 >= L) return fail(e, DORY_EINVAL, "apply_vertex backward: layer %u out of range", layer);
+    const DevMat &aTg = *find_tensor(e, layer, "aTg");
+    const DevMat &h = *find_tensor(e, layer, "h");
+    const DevMat &ah = *find_tensor(e, layer, "ah");
+    WeightSet &W = e->W[layer];
+    float *g = e->scratchA.as<float>();
+    LAUNCHED(launch_tanh_backward(aTg.p, h.p, g, (uint64_t)e->V * aTg.ld, e->stream));
+    int rc = gemm_tn(e, ah, g, aTg.ld, W, W.dw.as<float>());
+    if (rc) return rc;
+    if (layer != 0) rc = gemm_nt(e, g, aTg.ld, e->V, W, *find_tensor(e, layer, "grad"));
+    return rc;
+}
+
+// Engine::scatterGCN + ghostReceiverGCN: rows of `name`[srcLayer] -> peers' ghost block.
+int exchange(dory_engine *e, uint32_t dir, const DevMat &local, const DevMat &ghost) {
+    if (e->cfg.num_nodes <= 1) return DORY_OK;
+    if (!e->comm) return fail(e, DORY_ESTATE, "scatter with %u partitions needs dory_comm_init", e->cfg.num_nodes);
+    int launches = 0;
+    std::string msg = e->comm->exchange(dir, local.p, ghost.p, local.ld, e->stream, launches);
+    if (!msg.empty()) return fail(e, DORY_ECOMM, "%s", msg.c_str());
+    e->stats.kernel_launches += launches;
+    return DORY_OK;
+}
+
+int scatter_gcn(dory_engine *e, const dory_chunk *c) {
+    const uint32_t L = e->L();
+    if (c->dir == DORY_FORWARD) {  // gcn_ops.cpp:207-209: h[layer-1] -> fg[layer]
+        if (c->layer == 0 || c->layer >= L) return fail(e, DORY_EINVAL, "scatter: forward layer %u out of range", c->layer);
+        return exchange(e, DORY_FORWARD, *find_tensor(e, c->layer - 1, "h"), *find_tensor(e, c->layer, "fg"));
+    }
+    if (c->layer == 0 || c->layer >= L) return fail(e, DORY_EINVAL, "scatter: backward layer %u out of range", c->layer);
+    return exchange(e, DORY_BACKWARD, *find_tensor(e, c->layer, "grad"), *find_tensor(e, c->layer - 1, "bg"));
+}
+
+void inc_layer_gcn(const dory_engine *e, dory_chunk *c) {  // engine/utils.cpp:714-732
+    if (c->dir == DORY_FORWARD) {
+        c->layer++;
+        if (c->layer == e->L()) {
+            c->dir = DORY_BACKWARD;
+            c->layer--;
+        }
+    } else if (c->layer == 0) {
+        c->dir = DORY_FORWARD;
+        c->epoch++;
+    } else {
+        c->layer--;
+    }
+}
+
+void inc_layer_gat(const dory_engine *, dory_chunk *c) {  // engine/utils.cpp:734-748
+    if (c->dir == DORY_FORWARD) {
+        c->layer++;
+    } else if (c->layer == 0) {
+        c->dir = DORY_FORWARD;
+        c->vertex = 1;
+        c->epoch++;
+    } else {
+        c->layer--;
+    }
+}
+
+// ------------------------------------------------------------------ GAT operators
+int aggregate_gat(dory_engine *e, const dory_chunk *c) {
+    const uint32_t L = e->L();
+    if (c->layer == 0 || c->layer > L) return fail(e, DORY_EINVAL, "aggregateGAT: layer %u out of range", c->layer);
+    if (c->upBound > e->V || c->lowBound > c->upBound) return fail(e, DORY_EINVAL, "chunk bounds out of range");
+    const uint32_t fl = c->layer - 1;
+    const DevMat &z = *find_tensor(e, fl, "z");
+    if (c->dir == DORY_FORWARD) {  // gat_ops.cpp:201-220: ah = z + sum A[e] z_src
+        SpmmArgs a = spmm_args(e->fwd, nullptr, SELF_ONE, z, *find_tensor(e, fl, "ah"), c->lowBound, c->upBound, e->V);
+        LAUNCHED(launch_spmm(a, e->stream));
+        e->stats.edges_aggregated += edges_in_range(e, e->fwd, c->lowBound, c->upBound);
+        return DORY_OK;
+    }
+    // gat_ops.cpp:221-241: aTg = sum_out bvals * grad_dst  +  sum_in dA * z_src   (zero-initialised, Q11)
+    const DevMat &aTg = *find_tensor(e, fl, "aTg");
+    SpmmArgs a1 = spmm_args(e->bwd, nullptr, SELF_ZERO, *find_tensor(e, fl, "grad"), aTg, c->lowBound, c->upBound, e->V);
+    LAUNCHED(launch_spmm(a1, e->stream));
+    SpmmArgs a2 = spmm_args(e->fwd, nullptr, SELF_ACCUM, z, aTg, c->lowBound, c->upBound, e->V);
+    a2.vals = find_tensor(e, fl, "dA")->p;
+    LAUNCHED(launch_spmm(a2, e->stream));
+    e->stats.edges_aggregated += edges_in_range(e, e->bwd, c->lowBound, c->upBound) +
+                                 edges_in_range(e, e->fwd, c->lowBound, c->upBound);
+    return DORY_OK;
+}
+
+const DevMat &gat_layer_input(dory_engine *e, uint32_t layer) {  // CPU_comm.cpp:162-164
+    return layer == 0 ? *find_tensor(e, 0, "h") : *find_tensor(e, layer - 1, "ah");
+}
+
+int vtx_forward_gat(dory_engine *e, uint32_t layer) {  // CPU_comm.cpp:161-169
+    if (layer >= e->L()) return fail(e, DORY_EINVAL, "apply_vertex: layer %u out of range", layer);
+    return gemm_nn(e, gat_layer_input(e, layer), e->W[layer], *find_tensor(e, layer, "z"), nullptr);
+}
+
+int vtx_backward_gat(dory_engine *e, uint32_t layer) {  // CPU_comm.cpp:171-188
+    if (layer >= e->L()) return fail(e, DORY_EINVAL, "apply_vertex backward: layer %u out of range", layer);
+    const DevMat &aTg = *find_tensor(e, layer, "aTg");
+    WeightSet &W = e->W[layer];
+    int rc = gemm_tn(e, gat_layer_input(e, layer), aTg.p, aTg.ld, W, W.dw.as<float>());
+    if (rc) return rc;
+    if (layer != 0) rc = gemm_nt(e, aTg.p, aTg.ld, e->V, W, *find_tensor(e, layer - 1, "grad"));
+    return rc;
+}
+
+int edge_forward_gat(dory_engine *e, uint32_t layer) {  // CPU_comm.cpp:190-203
+    if (layer >= e->L()) return fail(e, DORY_EINVAL, "apply_edge: layer %u out of range", layer);
+    const DevMat &z = *find_tensor(e, layer, "z");
+    LAUNCHED(launch_gat_edge_forward(z.p, z.ld, z.cols, e->Ai[layer].w.as<float>(), e->fwd.ptrs.as<uint64_t>(),
+                                     e->V, find_tensor(e, layer, "az")->p, e->fwd.vals.as<float>(), e->stream));
+    return DORY_OK;
+}
+
+int edge_backward_gat(dory_engine *e, uint32_t layer) {  // CPU_comm.cpp:205-242
+    if (layer >= e->L()) return fail(e, DORY_EINVAL, "apply_edge backward: layer %u out of range", layer);
+    const DevMat &z = *find_tensor(e, layer, "z");
+    const DevMat &grad = *find_tensor(e, layer, "grad");
+    GatEdgeBackwardArgs a{};
+    a.grad = grad.p; a.z = z.p; a.ld = z.ld; a.F = z.cols; a.V = e->V;
+    a.a = e->Ai[layer].w.as<float>();
+    a.az = find_tensor(e, layer, "az")->p;
+    a.colPtrs = e->fwd.ptrs.as<uint64_t>();
+    a.dA = find_tensor(e, layer, "dA")->p;
+    a.da = e->Ai[layer].dw.as<float>();
+    a.scratch = e->scratchA.as<float>();
+    a.scratch_floats = e->scratchA.bytes / 4;
+    a.ws = e->gemm_ws.as<float>();
+    a.ws_floats = e->gemm_ws.bytes / 4;
+    LAUNCHED(launch_gat_edge_backward(a, e->stream));
+    return DORY_OK;
+}
+
+int scatter_gat(dory_engine *e, const dory_chunk *c) {  // gat_ops.cpp:277-333
+    if (c->layer == 0 || c->layer > e->L()) return fail(e, DORY_EINVAL, "scatterGAT: layer %u out of range", c->layer);
+    const uint32_t ol = c->layer - 1;
+    if (c->dir == DORY_FORWARD)
+        return exchange(e, DORY_FORWARD, *find_tensor(e, ol, "z"), *find_tensor(e, ol, "fg_z"));
+    return exchange(e, DORY_BACKWARD, *find_tensor(e, ol, "grad"), *find_tensor(e, ol, "bg_d"));
+}
+
+int predict_gat(dory_engine *e, const dory_chunk *c) {  // gat_ops.cpp:247-265
+    if (c->layer == 0 || c->layer > e->L()) return fail(e, DORY_EINVAL, "predictGAT: layer %u out of range", c->layer);
+    const uint32_t fl = c->layer - 1;
+    const DevMat *lab = find_tensor(e, fl, "lab");
+    if (!lab) return fail(e, DORY_EINVAL, "predictGAT: no labels at layer %u", fl);
+    const DevMat &grad = *find_tensor(e, fl, "grad");
+    const float *logits;
+    uint32_t ldl;
+    if (e->cfg.flags & DORY_FLAG_GAT_PREDICT_AH) {
+        const DevMat &ah = *find_tensor(e, fl, "ah");
+        logits = ah.p;
+        ldl = ah.ld;
+    } else {  // quirk Q9: "az" (E x 1) reinterpreted as a dense V x C array
+        if (e->Ein < (uint64_t)e->V * lab->cols)
+            return fail(e, DORY_EINVAL, "predictGAT quirk mode reads az as V x C but E_in (%llu) < V*C; "
+                        "the reference reads out of bounds here -- use DORY_FLAG_GAT_PREDICT_AH",
+                        (unsigned long long)e->Ein);
+        logits = find_tensor(e, fl, "az")->p;
+        ldl = lab->cols;
+    }
+    LAUNCHED(launch_gat_predict(logits, ldl, lab->p, grad.p, lab->ld, lab->cols, c->lowBound, c->upBound, e->stream));
+    return DORY_OK;
+}
+
+int apply_update_impl(dory_engine *e, uint32_t layer) {
+    WeightSet &W = e->W[layer];
+    if (e->comm && e->cfg.num_nodes > 1) {  // weighttensor.cpp:263-267: local + ghost updates summed
+        std::string msg = e->comm->allreduce_sum(W.dw.as<float>(), W.floats(), e->stream);
+        if (!msg.empty()) return fail(e, DORY_ECOMM, "%s", msg.c_str());
+    }
+    if (e->cfg.gnn_type == DORY_GAT) return DORY_OK;  // tryApplyUpdateFake, weightserver.cpp:112-116 (Q10)
+    LAUNCHED(launch_adam(W.w.as<float>(), W.dw.as<float>(), W.m.as<float>(), W.v.as<float>(), W.floats(),
+                         e->lr_t, e->beta1, e->beta2, e->eps, e->stream));
+    if (layer == 0) adam_next_iteration(e);  // AdamOptimizer.cpp:49-50
+    return DORY_OK;
+}
+
+int fetch_stats(dory_engine *e) {
+    float hs[2] = {0.f, 0.f};
+    CU(cudaMemcpyAsync(hs, e->stats_dev.p, sizeof hs, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->stats.acc_sum = hs[0];
+    e->stats.loss_sum = hs[1];
+    return DORY_OK;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+int dory_abi_version(void) { return DORY_ABI_VERSION; }
+
+const char *dory_last_error(const dory_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int dory_create(dory_engine **out, const dory_config *cfg) {
+    dory_engine *e = nullptr;  // for fail()
+    if (!out || !cfg) return fail(e, DORY_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != DORY_ABI_VERSION) return fail(e, DORY_EINVAL, "ABI version %u != %u", cfg->abi_version, DORY_ABI_VERSION);
+    if (cfg->n_layers < 1 || cfg->n_layers > DORY_MAX_LAYERS) return fail(e, DORY_EINVAL, "n_layers %u out of range", cfg->n_layers);
+    if (cfg->gnn_type == DORY_GCN && cfg->n_layers < 2)
+        return fail(e, DORY_EINVAL, "GCN needs >= 2 layers (the reference's last layer writes grad[layer], which only exists for layer > 0)");
+    if (cfg->gnn_type != DORY_GCN && cfg->gnn_type != DORY_GAT) return fail(e, DORY_EINVAL, "unknown gnn_type %u", cfg->gnn_type);
+    for (uint32_t i = 0; i <= cfg->n_layers; ++i)
+        if (cfg->dims[i] == 0) return fail(e, DORY_EINVAL, "layer width %u is zero", i);
+    if (cfg->dims[cfg->n_layers] > 256) return fail(e, DORY_EINVAL, "more than 256 classes not supported");
+    if (cfg->num_nodes == 0 || cfg->node_id >= cfg->num_nodes) return fail(e, DORY_EINVAL, "node_id/num_nodes invalid");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(e, DORY_ENODEV, "no CUDA device visible; dorylus_b200 has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(e, DORY_EINVAL, "device %d out of range (%d visible)", cfg->device, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(e, DORY_ECUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(e, DORY_ENODEV, "device %d is sm_%d%d; this library only carries sm_100a code", cfg->device, prop.major, prop.minor);
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(e, DORY_ECUDA, "cudaSetDevice failed");
+    std::unique_ptr<dory_engine> eng(new dory_engine());
+    eng->cfg = *cfg;
+    if (cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(e, DORY_ECUDA, "cudaStreamCreate failed");
+    for (auto &ev : eng->events)
+        if (cudaEventCreate(&ev) != cudaSuccess) return fail(e, DORY_ECUDA, "cudaEventCreate failed");
+    eng->adam_epochs = 0;
+    adam_next_iteration(eng.get());  // AdamOptimizer ctor, AdamOptimizer.cpp:6-8
+    *out = eng.release();
+    return DORY_OK;
+}
+
+void dory_destroy(dory_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    e->comm.reset();
+    for (auto &ev : e->events)
+        if (ev) cudaEventDestroy(ev);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int dory_sync(dory_engine *e) {
+    if (!e) return DORY_EINVAL;
+    CU(cudaStreamSynchronize(e->stream));
+    return DORY_OK;
+}
+
+void dory_free(void *p) { std::free(p); }
+
+int dory_preprocess_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_edges, const int32_t *parts,
+                          uint32_t n_vertices, uint32_t part, uint32_t n_parts, int undirected, void **image,
+                          size_t *image_len) {
+    dory_engine *e = nullptr;
+    if (!parts || !image || !image_len || (n_edges && (!src || !dst))) return fail(e, DORY_EINVAL, "null argument");
+    EdgeList el;
+    el.src = src; el.dst = dst; el.stride = 1; el.n = n_edges;
+    std::vector<uint8_t> img;
+    std::string msg = preprocess_partition(el, parts, n_vertices, part, n_parts, undirected != 0, img);
+    if (!msg.empty()) return fail(e, DORY_EINVAL, "%s", msg.c_str());
+    void *p = std::malloc(img.size());
+    if (!p) return fail(e, DORY_ENOMEM, "out of host memory for a %zu-byte image", img.size());
+    std::memcpy(p, img.data(), img.size());
+    *image = p;
+    *image_len = img.size();
+    return DORY_OK;
+}
+
+int dory_preprocess_dir(const char *dir, uint32_t part, uint32_t n_parts, int undirected) {
+    dory_engine *e = nullptr;
+    if (!dir) return fail(e, DORY_EINVAL, "null argument");
+    const std::string d(dir);
+    // graph.bsnap.edges: BSHeaderType {int32, uint32, uint64} then (src, dst) pairs (dataloader.hpp:11-15)
+    FILE *f = std::fopen((d + "graph.bsnap.edges").c_str(), "rb");
+    if (!f) return fail(e, DORY_EFORMAT, "cannot open %sgraph.bsnap.edges", dir);
+    struct { int32_t sz; uint32_t nv; uint64_t ne; } hdr;
+    if (std::fread(&hdr, sizeof hdr, 1, f) != 1 || hdr.sz != 4) {
+        std::fclose(f);
+        return fail(e, DORY_EFORMAT, "bad bsnap header");
+    }
+    std::vector<uint32_t> pairs;
+    {
+        std::fseek(f, 0, SEEK_END);
+        long end = std::ftell(f);
+        std::fseek(f, sizeof hdr, SEEK_SET);
+        size_t n = ((size_t)end - sizeof hdr) / 8;
+        pairs.resize(2 * n);
+        if (n && std::fread(pairs.data(), 8, n, f) != n) {
+            std::fclose(f);
+            return fail(e, DORY_EFORMAT, "short read on edge file");
+        }
+    }
+    std::fclose(f);
+    // graph.bsnap.parts: one id per line; lines not starting with a digit are skipped (dataloader.cpp:66-68)
+    std::vector<int32_t> parts;
+    {
+        FILE *pf = std::fopen((d + "graph.bsnap.parts").c_str(), "r");
+        if (!pf) return fail(e, DORY_EFORMAT, "cannot open %sgraph.bsnap.parts", dir);
+        char line[256];
+        while (std::fgets(line, sizeof line, pf)) {
+            if (line[0] < '0' || line[0] > '9') continue;
+            parts.push_back((int32_t)std::strtol(line, nullptr, 10));
+        }
+        std::fclose(pf);
+    }
+    EdgeList el;
+    el.src = pairs.data(); el.dst = pairs.data() + 1; el.stride = 2; el.n = pairs.size() / 2;
+    std::vector<uint8_t> img;
+    std::string msg = preprocess_partition(el, parts.data(), (uint32_t)parts.size(), part, n_parts, undirected != 0, img);
+    if (!msg.empty()) return fail(e, DORY_EINVAL, "%s", msg.c_str());
+    char name[64];
+    std::snprintf(name, sizeof name, "graph.%u.bin", part);
+    FILE *of = std::fopen((d + name).c_str(), "wb");
+    if (!of) return fail(e, DORY_EFORMAT, "cannot write %s%s", dir, name);
+    const bool ok = std::fwrite(img.data(), 1, img.size(), of) == img.size();
+    std::fclose(of);
+    return ok ? DORY_OK : fail(e, DORY_EFORMAT, "short write on %s%s", dir, name);
+}
+
+int dory_load_partition(dory_engine *e, const void *graph_bin, size_t len) {
+    if (!e || !graph_bin) return DORY_EINVAL;
+    if (e->loaded) return fail(e, DORY_ESTATE, "a partition is already loaded on this engine");
+    CU(cudaSetDevice(e->cfg.device));
+    PartitionView pv;
+    std::string msg = parse_partition(graph_bin, len, pv);
+    if (!msg.empty()) return fail(e, DORY_EFORMAT, "%s", msg.c_str());
+    if (pv.numNodes != e->cfg.num_nodes)
+        return fail(e, DORY_EINVAL, "graph image was built for %u partitions, engine configured for %u", pv.numNodes, e->cfg.num_nodes);
+    e->V = pv.localVtxCnt; e->gV = pv.globalVtxCnt; e->Gs = pv.srcGhostCnt; e->Gd = pv.dstGhostCnt;
+    e->Ein = pv.localInEdgeCnt; e->Eout = pv.localOutEdgeCnt; e->Eglob = pv.globalEdgeCnt;
+    if (e->V == 0) return fail(e, DORY_EINVAL, "partition has no local vertices");
+    if (pv.fwdNnz != e->Ein || pv.bwdNnz != e->Eout) return fail(e, DORY_EFORMAT, "edge counts disagree with CSC/CSR nnz");
+    e->l2g.resize(e->V);
+    std::memcpy(e->l2g.data(), pv.localToGlobal, 4 * (size_t)e->V);
+    for (int dir = 0; dir < 2; ++dir) {
+        auto &lists = dir == 0 ? pv.fwdSend : pv.bwdSend;
+        e->sendIds[dir].assign(pv.numNodes, {});
+        for (uint32_t p = 0; p < pv.numNodes; ++p) {
+            e->sendIds[dir][p].resize(lists[p].second);
+            if (lists[p].second) std::memcpy(e->sendIds[dir][p].data(), lists[p].first, 4 * (size_t)lists[p].second);
+            for (uint32_t id : e->sendIds[dir][p])
+                if (id >= e->V) return fail(e, DORY_EFORMAT, "send list references vertex %u >= %u", id, e->V);
+        }
+    }
+    int rc = upload_adjacency(e, e->fwd, pv.colPtrs, pv.rowIdxs, pv.fwdVals, pv.fwdNnz, e->V, e->V + e->Gs);
+    if (rc) return rc;
+    rc = upload_adjacency(e, e->bwd, pv.rowPtrs, pv.colIdxs, pv.bwdVals, pv.bwdNnz, e->V, e->V + e->Gd);
+    if (rc) return rc;
+    CU(e->norms.alloc(4 * (size_t)e->V));
+    CU(cudaMemcpyAsync(e->norms.p, pv.norms, 4 * (size_t)e->V, cudaMemcpyHostToDevice, e->stream));
+
+    rc = e->cfg.gnn_type == DORY_GCN ? preallocate_gcn(e) : preallocate_gat(e);
+    if (rc) return rc;
+    const uint32_t L = e->L();
+    e->W.resize(L);
+    uint32_t maxld = 0;
+    for (uint32_t l = 0; l <= L; ++l) maxld = std::max(maxld, padded_ld(e->dim(l)));
+    for (uint32_t l = 0; l < L; ++l) {
+        rc = alloc_weight(e, e->W[l], e->dim(l), e->dim(l + 1));
+        if (rc) return rc;
+    }
+    if (e->cfg.gnn_type == DORY_GAT) {
+        e->Ai.resize(L);
+        for (uint32_t l = 0; l < L; ++l) {
+            rc = alloc_weight(e, e->Ai[l], e->dim(l + 1), 1);
+            if (rc) return rc;
+        }
+    }
+    const size_t scr = (size_t)e->V * maxld * sizeof(float);
+    CU(e->scratchA.alloc(scr));
+    CU(e->scratchB.alloc(scr));
+    CU(cudaMemsetAsync(e->scratchA.p, 0, scr, e->stream));
+    CU(cudaMemsetAsync(e->scratchB.p, 0, scr, e->stream));
+    size_t wmax = 0;
+    for (auto &w : e->W) wmax = std::max(wmax, w.floats());
+    CU(e->gemm_ws.alloc(std::max<size_t>(wmax * 64, (size_t)maxld * maxld * 64) * sizeof(float)));
+    CU(e->rowstat.alloc(2 * (size_t)e->V * sizeof(float)));
+    CU(e->stats_dev.alloc(2 * sizeof(float)));
+    CU(cudaMemsetAsync(e->stats_dev.p, 0, 2 * sizeof(float), e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->loaded = true;
+    return DORY_OK;
+}
+
+int dory_graph_counts(const dory_engine *e, uint64_t out[7]) {
+    if (!e || !out || !e->loaded) return DORY_EINVAL;
+    out[0] = e->V; out[1] = e->gV; out[2] = e->Gs; out[3] = e->Gd; out[4] = e->Ein; out[5] = e->Eout; out[6] = e->Eglob;
+    return DORY_OK;
+}
+
+int dory_tensor_shape(const dory_engine *e, uint32_t layer, const char *name, uint64_t *rows, uint32_t *cols) {
+    if (!e || !name || !e->loaded) return DORY_EINVAL;
+    const DevMat *m = find_tensor(e, layer, name);
+    if (!m) return DORY_EINVAL;
+    if (rows) *rows = m->rows;
+    if (cols) *cols = m->cols;
+    return DORY_OK;
+}
+
+int dory_tensor_device(const dory_engine *e, uint32_t layer, const char *name, void **dptr, uint64_t *rows,
+                       uint32_t *cols, uint32_t *ld) {
+    if (!e || !name || !e->loaded) return DORY_EINVAL;
+    const DevMat *m = find_tensor(e, layer, name);
+    if (!m) return DORY_EINVAL;
+    if (dptr) *dptr = m->p;
+    if (rows) *rows = m->rows;
+    if (cols) *cols = m->cols;
+    if (ld) *ld = m->ld;
+    return DORY_OK;
+}
+
+int dory_set_tensor(dory_engine *e, uint32_t layer, const char *name, const float *host, uint64_t rows, uint32_t cols) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!name || !host) return fail(e, DORY_EINVAL, "null argument");
+    const DevMat *m = find_tensor(e, layer, name);
+    if (!m) return fail(e, DORY_EINVAL, "no tensor '%s' at layer %u", name, layer);
+    if (m->rows != rows || m->cols != cols)
+        return fail(e, DORY_EINVAL, "tensor '%s'[%u] is %llu x %u, caller passed %llu x %u", name, layer,
+                    (unsigned long long)m->rows, m->cols, (unsigned long long)rows, cols);
+    return copy_in(e, *m, host);
+}
+
+int dory_get_tensor(dory_engine *e, uint32_t layer, const char *name, float *host, uint64_t rows, uint32_t cols) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!name || !host) return fail(e, DORY_EINVAL, "null argument");
+    const DevMat *m = find_tensor(e, layer, name);
+    if (!m) return fail(e, DORY_EINVAL, "no tensor '%s' at layer %u", name, layer);
+    if (m->rows != rows || m->cols != cols)
+        return fail(e, DORY_EINVAL, "tensor '%s'[%u] is %llu x %u, caller passed %llu x %u", name, layer,
+                    (unsigned long long)m->rows, m->cols, (unsigned long long)rows, cols);
+    return copy_out(e, *m, host);
+}
+
+static int weight_ref(dory_engine *e, uint32_t layer, const char *name, WeightSet **w) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!name) return fail(e, DORY_EINVAL, "null argument");
+    if (layer >= e->L()) return fail(e, DORY_EINVAL, "weight layer %u out of range", layer);
+    if (std::strcmp(name, "w") == 0) *w = &e->W[layer];
+    else if (std::strcmp(name, "a_i") == 0 && e->cfg.gnn_type == DORY_GAT) *w = &e->Ai[layer];
+    else return fail(e, DORY_EINVAL, "unknown weight '%s'", name);
+    return DORY_OK;
+}
+
+static int weight_copy(dory_engine *e, WeightSet *w, float *dev, float *host, uint32_t rows, uint32_t cols, bool to_dev) {
+    if (!host) return fail(e, DORY_EINVAL, "null argument");
+    if (rows != w->rows || cols != w->cols) return fail(e, DORY_EINVAL, "weight is %u x %u, caller passed %u x %u", w->rows, w->cols, rows, cols);
+    if (to_dev)
+        CU(cudaMemcpy2DAsync(dev, (size_t)w->ld * 4, host, (size_t)cols * 4, (size_t)cols * 4, rows, cudaMemcpyHostToDevice, e->stream));
+    else
+        CU(cudaMemcpy2DAsync(host, (size_t)cols * 4, dev, (size_t)w->ld * 4, (size_t)cols * 4, rows, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return DORY_OK;
+}
+
+int dory_set_weights(dory_engine *e, uint32_t layer, const char *name, const float *host, uint32_t rows, uint32_t cols) {
+    WeightSet *w = nullptr;
+    int rc = weight_ref(e, layer, name, &w);
+    if (rc) return rc;
+    return weight_copy(e, w, w->w.as<float>(), const_cast<float *>(host), rows, cols, true);
+}
+
+int dory_get_weights(dory_engine *e, uint32_t layer, const char *name, float *host, uint32_t rows, uint32_t cols) {
+    WeightSet *w = nullptr;
+    int rc = weight_ref(e, layer, name, &w);
+    if (rc) return rc;
+    return weight_copy(e, w, w->w.as<float>(), host, rows, cols, false);
+}
+
+int dory_get_weight_grad(dory_engine *e, uint32_t layer, const char *name, float *host, uint32_t rows, uint32_t cols) {
+    WeightSet *w = nullptr;
+    int rc = weight_ref(e, layer, name, &w);
+    if (rc) return rc;
+    return weight_copy(e, w, w->dw.as<float>(), host, rows, cols, false);
+}
+
+int dory_init_weights(dory_engine *e) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    // WeightServer::xavierInitializer (weightserver.cpp:567-585): U(-1,1) * sqrt(6/(d1+d2)) from a
+    // std::default_random_engine seeded with 8888 for EVERY matrix; kaiming (:593-612) likewise with
+    // N(0,1) * sqrt(2/d1).  libstdc++'s engine/distributions make this bit-reproducible.
+    for (uint32_t l = 0; l < e->L(); ++l) {
+        const uint32_t d1 = e->dim(l), d2 = e->dim(l + 1);
+        std::vector<float> w((size_t)d1 * d2);
+        {
+            std::default_random_engine dre(8888);
+            std::uniform_real_distribution<float> dist(-1, 1);
+            for (auto &x : w) x = dist(dre);
+            const float nf = std::sqrt(6.0 / (float(d1 + d2)));
+            for (auto &x : w) x *= nf;
+        }
+        rc = dory_set_weights(e, l, "w", w.data(), d1, d2);
+        if (rc) return rc;
+        if (e->cfg.gnn_type == DORY_GAT) {
+            std::vector<float> a(d2);
+            std::default_random_engine dre(8888);
+            std::normal_distribution<float> dist(0, 1);
+            for (auto &x : a) x = dist(dre);
+            const float nf = std::sqrt(2.0 / (float(d2)));
+            for (auto &x : a) x *= nf;
+            rc = dory_set_weights(e, l, "a_i", a.data(), d2, 1);
+            if (rc) return rc;
+        }
+    }
+    return DORY_OK;
+}
+
+int dory_apply_update(dory_engine *e, uint32_t layer) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (layer >= e->L()) return fail(e, DORY_EINVAL, "layer %u out of range", layer);
+    return apply_update_impl(e, layer);
+}
+
+int dory_inc_layer(const dory_engine *e, dory_chunk *c) {
+    if (!e || !c) return DORY_EINVAL;
+    if (e->cfg.gnn_type == DORY_GCN) inc_layer_gcn(e, c); else inc_layer_gat(e, c);
+    return DORY_OK;
+}
+
+int dory_aggregate(dory_engine *e, const dory_chunk *c) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!c) return fail(e, DORY_EINVAL, "null chunk");
+    return e->cfg.gnn_type == DORY_GCN ? aggregate_gcn(e, c) : aggregate_gat(e, c);
+}
+
+int dory_apply_vertex(dory_engine *e, const dory_chunk *c) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!c) return fail(e, DORY_EINVAL, "null chunk");
+    if (e->cfg.gnn_type == DORY_GCN) {
+        if (c->dir == DORY_FORWARD) return vtx_forward_gcn(e, c->layer);
+        dory_chunk n = *c;  // applyVertexGCN, gcn_ops.cpp:198-200: inc layer first
+        inc_layer_gcn(e, &n);
+        if (n.dir != DORY_BACKWARD) return fail(e, DORY_EINVAL, "apply_vertex: backward chunk at layer 0 has nothing to apply");
+        return vtx_backward_gcn(e, n.layer);
+    }
+    if (c->dir == DORY_FORWARD) return vtx_forward_gat(e, c->layer);
+    dory_chunk n = *c;  // applyVertexGAT, gat_ops.cpp:271-273
+    inc_layer_gat(e, &n);
+    if (n.dir != DORY_BACKWARD) return fail(e, DORY_EINVAL, "apply_vertex: backward chunk at layer 0 has nothing to apply");
+    return vtx_backward_gat(e, n.layer);
+}
+
+int dory_scatter(dory_engine *e, const dory_chunk *c) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!c) return fail(e, DORY_EINVAL, "null chunk");
+    return e->cfg.gnn_type == DORY_GCN ? scatter_gcn(e, c) : scatter_gat(e, c);
+}
+
+int dory_apply_edge(dory_engine *e, const dory_chunk *c) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!c) return fail(e, DORY_EINVAL, "null chunk");
+    if (e->cfg.gnn_type == DORY_GCN) return DORY_OK;  // applyEdgeGCN, gcn_ops.cpp:364-366
+    if (c->layer == 0) return fail(e, DORY_EINVAL, "apply_edge: chunk layer 0 (NNCompute does layer--, CPU_comm.cpp:33)");
+    return c->dir == DORY_FORWARD ? edge_forward_gat(e, c->layer - 1) : edge_backward_gat(e, c->layer - 1);
+}
+
+int dory_predict(dory_engine *e, const dory_chunk *c) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!c) return fail(e, DORY_EINVAL, "null chunk");
+    if (e->cfg.gnn_type != DORY_GAT) return fail(e, DORY_EINVAL, "predict is a GAT operator");
+    return predict_gat(e, c);
+}
+
+int dory_forward(dory_engine *e, uint32_t layer) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    dory_chunk c{0, e->cfg.node_id, 0, e->V, layer, DORY_FORWARD, 0, 1};
+    if (e->cfg.gnn_type == DORY_GCN) {  // GA -> AV -> SC -> AE
+        if ((rc = dory_aggregate(e, &c))) return rc;
+        if ((rc = dory_apply_vertex(e, &c))) return rc;
+        inc_layer_gcn(e, &c);
+        if ((rc = dory_scatter(e, &c))) return rc;
+        return dory_apply_edge(e, &c);
+    }
+    // GAT: AV -> SC -> AE -> GA (-> predict on the last layer)   
+    if ((rc = dory_apply_vertex(e, &c))) return rc;
+    inc_layer_gat(e, &c);
+    if ((rc = dory_scatter(e, &c))) return rc;
+    c.vertex = 0;
+    if ((rc = dory_apply_edge(e, &c))) return rc;
+    if ((rc = dory_aggregate(e, &c))) return rc;
+    if (c.layer == e->L()) rc = dory_predict(e, &c);
+    return rc;
+}
+
+int dory_backward(dory_engine *e, uint32_t layer) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    dory_chunk c{0, e->cfg.node_id, 0, e->V, layer, DORY_BACKWARD, 0, 1};
+    if (e->cfg.gnn_type == DORY_GCN) {  // GA -> AV(B) -> SC -> AE for the next backward layer
+        if ((rc = dory_aggregate(e, &c))) return rc;
+        if ((rc = dory_apply_vertex(e, &c))) return rc;
+        inc_layer_gcn(e, &c);
+        if (c.layer == 0) return DORY_OK;  // vtxNNBackward(0) ended the epoch
+        if ((rc = dory_scatter(e, &c))) return rc;
+        return dory_apply_edge(e, &c);
+    }
+    // GAT backward at chunk.layer = layer (feature layer layer-1): SC -> AE -> GA -> AV
+    if ((rc = dory_scatter(e, &c))) return rc;
+    c.vertex = 0;
+    if ((rc = dory_apply_edge(e, &c))) return rc;
+    if ((rc = dory_aggregate(e, &c))) return rc;
+    c.vertex = 1;
+    return dory_apply_vertex(e, &c);
+}
+
+int dory_epoch(dory_engine *e, dory_stats *stats) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    const uint32_t L = e->L();
+    if (e->cfg.gnn_type == DORY_GCN) {
+        for (uint32_t l = 0; l < L; ++l)
+            if ((rc = dory_forward(e, l))) return rc;
+        for (uint32_t l = L - 1; l > 0; --l)
+            if ((rc = dory_backward(e, l))) return rc;
+    } else {
+        for (uint32_t l = 0; l < L; ++l)
+            if ((rc = dory_forward(e, l))) return rc;
+        for (uint32_t l = L; l > 0; --l)
+            if ((rc = dory_backward(e, l))) return rc;
+    }
+    // weight updates in the order the weight server receives them: last layer first
+    for (uint32_t l = L; l-- > 0;)
+        if ((rc = apply_update_impl(e, l))) return rc;
+    e->stats.epochs_done++;
+    if (stats) return dory_get_stats(e, stats);
+    return DORY_OK;
+}
+
+int dory_get_stats(dory_engine *e, dory_stats *stats) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!stats) return fail(e, DORY_EINVAL, "null argument");
+    if ((rc = fetch_stats(e))) return rc;
+    *stats = e->stats;
+    return DORY_OK;
+}
+
+int dory_comm_unique_id(void *id128) {
+    dory_engine *e = nullptr;
+    if (!id128) return fail(e, DORY_EINVAL, "null argument");
+    std::string msg = dory::Comm::unique_id(id128);
+    if (!msg.empty()) return fail(e, DORY_ECOMM, "%s", msg.c_str());
+    return DORY_OK;
+}
+
+int dory_comm_init(dory_engine *e, const void *id128) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!id128) return fail(e, DORY_EINVAL, "null argument");
+    if (e->comm) return fail(e, DORY_ESTATE, "communicator already initialised");
+    auto comm = std::make_unique<dory::Comm>();
+    std::string msg = comm->init(id128, (int)e->cfg.node_id, (int)e->cfg.num_nodes, e->cfg.device);
+    if (!msg.empty()) return fail(e, DORY_ECOMM, "%s", msg.c_str());
+    uint32_t maxld = 0;
+    for (uint32_t l = 0; l <= e->L(); ++l) maxld = std::max(maxld, padded_ld(e->dim(l)));
+    for (int dir = 0; dir < 2; ++dir) {
+        msg = comm->set_send_lists(dir, e->sendIds[dir], maxld, e->stream);
+        if (!msg.empty()) return fail(e, DORY_ECOMM, "%s", msg.c_str());
+    }
+    e->comm = std::move(comm);
+    return DORY_OK;
+}
+
+int dory_comm_set_recv_slots(dory_engine *e, uint32_t dir, uint32_t peer, const uint32_t *slots, uint32_t n) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!e->comm) return fail(e, DORY_ESTATE, "dory_comm_init first");
+    if (dir > 1 || peer >= e->cfg.num_nodes || (n && !slots)) return fail(e, DORY_EINVAL, "bad argument");
+    const uint32_t G = dir == 0 ? e->Gs : e->Gd;
+    for (uint32_t i = 0; i < n; ++i)
+        if (slots[i] >= G) return fail(e, DORY_EINVAL, "recv slot %u >= ghost count %u", slots[i], G);
+    uint32_t maxld = 0;
+    for (uint32_t l = 0; l <= e->L(); ++l) maxld = std::max(maxld, padded_ld(e->dim(l)));
+    std::string msg = e->comm->set_recv_slots((int)dir, (int)peer, slots, n, maxld, e->stream);
+    if (!msg.empty()) return fail(e, DORY_ECOMM, "%s", msg.c_str());
+    return DORY_OK;
+}
+
+int dory_comm_send_gvids(const dory_engine *e, uint32_t dir, uint32_t peer, uint32_t *ids, uint32_t *n) {
+    if (!e || !e->loaded || dir > 1 || peer >= e->cfg.num_nodes || !n) return DORY_EINVAL;
+    const auto &l = e->sendIds[dir][peer];
+    *n = (uint32_t)l.size();
+    if (ids)
+        for (size_t i = 0; i < l.size(); ++i) ids[i] = e->l2g[l[i]];
+    return DORY_OK;
+}
+
+int dory_event_record(dory_engine *e, uint32_t slot) {
+    if (!e || slot >= kNumEvents) return DORY_EINVAL;
+    CU(cudaEventRecord(e->events[slot], e->stream));
+    return DORY_OK;
+}
+
+int dory_event_elapsed_ms(dory_engine *e, uint32_t a, uint32_t b, float *ms) {
+    if (!e || a >= kNumEvents || b >= kNumEvents || !ms) return DORY_EINVAL;
+    CU(cudaEventSynchronize(e->events[b]));
+    CU(cudaEventElapsedTime(ms, e->events[a], e->events[b]));
+    return DORY_OK;
+}
+
+int dory_flush_l2(dory_engine *e, size_t bytes) {
+    if (!e) return DORY_EINVAL;
+    if (e->flush.bytes < bytes) CU(e->flush.alloc(bytes));
+    LAUNCHED(launch_fill(e->flush.as<float>(), bytes / 4, 0.f, e->stream));
+    return DORY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,250 @@
+// Neighbour aggregation: out[v,:] = self(v) + sum_{e in adj(v)} vals[e] * src[idx[e],:]
+//
+// Stands in for Engine::aggregateGCN / aggregateGAT (reference engine/ops/gcn_ops.cpp:130-191,
+// gat_ops.cpp:173-243) and for the reference GPU backend's cusparseSpMM + cublasSgeam +
+// cublasSdgmm + thrust::plus chain (GPU-Computation/comp_unit.cu:48-91), as ONE kernel with the
+// self term fused.
+//
+// Mapping to B200:
+//   * a destination row is owned by one warp (rows below the heavy threshold) or by one CTA of
+//     8 warps (heavy rows; the warps split the edge list and combine through shared memory in a
+//     fixed order) -- no atomics, so results are bit-reproducible run to run;
+//   * lanes are grouped LG per source row and read VEC float4 each: every gather of a source row
+//     is a run of fully coalesced 128-bit loads covering whole 128 B lines (rows are padded to
+//     a line multiple, common.cuh), 32/LG edges are in flight per instruction;
+//   * edge ids / weights are read once per 32 edges with one coalesced 128 B load each and
+//     distributed by warp shuffles; they bypass L1 (streamed once) so that L1 keeps hub rows;
+//   * rows are issued in degree-descending order (longest-processing-time-first), so the
+//     power-law tail fills in behind the hubs instead of stretching the last wave;
+//   * wide rows can be cut into column slabs (gridDim.y) so that a slab of the source block stays
+//     resident in the 126 MB L2 while the adjacency is walked once per slab.
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace dory {
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream_f32(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void fma4(float4 &a, const float4 &x, float w) {
+    a.x = fmaf(x.x, w, a.x);
+    a.y = fmaf(x.y, w, a.y);
+    a.z = fmaf(x.z, w, a.z);
+    a.w = fmaf(x.w, w, a.w);
+}
+__device__ __forceinline__ void add4(float4 &a, const float4 &b) {
+    a.x += b.x;
+    a.y += b.y;
+    a.z += b.z;
+    a.w += b.w;
+}
+
+// LG   : lanes cooperating on one source row (power of two, 4..32)
+// VEC  : float4 per lane  -> a CTA column slab is LG*VEC float4 wide
+// TEAM : warps per destination row (1: warp-per-row, kWarpsPerCta: CTA-per-row)
+template <int LG, int VEC, int TEAM>
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nrows) {
+    constexpr int EPW = 32 / LG;  // edges in flight per warp-wide load
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane / LG, l = lane % LG;
+
+    uint32_t rid;
+    int team_rank;
+    if (TEAM == 1) {
+        rid = blockIdx.x * kWarpsPerCta + warp;
+        team_rank = 0;
+        if (rid >= nrows) return;
+    } else {
+        rid = blockIdx.x;
+        team_rank = warp;
+    }
+    const uint32_t row = rowlist ? rowlist[rid] : a.low + rid;
+    const uint32_t col0 = blockIdx.y * (LG * VEC);  // slab start, float4 units
+    const uint64_t e_begin = a.ptrs[row], e_end = a.ptrs[row + 1];
+    const float4 *__restrict__ src4 = reinterpret_cast<const float4 *>(a.src);
+    const uint32_t ld4 = a.ld >> 2;
+
+    float4 acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool act[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) act[j] = (col0 + l + j * LG) < a.nvec;
+
+    for (uint64_t e0 = e_begin + (uint64_t)team_rank * 32; e0 < e_end; e0 += 32 * TEAM) {
+        const uint64_t my = e0 + lane;
+        uint32_t s_l = 0;
+        float w_l = 0.f;  // edges past the end carry weight 0 and point at row 0 (a valid address)
+        if (my < e_end) {
+            s_l = ld_stream_u32(a.idx + my);
+            w_l = ld_stream_f32(a.vals + my);
+        }
+        const int n = (int)min((uint64_t)32, e_end - e0);
+#pragma unroll 4
+        for (int k = 0; k < LG; ++k) {
+            if (k * EPW >= n) break;  // warp-uniform
+            const uint32_t s = __shfl_sync(kFull, s_l, k * EPW + g);
+            const float w = __shfl_sync(kFull, w_l, k * EPW + g);
+            const float4 *rp = src4 + (size_t)s * ld4 + col0 + l;
+            const bool ev = (k * EPW + g) < n;  // never touch a row for a padding edge (0 * Inf)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                if (act[j] && ev) {
+                    const float4 x = __ldg(rp + j * LG);
+                    fma4(acc[j], x, w);
+                }
+            }
+        }
+    }
+
+    // combine the EPW edge groups of the warp (fixed butterfly order)
+#pragma unroll
+    for (int off = LG; off < 32; off <<= 1) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            acc[j].x += __shfl_xor_sync(kFull, acc[j].x, off);
+            acc[j].y += __shfl_xor_sync(kFull, acc[j].y, off);
+            acc[j].z += __shfl_xor_sync(kFull, acc[j].z, off);
+            acc[j].w += __shfl_xor_sync(kFull, acc[j].w, off);
+        }
+    }
+
+    if (TEAM > 1) {
+        __shared__ float4 part[TEAM][LG * VEC];
+        if (g == 0) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) part[warp][l + j * LG] = acc[j];
+        }
+        __syncthreads();
+        // every thread of the CTA finishes a strided share of the slab's columns
+        for (int c = threadIdx.x; c < LG * VEC; c += 32 * TEAM) {
+            if (col0 + c >= a.nvec) continue;
+            float4 t = part[0][c];
+#pragma unroll
+            for (int wv = 1; wv < TEAM; ++wv) add4(t, part[wv][c]);
+            const size_t o = (size_t)row * ld4 + col0 + c;
+            float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.self_mode == SELF_NORM) {
+                const float sw = a.selfw[row];
+                const float4 x = src4[o];
+                self = make_float4(x.x * sw, x.y * sw, x.z * sw, x.w * sw);
+            } else if (a.self_mode == SELF_ONE) {
+                self = src4[o];
+            } else if (a.self_mode == SELF_ACCUM) {
+                self = reinterpret_cast<const float4 *>(a.out)[o];
+            }
+            add4(self, t);
+            reinterpret_cast<float4 *>(a.out)[o] = self;
+        }
+    } else if (g == 0) {
+        float sw = 0.f;
+        if (a.self_mode == SELF_NORM) sw = a.selfw[row];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            if (!act[j]) continue;
+            const size_t o = (size_t)row * ld4 + col0 + l + j * LG;
+            float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.self_mode == SELF_NORM) {
+                const float4 x = src4[o];
+                self = make_float4(x.x * sw, x.y * sw, x.z * sw, x.w * sw);
+            } else if (a.self_mode == SELF_ONE) {
+                self = src4[o];
+            } else if (a.self_mode == SELF_ACCUM) {
+                self = reinterpret_cast<const float4 *>(a.out)[o];
+            }
+            add4(self, acc[j]);
+            reinterpret_cast<float4 *>(a.out)[o] = self;
+        }
+    }
+}
+
+int g_cfg_lg = 0, g_cfg_vec = 0;
+bool g_cfg_read = false;
+
+void read_env_cfg() {
+    if (g_cfg_read) return;
+    g_cfg_read = true;
+    if (const char *s = std::getenv("DORY_SPMM_CFG")) {
+        int lg = 0, vec = 0;
+        if (std::sscanf(s, "%d,%d", &lg, &vec) == 2) {
+            g_cfg_lg = lg;
+            g_cfg_vec = vec;
+        }
+    }
+}
+
+template <int LG, int VEC>
+int launch_cfg(const SpmmArgs &a, cudaStream_t s) {
+    int launches = 0;
+    const uint32_t slab = LG * VEC;
+    const uint32_t nslab = (a.nvec + slab - 1) / slab;
+    if (a.n_heavy) {
+        dim3 grid(a.n_heavy, nslab);
+        spmm_kernel<LG, VEC, kWarpsPerCta><<<grid, 32 * kWarpsPerCta, 0, s>>>(a, a.heavy, a.n_heavy);
+        ++launches;
+    }
+    if (a.n_light) {
+        dim3 grid((a.n_light + kWarpsPerCta - 1) / kWarpsPerCta, nslab);
+        spmm_kernel<LG, VEC, 1><<<grid, 32 * kWarpsPerCta, 0, s>>>(a, a.light, a.n_light);
+        ++launches;
+    }
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return launches;
+}
+
+}  // namespace
+
+void spmm_set_config(int lg, int vec) {
+    g_cfg_read = true;
+    g_cfg_lg = lg;
+    g_cfg_vec = vec;
+}
+
+#define DORY_SPMM_CASE(LG_, VEC_) \
+    if (lg == LG_ && vec == VEC_) return launch_cfg<LG_, VEC_>(a, s)
+
+int launch_spmm(const SpmmArgs &a, cudaStream_t s) {
+    read_env_cfg();
+    int lg = g_cfg_lg, vec = g_cfg_vec;
+    if (lg == 0) {  // default: one slab covering the whole row when it fits 5 float4 per lane
+        const uint32_t n = a.nvec;
+        if (n <= 4) lg = 4, vec = 1;
+        else if (n <= 8) lg = 8, vec = 1;
+        else if (n <= 16) lg = 16, vec = 1;
+        else if (n <= 32) lg = 32, vec = 1;
+        else if (n <= 64) lg = 32, vec = 2;
+        else if (n <= 96) lg = 32, vec = 3;
+        else if (n <= 128) lg = 32, vec = 4;
+        else if (n <= 160) lg = 32, vec = 5;
+        else lg = 32, vec = 4;  // wider rows: 128-float4 slabs
+    }
+    DORY_SPMM_CASE(4, 1);
+    DORY_SPMM_CASE(8, 1);
+    DORY_SPMM_CASE(8, 2);
+    DORY_SPMM_CASE(8, 4);
+    DORY_SPMM_CASE(16, 1);
+    DORY_SPMM_CASE(16, 2);
+    DORY_SPMM_CASE(16, 4);
+    DORY_SPMM_CASE(32, 1);
+    DORY_SPMM_CASE(32, 2);
+    DORY_SPMM_CASE(32, 3);
+    DORY_SPMM_CASE(32, 4);
+    DORY_SPMM_CASE(32, 5);
+    return -1;
+}
+
+}  // namespace dory

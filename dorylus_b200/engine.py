@@ -1,0 +1,300 @@
+"""Host-side mirror of the reference's Engine / ResourceComm interface over the C ABI.
+
+Method names, argument meaning and the (layer, name) tensor addressing follow the reference
+(src/graph-server/engine/engine.hpp:84-94, commmanager/resource_comm.hpp:13-28) so that the parity
+tests read like calls into the reference; every method is a thin wrapper over one ``dory_*`` entry
+point of include/dorylus_b200.h -- no arithmetic happens in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import (BACKWARD, FORWARD, GAT, GCN, DoryChunk, DoryConfig, DoryError, DoryStats)
+
+_f32p = C.POINTER(C.c_float)
+
+
+class Chunk:
+    """== struct Chunk (src/common/utils.hpp:64-105)."""
+
+    __slots__ = ("localId", "globalId", "lowBound", "upBound", "layer", "dir", "epoch", "vertex")
+
+    def __init__(self, localId=0, globalId=0, lowBound=0, upBound=0, layer=0, dir=FORWARD, epoch=0, vertex=True):
+        self.localId, self.globalId, self.lowBound, self.upBound = localId, globalId, lowBound, upBound
+        self.layer, self.dir, self.epoch, self.vertex = layer, dir, epoch, vertex
+
+    def c(self) -> DoryChunk:
+        return DoryChunk(self.localId, self.globalId, self.lowBound, self.upBound, self.layer, self.dir,
+                         self.epoch, 1 if self.vertex else 0)
+
+    def copy(self) -> "Chunk":
+        return Chunk(self.localId, self.globalId, self.lowBound, self.upBound, self.layer, self.dir,
+                     self.epoch, self.vertex)
+
+    def isFirstLayer(self) -> bool:
+        return self.dir == FORWARD and self.layer == 0 and self.vertex
+
+    def isLastLayer(self) -> bool:
+        return self.dir == BACKWARD and self.layer == 0 and self.vertex
+
+    def __repr__(self):
+        return "%u:%s:%u:%u/%u: vtx %u" % (self.epoch, "F" if self.dir == FORWARD else "B", self.layer,
+                                          self.localId, self.globalId, int(self.vertex))
+
+
+def preprocess_edges(src: np.ndarray, dst: np.ndarray, parts: np.ndarray, num_vertices: int, part: int,
+                     num_parts: int, undirected: bool = False) -> bytes:
+    """== DataLoader::preprocess on an in-memory edge list; returns the graph.<part>.bin image."""
+    lib = _lib.load()
+    src = np.ascontiguousarray(src, dtype=np.uint32)
+    dst = np.ascontiguousarray(dst, dtype=np.uint32)
+    parts = np.ascontiguousarray(parts, dtype=np.int32)
+    if parts.size != num_vertices:
+        raise ValueError("parts must have one entry per global vertex")
+    img, n = C.c_void_p(), C.c_size_t()
+    rc = lib.dory_preprocess_edges(src.ctypes.data_as(C.POINTER(C.c_uint32)), dst.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                   src.size, parts.ctypes.data_as(C.POINTER(C.c_int32)), num_vertices, part,
+                                   num_parts, int(undirected), C.byref(img), C.byref(n))
+    if rc != 0:
+        raise DoryError(rc, lib.dory_last_error(None).decode())
+    try:
+        return C.string_at(img, n.value)
+    finally:
+        lib.dory_free(img)
+
+
+def preprocess_dir(dataset_dir: str, part: int, num_parts: int, undirected: bool = False) -> str:
+    lib = _lib.load()
+    d = dataset_dir if dataset_dir.endswith("/") else dataset_dir + "/"
+    rc = lib.dory_preprocess_dir(d.encode(), part, num_parts, int(undirected))
+    if rc != 0:
+        raise DoryError(rc, lib.dory_last_error(None).decode())
+    return d + "graph.%d.bin" % part
+
+
+class Engine:
+    """One partition on one B200.  Mirrors ``Engine`` + the ``ResourceComm`` backend it owns."""
+
+    def __init__(self, dims: Sequence[int], gnn_type: int = GCN, node_id: int = 0, num_nodes: int = 1,
+                 device: int = 0, learning_rate: float = 0.01, flags: int = 0):
+        self._lib = _lib.load()
+        cfg = DoryConfig()
+        cfg.abi_version = _lib.DORY_ABI_VERSION
+        cfg.gnn_type = gnn_type
+        cfg.n_layers = len(dims) - 1
+        for i, d in enumerate(dims):
+            cfg.dims[i] = int(d)
+        cfg.node_id, cfg.num_nodes, cfg.device = node_id, num_nodes, device
+        cfg.learning_rate, cfg.flags = learning_rate, flags
+        self.layerConfig = list(dims)
+        self.numLayers = len(dims) - 1
+        self.gnn_type, self.nodeId, self.numNodes = gnn_type, node_id, num_nodes
+        h = C.c_void_p()
+        rc = self._lib.dory_create(C.byref(h), C.byref(cfg))
+        if rc != 0:
+            raise DoryError(rc, self._lib.dory_last_error(None).decode())
+        self._h = h
+        self._image = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int):
+        if rc != 0:
+            raise DoryError(rc, self._lib.dory_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dory_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sync(self):
+        self._check(self._lib.dory_sync(self._h))
+
+    # ------------------------------------------------------------------ graph + tensors
+    def load_partition(self, image: bytes):
+        """== Graph::init + preallocateGCN/GAT."""
+        if isinstance(image, np.ndarray):
+            ptr, n = C.c_void_p(image.ctypes.data), image.nbytes
+        else:
+            ptr, n = bytes(image) if not isinstance(image, bytes) else image, len(image)
+        self._check(self._lib.dory_load_partition(self._h, ptr, n))
+        cnt = (C.c_uint64 * 7)()
+        self._check(self._lib.dory_graph_counts(self._h, cnt))
+        (self.localVtxCnt, self.globalVtxCnt, self.srcGhostCnt, self.dstGhostCnt, self.localInEdgeCnt,
+         self.localOutEdgeCnt, self.globalEdgeCnt) = (int(x) for x in cnt)
+
+    def tensor_shape(self, layer: int, name: str):
+        r, c = C.c_uint64(), C.c_uint32()
+        self._check_name(self._lib.dory_tensor_shape(self._h, layer, name.encode(), C.byref(r), C.byref(c)), layer, name)
+        return int(r.value), int(c.value)
+
+    def _check_name(self, rc, layer, name):
+        if rc != 0:
+            raise DoryError(rc, "no tensor '%s' at layer %d" % (name, layer))
+
+    def set_tensor(self, layer: int, name: str, host: np.ndarray):
+        """savedNNTensors[layer][name] <- host."""
+        host = np.ascontiguousarray(host, dtype=np.float32)
+        if host.ndim == 1:
+            host = host.reshape(-1, 1)
+        self._check(self._lib.dory_set_tensor(self._h, layer, name.encode(), host.ctypes.data_as(_f32p),
+                                              host.shape[0], host.shape[1]))
+
+    def get_tensor(self, layer: int, name: str) -> np.ndarray:
+        """savedNNTensors[layer][name] -> host (synchronises)."""
+        r, c = self.tensor_shape(layer, name)
+        out = np.empty((r, c), dtype=np.float32)
+        if r:
+            self._check(self._lib.dory_get_tensor(self._h, layer, name.encode(), out.ctypes.data_as(_f32p), r, c))
+        return out
+
+    def tensor_device(self, layer: int, name: str):
+        p, r, c, ld = C.c_void_p(), C.c_uint64(), C.c_uint32(), C.c_uint32()
+        self._check_name(self._lib.dory_tensor_device(self._h, layer, name.encode(), C.byref(p), C.byref(r),
+                                                      C.byref(c), C.byref(ld)), layer, name)
+        return p.value, int(r.value), int(c.value), int(ld.value)
+
+    # ------------------------------------------------------------------ weights
+    def init_weights(self):
+        self._check(self._lib.dory_init_weights(self._h))
+
+    def weight_shape(self, layer: int, name: str = "w"):
+        return (self.layerConfig[layer], self.layerConfig[layer + 1]) if name == "w" else (self.layerConfig[layer + 1], 1)
+
+    def set_weights(self, layer: int, host: np.ndarray, name: str = "w"):
+        host = np.ascontiguousarray(host, dtype=np.float32)
+        if host.ndim == 1:
+            host = host.reshape(-1, 1)
+        self._check(self._lib.dory_set_weights(self._h, layer, name.encode(), host.ctypes.data_as(_f32p),
+                                               host.shape[0], host.shape[1]))
+
+    def get_weights(self, layer: int, name: str = "w") -> np.ndarray:
+        r, c = self.weight_shape(layer, name)
+        out = np.empty((r, c), dtype=np.float32)
+        self._check(self._lib.dory_get_weights(self._h, layer, name.encode(), out.ctypes.data_as(_f32p), r, c))
+        return out
+
+    def get_weight_grad(self, layer: int, name: str = "w") -> np.ndarray:
+        r, c = self.weight_shape(layer, name)
+        out = np.empty((r, c), dtype=np.float32)
+        self._check(self._lib.dory_get_weight_grad(self._h, layer, name.encode(), out.ctypes.data_as(_f32p), r, c))
+        return out
+
+    def apply_update(self, layer: int):
+        self._check(self._lib.dory_apply_update(self._h, layer))
+
+    # ------------------------------------------------------------------ SAGA operators (reference names)
+    def _op(self, fn, chunk: Chunk):
+        c = chunk.c()
+        self._check(fn(self._h, C.byref(c)))
+
+    def aggregate(self, chunk: Chunk):
+        self._op(self._lib.dory_aggregate, chunk)
+
+    def applyVertex(self, chunk: Chunk):
+        self._op(self._lib.dory_apply_vertex, chunk)
+
+    def scatter(self, chunk: Chunk):
+        self._op(self._lib.dory_scatter, chunk)
+
+    def applyEdge(self, chunk: Chunk):
+        self._op(self._lib.dory_apply_edge, chunk)
+
+    def predictGAT(self, chunk: Chunk):
+        self._op(self._lib.dory_predict, chunk)
+
+    aggregateGCN = aggregateGAT = aggregate
+    applyVertexGCN = applyVertexGAT = applyVertex
+    scatterGCN = scatterGAT = scatter
+    applyEdgeGCN = applyEdgeGAT = applyEdge
+
+    def incLayer(self, chunk: Chunk) -> Chunk:
+        """== incLayerGCN / incLayerGAT: returns the next chunk."""
+        c = chunk.c()
+        self._check(self._lib.dory_inc_layer(self._h, C.byref(c)))
+        return Chunk(c.localId, c.globalId, c.lowBound, c.upBound, c.layer, c.dir, c.epoch, bool(c.vertex))
+
+    incLayerGCN = incLayerGAT = incLayer
+
+    def whole_chunk(self, layer: int = 0, dir: int = FORWARD, epoch: int = 1, vertex: bool = True) -> Chunk:
+        """The single chunk CPU/GPU mode uses per partition (loadChunks, engine/utils.cpp:598-609)."""
+        return Chunk(0, self.nodeId, 0, self.localVtxCnt, layer, dir, epoch, vertex)
+
+    # ------------------------------------------------------------------ coarse entry points
+    def forward(self, layer: int):
+        self._check(self._lib.dory_forward(self._h, layer))
+
+    def backward(self, layer: int):
+        self._check(self._lib.dory_backward(self._h, layer))
+
+    def epoch(self) -> dict:
+        s = DoryStats()
+        self._check(self._lib.dory_epoch(self._h, C.byref(s)))
+        return self._stats(s)
+
+    def epoch_async(self):
+        """Enqueue one epoch without reading the statistics back (no synchronisation)."""
+        self._check(self._lib.dory_epoch(self._h, None))
+
+    def stats(self) -> dict:
+        s = DoryStats()
+        self._check(self._lib.dory_get_stats(self._h, C.byref(s)))
+        return self._stats(s)
+
+    @staticmethod
+    def _stats(s: DoryStats) -> dict:
+        return dict(acc_sum=s.acc_sum, loss_sum=s.loss_sum, val_rows=s.val_rows, epochs_done=s.epochs_done,
+                    kernel_launches=int(s.kernel_launches), edges_aggregated=int(s.edges_aggregated))
+
+    # ------------------------------------------------------------------ multi-GPU
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        lib = _lib.load()
+        buf = C.create_string_buffer(_lib.DORY_UNIQUE_ID_BYTES)
+        rc = lib.dory_comm_unique_id(C.cast(buf, C.c_void_p))
+        if rc != 0:
+            raise DoryError(rc, lib.dory_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, _lib.DORY_UNIQUE_ID_BYTES)
+        self._check(self._lib.dory_comm_init(self._h, C.cast(buf, C.c_void_p)))
+
+    def comm_send_gvids(self, dir: int, peer: int) -> np.ndarray:
+        n = C.c_uint32()
+        self._check(self._lib.dory_comm_send_gvids(self._h, dir, peer, None, C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=np.uint32)
+        self._check(self._lib.dory_comm_send_gvids(self._h, dir, peer, out.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(n)))
+        return out[: n.value]
+
+    def comm_set_recv_slots(self, dir: int, peer: int, slots: np.ndarray):
+        slots = np.ascontiguousarray(slots, dtype=np.uint32)
+        self._check(self._lib.dory_comm_set_recv_slots(self._h, dir, peer, slots.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                       slots.size))
+
+    # ------------------------------------------------------------------ timing helpers
+    def event_record(self, slot: int):
+        self._check(self._lib.dory_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self._check(self._lib.dory_event_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return float(ms.value)
+
+    def flush_l2(self, nbytes: int = 256 << 20):
+        self._check(self._lib.dory_flush_l2(self._h, nbytes))

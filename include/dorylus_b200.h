@@ -1,0 +1,219 @@
+/* dorylus_b200 — C ABI of the B200-native GNN aggregation engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of uclasystem/dorylus that this repo
+ * implements: per-layer Gather (normalised-adjacency SpMM, CSC forward / CSR
+ * backward) -> ApplyVertex (H.W + activation / softmax-CE) -> Scatter (ghost rows) -> ApplyEdge.
+ * Plain pointers and sizes only; no C++ / torch types cross it.  Every entry point names the
+ * reference interface it stands in for (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - every call returns DORY_OK (0) or a negative DORY_E* code; nothing calls exit()/abort()
+ *     (the reference asserts or exit(EXIT_FAILURE)s: engine/engine.cpp:141-163);
+ *     dory_last_error() returns the message of the last failing call on that engine.
+ *   - compute calls ENQUEUE work on the engine's CUDA stream and return; dory_sync(),
+ *     dory_get_tensor() and dory_get_stats() synchronise.
+ *   - host pointers are caller-owned and only touched during the call.
+ *   - one caller thread per engine (the reference drives one chunk per partition in CPU/GPU mode,
+ *     run/run-onnode:62-70); one engine per GPU, one process per GPU.
+ *   - tensors are addressed by (layer, name) exactly like Engine::savedNNTensors[layer][name]
+ *     (engine/engine.hpp:157-158): GCN "x fg ah z h lab grad bg aTg" (engine/ops/gcn_ops.cpp:27-93),
+ *     GAT "h z az fg_z A ah grad dA aTg bg_d lab" (engine/ops/gat_ops.cpp:27-115).
+ *     They are row-major fp32 on the host side of this ABI; in HBM rows are padded.
+ */
+#ifndef DORYLUS_B200_H
+#define DORYLUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DORY_ABI_VERSION 1
+#define DORY_MAX_LAYERS 8
+
+enum {
+    DORY_OK = 0,
+    DORY_EINVAL = -1,   /* bad argument / unknown tensor / shape mismatch */
+    DORY_ESTATE = -2,   /* call out of order (no partition loaded, no comm, ...) */
+    DORY_ECUDA = -3,    /* a CUDA runtime call or kernel failed */
+    DORY_ENOMEM = -4,
+    DORY_ECOMM = -5,    /* NCCL / peer-memory failure */
+    DORY_EFORMAT = -6,  /* malformed graph.<id>.bin / dataset file */
+    DORY_ENODEV = -7    /* no usable sm_100 device: there is NO CPU fallback */
+};
+
+/* PROP_TYPE and GNN, src/common/utils.hpp:46,48 */
+enum { DORY_FORWARD = 0, DORY_BACKWARD = 1 };
+enum { DORY_GCN = 0, DORY_GAT = 1 };
+
+/* == struct Chunk, src/common/utils.hpp:64-74 (same fields, fixed-width types). */
+typedef struct dory_chunk {
+    uint32_t localId;
+    uint32_t globalId;
+    uint32_t lowBound;
+    uint32_t upBound;
+    uint32_t layer;
+    uint32_t dir;    /* DORY_FORWARD | DORY_BACKWARD */
+    uint32_t epoch;
+    uint8_t vertex;  /* 1: vertex NN (AV), 0: edge NN (AE) */
+} dory_chunk;
+
+/* flags */
+#define DORY_FLAG_STRICT_MASK 0x1u  /* maskout whole non-train ROWS instead of replicating quirk Q6
+                                       (CPU_comm.cpp:464-471 copies (end-stt) floats, not rows) */
+#define DORY_FLAG_GAT_PREDICT_AH 0x2u /* predictGAT reads "ah" instead of replicating quirk Q9
+                                       (gat_ops.cpp:252 reads "az") */
+#define DORY_FLAG_NO_TENSOR_CORES 0x4u /* force the fp32 SIMT GEMM path for H.W */
+
+/* What Engine::init gathers from its CLI + layer config file (engine/utils.cpp:313-479). */
+typedef struct dory_config {
+    uint32_t abi_version;                /* DORY_ABI_VERSION */
+    uint32_t gnn_type;                   /* DORY_GCN | DORY_GAT            (--gnn) */
+    uint32_t n_layers;                   /* numLayers = #widths - 1 */
+    uint32_t dims[DORY_MAX_LAYERS + 1];  /* layerConfig: F0 ... C */
+    uint32_t node_id;                    /* partition / rank id            (nodeId) */
+    uint32_t num_nodes;                  /* number of partitions           (numNodes) */
+    int32_t device;                      /* CUDA device ordinal */
+    float learning_rate;                 /* weight-server argv, run/run-onnode:226 (0.01) */
+    uint32_t flags;
+} dory_config;
+
+/* Per-epoch results the reference logs ("batch Acc/Loss", CPU_comm.cpp:112-116) and the
+ * counters bench.py reports. */
+typedef struct dory_stats {
+    float acc_sum;            /* getTrainStat acc over this partition's validation slice */
+    float loss_sum;           /* getTrainStat loss (sum, not mean) */
+    uint32_t val_rows;        /* (unsigned)(V_p * VAL_PORTION) */
+    uint32_t epochs_done;
+    uint64_t kernel_launches; /* kernels of THIS library launched since create */
+    uint64_t edges_aggregated;/* edges walked by dory_aggregate since create */
+} dory_stats;
+
+typedef struct dory_engine dory_engine;
+
+/* ---- lifecycle ---------------------------------------------------------------------------
+ * dory_create        == Engine::init up to (not including) graph loading, engine/engine.cpp:40-61
+ * dory_destroy       == Engine::destroy, engine/engine.cpp:316 ff. */
+int dory_create(dory_engine **out, const dory_config *cfg);
+void dory_destroy(dory_engine *e);
+const char *dory_last_error(const dory_engine *e); /* e may be NULL: error of a failed dory_create */
+int dory_abi_version(void);
+int dory_sync(dory_engine *e);
+
+/* ---- dataset preprocessing (host only, no GPU needed) --------------------------------------
+ * dory_preprocess_edges == DataLoader::preprocess (graph/dataloader.cpp:225-330) + RawGraph::dump
+ * (graph/graph.cpp:200-273) on an in-memory edge list: returns a malloc'ed byte image that is
+ * byte-identical to the reference's graph.<part>.bin.  `parts[v]` is the owner of global vertex v
+ * (graph.bsnap.parts).  Free the image with dory_free().
+ * dory_preprocess_dir  == the same, reading <dir>graph.bsnap.edges / .parts and writing
+ * <dir>graph.<part>.bin like the reference (engine/engine.cpp:62-71).  `dir` ends with '/'. */
+int dory_preprocess_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_edges,
+                          const int32_t *parts, uint32_t n_vertices, uint32_t part,
+                          uint32_t n_parts, int undirected, void **image, size_t *image_len);
+int dory_preprocess_dir(const char *dir, uint32_t part, uint32_t n_parts, int undirected);
+void dory_free(void *p);
+
+/* ---- partition + tensors --------------------------------------------------------------------
+ * dory_load_partition == Graph::init (graph/graph.cpp:7-115) + Engine::preallocateGCN/GAT
+ * (gcn_ops.cpp:27-93, gat_ops.cpp:27-115): parses a graph.<id>.bin image, uploads CSC/CSR/norms/
+ * send lists to HBM and allocates every named tensor of every layer. */
+int dory_load_partition(dory_engine *e, const void *graph_bin, size_t len);
+
+/* Counts as Graph exposes them (graph/graph.hpp:70-77):
+ * out[0..6] = localVtxCnt, globalVtxCnt, srcGhostCnt, dstGhostCnt, localInEdgeCnt, localOutEdgeCnt,
+ * globalEdgeCnt. */
+int dory_graph_counts(const dory_engine *e, uint64_t out[7]);
+
+/* savedNNTensors[layer][name] <- host (readFeaturesFile / readLabelsFile, engine/utils.cpp:486-596)
+ * and -> host.  rows/cols must match the tensor's shape (dory_tensor_shape). */
+int dory_set_tensor(dory_engine *e, uint32_t layer, const char *name, const float *host,
+                    uint64_t rows, uint32_t cols);
+int dory_get_tensor(dory_engine *e, uint32_t layer, const char *name, float *host, uint64_t rows,
+                    uint32_t cols);
+int dory_tensor_shape(const dory_engine *e, uint32_t layer, const char *name, uint64_t *rows,
+                      uint32_t *cols);
+/* Zero-copy view for callers that already hold data in HBM: device pointer + leading dimension
+ * (in floats) of the padded row-major storage. */
+int dory_tensor_device(const dory_engine *e, uint32_t layer, const char *name, void **dptr,
+                       uint64_t *rows, uint32_t *cols, uint32_t *ld);
+
+/* ---- weights (stand-in for the weight server the CPU/GPU backends talk to) -------------------
+ * dory_init_weights  == WeightServer::initWeightsMasterGCN/GAT (weightserver.cpp:515-559):
+ *                       xavier "w" per layer, kaiming "a_i" for GAT, seed 8888.
+ * dory_set/get_weights == MessageService::prefetchWeightsMatrix / getWeightMatrix / getaMatrix
+ *                       (commmanager/message_service.cpp:188-222); name is "w" or "a_i".
+ * dory_get_weight_grad == the matrix handed to MessageService::sendWeightUpdate / sendaUpdate
+ *                       (message_service.cpp:148-162); name "w" or "a_i".
+ * dory_apply_update   == WeightTensor::tryApplyUpdate sync branch + AdamOptimizer::update
+ *                       (weighttensor.cpp:263-284, AdamOptimizer.cpp:36-51): sums dW over all
+ *                       partitions (all-reduce when a communicator exists) and steps Adam. */
+int dory_init_weights(dory_engine *e);
+int dory_set_weights(dory_engine *e, uint32_t layer, const char *name, const float *host,
+                     uint32_t rows, uint32_t cols);
+int dory_get_weights(dory_engine *e, uint32_t layer, const char *name, float *host, uint32_t rows,
+                     uint32_t cols);
+int dory_get_weight_grad(dory_engine *e, uint32_t layer, const char *name, float *host,
+                         uint32_t rows, uint32_t cols);
+int dory_apply_update(dory_engine *e, uint32_t layer);
+
+/* ---- the SAGA operators (engine/engine.hpp:84-94) -------------------------------------------
+ * dory_aggregate    == Engine::aggregateGCN / aggregateGAT   (gcn_ops.cpp:130-191, gat_ops.cpp:173-243)
+ *                      honours chunk->lowBound/upBound (destination row range).
+ * dory_apply_vertex == Engine::applyVertexGCN/GAT -> ResourceComm::NNCompute(vertex=true)
+ *                      -> CPUComm::vtxNNForward{GCN,GAT} / vtxNNBackward{GCN,GAT}   (CPU_comm.cpp:98-188).
+ *                      Like CPUComm it always processes the whole partition.
+ * dory_scatter      == Engine::scatterGCN/GAT + ghostReceiver* + the scatter barrier
+ *                      (gcn_ops.cpp:204-362, gat_ops.cpp:277-435, ops/pipeline.cpp:256-342).
+ * dory_apply_edge   == Engine::applyEdgeGCN/GAT -> NNCompute(vertex=false)
+ *                      -> CPUComm::edgNNForwardGAT/edgNNBackwardGAT (CPU_comm.cpp:190-242); GCN: no-op.
+ * dory_predict      == Engine::predictGAT (gat_ops.cpp:247-265).
+ * dory_inc_layer    == Engine::incLayerGCN / incLayerGAT (engine/utils.cpp:714-748), in place. */
+int dory_aggregate(dory_engine *e, const dory_chunk *c);
+int dory_apply_vertex(dory_engine *e, const dory_chunk *c);
+int dory_scatter(dory_engine *e, const dory_chunk *c);
+int dory_apply_edge(dory_engine *e, const dory_chunk *c);
+int dory_predict(dory_engine *e, const dory_chunk *c);
+int dory_inc_layer(const dory_engine *e, dory_chunk *c);
+
+/* Coarser granularity named by BASELINE.json ("per-layer forward()/backward()"):
+ * dory_forward(l)  = one chunk's GA->AV->SC->AE pass with dir == FORWARD at layer l,
+ * dory_backward(l) = the same with dir == BACKWARD,
+ * dory_epoch       = the whole state machine for one synchronous epoch incl. weight updates
+ *                    (what Engine::runPipeline does for one epoch, engine/engine.cpp:237-314). */
+int dory_forward(dory_engine *e, uint32_t layer);
+int dory_backward(dory_engine *e, uint32_t layer);
+int dory_epoch(dory_engine *e, dory_stats *stats /* may be NULL */);
+int dory_get_stats(dory_engine *e, dory_stats *stats);
+
+/* ---- multi-GPU (replaces CommManager / NodeManager, commmanager/commmanager.cpp:11-279) -------
+ * One process per GPU.  Rank 0 calls dory_comm_unique_id, the host distributes the 128 bytes
+ * (bench.py uses torch.distributed), every rank calls dory_comm_init. */
+#define DORY_UNIQUE_ID_BYTES 128
+int dory_comm_unique_id(void *id128);
+int dory_comm_init(dory_engine *e, const void *id128);
+/* The send side of an exchange is in graph.<id>.bin (forwardLocalVtxDsts / backwardLocalVtxDsts,
+ * graph/graph.cpp:50-65).  The receive side replaces the per-row gvid + std::map lookup of
+ * ghostReceiverGCN (gcn_ops.cpp:310-318): once, at start-up, the host tells the engine for each
+ * (direction, peer) which ghost slots (0-based inside the fg / bg block) that peer's rows land in,
+ * in the order the peer sends them.  dorylus_b200.dist.GhostPlan computes it. */
+int dory_comm_set_recv_slots(dory_engine *e, uint32_t dir, uint32_t peer, const uint32_t *slots,
+                             uint32_t n);
+/* Global ids of the rows this partition sends to `peer` in direction `dir` (send-list order);
+ * returns the count through *n; ids may be NULL to query the count. */
+int dory_comm_send_gvids(const dory_engine *e, uint32_t dir, uint32_t peer, uint32_t *ids,
+                         uint32_t *n);
+
+/* ---- timing on the engine's own stream (bench.py's roofline leg) ------------------------------
+ * CUDA events recorded on the stream the kernels are launched on; slots 0..63. */
+int dory_event_record(dory_engine *e, uint32_t slot);
+int dory_event_elapsed_ms(dory_engine *e, uint32_t slot_start, uint32_t slot_stop, float *ms);
+/* Writes `bytes` of HBM on the engine's stream (bench.py flushes the 126 MB L2 between timed
+ * iterations with this). */
+int dory_flush_l2(dory_engine *e, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DORYLUS_B200_H */

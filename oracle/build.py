@@ -1,0 +1,101 @@
+"""Build recipe for the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Two artefacts, both plain g++ invocations (the reference's own CMake build is NOT run):
+
+* ``oracle/_build/liboracle.so``  -- our line-faithful restatement (oracle/oracle.cpp), built with
+  the flags of the reference's CPU backend: ``-O3 -march=native -fopenmp``
+  (reference CMakeLists.txt:7, ``_CPU_ENABLED_`` pragma at engine/ops/gcn_ops.cpp:159-161).
+* ``oracle/_ref/libdoryref.so``   -- the reference's own loader / Matrix / Adam translation units
+  compiled *where they lie* under /root/reference (never copied), plus oracle/ref_driver.cpp.
+  Only buildable where /root/reference exists; the prebuilt .so travels to the GPU box.
+
+Nothing in the product path imports this module.
+"""
+from __future__ import annotations
+
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_ROOT = os.environ.get("DORYLUS_REFERENCE", "/root/reference")
+BUILD_DIR = os.path.join(HERE, "_build")
+REF_DIR = os.path.join(HERE, "_ref")
+
+REF_SOURCES = [
+    "src/common/matrix.cpp",
+    "src/common/utils.cpp",
+    "src/graph-server/graph/graph.cpp",
+    "src/graph-server/graph/vertex.cpp",
+    "src/graph-server/graph/edge.cpp",
+    "src/graph-server/graph/dataloader.cpp",
+    "src/graph-server/utils/utils.cpp",
+    "src/weight-server/AdamOptimizer.cpp",
+]
+
+
+def openblas_path() -> str:
+    """The LP64 OpenBLAS bundled with scipy (exports scipy_cblas_sgemm)."""
+    import scipy  # noqa: F401  (only to locate site-packages)
+
+    libs = os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs")
+    hits = sorted(glob.glob(os.path.join(libs, "libscipy_openblas-*.so")))
+    if not hits:
+        raise RuntimeError("scipy's bundled OpenBLAS not found under %s" % libs)
+    return hits[0]
+
+
+def _newer(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _run(cmd: list[str]) -> None:
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("oracle build failed")
+
+
+def build_oracle(force: bool = False) -> str:
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    out = os.path.join(BUILD_DIR, "liboracle.so")
+    src = os.path.join(HERE, "oracle.cpp")
+    if force or _newer(out, [src, os.path.join(HERE, "shim", "cblas.h"), __file__]):
+        blas = openblas_path()
+        _run(["g++", "-std=c++14", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared",
+              "-I" + os.path.join(HERE, "shim"), src, "-o", out,
+              blas, "-Wl,-rpath," + os.path.dirname(blas)])
+    return out
+
+
+def build_ref(force: bool = False) -> str | None:
+    """Compile the reference translation units in place.  Returns None when /root/reference is
+    absent and no prebuilt library exists (e.g. a fresh GPU box without the snapshot)."""
+    out = os.path.join(REF_DIR, "libdoryref.so")
+    if not os.path.isdir(REF_ROOT):
+        return out if os.path.exists(out) else None
+    os.makedirs(REF_DIR, exist_ok=True)
+    srcs = [os.path.join(REF_ROOT, s) for s in REF_SOURCES]
+    drv = os.path.join(HERE, "ref_driver.cpp")
+    if force or _newer(out, srcs + [drv, __file__]):
+        blas = openblas_path()
+        objs = []
+        for i, s in enumerate(srcs + [drv]):
+            o = os.path.join(REF_DIR, "obj%d_%s.o" % (i, os.path.basename(s).replace(".cpp", "")))
+            # -O2 as in the survey probe; -march=native -O3 is the reference's Release flag set but
+            # the loader is integer work and Matrix::dot is a BLAS call, so the level is immaterial.
+            _run(["g++", "-std=c++11", "-O2", "-fPIC", "-w", "-I" + os.path.join(HERE, "shim"),
+                  "-I" + os.path.join(REF_ROOT, "src"), "-c", s, "-o", o])
+            objs.append(o)
+        _run(["g++", "-shared", "-o", out] + objs +
+             [blas, "-Wl,-rpath," + os.path.dirname(blas), "-lpthread"])
+    return out
+
+
+if __name__ == "__main__":
+    print(build_oracle(force="--force" in sys.argv))
+    print(build_ref(force="--force" in sys.argv))
