@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: aggregated edges/sec of the GCN epoch on the Reddit-shaped graph.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload reddit]
+
+One "step" = one synchronous GCN epoch of the hot path over the whole graph: 3 aggregations
+(layer-0 forward at F=602, layer-1 forward and layer-1 backward at F=128), the 5 dense products,
+2 ghost exchanges (N > 1) and the Adam update -- every kernel of the path, nothing skipped.
+Prints ONE JSON line (rank 0).  Contract: see the task statement / DESIGN.md §7.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from dorylus_b200 import formats, synth  # noqa: E402
+
+METRIC = "aggregated_edges_per_sec"
+UNIT = "edges/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------ workload
+def build_workload(name: str, world: int, rank: int):
+    """Synthetic graph of the named shape (generator: dorylus_b200/synth.py), partitioned into
+    `world` contiguous vertex ranges; returns this rank's partition image + global inputs."""
+    from dorylus_b200 import engine as dengine
+
+    spec = synth.CONFIGS[name]
+    t0 = time.time()
+    src, dst = synth.generate_edges(spec)
+    parts = synth.contiguous_parts(spec.num_vertices, world)
+    t1 = time.time()
+    image = dengine.preprocess_edges(src, dst, parts, spec.num_vertices, rank, world, False)
+    t2 = time.time()
+    cut = synth.edge_cut(src, dst, parts) if world > 1 else 0.0
+    n_edges = int(src.size)
+    del src, dst
+    graph = formats.parse_graph_bin(image)
+    feats = synth.generate_features(spec.num_vertices, spec.dims[0], spec.seed + 1, dense=True)
+    labels = synth.generate_labels(spec.num_vertices, spec.dims[-1], spec.seed + 2)
+    log("[bench] %s: V=%d E=%d gen %.1fs preprocess %.1fs (rank %d: V_p=%d E_in=%d ghosts %d/%d, cut %.3f)"
+        % (name, spec.num_vertices, n_edges, t1 - t0, t2 - t1, rank, graph.local_vtx_cnt,
+           graph.local_in_edge_cnt, graph.src_ghost_cnt, graph.dst_ghost_cnt, cut))
+    return spec, image, graph, feats, labels, n_edges, cut
+
+
+def alg_bytes_spmm(V_p, G_p, E_p, F):
+    """ALGORITHMIC (compulsory) bytes of one aggregation: every distinct source
+    row read once, output written once, fp32 values + u32 indices, u64 offsets, fp32 self norm."""
+    return 4 * F * (V_p + G_p) + 4 * F * V_p + 8 * E_p + 8 * (V_p + 1) + 4 * V_p
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_run(spec, graph, feats, labels, steps: int, warmup: int, target_s: float):
+    """The reference's CPU graph-server + local-apply path (oracle port, oracle/oracle.cpp) timed on
+    this box's host cores on a BOUNDED sample: the first `n` destination vertices of the partition go
+    through the whole epoch (3 aggregations + the dense apply on those rows)."""
+    from oracle.pyoracle import Oracle
+
+    o = Oracle()
+    cores = os.cpu_count() or 1
+    o.set_threads(cores)
+    g = graph
+    V = g.local_vtx_cnt
+    dims = spec.dims
+    L = len(dims) - 1
+    x_loc, x_gh = formats.partition_rows(g, feats)
+    x_loc = np.ascontiguousarray(x_loc)
+    x_gh = np.ascontiguousarray(x_gh)
+    rng = np.random.default_rng(0)
+    h_loc = rng.standard_normal((V, dims[1])).astype(np.float32)
+    h_gh = rng.standard_normal((max(g.src_ghost_cnt, 1), dims[1])).astype(np.float32)
+    gr_loc = rng.standard_normal((V, dims[1])).astype(np.float32)
+    gr_gh = rng.standard_normal((max(g.dst_ghost_cnt, 1), dims[1])).astype(np.float32)
+    W = [o.xavier(dims[l], dims[l + 1]) for l in range(L)]
+    onehot = formats.one_hot(labels[g.local_to_global], dims[-1])
+
+    def run(n):
+        e_f = int(g.col_ptrs[n])
+        e_b = int(g.row_ptrs[n])
+        t_x = o.edge_table(g.col_ptrs, g.row_idxs, x_loc, x_gh, 0, n)
+        t_h = o.edge_table(g.col_ptrs, g.row_idxs, h_loc, h_gh, 0, n)
+        t_g = o.edge_table(g.row_ptrs, g.col_idxs, gr_loc, gr_gh, 0, n)
+        ah0 = np.zeros((V, dims[0]), np.float32)
+        ah1 = np.zeros((V, dims[1]), np.float32)
+        aTg = np.zeros((V, dims[1]), np.float32)
+        t0 = time.perf_counter()
+        o.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, x_loc, x_gh, 0, n, out=ah0, table=t_x)
+        ta = time.perf_counter()
+        z, h = o.vtx_forward_gcn_hidden(ah0[:n], W[0])
+        o.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, h_loc, h_gh, 0, n, out=ah1, table=t_h)
+        o.vtx_forward_gcn_last(ah1[:n], W[1], onehot[:n], g.global_vtx_cnt)
+        o.aggregate_gcn(g.row_ptrs, g.col_idxs, g.bwd_vals, g.norms, gr_loc, gr_gh, 0, n, out=aTg, table=t_g)
+        o.vtx_backward_gcn(aTg[:n], z, ah0[:n], W[0], False)
+        t1 = time.perf_counter()
+        for t in (t_x, t_h, t_g):
+            o.free_edge_table(t)
+        return 2 * e_f + e_b, t1 - t0, (e_f, ta - t0)
+
+    # size the sample: probe 1 % of the rows, then scale to the time budget
+    n = max(64, V // 100)
+    edges, dt, _ = run(n)
+    per_step = target_s / max(steps + warmup, 1)
+    n = int(min(V, max(64, n * per_step / max(dt, 1e-6))))
+    for _ in range(warmup):
+        run(n)
+    tot_e, tot_t, l0 = 0, 0.0, (0, 0.0)
+    for _ in range(steps):
+        e, dt, l0s = run(n)
+        tot_e += e
+        tot_t += dt
+        l0 = (l0[0] + l0s[0], l0[1] + l0s[1])
+    return dict(value=tot_e / tot_t, unit=UNIT, cores=cores, kind="port",
+                sample="first %d of %d destination vertices (%d aggregated edges/step), full epoch on those rows, "
+                       "%d steps" % (n, V, tot_e // max(steps, 1), steps),
+                ms_per_step=1e3 * tot_t / max(steps, 1), l0_fwd_edges_per_s=l0[0] / max(l0[1], 1e-9))
+
+
+# ------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="reddit")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU baseline budget (rank 0, N=1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        log("[bench] WORLD_SIZE %d != --gpus %d; using WORLD_SIZE" % (world, args.gpus))
+    n_gpus = world
+
+    cfg_common = {"workload": "%s GCN 2-layer" % args.workload, "parallelism": "edge-cut x%d" % n_gpus,
+                  "l2_policy": "inputs larger than L2 (x: 0.56 GB, adjacency: 1.8 GB vs 126 MB L2)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        spec, image, graph, feats, labels, n_edges, cut = build_workload(args.workload, 1, 0)
+        r = cpu_reference_run(spec, graph, feats, labels, args.steps, args.warmup, target_s=90.0)
+        cfg_common.update(V=spec.num_vertices, E=n_edges, dims=spec.dims)
+        out = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "impl": "reference", "config": cfg_common,
+               "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                "sample": r["sample"]},
+               "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "gpu_launches": 0}
+        print(json.dumps(out), flush=True)
+        return 0
+
+    import torch
+
+    if not torch.cuda.is_available():
+        log("[bench] no CUDA device: dorylus_b200 has no CPU fallback")
+        return 2
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    from dorylus_b200 import dist as ddist
+    from dorylus_b200.engine import BACKWARD, FORWARD, GCN, Engine
+
+    spec, image, graph, feats, labels, n_edges, cut = build_workload(args.workload, world, rank)
+    dims = spec.dims
+    L = len(dims) - 1
+    E_global = n_edges
+    n_spmm = 2 * L - 1
+
+    eng = Engine(dims, GCN, node_id=rank, num_nodes=world, device=local_rank)
+    eng.load_partition(image)
+    del image
+    x_loc, x_gh = formats.partition_rows(graph, feats)
+    onehot = formats.one_hot(labels[graph.local_to_global], dims[-1])
+    # pinned host staging (the e2e leg copies from here every step)
+    pin_x = torch.from_numpy(np.ascontiguousarray(x_loc)).pin_memory()
+    pin_g = torch.from_numpy(np.ascontiguousarray(x_gh)).pin_memory() if graph.src_ghost_cnt else None
+    pin_l = torch.from_numpy(onehot).pin_memory()
+    del feats, x_loc, x_gh
+
+    def upload_inputs():
+        eng.set_tensor(0, "x", pin_x.numpy())
+        if pin_g is not None:
+            eng.set_tensor(0, "fg", pin_g.numpy())
+        eng.set_tensor(L - 1, "lab", pin_l.numpy())
+
+    upload_inputs()
+    eng.init_weights()
+    if world > 1:
+        ddist.setup_engine_comm(eng, graph, rank, world)
+
+    def barrier():
+        eng.sync()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: W warm-up epochs, then K timed epochs
+    for _ in range(args.warmup):
+        eng.epoch_async()
+    barrier()
+    launches0 = eng.stats()["kernel_launches"]
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    eng.event_record(0)
+    for _ in range(args.steps):
+        eng.epoch_async()
+    eng.event_record(1)
+    barrier()
+    ms_total = eng.event_elapsed_ms(0, 1)
+    clk = clocks.stop() if rank == 0 else None
+    st = eng.stats()
+    launches = st["kernel_launches"] - launches0
+
+    # ---- per-aggregation timings (CUDA events on the engine's stream), same warm state
+    agg_ms = {}
+    for name, layer, d in (("L0_fwd", 0, FORWARD), ("L1_fwd", 1, FORWARD), ("L1_bwd", 1, BACKWARD)):
+        c = eng.whole_chunk(layer, d)
+        for _ in range(2):
+            eng.aggregate(c)
+        reps = max(3, min(args.steps, 10))
+        eng.event_record(2)
+        for _ in range(reps):
+            eng.aggregate(c)
+        eng.event_record(3)
+        eng.sync()
+        agg_ms[name] = eng.event_elapsed_ms(2, 3) / reps
+
+    # ---- end to end through the public API: H2D of the step's inputs + epoch + D2H of the result
+    eng.sync()
+    h2d = pin_x.numel() * 4 + (pin_g.numel() * 4 if pin_g is not None else 0) + pin_l.numel() * 4
+    for _ in range(2):
+        upload_inputs()
+        eng.epoch()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        upload_inputs()
+        res = eng.epoch()  # reads acc / loss back (synchronises)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    def allmax(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_total = allmax(ms_total)
+    e2e_s = allmax(e2e_s)
+    agg_ms = {k: allmax(v) for k, v in agg_ms.items()}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        feats_again = synth.generate_features(spec.num_vertices, dims[0], spec.seed + 1, dense=True)
+        cpu = cpu_reference_run(spec, graph, feats_again, labels, steps=2, warmup=1, target_s=args.cpu_seconds)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        V_p, G_p, E_p = graph.local_vtx_cnt, graph.src_ghost_cnt, graph.local_in_edge_cnt
+        b_alg = alg_bytes_spmm(V_p, G_p, E_p, dims[0])
+        achieved = b_alg / (agg_ms["L0_fwd"] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_aggregate_L0_fwd")
+        value = n_spmm * E_global * args.steps / (ms_total * 1e-3)
+        cfg_common.update(V=spec.num_vertices, E=E_global, dims=dims, edge_cut=cut,
+                          aggregations_per_step=n_spmm)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg_common,
+            "per_layer_edges_per_sec": {k: E_global / (v * 1e-3) for k, v in agg_ms.items()},
+            "per_layer_ms": agg_ms,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "spmm_kernel (layer-0 forward aggregation, F=602; heavy + light launch)",
+                         "algorithmic_bytes": b_alg,
+                         "note": "min-traffic model; the gather itself moves E*F*4 bytes L2->SM (DESIGN.md §5)"},
+            "e2e": {"value": n_spmm * E_global * args.steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "loss_sum": res["loss_sum"], "acc_sum": res["acc_sum"],
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"],
+                                   "sample": cpu["sample"], "ms_per_step": cpu["ms_per_step"]}
+        print(json.dumps(out), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

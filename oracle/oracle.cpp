@@ -116,13 +116,17 @@ int orc_get_threads(void) { return omp_get_max_threads(); }
  * one FeatType* per edge pointing at the source row (local tensor or ghost tensor).
  * Only the first half (the "src" pointers) is consumed by aggregate*. */
 FeatType **orc_build_edge_table(const uint64_t *ptrs, const unsigned *idxs, unsigned vtcsCnt,
-                                FeatType *vtcsTensor, FeatType *ghostTensor, unsigned featDim) {
+                                FeatType *vtcsTensor, FeatType *ghostTensor, unsigned featDim,
+                                unsigned start, unsigned end) {
+    /* [start, end) bounds the rows whose entries are filled (bench.py's bounded CPU sample); the
+     * reference always fills all of them (start = 0, end = vtcsCnt).  The array keeps its full
+     * size so that entries stay addressed by global edge id. */
     const uint64_t edgeCnt = ptrs[vtcsCnt];
     FeatType **eVtxFeatsBuf = new FeatType *[2 * edgeCnt];
     FeatType **eSrcVtxFeats = eVtxFeatsBuf;
     FeatType **eDstVtxFeats = eSrcVtxFeats + edgeCnt;
-    unsigned long long edgeItr = 0;
-    for (unsigned lvid = 0; lvid < vtcsCnt; ++lvid) {
+    unsigned long long edgeItr = ptrs[start];
+    for (unsigned lvid = start; lvid < end; ++lvid) {
         for (unsigned long long eid = ptrs[lvid]; eid < ptrs[lvid + 1]; ++eid) {
             unsigned srcVid = idxs[eid];
             if (srcVid < vtcsCnt)

@@ -53,12 +53,14 @@ class Oracle:
         return int(self.lib.orc_get_threads())
 
     # ------------------------------------------------------------------ aggregation
-    def edge_table(self, ptrs, idxs, local, ghost):
+    def edge_table(self, ptrs, idxs, local, ghost, low=0, up=None):
         """Engine::srcVFeats2eFeats / dstVFeats2eFeats.  Keeps `local`/`ghost` alive via the handle."""
         V, F = local.shape
         if ghost is None or ghost.size == 0:
             ghost = np.zeros((1, F), np.float32)
-        h = self.lib.orc_build_edge_table(_q(ptrs), _u(idxs), C.c_uint(V), _f(local), _f(ghost), C.c_uint(F))
+        up = V if up is None else up
+        h = self.lib.orc_build_edge_table(_q(ptrs), _u(idxs), C.c_uint(V), _f(local), _f(ghost), C.c_uint(F),
+                                          C.c_uint(low), C.c_uint(up))
         return (C.c_void_p(h), local, ghost)
 
     def free_edge_table(self, t):

@@ -1,0 +1,112 @@
+"""Regenerates tests/golden/*.npz from the reference tree (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+Sources of truth (all under /root/reference, never copied as source code):
+  * miscs/dgl-non-sampling/data/raw0, raw1  -- text dumps of WeightServer::xavierInitializer
+    (602x128 and 128x41, seed 8888) that the reference authors used to make DGL "computationally the
+    same"; we keep raw1 whole and a row subsample of raw0.
+  * miscs/dgl-non-sampling/data/{tm,vm,sm}.pt + gendata.py -- the 66/10/24 % mask layout.
+  * the reference's own loader / Matrix::dot / AdamOptimizer compiled in oracle/_ref and run on
+    small seeded inputs (graph.<id>.bin images, sgemm results, Adam trajectories).
+The GPU box has no /root/reference: tests read only the .npz files written here.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+from dorylus_b200 import formats  # noqa: E402
+from oracle.pyoracle import Ref  # noqa: E402
+
+
+def xavier_fixture():
+    d = os.path.join(REF, "miscs/dgl-non-sampling/data")
+    raw0 = np.loadtxt(os.path.join(d, "raw0"), dtype=np.float64)
+    raw1 = np.loadtxt(os.path.join(d, "raw1"), dtype=np.float64)
+    assert raw0.shape == (602, 128) and raw1.shape == (128, 41), (raw0.shape, raw1.shape)
+    rows0 = np.unique(np.concatenate([np.arange(4), np.arange(0, 602, 13), [601]]))
+    np.savez_compressed(os.path.join(HERE, "xavier.npz"), raw0_rows=rows0, raw0=raw0[rows0], raw1=raw1,
+                        raw0_sum=raw0.sum(), raw0_abs_sum=np.abs(raw0).sum())
+
+
+def mask_fixture():
+    import torch
+
+    d = os.path.join(REF, "miscs/dgl-non-sampling/data")
+    tm, vm, sm = (torch.load(os.path.join(d, n)).numpy() for n in ("tm.pt", "vm.pt", "sm.pt"))
+    blk = 232965 // 60
+    np.savez_compressed(os.path.join(HERE, "masks.npz"), vtcs=232965, parts=60, block=blk,
+                        train_count=int(tm.sum()), val_count=int(vm.sum()), test_count=int(sm.sum()),
+                        first_block_train=tm[:blk], first_block_val=vm[:blk])
+
+
+def ref_fixture():
+    ref = Ref()
+    rng = np.random.default_rng(2024)
+    out = {}
+    # ---- loader: a 60-vertex graph with self loops, duplicates, one-directional edges, 3 parts
+    V, P = 60, 3
+    src = rng.integers(0, V, 420).astype(np.uint32)
+    dst = rng.integers(0, V, 420).astype(np.uint32)
+    src[:6] = dst[:6]  # self loops (dropped on read)
+    src[6:12], dst[6:12] = src[12:18], dst[12:18]  # duplicates (kept)
+    parts = rng.integers(0, P, V).astype(np.int32)
+    parts[:3] = [0, 1, 2]
+    out.update(ld_src=src, ld_dst=dst, ld_parts=parts, ld_V=V, ld_P=P)
+    for und in (0, 1):
+        d = tempfile.mkdtemp() + "/"
+        formats.write_bsnap_edges(d + "graph.bsnap.edges", V, src, dst)
+        formats.write_parts(d + "graph.bsnap.parts", parts)
+        for p in range(P):
+            f = ref.preprocess(d, p, P, bool(und))
+            out["graph_u%d_p%d" % (und, p)] = np.frombuffer(open(f, "rb").read(), dtype=np.uint8)
+    # ---- a single-partition graph (config 1 style) of 40 vertices
+    V1 = 40
+    s1 = rng.integers(0, V1, 300).astype(np.uint32)
+    d1 = rng.integers(0, V1, 300).astype(np.uint32)
+    dd = tempfile.mkdtemp() + "/"
+    formats.write_bsnap_edges(dd + "graph.bsnap.edges", V1, s1, d1)
+    formats.write_parts(dd + "graph.bsnap.parts", np.zeros(V1, np.int32))
+    f = ref.preprocess(dd, 0, 1, False)
+    out.update(single_src=s1, single_dst=d1, single_graph=np.frombuffer(open(f, "rb").read(), dtype=np.uint8))
+    # ---- Matrix::dot, the four transpose cases
+    A = rng.standard_normal((37, 19)).astype(np.float32)
+    B = rng.standard_normal((19, 11)).astype(np.float32)
+    Bt = np.ascontiguousarray(B.T)
+    At = np.ascontiguousarray(A.T)
+    out.update(dot_A=A, dot_B=B,
+               dot_nn=ref.dot(A, B), dot_nt=ref.dot(A, Bt, False, True), dot_tn=ref.dot(At, B, True, False),
+               dot_tt=ref.dot(At, Bt, True, True), dot_scaled=ref.dot(A, B, scale=0.5))
+    # ---- AdamOptimizer: 4 synchronous "epochs" (layer 1 then layer 0, as the weight server applies them)
+    dims = [6, 5, 3]
+    w = [rng.standard_normal((dims[i], dims[i + 1])).astype(np.float32) for i in range(2)]
+    out.update(adam_dims=np.asarray(dims), adam_w0_init=w[0].copy(), adam_w1_init=w[1].copy())
+    adam = ref.adam(0.01, dims)
+    grads = []
+    for ep in range(4):
+        g1 = rng.standard_normal(w[1].shape).astype(np.float32)
+        g0 = rng.standard_normal(w[0].shape).astype(np.float32)
+        grads.append((g0, g1))
+        adam.update(1, w[1], g1)
+        adam.update(0, w[0], g0)
+        out["adam_w0_ep%d" % ep] = w[0].copy()
+        out["adam_w1_ep%d" % ep] = w[1].copy()
+        out["adam_g0_ep%d" % ep] = g0
+        out["adam_g1_ep%d" % ep] = g1
+    adam.close()
+    np.savez_compressed(os.path.join(HERE, "reference_runs.npz"), **out)
+
+
+if __name__ == "__main__":
+    xavier_fixture()
+    mask_fixture()
+    ref_fixture()
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))

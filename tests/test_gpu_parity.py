@@ -1,0 +1,245 @@
+"""GPU parity: the CUDA path through the C ABI against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): vertex/edge indexing bit-exact, fp32 tensors within 1e-5 relative
+(norm-wise max|a-b| / max|b|)."""
+import numpy as np
+import pytest
+
+from helpers import dense_normalized_adjacency, random_dataset, rel_err
+from dorylus_b200.engine import BACKWARD, FORWARD, GAT, GCN, Chunk, DoryError, Engine
+from dorylus_b200 import _lib
+from oracle.driver import OracleGAT, OracleGCN
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def gcn_engine(ds, p=0, flags=0):
+    e = Engine(ds.dims, GCN, node_id=p, num_nodes=ds.P, flags=flags)
+    e.load_partition(ds.images[p])
+    g = ds.graphs[p]
+    e.set_tensor(0, "x", ds.feats[g.local_to_global])
+    if g.src_ghost_cnt:
+        e.set_tensor(0, "fg", ds.feats[g.src_ghost_gvid])
+    e.set_tensor(len(ds.dims) - 2, "lab", ds.onehot[g.local_to_global])
+    e.init_weights()
+    return e
+
+
+HUB = (np.concatenate([np.arange(1, 1500), np.zeros(1499, np.int64)]),
+       np.concatenate([np.zeros(1499, np.int64), np.arange(1, 1500)]))  # vertex 0 gets degree >= 1499
+
+SHAPES = [
+    dict(V=300, E_und=2400, dims=[24, 8, 5]),                     # tiny, odd widths
+    dict(V=600, E_und=7200, dims=[602, 128, 41]),                 # Reddit widths (BASELINE configs[1])
+    dict(V=2708, E_und=5278, dims=[1433, 16, 7]),                 # Cora shape (BASELINE configs[0])
+    dict(V=2000, E_und=9000, dims=[100, 64, 64, 25]),             # 3-layer Amazon widths (configs[3])
+    dict(V=1800, E_und=6000, dims=[16, 48, 51], extra_edges=HUB), # Friendster widths + a CTA-per-row hub
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s["dims"])))
+def test_aggregate_forward_and_backward(oracle, shape):
+    ds = random_dataset(seed=5, **shape)
+    g = ds.graphs[0]
+    with gcn_engine(ds) as e:
+        c = e.whole_chunk(0, FORWARD)
+        e.aggregateGCN(c)
+        got = e.get_tensor(0, "ah")
+        want = oracle.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, ds.feats, None)
+        assert rel_err(got, want) < TOL
+        # the dense statement (D^-1/2 A D^-1/2 + D^-1) X
+        if ds.V <= 3000:
+            A = dense_normalized_adjacency(ds.V, ds.src, ds.dst)
+            assert rel_err(got, A @ ds.feats.astype(np.float64)) < TOL
+        # backward aggregation of a random grad[1]
+        rng = np.random.default_rng(3)
+        grad = rng.standard_normal((ds.V, ds.dims[1])).astype(np.float32)
+        e.set_tensor(1, "grad", grad)
+        e.aggregateGCN(e.whole_chunk(1, BACKWARD))
+        want_b = oracle.aggregate_gcn(g.row_ptrs, g.col_idxs, g.bwd_vals, g.norms, grad, None)
+        assert rel_err(e.get_tensor(0, "aTg"), want_b) < TOL
+
+
+def test_aggregate_is_bit_reproducible_and_linear():
+    ds = random_dataset(V=1200, E_und=30000, dims=[128, 32, 8], seed=8, extra_edges=HUB)
+    with gcn_engine(ds) as e:
+        c = e.whole_chunk(0, FORWARD)
+        e.aggregateGCN(c)
+        a1 = e.get_tensor(0, "ah")
+        e.aggregateGCN(c)
+        a2 = e.get_tensor(0, "ah")
+        assert np.array_equal(a1, a2)  # no atomics: same bits every run
+        e.set_tensor(0, "x", 2.0 * ds.feats)  # power-of-two scaling is exact in fp32
+        e.aggregateGCN(c)
+        assert np.array_equal(e.get_tensor(0, "ah"), 2.0 * a1)
+        # rows of A_hat applied to the all-ones vector: norm[v] + sum of the edge weights
+        e.set_tensor(0, "x", np.ones_like(ds.feats))
+        e.aggregateGCN(c)
+        g = ds.graphs[0]
+        dst_of_edge = np.repeat(np.arange(ds.V), np.diff(g.col_ptrs).astype(np.int64))
+        rowsum = g.norms.astype(np.float64) + np.bincount(dst_of_edge, weights=g.fwd_vals.astype(np.float64),
+                                                          minlength=ds.V)
+        assert rel_err(e.get_tensor(0, "ah")[:, 0], rowsum) < TOL
+
+
+def test_chunk_subrange_matches_reference_semantics(oracle):
+    ds = random_dataset(V=500, E_und=4000, dims=[40, 8, 3], seed=12)
+    g = ds.graphs[0]
+    with gcn_engine(ds) as e:
+        full = oracle.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, ds.feats, None)
+        e.aggregateGCN(Chunk(0, 0, 100, 333, 0, FORWARD, 1, True))
+        got = e.get_tensor(0, "ah")
+        assert rel_err(got[100:333], full[100:333]) < TOL
+        assert not got[:100].any() and not got[333:].any()  # rows outside the chunk untouched
+        with pytest.raises(DoryError):
+            e.aggregateGCN(Chunk(0, 0, 10, 999, 0, FORWARD, 1, True))
+
+
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_NO_TENSOR_CORES], ids=["default", "simt"])
+@pytest.mark.parametrize("shape", SHAPES[:4], ids=lambda s: "x".join(map(str, s["dims"])))
+def test_epochs_match_oracle(oracle, shape, flags):
+    """Three synchronous epochs: every named tensor, the weight gradients, the Adam-updated weights
+    and the validation statistics."""
+    ds = random_dataset(seed=21, **shape)
+    L = len(ds.dims) - 1
+    orc = OracleGCN(oracle, ds.graphs, ds.dims)
+    orc.load_features(ds.feats, ds.onehot)
+    with gcn_engine(ds, flags=flags) as e:
+        for l in range(L):
+            assert np.array_equal(e.get_weights(l), orc.W[l])  # xavier init is bit-exact
+        for ep in range(3):
+            want = orc.epoch()
+            st = e.epoch()
+            t = orc.saved[0]
+            for l in range(L):
+                assert rel_err(e.get_tensor(l, "ah"), t[l]["ah"]) < TOL, (ep, l, "ah")
+                if l < L - 1:
+                    assert rel_err(e.get_tensor(l, "z"), t[l]["z"]) < TOL, (ep, l, "z")
+                    assert rel_err(e.get_tensor(l, "h"), t[l]["h"]) < TOL, (ep, l, "h")
+                    assert rel_err(e.get_tensor(l, "aTg"), t[l]["aTg"]) < TOL, (ep, l, "aTg")
+                if l > 0:
+                    assert rel_err(e.get_tensor(l, "grad"), t[l]["grad"]) < TOL, (ep, l, "grad")
+                assert rel_err(e.get_weight_grad(l), orc.dW[0][l]) < TOL, (ep, l, "dW")
+                assert rel_err(e.get_weights(l), orc.W[l]) < TOL, (ep, l, "W")
+            assert st["acc_sum"] == want["acc"][0]
+            assert abs(st["loss_sum"] - want["loss"][0]) <= 1e-4 * max(1.0, abs(want["loss"][0]))
+            assert st["val_rows"] == int(ds.V * 0.1)
+
+
+def test_operator_sequence_equals_epoch(oracle):
+    """Driving GA/AV/SC/AE chunk by chunk (the reference's queues) == dory_epoch."""
+    ds = random_dataset(V=400, E_und=3000, dims=[32, 16, 4], seed=31)
+    with gcn_engine(ds) as a, gcn_engine(ds) as b:
+        a.epoch()
+        c = b.whole_chunk(0, FORWARD)
+        while True:
+            b.aggregateGCN(c)
+            b.applyVertexGCN(c)
+            if c.dir == BACKWARD:
+                c = b.incLayerGCN(c)  # applyVertexGCN ran NNCompute on the incremented chunk
+                if c.isLastLayer():
+                    break
+            else:
+                c = b.incLayerGCN(c)
+            b.scatterGCN(c)
+            b.applyEdgeGCN(c)
+        for l in (1, 0):
+            b.apply_update(l)
+        for l in range(2):
+            assert np.array_equal(a.get_weights(l), b.get_weights(l))
+        assert np.array_equal(a.get_tensor(0, "aTg"), b.get_tensor(0, "aTg"))
+
+
+def test_strict_mask_flag(oracle):
+    ds = random_dataset(V=300, E_und=2000, dims=[12, 6, 4], seed=41)
+    with gcn_engine(ds, flags=_lib.FLAG_STRICT_MASK) as e:
+        e.epoch()
+        grad = e.get_tensor(1, "grad")
+        stt = int(ds.V * 0.66)
+        assert not grad[stt:].any() and grad[:stt].any()  # masked rows carry no gradient
+
+
+def test_partitions_with_ghosts_single_gpu(oracle):
+    """Two partitions run on the same GPU with the ghost rows copied by the test (what Scatter does):
+    aggregation over [local; ghost] blocks matches the oracle per partition."""
+    ds = random_dataset(V=700, E_und=6000, dims=[48, 16, 5], P=2, seed=51)
+    rng = np.random.default_rng(1)
+    for p, g in enumerate(ds.graphs):
+        with gcn_engine(ds, p=p) as e:
+            e.aggregateGCN(e.whole_chunk(0, FORWARD))
+            want = oracle.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, ds.feats[g.local_to_global],
+                                        ds.feats[g.src_ghost_gvid])
+            assert rel_err(e.get_tensor(0, "ah"), want) < TOL
+            grad = rng.standard_normal((g.local_vtx_cnt, 16)).astype(np.float32)
+            bg = rng.standard_normal((g.dst_ghost_cnt, 16)).astype(np.float32)
+            e.set_tensor(1, "grad", grad)
+            e.set_tensor(0, "bg", bg)
+            e.aggregateGCN(e.whole_chunk(1, BACKWARD))
+            want_b = oracle.aggregate_gcn(g.row_ptrs, g.col_idxs, g.bwd_vals, g.norms, grad, bg)
+            assert rel_err(e.get_tensor(0, "aTg"), want_b) < TOL
+            with pytest.raises(DoryError) as ei:  # exchanging without a communicator is an error, not a no-op
+                e.scatterGCN(e.whole_chunk(1, FORWARD))
+            assert ei.value.code == _lib.ESTATE
+
+
+def test_shape_and_state_errors():
+    ds = random_dataset(V=100, E_und=300, dims=[8, 4, 2], seed=61)
+    e = Engine(ds.dims)
+    with pytest.raises(DoryError) as ei:
+        e.aggregateGCN(Chunk(0, 0, 0, 10, 0, FORWARD, 1, True))
+    assert ei.value.code == _lib.ESTATE
+    e.load_partition(ds.images[0])
+    with pytest.raises(DoryError):
+        e.set_tensor(0, "x", np.zeros((ds.V, 9), np.float32))
+    with pytest.raises(DoryError):
+        e.get_tensor(0, "nope")
+    with pytest.raises(DoryError):
+        e.load_partition(ds.images[0])
+    with pytest.raises(DoryError):
+        e.load_partition(ds.images[0][:100])
+    e.close()
+    with pytest.raises(DoryError):
+        Engine([8, 4], GCN)  # one layer: the reference's last layer needs grad[layer > 0]
+
+
+# ------------------------------------------------------------------------------------- GAT
+def gat_engine(ds, flags):
+    e = Engine(ds.dims, GAT, flags=flags)
+    e.load_partition(ds.images[0])
+    e.set_tensor(0, "h", ds.feats)
+    e.set_tensor(len(ds.dims) - 2, "lab", ds.onehot)
+    e.init_weights()
+    return e
+
+
+@pytest.mark.parametrize("mode", ["ah", "az"])
+def test_gat_epoch_matches_oracle(oracle, mode):
+    """mode 'az' replicates quirk Q9 (predictGAT reads the per-edge scores as logits); it needs
+    E_in >= V * C, which the denser graph provides."""
+    ds = random_dataset(V=300, E_und=3000 if mode == "az" else 1500, dims=[24, 12, 5], seed=71)
+    orc = OracleGAT(oracle, ds.graphs, ds.dims, predict_from=mode)
+    orc.load_features(ds.feats, ds.onehot)
+    orc.epoch()
+    flags = _lib.FLAG_GAT_PREDICT_AH if mode == "ah" else 0
+    with gat_engine(ds, flags) as e:
+        for l in range(2):
+            assert np.array_equal(e.get_weights(l), orc.W[l])
+            assert np.array_equal(e.get_weights(l, "a_i"), orc.a[l])
+        e.epoch()
+        t = orc.saved[0]
+        for l in range(2):
+            for name in ("z", "ah", "grad", "aTg"):
+                assert rel_err(e.get_tensor(l, name), t[l][name]) < TOL, (l, name)
+            assert rel_err(e.get_tensor(l, "az").reshape(-1), t[l]["az"]) < TOL
+            assert rel_err(e.get_tensor(l, "dA").reshape(-1), t[l]["dA"]) < TOL
+            assert rel_err(e.get_weight_grad(l), orc.dW[0][l]) < TOL
+            assert rel_err(e.get_weight_grad(l, "a_i").reshape(-1), orc.da[0][l]) < 5e-5
+        assert rel_err(e.get_tensor(1, "A").reshape(-1), orc.A[0]) < TOL  # last layer's attention (Q12)
+
+
+def test_gat_quirk_mode_refuses_out_of_bounds_read():
+    ds = random_dataset(V=300, E_und=200, dims=[8, 6, 5], seed=81)
+    with gat_engine(ds, 0) as e:
+        with pytest.raises(DoryError):
+            e.epoch()

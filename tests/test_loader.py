@@ -1,0 +1,88 @@
+"""Partition preprocessor / graph.<id>.bin parser: byte parity with the reference loader."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from dorylus_b200 import engine as dengine
+from dorylus_b200 import formats
+
+
+def test_images_match_reference_golden(golden):
+    """Fixtures were written by the reference's own DataLoader::preprocess (tests/golden/make_golden.py)."""
+    r = golden["reference_runs"]
+    V, P = int(r["ld_V"]), int(r["ld_P"])
+    for und in (0, 1):
+        for p in range(P):
+            want = r["graph_u%d_p%d" % (und, p)].tobytes()
+            got = dengine.preprocess_edges(r["ld_src"], r["ld_dst"], r["ld_parts"], V, p, P, bool(und))
+            assert got == want, (und, p)
+    want = r["single_graph"].tobytes()
+    got = dengine.preprocess_edges(r["single_src"], r["single_dst"], np.zeros(40, np.int32), 40, 0, 1, False)
+    assert got == want
+
+
+def test_parse_roundtrip_and_invariants(golden):
+    r = golden["reference_runs"]
+    g = formats.parse_graph_bin(r["graph_u0_p1"].tobytes())
+    V = g.local_vtx_cnt
+    assert g.col_ptrs[0] == 0 and g.col_ptrs[-1] == g.local_in_edge_cnt == g.row_idxs.size
+    assert g.row_ptrs[-1] == g.local_out_edge_cnt == g.col_idxs.size
+    assert (np.diff(g.src_ghost_gvid.astype(np.int64)) > 0).all()  # ghost slots ascend by global id
+    assert np.array_equal(g.src_ghost_lvid, V + np.arange(g.src_ghost_cnt))
+    assert np.array_equal(g.dst_ghost_lvid, V + np.arange(g.dst_ghost_cnt))
+    assert g.row_idxs.max(initial=0) < V + g.src_ghost_cnt
+    deg = np.diff(g.col_ptrs).astype(np.float64) + 1
+    assert np.allclose(g.norms, 1.0 / deg, rtol=1e-6)
+    assert g.fwd_send[1].size == 0 and g.bwd_send[1].size == 0  # nothing sent to self
+
+
+def test_live_against_compiled_reference(ref):
+    rng = np.random.default_rng(77)
+    V, P = 500, 4
+    src = rng.integers(0, V, 6000).astype(np.uint32)
+    dst = rng.integers(0, V, 6000).astype(np.uint32)
+    parts = rng.integers(0, P, V).astype(np.int32)
+    d = tempfile.mkdtemp() + "/"
+    formats.write_bsnap_edges(d + "graph.bsnap.edges", V, src, dst)
+    formats.write_parts(d + "graph.bsnap.parts", parts)
+    for p in range(P):
+        f = ref.preprocess(d, p, P, False)
+        want = open(f, "rb").read()
+        assert dengine.preprocess_edges(src, dst, parts, V, p, P, False) == want
+        os.remove(f)
+        assert open(dengine.preprocess_dir(d, p, P, False), "rb").read() == want
+        r = ref.load_graph(d + "graph.%d.bin" % p)  # the reference's Graph::init reads our file
+        g = formats.parse_graph_bin(want)
+        for k in ("col_ptrs", "row_idxs", "fwd_vals", "row_ptrs", "col_idxs", "bwd_vals", "norms", "local_to_global"):
+            assert np.array_equal(getattr(g, k), r[k]), k
+
+
+def test_edge_cases():
+    # empty edge list, a partition without local edges, isolated vertices
+    parts = np.array([0, 0, 1, 1], np.int32)
+    img = dengine.preprocess_edges(np.zeros(0, np.uint32), np.zeros(0, np.uint32), parts, 4, 0, 2)
+    g = formats.parse_graph_bin(img)
+    assert g.local_vtx_cnt == 2 and g.local_in_edge_cnt == 0 and (g.norms == 1.0).all()
+    # only self loops -> all dropped
+    img = dengine.preprocess_edges(np.array([1, 2], np.uint32), np.array([1, 2], np.uint32), parts, 4, 1, 2)
+    g = formats.parse_graph_bin(img)
+    assert g.global_edge_cnt == 0 and g.src_ghost_cnt == 0
+    # a cross edge 0 -> 3 creates one dst ghost on part 0 and one src ghost on part 1
+    img0 = dengine.preprocess_edges(np.array([0], np.uint32), np.array([3], np.uint32), parts, 4, 0, 2)
+    img1 = dengine.preprocess_edges(np.array([0], np.uint32), np.array([3], np.uint32), parts, 4, 1, 2)
+    g0, g1 = formats.parse_graph_bin(img0), formats.parse_graph_bin(img1)
+    assert g0.dst_ghost_gvid.tolist() == [3] and g0.fwd_send[1].tolist() == [0] and g0.col_idxs.tolist() == [2]
+    assert g1.src_ghost_gvid.tolist() == [0] and g1.bwd_send[0].tolist() == [1] and g1.row_idxs.tolist() == [2]
+    # value = (indeg(0)+1)^-1/2 (indeg(3)+1)^-1/2 = 1 * 2^-1/2
+    assert abs(float(g1.fwd_vals[0]) - 2 ** -0.5) < 1e-7 and g0.bwd_vals[0] == g1.fwd_vals[0]
+
+
+def test_bad_inputs_raise():
+    with pytest.raises(dengine.DoryError):
+        dengine.preprocess_edges(np.array([9], np.uint32), np.array([0], np.uint32), np.zeros(4, np.int32), 4, 0, 1)
+    with pytest.raises(dengine.DoryError):
+        dengine.preprocess_edges(np.array([0], np.uint32), np.array([1], np.uint32), np.array([0, 5, 0, 0], np.int32), 4, 0, 2)
+    with pytest.raises(ValueError):
+        formats.parse_graph_bin(b"\x00" * 10)

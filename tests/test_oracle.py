@@ -1,0 +1,187 @@
+"""Pins the CPU oracle (oracle/oracle.cpp) against the reference's golden vectors, the compiled
+reference (oracle/_ref) and the dense numpy statement of the model (miscs/numpy-gnn)."""
+import numpy as np
+import pytest
+
+from helpers import dense_normalized_adjacency, random_dataset, rel_err
+from oracle.driver import BACKWARD, FORWARD, OracleGCN
+
+
+# ---------------------------------------------------------------- golden vectors of the reference
+def test_xavier_matches_reference_dumps(oracle, golden):
+    """raw0 / raw1 are the reference authors' dumps of xavierInitializer (seed 8888), 8 decimals."""
+    g = golden["xavier"]
+    w0 = oracle.xavier(602, 128)
+    w1 = oracle.xavier(128, 41)
+    assert np.max(np.abs(w0[g["raw0_rows"]].astype(np.float64) - g["raw0"])) <= 6e-9
+    assert np.max(np.abs(w1.astype(np.float64) - g["raw1"])) <= 6e-9
+    assert abs(float(w0.astype(np.float64).sum()) - float(g["raw0_sum"])) < 1e-4
+
+
+def test_mask_layout_matches_gendata(golden):
+    """gendata.py: per block of V/60 vertices, first int(blk*0.66) train, next int(blk*0.1) val."""
+    m = golden["masks"]
+    blk = int(m["block"])
+    tr = int(blk * 0.66)
+    va = int(blk * 0.1)
+    assert m["first_block_train"][:tr].all() and not m["first_block_train"][tr:].any()
+    assert m["first_block_val"][tr:tr + va].all() and not m["first_block_val"][:tr].any()
+    assert int(m["train_count"]) == 60 * tr and int(m["val_count"]) == 60 * va
+
+
+# ---------------------------------------------------------------- reference-generated fixtures
+@pytest.mark.parametrize("case", ["nn", "nt", "tn", "tt"])
+def test_dot_matches_reference_matrix_dot(oracle, golden, case):
+    r = golden["reference_runs"]
+    A, B = r["dot_A"], r["dot_B"]
+    args = dict(nn=(A, B, False, False), nt=(A, np.ascontiguousarray(B.T), False, True),
+                tn=(np.ascontiguousarray(A.T), B, True, False),
+                tt=(np.ascontiguousarray(A.T), np.ascontiguousarray(B.T), True, True))[case]
+    got = oracle.dot(*args)
+    assert np.array_equal(got, r["dot_" + case])  # same OpenBLAS, same call => same bits
+    assert rel_err(got, A.astype(np.float64) @ B.astype(np.float64)) < 1e-6
+
+
+def test_dot_scale(oracle, golden):
+    r = golden["reference_runs"]
+    assert np.array_equal(oracle.dot(r["dot_A"], r["dot_B"], scale=0.5), r["dot_scaled"])
+
+
+def test_adam_matches_reference_trajectory(oracle, golden):
+    r = golden["reference_runs"]
+    dims = [int(x) for x in r["adam_dims"]]
+    w = [r["adam_w0_init"].copy(), r["adam_w1_init"].copy()]
+    adam = oracle.adam(0.01, dims)
+    for ep in range(4):
+        adam.update(1, w[1], r["adam_g1_ep%d" % ep])
+        adam.update(0, w[0], r["adam_g0_ep%d" % ep])
+        assert np.array_equal(w[0], r["adam_w0_ep%d" % ep])
+        assert np.array_equal(w[1], r["adam_w1_ep%d" % ep])
+    adam.close()
+
+
+def test_adam_matches_compiled_reference_live(oracle, ref):
+    rng = np.random.default_rng(3)
+    dims = [9, 7, 4]
+    w_o = [rng.standard_normal((dims[i], dims[i + 1])).astype(np.float32) for i in range(2)]
+    w_r = [w.copy() for w in w_o]
+    a_o, a_r = oracle.adam(0.05, dims), ref.adam(0.05, dims)
+    for _ in range(6):
+        for l in (1, 0):
+            g = rng.standard_normal(w_o[l].shape).astype(np.float32)
+            a_o.update(l, w_o[l], g)
+            a_r.update(l, w_r[l], g)
+    assert np.array_equal(w_o[0], w_r[0]) and np.array_equal(w_o[1], w_r[1])
+
+
+# ---------------------------------------------------------------- aggregation vs the dense statement
+@pytest.mark.parametrize("P", [1, 3])
+def test_aggregate_equals_dense_normalized_adjacency(oracle, P):
+    ds = random_dataset(V=300, E_und=2400, dims=[24, 8, 5], P=P, seed=7)
+    A = dense_normalized_adjacency(ds.V, ds.src, ds.dst)
+    want_f = A @ ds.feats.astype(np.float64)
+    want_b = A.T @ ds.feats.astype(np.float64)
+    for g in ds.graphs:
+        loc, gho = ds.feats[g.local_to_global], ds.feats[g.src_ghost_gvid]
+        got = oracle.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, loc, gho)
+        assert rel_err(got, want_f[g.local_to_global]) < 2e-6
+        ghd = ds.feats[g.dst_ghost_gvid]
+        got_b = oracle.aggregate_gcn(g.row_ptrs, g.col_idxs, g.bwd_vals, g.norms, loc, ghd)
+        assert rel_err(got_b, want_b[g.local_to_global]) < 2e-6
+
+
+def test_aggregate_respects_chunk_bounds(oracle):
+    ds = random_dataset(V=120, E_und=600, dims=[10, 4, 3], seed=9)
+    g = ds.graphs[0]
+    full = oracle.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, ds.feats, None)
+    part = np.full_like(full, 123.0)
+    oracle.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, ds.feats, None, low=30, up=77, out=part)
+    assert np.array_equal(part[30:77], full[30:77])
+    assert (part[:30] == 123.0).all() and (part[77:] == 123.0).all()
+
+
+# ---------------------------------------------------------------- apply vertex vs numpy
+def test_vtx_forward_hidden(oracle):
+    rng = np.random.default_rng(1)
+    ah = rng.standard_normal((50, 12)).astype(np.float32)
+    W = rng.standard_normal((12, 6)).astype(np.float32)
+    z, h = oracle.vtx_forward_gcn_hidden(ah, W)
+    assert rel_err(z, ah.astype(np.float64) @ W) < 1e-6
+    assert rel_err(h, np.tanh(ah.astype(np.float64) @ W)) < 1e-6
+
+
+def test_vtx_forward_last_replicates_maskout_quirk(oracle):
+    """Q6: maskout copies (end - stt) FLOATS after row stt, not rows (CPU_comm.cpp:464-471)."""
+    rng = np.random.default_rng(2)
+    V, Fin, C, gV = 200, 10, 7, 200
+    ah = rng.standard_normal((V, Fin)).astype(np.float32)
+    W = rng.standard_normal((Fin, C)).astype(np.float32)
+    lab = np.zeros((V, C), np.float32)
+    lab[np.arange(V), rng.integers(0, C, V)] = 1
+    r = oracle.vtx_forward_gcn_last(ah, W, lab, gV)
+    z = ah.astype(np.float64) @ W
+    p = np.exp(z - z.max(1, keepdims=True))
+    p /= p.sum(1, keepdims=True)
+    assert rel_err(r["pred"], p) < 1e-6
+    stt = int(V * 0.66)
+    flat = p.copy().reshape(-1)
+    flat[stt * C: stt * C + (V - stt)] = lab.reshape(-1)[stt * C: stt * C + (V - stt)]
+    d = (flat.reshape(V, C) - lab) / np.float32(gV * 0.66)
+    assert rel_err(r["d"], d) < 1e-6
+    assert rel_err(r["grad"], d @ W.T.astype(np.float64)) < 1e-5
+    assert rel_err(r["dW"], ah.T.astype(np.float64) @ d) < 1e-5
+    # validation statistics over rows [0.66 V, 0.66 V + 0.1 V)
+    val = slice(stt, stt + int(V * 0.1))
+    acc = float((p[val].argmax(1) == lab[val].argmax(1)).sum())
+    loss = float(-np.log(p[val][np.arange(int(V * 0.1)), lab[val].argmax(1)]).sum())
+    assert r["acc"] == acc and abs(r["loss"] - loss) < 1e-3
+
+
+def test_vtx_backward(oracle):
+    rng = np.random.default_rng(4)
+    V, Fin, Fout = 64, 9, 5
+    aTg, z = rng.standard_normal((V, Fout)).astype(np.float32), rng.standard_normal((V, Fout)).astype(np.float32)
+    ah, W = rng.standard_normal((V, Fin)).astype(np.float32), rng.standard_normal((Fin, Fout)).astype(np.float32)
+    dW, grad = oracle.vtx_backward_gcn(aTg, z, ah, W, True)
+    g = aTg * (1 - np.tanh(z.astype(np.float64)) ** 2)
+    assert rel_err(dW, ah.T.astype(np.float64) @ g) < 1e-5
+    assert rel_err(grad, g @ W.T.astype(np.float64)) < 1e-5
+    dW0, none = oracle.vtx_backward_gcn(aTg, z, ah, W, False)
+    assert none is None and np.array_equal(dW0, dW)
+
+
+# ---------------------------------------------------------------- whole epoch: partitions agree
+def test_epoch_partitioned_equals_single_partition(oracle):
+    """The per-partition state machine with ghost exchange reproduces the 1-partition run
+    (multi-GPU == single-GPU equivalence, stated on the oracle).  The loss mask is per partition
+    (quirk Q5: first 66 % of EACH partition's local order), so gradients are compared from a common
+    grad[1] rather than through the loss."""
+    dims = [20, 8, 5]
+    one = random_dataset(V=240, E_und=1500, dims=dims, P=1, seed=11)
+    many = random_dataset(V=240, E_und=1500, dims=dims, P=3, seed=11)
+    r1, r3 = OracleGCN(oracle, one.graphs, dims), OracleGCN(oracle, many.graphs, dims)
+    r1.load_features(one.feats, one.onehot)
+    r3.load_features(many.feats, many.onehot)
+    r1.epoch()
+    for l in range(2):
+        for p in range(3):
+            r3.aggregate(p, l, FORWARD)
+            r3.apply_vertex_forward(p, l)
+        if l == 0:
+            r3.scatter(1, FORWARD)
+    for name, layer in (("ah", 0), ("z", 0), ("h", 0), ("ah", 1)):
+        full = r1.saved[0][layer][name]
+        for p, g in enumerate(many.graphs):
+            assert rel_err(r3.saved[p][layer][name], full[g.local_to_global]) < 1e-5, (name, layer, p)
+    for p, g in enumerate(many.graphs):
+        r3.saved[p][1]["grad"][:] = r1.saved[0][1]["grad"][g.local_to_global]
+    r3.scatter(1, BACKWARD)
+    for p, g in enumerate(many.graphs):
+        r3.aggregate(p, 1, BACKWARD)
+        assert rel_err(r3.saved[p][0]["aTg"], r1.saved[0][0]["aTg"][g.local_to_global]) < 1e-5
+    # weight gradients sum over partitions to the single-partition gradient (same g, same ah)
+    tot = None
+    for p in range(3):
+        r3.apply_vertex_backward(p, 0)
+        tot = r3.dW[p][0] if tot is None else tot + r3.dW[p][0]
+    assert rel_err(tot, r1.dW[0][0]) < 1e-5
