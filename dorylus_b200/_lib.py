@@ -55,6 +55,7 @@ SYMBOLS = {
     "dory_last_error": (C.c_char_p, [_P]),
     "dory_abi_version": (C.c_int, []),
     "dory_sync": (C.c_int, [_P]),
+    "dory_set_option": (C.c_int, [_P, C.c_char_p, C.c_char_p]),
     "dory_preprocess_edges": (C.c_int, [_u32p, _u32p, _u64, C.POINTER(C.c_int32), _u32, _u32, _u32, C.c_int,
                                         C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "dory_preprocess_dir": (C.c_int, [C.c_char_p, _u32, _u32, C.c_int]),

@@ -53,6 +53,7 @@ struct SpmmArgs {
     const uint32_t *light;  // remaining row ids, degree-descending; null => rows low..low+n_light-1
     uint32_t n_light;
     uint32_t low;           // first row when `light` is null
+    int cfg_lg, cfg_vec;    // kernel shape override (0 = derive from nvec)
 };
 
 // Launches the aggregation; returns the number of kernels launched, or -1 on a launch error.
@@ -112,6 +113,9 @@ int launch_adam(float *w, const float *grad, float *m, float *v, size_t n, float
                 float beta2, float eps, cudaStream_t s);
 
 int launch_fill(float *p, size_t n, float value, cudaStream_t s);
+// dst[r*ldd + c] = src[r*lds + c] for c < cols (changes the row pitch; either side may be dense).
+int launch_repitch(const float *src, uint32_t lds, float *dst, uint32_t ldd, uint64_t rows, uint32_t cols,
+                   cudaStream_t s);
 
 // ---- ghost exchange (comm.cu) ---------------------------------------------------------------
 // Packs rows `ids[i]` of src into dst[i] (row pitch ld floats, nvec float4 per row).

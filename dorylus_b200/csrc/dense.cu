@@ -8,6 +8,7 @@
 // gemm_simt_kernel is the exact-fp32 path: it is used for the skinny products (N = #classes), the
 // transposed products (dW = AH^T . G with a deterministic split-K, grad = G . W^T) and as the
 // fallback when tensor cores are disabled; the large H.W contraction runs on tcgen05 (gemm_tc.cu).
+#include <algorithm>
 #include <cmath>
 
 #include "common.cuh"
@@ -274,6 +275,17 @@ __global__ void fill_kernel(float *__restrict__ p, size_t n, float value) {
     if (i < n) p[i] = value;
 }
 
+__global__ void __launch_bounds__(256)
+repitch_kernel(const float *__restrict__ src, uint32_t lds, float *__restrict__ dst, uint32_t ldd, uint64_t rows,
+               uint32_t cols) {
+    // one warp per row; dense rows are only 4 B-aligned in general, so scalar (still coalesced) accesses
+    for (uint64_t r = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (uint64_t)gridDim.x * 8) {
+        const float *s = src + r * lds;
+        float *d = dst + r * ldd;
+        for (uint32_t c = threadIdx.x & 31; c < cols; c += 32) d[c] = s[c];
+    }
+}
+
 __global__ void gather_rows_kernel(const float4 *__restrict__ src, const uint32_t *__restrict__ ids,
                                    uint32_t n, float4 *__restrict__ dst, uint32_t ld4) {
     // one warp per row
@@ -351,6 +363,14 @@ int launch_adam(float *w, const float *grad, float *m, float *v, size_t n, float
 int launch_fill(float *p, size_t n, float value, cudaStream_t s) {
     if (n == 0) return 0;
     fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n, value);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_repitch(const float *src, uint32_t lds, float *dst, uint32_t ldd, uint64_t rows, uint32_t cols,
+                   cudaStream_t s) {
+    if (rows == 0) return 0;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((rows + 7) / 8, 148 * 16);
+    repitch_kernel<<<blocks, 256, 0, s>>>(src, lds, dst, ldd, rows, cols);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

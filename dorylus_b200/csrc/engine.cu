@@ -31,7 +31,7 @@ namespace {
 
 constexpr double kTrainPortion = 0.66;  // src/common/utils.hpp:60
 constexpr double kValPortion = 0.1;     // src/common/utils.hpp:61
-constexpr uint32_t kHeavyDegree = 1024; // rows with more edges get a whole CTA (spmm.cu)
+constexpr uint32_t kHeavyDegree = 1024; // default: rows with more edges get a whole CTA (spmm.cu)
 constexpr int kNumEvents = 64;
 
 thread_local std::string g_create_error;
@@ -101,6 +101,9 @@ struct dory_engine {
     DevBuf gemm_ws;              // split-K partials
     DevBuf rowstat, stats_dev;   // softmax-CE reduction scratch
     DevBuf flush;                // L2 flush target
+    DevBuf stage;                // dense staging for host <-> padded-row copies
+    int spmm_lg = 0, spmm_vec = 0;
+    uint32_t heavy_degree = kHeavyDegree;
 
     // Adam (AdamOptimizer.hpp:69-84)
     float beta1 = .9f, beta2 = .999f, eps = 1e-07f, lr_t = 0.f;
@@ -163,7 +166,7 @@ const DevMat *find_tensor(const dory_engine *e, uint32_t layer, const char *name
 }
 
 // Degree-descending row lists (longest-processing-time-first issue order for spmm.cu).
-void build_row_lists(const std::vector<uint64_t> &ptrs, std::vector<uint32_t> &heavy,
+void build_row_lists(const std::vector<uint64_t> &ptrs, uint32_t heavyDegree, std::vector<uint32_t> &heavy,
                      std::vector<uint32_t> &light) {
     const uint32_t V = (uint32_t)ptrs.size() - 1;
     std::vector<uint32_t> order(V);
@@ -173,7 +176,7 @@ void build_row_lists(const std::vector<uint64_t> &ptrs, std::vector<uint32_t> &h
     });
     heavy.clear();
     light.clear();
-    for (uint32_t v : order) ((ptrs[v + 1] - ptrs[v]) >= kHeavyDegree ? heavy : light).push_back(v);
+    for (uint32_t v : order) ((ptrs[v + 1] - ptrs[v]) >= heavyDegree ? heavy : light).push_back(v);
 }
 
 int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const uint8_t *idx,
@@ -200,7 +203,7 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
         CU(cudaMemcpyAsync(adj.vals.p, vals, 4 * nnz, cudaMemcpyHostToDevice, e->stream));
     }
     std::vector<uint32_t> heavy, light;
-    build_row_lists(hp, heavy, light);
+    build_row_lists(hp, e->heavy_degree, heavy, light);
     adj.n_heavy = (uint32_t)heavy.size();
     adj.n_light = (uint32_t)light.size();
     CU(adj.heavy.alloc(4 * heavy.size()));
@@ -319,10 +322,20 @@ int preallocate_gat(dory_engine *e) {
 
 bool is_edge_vector(const DevMat &m) { return m.ld == 1 && m.cols == 1; }
 
+// Host rows are dense (pitch = cols), HBM rows are padded (pitch = ld).  Large tensors cross PCIe as
+// ONE contiguous DMA into a staging buffer and are re-pitched by a kernel: a strided
+// cudaMemcpy2D of 2408-byte rows runs at a fraction of the link rate.
+constexpr size_t kStageThreshold = 1u << 20;
+
 int copy_in(dory_engine *e, const DevMat &m, const float *host) {
     if (m.rows == 0) return DORY_OK;
-    if (is_edge_vector(m)) {
-        CU(cudaMemcpyAsync(m.p, host, 4 * m.rows, cudaMemcpyHostToDevice, e->stream));
+    const size_t dense = (size_t)m.rows * m.cols * 4;
+    if (is_edge_vector(m) || m.ld == m.cols) {
+        CU(cudaMemcpyAsync(m.p, host, dense, cudaMemcpyHostToDevice, e->stream));
+    } else if (dense >= kStageThreshold) {
+        if (e->stage.bytes < dense) CU(e->stage.alloc(dense));
+        CU(cudaMemcpyAsync(e->stage.p, host, dense, cudaMemcpyHostToDevice, e->stream));
+        LAUNCHED(launch_repitch(e->stage.as<float>(), m.cols, m.p, m.ld, m.rows, m.cols, e->stream));
     } else {
         CU(cudaMemcpy2DAsync(m.p, (size_t)m.ld * 4, host, (size_t)m.cols * 4, (size_t)m.cols * 4, m.rows,
                              cudaMemcpyHostToDevice, e->stream));
@@ -333,8 +346,13 @@ int copy_in(dory_engine *e, const DevMat &m, const float *host) {
 
 int copy_out(dory_engine *e, const DevMat &m, float *host) {
     if (m.rows == 0) return DORY_OK;
-    if (is_edge_vector(m)) {
-        CU(cudaMemcpyAsync(host, m.p, 4 * m.rows, cudaMemcpyDeviceToHost, e->stream));
+    const size_t dense = (size_t)m.rows * m.cols * 4;
+    if (is_edge_vector(m) || m.ld == m.cols) {
+        CU(cudaMemcpyAsync(host, m.p, dense, cudaMemcpyDeviceToHost, e->stream));
+    } else if (dense >= kStageThreshold) {
+        if (e->stage.bytes < dense) CU(e->stage.alloc(dense));
+        LAUNCHED(launch_repitch(m.p, m.ld, e->stage.as<float>(), m.cols, m.rows, m.cols, e->stream));
+        CU(cudaMemcpyAsync(host, e->stage.p, dense, cudaMemcpyDeviceToHost, e->stream));
     } else {
         CU(cudaMemcpy2DAsync(host, (size_t)m.cols * 4, m.p, (size_t)m.ld * 4, (size_t)m.cols * 4, m.rows,
                              cudaMemcpyDeviceToHost, e->stream));
@@ -358,9 +376,11 @@ int check_loaded(dory_engine *e) {
     return DORY_OK;
 }
 
-SpmmArgs spmm_args(const Adjacency &adj, const float *selfw, int mode, const DevMat &src, const DevMat &out,
-                   uint32_t low, uint32_t up, uint32_t V) {
+SpmmArgs spmm_args(const dory_engine *e, const Adjacency &adj, const float *selfw, int mode, const DevMat &src,
+                   const DevMat &out, uint32_t low, uint32_t up, uint32_t V) {
     SpmmArgs a{};
+    a.cfg_lg = e->spmm_lg;
+    a.cfg_vec = e->spmm_vec;
     a.ptrs = adj.ptrs.as<uint64_t>();
     a.idx = adj.idx.as<uint32_t>();
     a.vals = adj.vals.as<float>();
@@ -408,7 +428,7 @@ int aggregate_gcn(dory_engine *e, const dory_chunk *c) {
         out = find_tensor(e, c->layer - 1, "aTg");
         adj = &e->bwd;
     }
-    SpmmArgs a = spmm_args(*adj, e->norms.as<float>(), SELF_NORM, *src, *out, c->lowBound, c->upBound, e->V);
+    SpmmArgs a = spmm_args(e, *adj, e->norms.as<float>(), SELF_NORM, *src, *out, c->lowBound, c->upBound, e->V);
     LAUNCHED(launch_spmm(a, e->stream));
     e->stats.edges_aggregated += edges_in_range(e, *adj, c->lowBound, c->upBound);
     return DORY_OK;
@@ -566,16 +586,16 @@ int aggregate_gat(dory_engine *e, const dory_chunk *c) {
     const uint32_t fl = c->layer - 1;
     const DevMat &z = *find_tensor(e, fl, "z");
     if (c->dir == DORY_FORWARD) {  // gat_ops.cpp:201-220: ah = z + sum A[e] z_src
-        SpmmArgs a = spmm_args(e->fwd, nullptr, SELF_ONE, z, *find_tensor(e, fl, "ah"), c->lowBound, c->upBound, e->V);
+        SpmmArgs a = spmm_args(e, e->fwd, nullptr, SELF_ONE, z, *find_tensor(e, fl, "ah"), c->lowBound, c->upBound, e->V);
         LAUNCHED(launch_spmm(a, e->stream));
         e->stats.edges_aggregated += edges_in_range(e, e->fwd, c->lowBound, c->upBound);
         return DORY_OK;
     }
     // gat_ops.cpp:221-241: aTg = sum_out bvals * grad_dst  +  sum_in dA * z_src   (zero-initialised, Q11)
     const DevMat &aTg = *find_tensor(e, fl, "aTg");
-    SpmmArgs a1 = spmm_args(e->bwd, nullptr, SELF_ZERO, *find_tensor(e, fl, "grad"), aTg, c->lowBound, c->upBound, e->V);
+    SpmmArgs a1 = spmm_args(e, e->bwd, nullptr, SELF_ZERO, *find_tensor(e, fl, "grad"), aTg, c->lowBound, c->upBound, e->V);
     LAUNCHED(launch_spmm(a1, e->stream));
-    SpmmArgs a2 = spmm_args(e->fwd, nullptr, SELF_ACCUM, z, aTg, c->lowBound, c->upBound, e->V);
+    SpmmArgs a2 = spmm_args(e, e->fwd, nullptr, SELF_ACCUM, z, aTg, c->lowBound, c->upBound, e->V);
     a2.vals = find_tensor(e, fl, "dA")->p;
     LAUNCHED(launch_spmm(a2, e->stream));
     e->stats.edges_aggregated += edges_in_range(e, e->bwd, c->lowBound, c->upBound) +
@@ -744,6 +764,27 @@ int dory_sync(dory_engine *e) {
 }
 
 void dory_free(void *p) { std::free(p); }
+
+int dory_set_option(dory_engine *e, const char *key, const char *value) {
+    if (!e) return DORY_EINVAL;
+    if (!key || !value) return fail(e, DORY_EINVAL, "null argument");
+    char *end = nullptr;
+    const long v = std::strtol(value, &end, 10);
+    if (end == value || v < 0) return fail(e, DORY_EINVAL, "option '%s': bad value '%s'", key, value);
+    if (std::strcmp(key, "spmm_lg") == 0) {
+        if (v != 0 && v != 4 && v != 8 && v != 16 && v != 32) return fail(e, DORY_EINVAL, "spmm_lg must be 0, 4, 8, 16 or 32");
+        e->spmm_lg = (int)v;
+    } else if (std::strcmp(key, "spmm_vec") == 0) {
+        if (v > 5) return fail(e, DORY_EINVAL, "spmm_vec must be 0..5");
+        e->spmm_vec = (int)v;
+    } else if (std::strcmp(key, "heavy_degree") == 0) {
+        if (e->loaded) return fail(e, DORY_ESTATE, "heavy_degree must be set before dory_load_partition");
+        e->heavy_degree = (uint32_t)std::max<long>(v, 1);
+    } else {
+        return fail(e, DORY_EINVAL, "unknown option '%s'", key);
+    }
+    return DORY_OK;
+}
 
 int dory_preprocess_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_edges, const int32_t *parts,
                           uint32_t n_vertices, uint32_t part, uint32_t n_parts, int undirected, void **image,

@@ -11,9 +11,13 @@
 // high-water mark is the image itself plus O(V_global) integers.
 #include "loader.h"
 
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
+#include <thread>
 
 namespace dory {
 namespace {
@@ -63,6 +67,26 @@ struct Writer {
 // (in-degree + 1)^-1/2 evaluated like the reference: pow in double, narrowed to float
 // (dataloader.cpp:155-156: `float vtxNorm = std::pow(vtxDeg, -.5)` with an unsigned degree).
 inline float inv_sqrt_deg(uint32_t degPlusOne) { return (float)std::pow((double)degPlusOne, -.5); }
+
+unsigned loader_threads(uint64_t nEdges) {
+    if (const char *s = std::getenv("DORY_LOADER_THREADS")) {
+        int n = std::atoi(s);
+        if (n > 0) return (unsigned)n;
+    }
+    if (nEdges < (1u << 20)) return 1;
+    unsigned hw = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(hw ? hw : 1u, 32u));
+}
+
+void run_threads(unsigned n, const std::function<void(unsigned)> &fn) {
+    if (n <= 1) {
+        fn(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < n; ++t) th.emplace_back(fn, t);
+    for (auto &x : th) x.join();
+}
 
 }  // namespace
 
@@ -140,35 +164,51 @@ std::string preprocess_partition(const EdgeList &el, const int32_t *parts, uint3
             fwdFlag[p].assign(V, 0);
             bwdFlag[p].assign(V, 0);
         }
-    uint64_t globalEdges = 0;
-    auto visit = [&](uint32_t from, uint32_t to) {  // processEdge, dataloader.cpp:94-146 (counting)
-        const uint32_t pf = (uint32_t)parts[from], pt = (uint32_t)parts[to];
-        if (pf == me) {
-            const uint32_t lf = g2l[from];
-            ++outPtr[lf + 1];
-            if (pt != me) {
-                dstGhostSlot[to] = 0;  // discovered
-                fwdFlag[pt][lf] = 1;
+    // Every update is keyed by one endpoint's global id; thread t applies exactly the updates whose
+    // key falls in its id range [lo, hi), so the threads stream the whole edge list but never write
+    // the same word.
+    const unsigned nThreads = loader_threads(el.n);
+    std::atomic<bool> bad{false};
+    std::vector<uint64_t> edgeCount(nThreads, 0);
+    run_threads(nThreads, [&](unsigned t) {
+        const uint32_t lo = (uint32_t)((uint64_t)nV * t / nThreads), hi = (uint32_t)((uint64_t)nV * (t + 1) / nThreads);
+        auto own = [&](uint32_t g) { return g >= lo && g < hi; };
+        auto visit = [&](uint32_t from, uint32_t to) {  // processEdge, dataloader.cpp:94-146 (counting)
+            const uint32_t pf = (uint32_t)parts[from], pt = (uint32_t)parts[to];
+            if (pf == me) {
+                if (own(from)) {
+                    const uint32_t lf = g2l[from];
+                    ++outPtr[lf + 1];
+                    if (pt != me) fwdFlag[pt][lf] = 1;
+                }
+                if (pt != me && own(to)) dstGhostSlot[to] = 0;  // discovered
             }
-        }
-        if (pt == me) {
-            const uint32_t lt = g2l[to];
-            ++inPtr[lt + 1];
-            if (pf != me) {
-                srcGhostSlot[from] = 0;
-                bwdFlag[pf][lt] = 1;
+            if (pt == me) {
+                if (own(to)) {
+                    const uint32_t lt = g2l[to];
+                    ++inPtr[lt + 1];
+                    if (pf != me) bwdFlag[pf][lt] = 1;
+                }
+                if (pf != me && own(from)) srcGhostSlot[from] = 0;
             }
+        };
+        uint64_t cnt = 0;
+        for (uint64_t i = 0; i < el.n; ++i) {
+            const uint32_t s = el.src[i * el.stride], d = el.dst[i * el.stride];
+            if (s >= nV || d >= nV) {
+                bad = true;
+                return;
+            }
+            if (s == d) continue;  // dataloader.cpp:268-269
+            if (own(d)) ++rawInDeg[d];
+            visit(s, d);
+            if (undirected) visit(d, s);
+            ++cnt;
         }
-    };
-    for (uint64_t i = 0; i < el.n; ++i) {
-        const uint32_t s = el.src[i * el.stride], d = el.dst[i * el.stride];
-        if (s >= nV || d >= nV) return "edge endpoint out of range";
-        if (s == d) continue;  // dataloader.cpp:268-269
-        ++rawInDeg[d];
-        visit(s, d);
-        if (undirected) visit(d, s);
-        ++globalEdges;
-    }
+        edgeCount[t] = cnt;
+    });
+    if (bad) return "edge endpoint out of range";
+    const uint64_t globalEdges = edgeCount[0];
     for (uint32_t v = 0; v < V; ++v) {
         inPtr[v + 1] += inPtr[v];
         outPtr[v + 1] += outPtr[v];
@@ -257,47 +297,51 @@ std::string preprocess_partition(const EdgeList &el, const int32_t *parts, uint3
 
     // ---- pass 2: place every in-/out-edge at its slot (insertion order == edge-file order, Q4)
     std::vector<uint64_t> inCur(inPtr.begin(), inPtr.end() - 1), outCur(outPtr.begin(), outPtr.end() - 1);
-    auto place = [&](uint32_t from, uint32_t to) {
-        const uint32_t pf = (uint32_t)parts[from], pt = (uint32_t)parts[to];
-        if (pf == me) {
-            const uint32_t lf = g2l[from];
-            uint32_t id;
-            float dn;
-            if (pt == me) {
-                id = g2l[to];
-                dn = locNorm[id];
-            } else {
-                id = dstGhostSlot[to];
-                dn = inv_sqrt_deg(rawInDeg[to] + 1);
+    run_threads(nThreads, [&](unsigned t) {
+        const uint32_t lo = (uint32_t)((uint64_t)nV * t / nThreads), hi = (uint32_t)((uint64_t)nV * (t + 1) / nThreads);
+        auto own = [&](uint32_t g) { return g >= lo && g < hi; };
+        auto place = [&](uint32_t from, uint32_t to) {
+            const uint32_t pf = (uint32_t)parts[from], pt = (uint32_t)parts[to];
+            if (pf == me && own(from)) {
+                const uint32_t lf = g2l[from];
+                uint32_t id;
+                float dn;
+                if (pt == me) {
+                    id = g2l[to];
+                    dn = locNorm[id];
+                } else {
+                    id = dstGhostSlot[to];
+                    dn = inv_sqrt_deg(rawInDeg[to] + 1);
+                }
+                const uint64_t k = outCur[lf]++;
+                const float val = locNorm[lf] * dn;  // dataloader.cpp:177,181
+                std::memcpy(csrIdx + 4 * k, &id, 4);
+                std::memcpy(csrVals + 4 * k, &val, 4);
             }
-            const uint64_t k = outCur[lf]++;
-            const float val = locNorm[lf] * dn;  // dataloader.cpp:177,181
-            std::memcpy(csrIdx + 4 * k, &id, 4);
-            std::memcpy(csrVals + 4 * k, &val, 4);
-        }
-        if (pt == me) {
-            const uint32_t lt = g2l[to];
-            uint32_t id;
-            float sn;
-            if (pf == me) {
-                id = g2l[from];
-                sn = locNorm[id];
-            } else {
-                id = srcGhostSlot[from];
-                sn = inv_sqrt_deg(rawInDeg[from] + 1);
+            if (pt == me && own(to)) {
+                const uint32_t lt = g2l[to];
+                uint32_t id;
+                float sn;
+                if (pf == me) {
+                    id = g2l[from];
+                    sn = locNorm[id];
+                } else {
+                    id = srcGhostSlot[from];
+                    sn = inv_sqrt_deg(rawInDeg[from] + 1);
+                }
+                const uint64_t k = inCur[lt]++;
+                const float val = sn * locNorm[lt];  // dataloader.cpp:164,168
+                std::memcpy(cscIdx + 4 * k, &id, 4);
+                std::memcpy(cscVals + 4 * k, &val, 4);
             }
-            const uint64_t k = inCur[lt]++;
-            const float val = sn * locNorm[lt];  // dataloader.cpp:164,168
-            std::memcpy(cscIdx + 4 * k, &id, 4);
-            std::memcpy(cscVals + 4 * k, &val, 4);
+        };
+        for (uint64_t i = 0; i < el.n; ++i) {
+            const uint32_t s = el.src[i * el.stride], d = el.dst[i * el.stride];
+            if (s == d) continue;
+            place(s, d);
+            if (undirected) place(d, s);
         }
-    };
-    for (uint64_t i = 0; i < el.n; ++i) {
-        const uint32_t s = el.src[i * el.stride], d = el.dst[i * el.stride];
-        if (s == d) continue;
-        place(s, d);
-        if (undirected) place(d, s);
-    }
+    });
     return "";
 }
 

@@ -219,8 +219,8 @@ void spmm_set_config(int lg, int vec) {
 
 int launch_spmm(const SpmmArgs &a, cudaStream_t s) {
     read_env_cfg();
-    int lg = g_cfg_lg, vec = g_cfg_vec;
-    if (lg == 0) {  // default: one slab covering the whole row when it fits 5 float4 per lane
+    int lg = a.cfg_lg ? a.cfg_lg : g_cfg_lg, vec = a.cfg_vec ? a.cfg_vec : g_cfg_vec;
+    if (lg == 0 || vec == 0) {  // default: one slab covering the whole row when it fits 5 float4 per lane
         const uint32_t n = a.nvec;
         if (n <= 4) lg = 4, vec = 1;
         else if (n <= 8) lg = 8, vec = 1;

@@ -125,6 +125,9 @@ class Engine:
     def sync(self):
         self._check(self._lib.dory_sync(self._h))
 
+    def set_option(self, key: str, value):
+        self._check(self._lib.dory_set_option(self._h, key.encode(), str(value).encode()))
+
     # ------------------------------------------------------------------ graph + tensors
     def load_partition(self, image: bytes):
         """== Graph::init + preallocateGCN/GAT."""

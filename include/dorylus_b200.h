@@ -101,6 +101,13 @@ void dory_destroy(dory_engine *e);
 const char *dory_last_error(const dory_engine *e); /* e may be NULL: error of a failed dory_create */
 int dory_abi_version(void);
 int dory_sync(dory_engine *e);
+/* Tuning knobs (no reference counterpart; results never depend on them beyond fp32 summation order).
+ *   "spmm_lg" / "spmm_vec"  lanes per gathered row and float4 per lane of the aggregation kernel
+ *                           (0 = choose from the row width); a slab narrower than the row walks the
+ *                           adjacency once per slab.
+ *   "heavy_degree"          rows with at least this many edges get a whole CTA (set before
+ *                           dory_load_partition). */
+int dory_set_option(dory_engine *e, const char *key, const char *value);
 
 /* ---- dataset preprocessing (host only, no GPU needed) --------------------------------------
  * dory_preprocess_edges == DataLoader::preprocess (graph/dataloader.cpp:225-330) + RawGraph::dump

@@ -62,7 +62,7 @@ def test_aggregate_forward_and_backward(oracle, shape):
 
 
 def test_aggregate_is_bit_reproducible_and_linear():
-    ds = random_dataset(V=1200, E_und=30000, dims=[128, 32, 8], seed=8, extra_edges=HUB)
+    ds = random_dataset(V=1600, E_und=30000, dims=[128, 32, 8], seed=8, extra_edges=HUB)
     with gcn_engine(ds) as e:
         c = e.whole_chunk(0, FORWARD)
         e.aggregateGCN(c)

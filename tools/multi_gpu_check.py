@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check, one rank per GPU (launch under torch.distributed.run).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 tools/multi_gpu_check.py [--parts random|contiguous]
+
+Every rank owns one edge-cut partition on its GPU, the ghost exchange runs over NCCL/NVLink, dW is
+all-reduced; the result of every rank is compared with the CPU oracle's multi-partition run
+(oracle/driver.py: OracleGCN with all partitions in one process).  Exit code 0 = parity.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--parts", default="random")
+    ap.add_argument("--epochs", type=int, default=2)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+
+    from helpers import random_dataset, rel_err
+    from dorylus_b200 import dist as ddist
+    from dorylus_b200.engine import GCN, Engine
+    from oracle.driver import OracleGCN
+    from oracle.pyoracle import Oracle
+
+    dims = [602, 128, 41]
+    ds = random_dataset(V=6000, E_und=90000, dims=dims, P=world, seed=17, parts=args.parts)
+    o = Oracle()
+    o.set_threads(max(1, (os.cpu_count() or 8) // world))
+    orc = OracleGCN(o, ds.graphs, dims)
+    orc.load_features(ds.feats, ds.onehot)
+
+    g = ds.graphs[rank]
+    e = Engine(dims, GCN, node_id=rank, num_nodes=world, device=local)
+    e.load_partition(ds.images[rank])
+    e.set_tensor(0, "x", ds.feats[g.local_to_global])
+    if g.src_ghost_cnt:
+        e.set_tensor(0, "fg", ds.feats[g.src_ghost_gvid])
+    e.set_tensor(1, "lab", ds.onehot[g.local_to_global])
+    e.init_weights()
+    ddist.setup_engine_comm(e, g, rank, world)
+
+    worst = 0.0
+    ok = True
+    for ep in range(args.epochs):
+        want = orc.epoch()
+        st = e.epoch()
+        t = orc.saved[rank]
+        errs = {
+            "ah0": rel_err(e.get_tensor(0, "ah"), t[0]["ah"]),
+            "h0": rel_err(e.get_tensor(0, "h"), t[0]["h"]),
+            "fg1": rel_err(e.get_tensor(1, "fg"), t[1]["fg"]) if g.src_ghost_cnt else 0.0,
+            "ah1": rel_err(e.get_tensor(1, "ah"), t[1]["ah"]),
+            "grad1": rel_err(e.get_tensor(1, "grad"), t[1]["grad"]),
+            "bg0": rel_err(e.get_tensor(0, "bg"), t[0]["bg"]) if g.dst_ghost_cnt else 0.0,
+            "aTg0": rel_err(e.get_tensor(0, "aTg"), t[0]["aTg"]),
+            "W0": rel_err(e.get_weights(0), orc.W[0]),
+            "W1": rel_err(e.get_weights(1), orc.W[1]),
+        }
+        # ghost rows are copies: they must be bit-identical to the owner's rows
+        worst = max(worst, max(errs.values()))
+        good = max(errs.values()) < 1e-5 and st["acc_sum"] == want["acc"][rank]
+        ok = ok and good
+        print("[rank %d] epoch %d %s errs %s acc %s/%s" % (rank, ep, "OK" if good else "FAIL",
+              {k: float("%.1e" % v) for k, v in errs.items()}, st["acc_sum"], want["acc"][rank]), flush=True)
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    e.close()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_GPU_CHECK %s world=%d parts=%s worst_rel_err=%.2e" % ("PASS" if flag.item() == 0 else "FAIL", world, args.parts, worst), flush=True)
+    sys.exit(0 if flag.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
