@@ -102,7 +102,7 @@ struct dory_engine {
     DevBuf rowstat, stats_dev;   // softmax-CE reduction scratch
     DevBuf flush;                // L2 flush target
     DevBuf stage;                // dense staging for host <-> padded-row copies
-    int spmm_lg = 0, spmm_vec = 0;
+    int spmm_lg = 0, spmm_vec = 0, spmm_unroll = 0;
     uint32_t heavy_degree = kHeavyDegree;
 
     // Adam (AdamOptimizer.hpp:69-84)
@@ -381,6 +381,7 @@ SpmmArgs spmm_args(const dory_engine *e, const Adjacency &adj, const float *self
     SpmmArgs a{};
     a.cfg_lg = e->spmm_lg;
     a.cfg_vec = e->spmm_vec;
+    a.cfg_unroll = e->spmm_unroll;
     a.ptrs = adj.ptrs.as<uint64_t>();
     a.idx = adj.idx.as<uint32_t>();
     a.vals = adj.vals.as<float>();
@@ -777,6 +778,9 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
     } else if (std::strcmp(key, "spmm_vec") == 0) {
         if (v > 5) return fail(e, DORY_EINVAL, "spmm_vec must be 0..5");
         e->spmm_vec = (int)v;
+    } else if (std::strcmp(key, "spmm_unroll") == 0) {
+        if (v > 8) return fail(e, DORY_EINVAL, "spmm_unroll must be 0..8");
+        e->spmm_unroll = (int)v;
     } else if (std::strcmp(key, "heavy_degree") == 0) {
         if (e->loaded) return fail(e, DORY_ESTATE, "heavy_degree must be set before dory_load_partition");
         e->heavy_degree = (uint32_t)std::max<long>(v, 1);

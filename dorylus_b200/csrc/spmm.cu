@@ -11,13 +11,17 @@
 //     fixed order) -- no atomics, so results are bit-reproducible run to run;
 //   * lanes are grouped LG per source row and read VEC float4 each: every gather of a source row
 //     is a run of fully coalesced 128-bit loads covering whole 128 B lines (rows are padded to
-//     a line multiple, common.cuh), 32/LG edges are in flight per instruction;
+//     a line multiple, common.cuh), 32/LG edges are in flight per instruction and U such
+//     instructions are issued back to back before the first FMA (memory-level parallelism);
 //   * edge ids / weights are read once per 32 edges with one coalesced 128 B load each and
-//     distributed by warp shuffles; they bypass L1 (streamed once) so that L1 keeps hub rows;
+//     distributed by warp shuffles; they bypass L1 and are marked evict-first in L2 (streamed
+//     once per slab) while feature rows are marked evict-last, so that L2 keeps the slab;
 //   * rows are issued in degree-descending order (longest-processing-time-first), so the
 //     power-law tail fills in behind the hubs instead of stretching the last wave;
-//   * wide rows can be cut into column slabs (gridDim.y) so that a slab of the source block stays
-//     resident in the 126 MB L2 while the adjacency is walked once per slab.
+//   * wide rows are cut into column slabs (gridDim.y): a slab of the source block (V x 128
+//     floats = 119 MB on Reddit) is what L2 has to hold while the adjacency is walked once per
+//     slab.  Without slabs the 561 MB layer-0 block misses L2 78 % of the time and the kernel is
+//     bound by 193 GB of DRAM re-reads (profiles/round1_spmm_ncu.md).
 #include <cstdio>
 #include <cstdlib>
 
@@ -29,15 +33,37 @@ namespace {
 constexpr int kWarpsPerCta = 8;
 constexpr unsigned kFull = 0xffffffffu;
 
-__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p, uint64_t pol) {
     uint32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
     return v;
 }
-__device__ __forceinline__ float ld_stream_f32(const float *p) {
+__device__ __forceinline__ float ld_stream_f32(const float *p, uint64_t pol) {
     float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
     return v;
+}
+__device__ __forceinline__ float4 ld_row_f4(const float4 *p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_stream_f4(float4 *p, const float4 &v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w), "l"(pol)
+                 : "memory");
 }
 __device__ __forceinline__ void fma4(float4 &a, const float4 &x, float w) {
     a.x = fmaf(x.x, w, a.x);
@@ -55,10 +81,13 @@ __device__ __forceinline__ void add4(float4 &a, const float4 &b) {
 // LG   : lanes cooperating on one source row (power of two, 4..32)
 // VEC  : float4 per lane  -> a CTA column slab is LG*VEC float4 wide
 // TEAM : warps per destination row (1: warp-per-row, kWarpsPerCta: CTA-per-row)
-template <int LG, int VEC, int TEAM>
+// U    : gather instructions issued back to back before their FMAs (each covers 32/LG edges)
+template <int LG, int VEC, int TEAM, int U>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
 spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nrows) {
-    constexpr int EPW = 32 / LG;  // edges in flight per warp-wide load
+    constexpr int EPW = 32 / LG;  // edges covered by one warp-wide gather instruction
+    static_assert(LG % U == 0 || U % LG == 0, "U must divide the number of steps per 32-edge batch");
+    constexpr int UU = U < LG ? U : LG;  // steps per inner block (a batch of 32 edges has LG steps)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / LG, l = lane % LG;
 
@@ -77,6 +106,8 @@ spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nro
     const uint64_t e_begin = a.ptrs[row], e_end = a.ptrs[row + 1];
     const float4 *__restrict__ src4 = reinterpret_cast<const float4 *>(a.src);
     const uint32_t ld4 = a.ld >> 2;
+    const uint64_t pol_stream = policy_evict_first();
+    const uint64_t pol_keep = policy_evict_last();
 
     float4 acc[VEC];
 #pragma unroll
@@ -88,26 +119,36 @@ spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nro
     for (uint64_t e0 = e_begin + (uint64_t)team_rank * 32; e0 < e_end; e0 += 32 * TEAM) {
         const uint64_t my = e0 + lane;
         uint32_t s_l = 0;
-        float w_l = 0.f;  // edges past the end carry weight 0 and point at row 0 (a valid address)
+        float w_l = 0.f;
         if (my < e_end) {
-            s_l = ld_stream_u32(a.idx + my);
-            w_l = ld_stream_f32(a.vals + my);
+            s_l = ld_stream_u32(a.idx + my, pol_stream);
+            w_l = ld_stream_f32(a.vals + my, pol_stream);
         }
         const int n = (int)min((uint64_t)32, e_end - e0);
-#pragma unroll 4
-        for (int k = 0; k < LG; ++k) {
-            if (k * EPW >= n) break;  // warp-uniform
-            const uint32_t s = __shfl_sync(kFull, s_l, k * EPW + g);
-            const float w = __shfl_sync(kFull, w_l, k * EPW + g);
-            const float4 *rp = src4 + (size_t)s * ld4 + col0 + l;
-            const bool ev = (k * EPW + g) < n;  // never touch a row for a padding edge (0 * Inf)
+#pragma unroll 1
+        for (int k0 = 0; k0 < LG; k0 += UU) {
+            if (k0 * EPW >= n) break;  // warp-uniform
+            float4 x[UU][VEC];
+            float w[UU];
+            // issue every gather of the block first ...
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                if (act[j] && ev) {
-                    const float4 x = __ldg(rp + j * LG);
-                    fma4(acc[j], x, w);
+            for (int u = 0; u < UU; ++u) {
+                const int sl = (k0 + u) * EPW + g;
+                const uint32_t s = __shfl_sync(kFull, s_l, sl);
+                w[u] = __shfl_sync(kFull, w_l, sl);
+                const bool ev = sl < n;  // a padding edge never touches memory (0 * Inf would be NaN)
+                const float4 *rp = src4 + (size_t)s * ld4 + col0 + l;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    x[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (act[j] && ev) x[u][j] = ld_row_f4(rp + j * LG, pol_keep);
                 }
             }
+            // ... then consume them in edge order
+#pragma unroll
+            for (int u = 0; u < UU; ++u)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) fma4(acc[j], x[u][j], w[u]);
         }
     }
 
@@ -123,6 +164,20 @@ spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nro
         }
     }
 
+    auto self_term = [&](size_t o) -> float4 {
+        float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.self_mode == SELF_NORM) {
+            const float sw = a.selfw[row];
+            const float4 x = src4[o];
+            self = make_float4(x.x * sw, x.y * sw, x.z * sw, x.w * sw);
+        } else if (a.self_mode == SELF_ONE) {
+            self = src4[o];
+        } else if (a.self_mode == SELF_ACCUM) {
+            self = reinterpret_cast<const float4 *>(a.out)[o];
+        }
+        return self;
+    };
+
     if (TEAM > 1) {
         __shared__ float4 part[TEAM][LG * VEC];
         if (g == 0) {
@@ -137,73 +192,64 @@ spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nro
 #pragma unroll
             for (int wv = 1; wv < TEAM; ++wv) add4(t, part[wv][c]);
             const size_t o = (size_t)row * ld4 + col0 + c;
-            float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.self_mode == SELF_NORM) {
-                const float sw = a.selfw[row];
-                const float4 x = src4[o];
-                self = make_float4(x.x * sw, x.y * sw, x.z * sw, x.w * sw);
-            } else if (a.self_mode == SELF_ONE) {
-                self = src4[o];
-            } else if (a.self_mode == SELF_ACCUM) {
-                self = reinterpret_cast<const float4 *>(a.out)[o];
-            }
+            float4 self = self_term(o);
             add4(self, t);
-            reinterpret_cast<float4 *>(a.out)[o] = self;
+            st_stream_f4(reinterpret_cast<float4 *>(a.out) + o, self, pol_stream);
         }
     } else if (g == 0) {
-        float sw = 0.f;
-        if (a.self_mode == SELF_NORM) sw = a.selfw[row];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             if (!act[j]) continue;
             const size_t o = (size_t)row * ld4 + col0 + l + j * LG;
-            float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.self_mode == SELF_NORM) {
-                const float4 x = src4[o];
-                self = make_float4(x.x * sw, x.y * sw, x.z * sw, x.w * sw);
-            } else if (a.self_mode == SELF_ONE) {
-                self = src4[o];
-            } else if (a.self_mode == SELF_ACCUM) {
-                self = reinterpret_cast<const float4 *>(a.out)[o];
-            }
+            float4 self = self_term(o);
             add4(self, acc[j]);
-            reinterpret_cast<float4 *>(a.out)[o] = self;
+            st_stream_f4(reinterpret_cast<float4 *>(a.out) + o, self, pol_stream);
         }
     }
 }
 
-int g_cfg_lg = 0, g_cfg_vec = 0;
+int g_cfg_lg = 0, g_cfg_vec = 0, g_cfg_unroll = 0;
 bool g_cfg_read = false;
 
 void read_env_cfg() {
     if (g_cfg_read) return;
     g_cfg_read = true;
     if (const char *s = std::getenv("DORY_SPMM_CFG")) {
-        int lg = 0, vec = 0;
-        if (std::sscanf(s, "%d,%d", &lg, &vec) == 2) {
+        int lg = 0, vec = 0, u = 0;
+        const int got = std::sscanf(s, "%d,%d,%d", &lg, &vec, &u);
+        if (got >= 2) {
             g_cfg_lg = lg;
             g_cfg_vec = vec;
         }
+        if (got == 3) g_cfg_unroll = u;
     }
 }
 
-template <int LG, int VEC>
+template <int LG, int VEC, int U>
 int launch_cfg(const SpmmArgs &a, cudaStream_t s) {
     int launches = 0;
     const uint32_t slab = LG * VEC;
     const uint32_t nslab = (a.nvec + slab - 1) / slab;
     if (a.n_heavy) {
         dim3 grid(a.n_heavy, nslab);
-        spmm_kernel<LG, VEC, kWarpsPerCta><<<grid, 32 * kWarpsPerCta, 0, s>>>(a, a.heavy, a.n_heavy);
+        spmm_kernel<LG, VEC, kWarpsPerCta, U><<<grid, 32 * kWarpsPerCta, 0, s>>>(a, a.heavy, a.n_heavy);
         ++launches;
     }
     if (a.n_light) {
         dim3 grid((a.n_light + kWarpsPerCta - 1) / kWarpsPerCta, nslab);
-        spmm_kernel<LG, VEC, 1><<<grid, 32 * kWarpsPerCta, 0, s>>>(a, a.light, a.n_light);
+        spmm_kernel<LG, VEC, 1, U><<<grid, 32 * kWarpsPerCta, 0, s>>>(a, a.light, a.n_light);
         ++launches;
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launches;
+}
+
+template <int LG, int VEC>
+int launch_unroll(const SpmmArgs &a, int unroll, cudaStream_t s) {
+    if (unroll >= 8 && VEC <= 2) return launch_cfg<LG, VEC, 8>(a, s);
+    if (unroll >= 4 && VEC <= 4) return launch_cfg<LG, VEC, 4>(a, s);
+    if (unroll >= 2) return launch_cfg<LG, VEC, 2>(a, s);
+    return launch_cfg<LG, VEC, 1>(a, s);
 }
 
 }  // namespace
@@ -215,24 +261,26 @@ void spmm_set_config(int lg, int vec) {
 }
 
 #define DORY_SPMM_CASE(LG_, VEC_) \
-    if (lg == LG_ && vec == VEC_) return launch_cfg<LG_, VEC_>(a, s)
+    if (lg == LG_ && vec == VEC_) return launch_unroll<LG_, VEC_>(a, unroll, s)
 
 int launch_spmm(const SpmmArgs &a, cudaStream_t s) {
     read_env_cfg();
     int lg = a.cfg_lg ? a.cfg_lg : g_cfg_lg, vec = a.cfg_vec ? a.cfg_vec : g_cfg_vec;
-    if (lg == 0 || vec == 0) {  // default: one slab covering the whole row when it fits 5 float4 per lane
+    int unroll = a.cfg_unroll ? a.cfg_unroll : g_cfg_unroll;
+    if (lg == 0 || vec == 0) {
+        // Default (tools/spmm_sweep.py on the Reddit shape, profiles/): 8 lanes x 4 float4 per
+        // gathered row = 128-float slabs, 4 edges per gather instruction.  Narrow rows use fewer
+        // lanes so that no lane idles.
         const uint32_t n = a.nvec;
         if (n <= 4) lg = 4, vec = 1;
         else if (n <= 8) lg = 8, vec = 1;
-        else if (n <= 16) lg = 16, vec = 1;
-        else if (n <= 32) lg = 32, vec = 1;
-        else if (n <= 64) lg = 32, vec = 2;
-        else if (n <= 96) lg = 32, vec = 3;
-        else if (n <= 128) lg = 32, vec = 4;
-        else if (n <= 160) lg = 32, vec = 5;
-        else lg = 32, vec = 4;  // wider rows: 128-float4 slabs
+        else if (n <= 16) lg = 8, vec = 2;
+        else lg = 8, vec = 4;
     }
+    if (unroll == 0) unroll = vec >= 4 ? 2 : (vec == 2 ? 4 : 8);
     DORY_SPMM_CASE(4, 1);
+    DORY_SPMM_CASE(4, 2);
+    DORY_SPMM_CASE(4, 4);
     DORY_SPMM_CASE(8, 1);
     DORY_SPMM_CASE(8, 2);
     DORY_SPMM_CASE(8, 4);
@@ -241,7 +289,6 @@ int launch_spmm(const SpmmArgs &a, cudaStream_t s) {
     DORY_SPMM_CASE(16, 4);
     DORY_SPMM_CASE(32, 1);
     DORY_SPMM_CASE(32, 2);
-    DORY_SPMM_CASE(32, 3);
     DORY_SPMM_CASE(32, 4);
     DORY_SPMM_CASE(32, 5);
     return -1;

@@ -121,10 +121,31 @@ def test_epochs_match_oracle(oracle, shape, flags):
                 if l > 0:
                     assert rel_err(e.get_tensor(l, "grad"), t[l]["grad"]) < TOL, (ep, l, "grad")
                 assert rel_err(e.get_weight_grad(l), orc.dW[0][l]) < TOL, (ep, l, "dW")
-                assert rel_err(e.get_weights(l), orc.W[l]) < TOL, (ep, l, "W")
+                # Adam's early steps are sign-like (delta ~ lr * g / |g|): entries whose gradient is
+                # at rounding-noise level move by O(lr) in a direction set by that noise, on the CPU
+                # as much as here.  Weights are therefore compared at a looser bar and then re-synced
+                # so that every epoch's tensors are checked from identical inputs; the optimizer step
+                # itself is pinned in test_adam_step_matches_oracle_on_identical_gradients.
+                assert rel_err(e.get_weights(l), orc.W[l]) < 5e-4, (ep, l, "W")
+                e.set_weights(l, orc.W[l])
             assert st["acc_sum"] == want["acc"][0]
             assert abs(st["loss_sum"] - want["loss"][0]) <= 1e-4 * max(1.0, abs(want["loss"][0]))
             assert st["val_rows"] == int(ds.V * 0.1)
+
+
+def test_adam_step_matches_oracle_on_identical_gradients(oracle):
+    """The optimizer kernel alone: feed the oracle's Adam the engine's own gradients, epoch by epoch."""
+    ds = random_dataset(V=500, E_und=3000, dims=[40, 16, 4], seed=33)
+    with gcn_engine(ds) as e:
+        W = [e.get_weights(l) for l in range(2)]
+        adam = oracle.adam(0.01, ds.dims)
+        for ep in range(4):
+            e.epoch()
+            for l in (1, 0):  # the weight server receives the last layer's update first
+                adam.update(l, W[l], e.get_weight_grad(l))
+            for l in range(2):
+                assert rel_err(e.get_weights(l), W[l]) < 1e-6, (ep, l)
+        adam.close()
 
 
 def test_operator_sequence_equals_epoch(oracle):
@@ -225,7 +246,11 @@ def test_gat_epoch_matches_oracle(oracle, mode):
     with gat_engine(ds, flags) as e:
         for l in range(2):
             assert np.array_equal(e.get_weights(l), orc.W[l])
-            assert np.array_equal(e.get_weights(l, "a_i"), orc.a[l])
+            # kaiming goes through std::normal_distribution (products and sums): the oracle is built
+            # -march=native like the reference (FMA contraction), nvcc's host pass is not -> last-bit
+            # differences; compare to 1e-6 and then share the exact values.
+            assert rel_err(e.get_weights(l, "a_i"), orc.a[l]) < 1e-6
+            e.set_weights(l, orc.a[l], "a_i")
         e.epoch()
         t = orc.saved[0]
         for l in range(2):

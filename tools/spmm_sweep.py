@@ -3,9 +3,9 @@
 
     python tools/spmm_sweep.py [--workload reddit] [--out gpurun_out/spmm_sweep.json]
 
-For every (lanes-per-row, float4-per-lane, heavy-degree) it times the layer-0 forward (F=602) and
-layer-1 forward (F=128) aggregations with CUDA events on the engine's stream.  Results feed the
-defaults in csrc/spmm.cu and DESIGN.md §5.
+For every (lanes-per-row LG, float4-per-lane VEC, gathers-in-flight U, heavy-degree) it times the
+layer-0 forward (F=602) and layer-1 forward (F=128) aggregations with CUDA events on the engine's
+stream.  Results feed the defaults in csrc/spmm.cu and DESIGN.md §5.
 """
 import argparse
 import json
@@ -19,8 +19,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from dorylus_b200 import engine as dengine  # noqa: E402
-from dorylus_b200 import formats, synth  # noqa: E402
+from dorylus_b200 import synth  # noqa: E402
 from dorylus_b200.engine import FORWARD, GCN, Engine  # noqa: E402
+
+SHAPES = {
+    0: [(0, 0, 0), (8, 4, 1), (8, 4, 2), (8, 4, 4), (4, 4, 2), (4, 4, 4), (16, 4, 2), (16, 2, 4), (16, 2, 8),
+        (16, 1, 8), (8, 2, 4), (8, 2, 8), (32, 1, 8), (32, 2, 4), (32, 4, 2), (32, 5, 2), (4, 2, 8), (8, 1, 8)],
+    1: [(0, 0, 0), (8, 4, 1), (8, 4, 2), (8, 4, 4), (4, 4, 2), (4, 4, 4), (16, 2, 4), (16, 2, 8), (32, 1, 8),
+        (4, 2, 8), (8, 2, 8)],
+}
 
 
 def main():
@@ -28,6 +35,7 @@ def main():
     ap.add_argument("--workload", default="reddit")
     ap.add_argument("--out", default="gpurun_out/spmm_sweep.json")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--heavy", default="1024,512,2048")
     args = ap.parse_args()
     spec = synth.CONFIGS[args.workload]
     src, dst = synth.generate_edges(spec)
@@ -39,9 +47,8 @@ def main():
     rng = np.random.default_rng(0)
     h = rng.standard_normal((spec.num_vertices, spec.dims[1])).astype(np.float32)
     results = []
-    shapes = {0: [(0, 0), (32, 5), (32, 4), (32, 3), (32, 2), (32, 1), (16, 4), (16, 2), (16, 1), (8, 4), (8, 2), (8, 1)],
-              1: [(0, 0), (32, 1), (16, 2), (16, 1), (8, 4), (8, 2), (8, 1), (4, 1)]}
-    for heavy in (1024, 256, 4096, 1 << 30):
+    heavies = [int(x) for x in args.heavy.split(",")]
+    for hi, heavy in enumerate(heavies):
         with Engine(spec.dims, GCN) as e:
             e.set_option("heavy_degree", heavy)
             e.load_partition(image)
@@ -49,11 +56,12 @@ def main():
             e.set_tensor(0, "h", h)
             for layer in (0, 1):
                 c = e.whole_chunk(layer, FORWARD)
-                for lg, vec in shapes[layer]:
-                    if heavy != 1024 and (lg, vec) not in ((0, 0), (16, 1), (32, 1)):
+                for lg, vec, un in SHAPES[layer]:
+                    if hi > 0 and (lg, vec, un) not in ((0, 0, 0), (8, 4, 2), (16, 2, 4)):
                         continue
                     e.set_option("spmm_lg", lg)
                     e.set_option("spmm_vec", vec)
+                    e.set_option("spmm_unroll", un)
                     try:
                         e.aggregate(c)
                         e.aggregate(c)
@@ -65,8 +73,8 @@ def main():
                         ms = e.event_elapsed_ms(0, 1) / args.reps
                     except dengine.DoryError as ex:
                         ms = None
-                        print("skip", layer, lg, vec, ex, flush=True)
-                    r = dict(layer=layer, F=spec.dims[layer], lg=lg, vec=vec, heavy=heavy, ms=ms,
+                        print("skip", layer, lg, vec, un, ex, flush=True)
+                    r = dict(layer=layer, F=spec.dims[layer], lg=lg, vec=vec, unroll=un, heavy=heavy, ms=ms,
                              gedges_per_s=None if ms is None else E / ms / 1e6)
                     results.append(r)
                     print(json.dumps(r), flush=True)
