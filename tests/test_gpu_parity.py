@@ -259,7 +259,17 @@ def test_gat_epoch_matches_oracle(oracle, mode):
             assert rel_err(e.get_tensor(l, "az").reshape(-1), t[l]["az"]) < TOL
             assert rel_err(e.get_tensor(l, "dA").reshape(-1), t[l]["dA"]) < TOL
             assert rel_err(e.get_weight_grad(l), orc.dW[0][l]) < TOL
-            assert rel_err(e.get_weight_grad(l, "a_i").reshape(-1), orc.da[0][l]) < 5e-5
+            # da = (z^T z) . colsum(dAct): the reference adds E x F' terms one by one in fp32
+            # (CPU_comm.cpp:366-382), so the ORACLE carries the larger rounding error here; both are
+            # checked against the float64 evaluation of the same formula.
+            g = ds.graphs[0]
+            dst_of_edge = np.repeat(np.arange(ds.V), np.diff(g.col_ptrs).astype(np.int64))
+            dl = np.where(t[l]["az"] > 0, 1.0, 0.01)
+            cvec = np.bincount(dst_of_edge, weights=dl, minlength=ds.V)
+            z64, g64 = t[l]["z"].astype(np.float64), t[l]["grad"].astype(np.float64)
+            da64 = (z64.T @ z64) @ (g64.T @ cvec)
+            assert rel_err(e.get_weight_grad(l, "a_i").reshape(-1), da64) < TOL
+            assert rel_err(orc.da[0][l], da64) < 5e-4
         assert rel_err(e.get_tensor(1, "A").reshape(-1), orc.A[0]) < TOL  # last layer's attention (Q12)
 
 
