@@ -103,6 +103,7 @@ struct dory_engine {
     DevBuf flush;                // L2 flush target
     DevBuf stage;                // dense staging for host <-> padded-row copies
     int spmm_lg = 0, spmm_vec = 0, spmm_unroll = 0;
+    int tensor_cores = 0;  // tcgen05 path for H.W (option "tensor_cores")
     uint32_t heavy_degree = kHeavyDegree;
 
     // Adam (AdamOptimizer.hpp:69-84)
@@ -435,7 +436,7 @@ int aggregate_gcn(dory_engine *e, const dory_chunk *c) {
     return DORY_OK;
 }
 
-bool use_tensor_cores(const dory_engine *e) { return !(e->cfg.flags & DORY_FLAG_NO_TENSOR_CORES); }
+bool use_tensor_cores(const dory_engine *e) { return e->tensor_cores && !(e->cfg.flags & DORY_FLAG_NO_TENSOR_CORES); }
 
 // Z = A . W (+ tanh): tcgen05 path when the shape qualifies, else fp32 SIMT.
 int gemm_nn(dory_engine *e, const DevMat &A, const WeightSet &W, const DevMat &C, const DevMat *C2) {
@@ -778,6 +779,8 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
     } else if (std::strcmp(key, "spmm_vec") == 0) {
         if (v > 5) return fail(e, DORY_EINVAL, "spmm_vec must be 0..5");
         e->spmm_vec = (int)v;
+    } else if (std::strcmp(key, "tensor_cores") == 0) {
+        e->tensor_cores = v != 0;
     } else if (std::strcmp(key, "spmm_unroll") == 0) {
         if (v > 8) return fail(e, DORY_EINVAL, "spmm_unroll must be 0..8");
         e->spmm_unroll = (int)v;

@@ -1,11 +1,396 @@
-// tcgen05 path for Z = AH . W.  (Round-1 placeholder: reports "unsupported" so the engine takes the
-// exact-fp32 SIMT path; the tensor-core kernel lands in this file.)
+// Dense apply Z = AH . W on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), with an
+// error-compensated 3xTF32 split so that the result keeps fp32-level accuracy (the parity bar is
+// 1e-5 against cblas_sgemm, which plain TF32 -- 10 mantissa bits -- cannot meet).
+//
+// Stands in for Matrix::dot -> cblas_sgemm in CPUComm::vtxNNForwardGCN/GAT (reference
+// commmanager/CPU_comm.cpp:98-107,161-169) and for cublasSgemm + cudnnActivationForward in the
+// reference GPU backend (GPU-Computation/comp_server.cu:104-176); the tanh epilogue is fused and
+// writes both z and h.
+//
+// Shape of the problem: M = |V_p| (232,965 on Reddit) is huge, K = F_in (608 padded), N = F_out
+// (128 / 64 padded).  One CTA owns a 128-row output tile and the whole N extent:
+//   warp 0     TMA producer: per 32-wide K block one box of A (128 x 32 fp32, 128B swizzle) and the
+//              matching boxes of W^T_hi and W^T_lo (pre-split once per call, K-major)
+//   warps 2-5  split the A box in place into hi = a & 0xffffe000 (exactly representable in TF32)
+//              and lo = a - hi (second buffer), then publish it to the async proxy
+//   warp 1     one elected lane issues, per K block, 4 x {hi.hi -> D0, hi.lo -> D1, lo.hi -> D1}
+//              tcgen05.mma.kind::tf32 (M=128, N, K=8); D0 / D1 are two fp32 accumulators in TMEM so
+//              that the small correction terms never round against the large partial sums
+//   warps 2-5  epilogue: tcgen05.ld D0 + D1 -> registers -> (tanh) -> 128-bit global stores
+// Stages are handed around with mbarriers (TMA -> converters -> MMA -> TMA); tcgen05.commit frees a
+// stage and finally signals the epilogue.
+#include <cuda.h>
+
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
 #include "gemm_tc.cuh"
 
 namespace dory {
+namespace {
 
-int launch_gemm_tc(const float *, uint32_t, uint64_t, const float *, uint32_t, uint32_t, float *, float *,
-                   uint32_t, int, cudaStream_t) {
+constexpr int BM = 128;      // rows per CTA tile (UMMA M, cta_group::1)
+constexpr int BK = 32;       // fp32 per K block = one 128-byte swizzle span
+constexpr int UMMA_K = 8;    // K per tcgen05.mma.kind::tf32
+constexpr int kThreads = 192;
+constexpr int kConvThreads = 128;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc], kind::tf32, issued by ONE thread for the CTA
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float *v) {
+    uint32_t *r = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO); the
+// leading-dimension offset is unused for swizzled K-major layouts (set to 1 like CUTLASS).
+// Bit layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor), version = 1, layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor (InstrDescriptor in the same header): c_format F32 (1) at bit 4,
+// a/b format TF32 (2) at bits 7 / 10, both operands K-major, N>>3 at bit 17, M>>4 at bit 24.
+template <int BN>
+__host__ __device__ constexpr uint32_t umma_idesc_tf32() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN>
+struct SmemLayout {
+    static constexpr int kStages = BN == 128 ? 3 : 4;
+    static constexpr uint32_t kABytes = BM * BK * 4;  // 16 KB
+    static constexpr uint32_t kBBytes = BN * BK * 4;  // 16 KB / 8 KB
+    static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
+    static constexpr uint32_t kTxBytes = kABytes + 2 * kBBytes;  // what TMA delivers per stage
+    static constexpr uint32_t kBarOffset = kStages * kStageBytes;
+    static constexpr uint32_t kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBhi,
+               const __grid_constant__ CUtensorMap mapBlo, float *__restrict__ C, float *__restrict__ C2,
+               uint32_t ldc, uint64_t M, uint32_t nkb, int epilogue) {
+    using L = SmemLayout<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle needs 1024 B alignment
+    uint8_t *gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    auto stage_a_hi = [&](int s) { return base + s * L::kStageBytes; };
+    auto stage_a_lo = [&](int s) { return base + s * L::kStageBytes + L::kABytes; };
+    auto stage_b_hi = [&](int s) { return base + s * L::kStageBytes + 2 * L::kABytes; };
+    auto stage_b_lo = [&](int s) { return base + s * L::kStageBytes + 2 * L::kABytes + L::kBBytes; };
+    const uint32_t bar0 = base + L::kBarOffset;
+    auto bar_full = [&](int s) { return bar0 + 8 * s; };                   // TMA bytes landed
+    auto bar_conv = [&](int s) { return bar0 + 8 * (L::kStages + s); };    // A split published
+    auto bar_empty = [&](int s) { return bar0 + 8 * (2 * L::kStages + s); };  // MMAs retired
+    const uint32_t bar_done = bar0 + 8 * (3 * L::kStages);                 // accumulators final
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen_base + L::kBarOffset + 8 * (3 * L::kStages + 1));
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapBhi);
+        tma_prefetch_desc(&mapBlo);
+        for (int s = 0; s < L::kStages; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_conv(s), kConvThreads);
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {  // TMEM: two fp32 accumulators of BN columns each
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(2 * BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int m0 = blockIdx.x * BM;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+                const int s = kb % L::kStages;
+                const uint32_t ph = (kb / L::kStages) & 1;
+                mbar_wait(bar_empty(s), ph ^ 1);
+                mbar_expect_tx(bar_full(s), L::kTxBytes);
+                tma_load_2d(stage_a_hi(s), &mapA, kb * BK, m0, bar_full(s));
+                tma_load_2d(stage_b_hi(s), &mapBhi, kb * BK, 0, bar_full(s));
+                tma_load_2d(stage_b_lo(s), &mapBlo, kb * BK, 0, bar_full(s));
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = umma_idesc_tf32<BN>();
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+            const int s = kb % L::kStages;
+            const uint32_t ph = (kb / L::kStages) & 1;
+            mbar_wait(bar_full(s), ph);
+            mbar_wait(bar_conv(s), ph);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint32_t koff = k * UMMA_K * 4;  // bytes along K inside the swizzle span
+                    const uint64_t a_hi = umma_desc_sw128(stage_a_hi(s) + koff);
+                    const uint64_t a_lo = umma_desc_sw128(stage_a_lo(s) + koff);
+                    const uint64_t b_hi = umma_desc_sw128(stage_b_hi(s) + koff);
+                    const uint64_t b_lo = umma_desc_sw128(stage_b_lo(s) + koff);
+                    const uint32_t acc = (kb | (uint32_t)k) ? 1u : 0u;
+                    tc_mma_tf32(tmem, a_hi, b_hi, idesc, acc);       // D0 += hi . hi
+                    tc_mma_tf32(tmem + BN, a_hi, b_lo, idesc, acc);  // D1 += hi . lo
+                    tc_mma_tf32(tmem + BN, a_lo, b_hi, idesc, 1u);   // D1 += lo . hi
+                }
+                tc_commit(bar_empty(s));                 // stage reusable once these MMAs retire
+                if (kb + 1 == nkb) tc_commit(bar_done);  // accumulators complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== A splitter, then epilogue =====================
+        const int t = threadIdx.x - 64;  // 0..127
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+            const int s = kb % L::kStages;
+            const uint32_t ph = (kb / L::kStages) & 1;
+            mbar_wait(bar_full(s), ph);
+            float4 *hi = reinterpret_cast<float4 *>(gen_base + s * L::kStageBytes);
+            float4 *lo = reinterpret_cast<float4 *>(gen_base + s * L::kStageBytes + L::kABytes);
+            // the split is element-wise, so the swizzled placement is preserved by construction
+#pragma unroll
+            for (int i = 0; i < (BM * BK / 4) / kConvThreads; ++i) {
+                const int idx = t + i * kConvThreads;
+                const float4 v = hi[idx];
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                l.x = v.x - h.x;
+                l.y = v.y - h.y;
+                l.z = v.z - h.z;
+                l.w = v.w - h.w;
+                hi[idx] = h;
+                lo[idx] = l;
+            }
+            fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
+            mbar_arrive(bar_conv(s));
+        }
+        // epilogue: TMEM lane quarter of this warp (warp % 4), one output row per thread
+        mbar_wait(bar_done, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const uint64_t m = (uint64_t)m0 + q * 32 + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            float d0[32], d1[32];
+            tc_ld_32x32(lane_base + c * 32, d0);
+            tc_ld_32x32(lane_base + BN + c * 32, d1);
+            tc_wait_ld();
+            if (m < M) {
+                float4 *out = reinterpret_cast<float4 *>(C + m * ldc + c * 32);
+                float4 *out2 = reinterpret_cast<float4 *>(C2 + m * ldc + c * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 v = make_float4(d0[4 * j] + d1[4 * j], d0[4 * j + 1] + d1[4 * j + 1],
+                                           d0[4 * j + 2] + d1[4 * j + 2], d0[4 * j + 3] + d1[4 * j + 3]);
+                    out[j] = v;
+                    if (epilogue == EPI_TANH) out2[j] = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN) : "memory");
+    }
+}
+
+// Wt_hi[n][k], Wt_lo[n][k] (K-major, [BN x Kpad]) from W[k][n] ([Kpad x ldw]); rows n >= ldw are zero.
+__global__ void split_transpose_kernel(const float *__restrict__ W, uint32_t ldw, uint32_t Kpad, uint32_t BN,
+                                       float *__restrict__ hi, float *__restrict__ lo) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = blockIdx.y;
+    if (k >= Kpad) return;
+    const float w = n < ldw ? W[(size_t)k * ldw + n] : 0.f;
+    const float h = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+    hi[(size_t)n * Kpad + k] = h;
+    lo[(size_t)n * Kpad + k] = w - h;
+}
+
+// ------------------------------------------------------------------ host side
+using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn encode_fn() {
+    static EncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeFn>(p);
+    }
+    return fn;
+}
+
+bool make_map(CUtensorMap *map, const float *ptr, uint64_t rows, uint32_t cols, uint32_t ld, uint32_t boxRows) {
+    EncodeFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, boxRows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct WeightSplit {
+    float *hi = nullptr, *lo = nullptr;
+    CUtensorMap mapHi, mapLo;
+};
+struct Cache {
+    std::mutex mu;
+    std::map<std::tuple<const float *, uint32_t, uint32_t>, WeightSplit> weights;  // (W, ldw, Kpad)
+    std::map<std::tuple<const float *, uint32_t, uint64_t>, CUtensorMap> amaps;    // (A, lda, M)
+};
+Cache &cache() {
+    static Cache c;
+    return c;
+}
+
+template <int BN>
+int launch_bn(const float *A, uint32_t lda, uint64_t M, const float *W, uint32_t ldw, uint32_t Kpad, float *C,
+              float *C2, uint32_t ldc, int epilogue, cudaStream_t s) {
+    using L = SmemLayout<BN>;
+    Cache &c = cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto wkey = std::make_tuple(W, ldw, Kpad);
+    auto wit = c.weights.find(wkey);
+    if (wit == c.weights.end()) {
+        WeightSplit ws;
+        const size_t bytes = (size_t)BN * Kpad * 4;
+        if (cudaMalloc(&ws.hi, bytes) != cudaSuccess || cudaMalloc(&ws.lo, bytes) != cudaSuccess) return -1;
+        if (!make_map(&ws.mapHi, ws.hi, BN, Kpad, Kpad, BN) || !make_map(&ws.mapLo, ws.lo, BN, Kpad, Kpad, BN)) return 0;
+        wit = c.weights.emplace(wkey, ws).first;
+    }
+    auto akey = std::make_tuple(A, lda, M);
+    auto ait = c.amaps.find(akey);
+    if (ait == c.amaps.end()) {
+        CUtensorMap m;
+        if (!make_map(&m, A, M, Kpad, lda, BM)) return 0;
+        ait = c.amaps.emplace(akey, m).first;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal) != cudaSuccess)
+            return -1;
+        attr_set = true;
+    }
+    // weights change every epoch (Adam): re-split them on every call (0.3 MB)
+    dim3 sg((Kpad + 127) / 128, BN);
+    split_transpose_kernel<<<sg, 128, 0, s>>>(W, ldw, Kpad, BN, wit->second.hi, wit->second.lo);
+    const unsigned grid = (unsigned)((M + BM - 1) / BM);
+    gemm_tc_kernel<BN><<<grid, kThreads, L::kTotal, s>>>(ait->second, wit->second.mapHi, wit->second.mapLo, C,
+                                                        C2 ? C2 : C, ldc, M, Kpad / BK, C2 ? epilogue : EPI_NONE);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return 2;
+}
+
+}  // namespace
+
+int launch_gemm_tc(const float *A, uint32_t lda, uint64_t M, const float *W, uint32_t ldw, uint32_t Kpad, float *C,
+                   float *C2, uint32_t ldc, int epilogue, cudaStream_t s) {
+    // Supported: K a multiple of the 32-float swizzle span, N (padded) exactly 64 or 128, and the
+    // output pitch equal to N.  Anything else takes the fp32 SIMT path (dense.cu).
+    if (Kpad % BK != 0 || Kpad == 0 || lda < Kpad || ldc != ldw || M == 0) return 0;
+    if (ldw == 128) return launch_bn<128>(A, lda, M, W, ldw, Kpad, C, C2, ldc, epilogue, s);
+    if (ldw == 64) return launch_bn<64>(A, lda, M, W, ldw, Kpad, C, C2, ldc, epilogue, s);
     return 0;
 }
 

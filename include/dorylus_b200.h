@@ -105,8 +105,11 @@ int dory_sync(dory_engine *e);
  *   "spmm_lg" / "spmm_vec"  lanes per gathered row and float4 per lane of the aggregation kernel
  *                           (0 = choose from the row width); a slab narrower than the row walks the
  *                           adjacency once per slab.
+ *   "spmm_unroll"           gather instructions issued back to back per lane group (0 = default).
  *   "heavy_degree"          rows with at least this many edges get a whole CTA (set before
- *                           dory_load_partition). */
+ *                           dory_load_partition).
+ *   "tensor_cores"          1: run H.W on tcgen05 (3xTF32, fp32-level accuracy) when the shape
+ *                           qualifies; 0: always the fp32 CUDA-core GEMM. */
 int dory_set_option(dory_engine *e, const char *key, const char *value);
 
 /* ---- dataset preprocessing (host only, no GPU needed) --------------------------------------

@@ -1,0 +1,57 @@
+"""tcgen05 (3xTF32) dense apply against float64 and against the fp32 CUDA-core path."""
+import numpy as np
+import pytest
+
+from helpers import random_dataset, rel_err
+from dorylus_b200.engine import FORWARD, GCN, Engine
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(ds, tc):
+    e = Engine(ds.dims, GCN)
+    e.set_option("tensor_cores", 1 if tc else 0)
+    e.load_partition(ds.images[0])
+    e.set_tensor(len(ds.dims) - 2, "lab", ds.onehot)
+    e.init_weights()
+    return e
+
+
+@pytest.mark.parametrize("dims,V", [([602, 128, 41], 3000), ([128, 64, 64, 25], 1111), ([96, 128, 7], 257)],
+                         ids=["reddit", "amazon", "odd"])
+def test_forward_apply_tensor_core_path(dims, V):
+    ds = random_dataset(V=V, E_und=4 * V, dims=dims, seed=91)
+    rng = np.random.default_rng(5)
+    ah = rng.standard_normal((V, dims[0])).astype(np.float32)
+    out = {}
+    for tc in (0, 1):
+        with _engine(ds, tc) as e:
+            e.set_tensor(0, "ah", ah)
+            W = e.get_weights(0)
+            e.applyVertexGCN(e.whole_chunk(0, FORWARD))
+            out[tc] = (e.get_tensor(0, "z"), e.get_tensor(0, "h"), e.stats()["kernel_launches"])
+    z64 = ah.astype(np.float64) @ W.astype(np.float64)
+    err_simt, err_tc = rel_err(out[0][0], z64), rel_err(out[1][0], z64)
+    print("dims", dims, "rel err vs float64: simt %.2e  tcgen05 3xTF32 %.2e" % (err_simt, err_tc))
+    assert err_tc < 1e-5 and err_simt < 1e-5
+    assert rel_err(out[1][1], np.tanh(z64)) < 1e-5
+    assert rel_err(out[1][0], out[0][0]) < 1e-5
+
+
+def test_epochs_with_tensor_cores_match_oracle(oracle):
+    from oracle.driver import OracleGCN
+
+    ds = random_dataset(V=1500, E_und=12000, dims=[602, 128, 41], seed=93)
+    orc = OracleGCN(oracle, ds.graphs, ds.dims)
+    orc.load_features(ds.feats, ds.onehot)
+    with _engine(ds, 1) as e:
+        e.set_tensor(0, "x", ds.feats)
+        for ep in range(2):
+            want = orc.epoch()
+            st = e.epoch()
+            for l, n in ((0, "ah"), (0, "z"), (0, "h"), (1, "ah"), (1, "grad"), (0, "aTg")):
+                assert rel_err(e.get_tensor(l, n), orc.saved[0][l][n]) < 1e-5, (ep, l, n)
+            for l in range(2):
+                assert rel_err(e.get_weight_grad(l), orc.dW[0][l]) < 1e-5
+                e.set_weights(l, orc.W[l])
+            assert st["acc_sum"] == want["acc"][0]
