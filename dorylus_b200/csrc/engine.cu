@@ -103,7 +103,7 @@ struct dory_engine {
     DevBuf flush;                // L2 flush target
     DevBuf stage;                // dense staging for host <-> padded-row copies
     int spmm_lg = 0, spmm_vec = 0, spmm_unroll = 0;
-    int tensor_cores = 0;  // tcgen05 path for H.W (option "tensor_cores")
+    int tensor_cores = 1;  // tcgen05 path for H.W (option "tensor_cores")
     uint32_t heavy_degree = kHeavyDegree;
 
     // Adam (AdamOptimizer.hpp:69-84)
