@@ -83,11 +83,12 @@ __device__ __forceinline__ void add4(float4 &a, const float4 &b) {
 // TEAM : warps per destination row (1: warp-per-row, kWarpsPerCta: CTA-per-row)
 // U    : gather instructions issued back to back before their FMAs (each covers 32/LG edges)
 template <int LG, int VEC, int TEAM, int U>
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, (U == 0 && VEC <= 4) ? 4 : 1)
 spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nrows) {
     constexpr int EPW = 32 / LG;  // edges covered by one warp-wide gather instruction
-    static_assert(LG % U == 0 || U % LG == 0, "U must divide the number of steps per 32-edge batch");
-    constexpr int UU = U < LG ? U : LG;  // steps per inner block (a batch of 32 edges has LG steps)
+    static_assert(U == 0 || LG % (U ? U : 1) == 0 || (U ? U : 1) % LG == 0,
+                  "U must divide the number of steps per 32-edge batch");
+    constexpr int UU = U == 0 ? 1 : (U < LG ? U : LG);  // steps per inner block (LG steps per 32 edges)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / LG, l = lane % LG;
 
@@ -116,7 +117,67 @@ spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nro
 #pragma unroll
     for (int j = 0; j < VEC; ++j) act[j] = (col0 + l + j * LG) < a.nvec;
 
-    for (uint64_t e0 = e_begin + (uint64_t)team_rank * 32; e0 < e_end; e0 += 32 * TEAM) {
+    if constexpr (U == 0) {
+        // Rotating two-deep software pipeline: the gather of step t+1 (or of the first step of the
+        // NEXT 32-edge batch, whose ids were prefetched one batch ahead) is always in flight while
+        // step t is consumed, so the dependent chain id-load -> shuffle -> gather never drains.
+        const uint64_t stride = 32 * TEAM;
+        uint64_t e0 = e_begin + (uint64_t)team_rank * 32;
+        uint32_t s_cur = 0, s_nxt = 0;
+        float w_cur = 0.f, w_nxt = 0.f;
+        auto fetch_ids = [&](uint64_t eb, uint32_t &s, float &w) {
+            s = 0;
+            w = 0.f;
+            const uint64_t my = eb + lane;
+            if (my < e_end) {
+                s = ld_stream_u32(a.idx + my, pol_stream);
+                w = ld_stream_f32(a.vals + my, pol_stream);
+            }
+        };
+        float4 x[2][VEC];
+        float wv[2];
+        auto issue = [&](int slot, uint32_t s_l, float w_l, int step, int n) {
+            const int sl = step * EPW + g;
+            const uint32_t s = __shfl_sync(kFull, s_l, sl);
+            wv[slot] = __shfl_sync(kFull, w_l, sl);
+            const bool ev = sl < n;
+            const float4 *rp = src4 + (size_t)s * ld4 + col0 + l;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                x[slot][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (act[j] && ev) x[slot][j] = ld_row_f4(rp + j * LG, pol_keep);
+            }
+        };
+        if (e0 < e_end) {
+            fetch_ids(e0, s_cur, w_cur);
+            fetch_ids(e0 + stride, s_nxt, w_nxt);
+            int n = (int)min((uint64_t)32, e_end - e0);
+            issue(0, s_cur, w_cur, 0, n);
+            while (true) {
+                const uint64_t e1 = e0 + stride;
+                const bool more = e1 < e_end;
+                const int n1 = more ? (int)min((uint64_t)32, e_end - e1) : 0;
+#pragma unroll 1
+                for (int k = 0; k < LG; k += 2) {  // two steps per trip: slots alternate 0, 1
+                    issue(1, s_cur, w_cur, k + 1, n);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) fma4(acc[j], x[0][j], wv[0]);
+                    // next step: same batch, or step 0 of the next batch
+                    if (k + 2 < LG) issue(0, s_cur, w_cur, k + 2, n);
+                    else issue(0, s_nxt, w_nxt, 0, n1);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) fma4(acc[j], x[1][j], wv[1]);
+                }
+                if (!more) break;
+                e0 = e1;
+                n = n1;
+                s_cur = s_nxt;
+                w_cur = w_nxt;
+                fetch_ids(e0 + stride, s_nxt, w_nxt);
+            }
+        }
+    }
+    for (uint64_t e0 = e_begin + (uint64_t)team_rank * 32; U > 0 && e0 < e_end; e0 += 32 * TEAM) {
         const uint64_t my = e0 + lane;
         uint32_t s_l = 0;
         float w_l = 0.f;
@@ -246,6 +307,7 @@ int launch_cfg(const SpmmArgs &a, cudaStream_t s) {
 
 template <int LG, int VEC>
 int launch_unroll(const SpmmArgs &a, int unroll, cudaStream_t s) {
+    if (unroll == 9) return launch_cfg<LG, VEC, 0>(a, s);  // rotating two-deep pipeline
     if (unroll >= 8 && VEC <= 2) return launch_cfg<LG, VEC, 8>(a, s);
     if (unroll >= 4 && VEC <= 4) return launch_cfg<LG, VEC, 4>(a, s);
     if (unroll >= 2) return launch_cfg<LG, VEC, 2>(a, s);

@@ -1,0 +1,153 @@
+// C++ host driver over the C ABI: what src/graph-server/main.cpp + Engine::init/run do for a
+// synchronous single-partition run in CPU/GPU mode (reference engine/engine.cpp:40-167,223-314),
+// minus the ZeroMQ / weight-server processes.  Reads the reference's dataset directory:
+//
+//   <datasetdir>/graph.bsnap.edges, graph.bsnap.parts   (preprocessed into graph.<id>.bin if absent,
+//                                                        like engine.cpp:62-71)
+//   --featuresfile features.bsnap   --labelsfile labels.bsnap   --layerfile <one width per line>
+//
+//   dorylus_b200_run --datasetdir D/ --featuresfile F --labelsfile L --layerfile C
+//                    [--numepochs 10] [--lr 0.01] [--gnn GCN|GAT] [--undirected 0]
+//
+// Prints one line per epoch in the weight server's format (weightserver.cpp:258-262:
+// "Epoch %u, acc: %.3f, loss: %.3f") plus the epoch time the graph server reports
+// (ops/pipeline.cpp:117-136).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "../include/dorylus_b200.h"
+
+namespace {
+
+bool read_file(const std::string &path, std::vector<char> &out) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f.good()) return false;
+    out.resize((size_t)f.tellg());
+    f.seekg(0);
+    f.read(out.data(), (std::streamsize)out.size());
+    return f.good() || f.eof();
+}
+
+[[noreturn]] void die(dory_engine *e, const char *what) {
+    std::fprintf(stderr, "dorylus_b200_run: %s: %s\n", what, dory_last_error(e));
+    std::exit(EXIT_FAILURE);
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    std::string dir, featuresFile, labelsFile, layerFile, gnn = "GCN";
+    unsigned epochs = 10, undirected = 0;
+    float lr = 0.01f;
+    for (int i = 1; i + 1 < argc; i += 2) {
+        const std::string k = argv[i], v = argv[i + 1];
+        if (k == "--datasetdir") dir = v;
+        else if (k == "--featuresfile") featuresFile = v;
+        else if (k == "--labelsfile") labelsFile = v;
+        else if (k == "--layerfile") layerFile = v;
+        else if (k == "--numepochs") epochs = (unsigned)std::atoi(v.c_str());
+        else if (k == "--lr") lr = (float)std::atof(v.c_str());
+        else if (k == "--gnn") gnn = v;
+        else if (k == "--undirected") undirected = (unsigned)std::atoi(v.c_str());
+        else {
+            std::fprintf(stderr, "unknown flag %s\n", k.c_str());
+            return EXIT_FAILURE;
+        }
+    }
+    if (dir.empty() || featuresFile.empty() || labelsFile.empty() || layerFile.empty()) {
+        std::fprintf(stderr, "usage: %s --datasetdir D/ --featuresfile F --labelsfile L --layerfile C "
+                             "[--numepochs N] [--lr 0.01] [--gnn GCN|GAT] [--undirected 0]\n", argv[0]);
+        return EXIT_FAILURE;
+    }
+    if (dir.back() != '/') dir += '/';
+
+    // readLayerConfigFile, engine/utils.cpp:460-479
+    dory_config cfg{};
+    cfg.abi_version = DORY_ABI_VERSION;
+    cfg.gnn_type = gnn == "GAT" ? DORY_GAT : DORY_GCN;
+    {
+        std::ifstream f(layerFile);
+        std::string line;
+        unsigned n = 0;
+        while (std::getline(f, line)) {
+            if (line.find_first_not_of(" \t\r\n") == std::string::npos) continue;
+            if (n > DORY_MAX_LAYERS) break;
+            cfg.dims[n++] = (uint32_t)std::stoul(line);
+        }
+        if (n < 2) {
+            std::fprintf(stderr, "layer file needs at least two widths\n");
+            return EXIT_FAILURE;
+        }
+        cfg.n_layers = n - 1;
+    }
+    cfg.node_id = 0;
+    cfg.num_nodes = 1;
+    cfg.device = 0;
+    cfg.learning_rate = lr;
+
+    dory_engine *e = nullptr;
+    if (dory_create(&e, &cfg) != DORY_OK) die(nullptr, "dory_create");
+
+    std::vector<char> image;
+    if (!read_file(dir + "graph.0.bin", image)) {
+        std::fprintf(stderr, "[ Node   0 ]  Preprocessing... Output to %sgraph.0.bin\n", dir.c_str());
+        if (dory_preprocess_dir(dir.c_str(), 0, 1, (int)undirected) != DORY_OK) die(nullptr, "dory_preprocess_dir");
+        if (!read_file(dir + "graph.0.bin", image)) die(nullptr, "cannot read graph.0.bin");
+    }
+    if (dory_load_partition(e, image.data(), image.size()) != DORY_OK) die(e, "dory_load_partition");
+    uint64_t cnt[7];
+    dory_graph_counts(e, cnt);
+    const uint64_t V = cnt[0];
+
+    // readFeaturesFile / readLabelsFile, engine/utils.cpp:486-596 (single partition: local order == global order)
+    std::vector<char> raw;
+    if (!read_file(featuresFile, raw) || raw.size() < 4) die(nullptr, "cannot read features file");
+    uint32_t nf;
+    std::memcpy(&nf, raw.data(), 4);
+    if (nf != cfg.dims[0] || raw.size() != 4 + (size_t)V * nf * 4) {
+        std::fprintf(stderr, "features file does not match layer config / vertex count\n");
+        return EXIT_FAILURE;
+    }
+    const char *in_name = cfg.gnn_type == DORY_GCN ? "x" : "h";
+    if (dory_set_tensor(e, 0, in_name, reinterpret_cast<const float *>(raw.data() + 4), V, nf) != DORY_OK)
+        die(e, "dory_set_tensor(features)");
+    if (!read_file(labelsFile, raw) || raw.size() < 4) die(nullptr, "cannot read labels file");
+    uint32_t kinds;
+    std::memcpy(&kinds, raw.data(), 4);
+    const uint32_t C = cfg.dims[cfg.n_layers];
+    if (kinds != C || raw.size() != 4 + (size_t)V * 4) {
+        std::fprintf(stderr, "labels file does not match layer config / vertex count\n");
+        return EXIT_FAILURE;
+    }
+    std::vector<float> onehot((size_t)V * C, 0.f);
+    for (uint64_t v = 0; v < V; ++v) {
+        uint32_t c;
+        std::memcpy(&c, raw.data() + 4 + 4 * v, 4);
+        if (c >= C) {
+            std::fprintf(stderr, "label %u out of range at vertex %llu\n", c, (unsigned long long)v);
+            return EXIT_FAILURE;
+        }
+        onehot[v * C + c] = 1.f;
+    }
+    if (dory_set_tensor(e, cfg.n_layers - 1, "lab", onehot.data(), V, C) != DORY_OK) die(e, "dory_set_tensor(labels)");
+    if (dory_init_weights(e) != DORY_OK) die(e, "dory_init_weights");
+
+    double total_ms = 0;
+    for (unsigned ep = 1; ep <= epochs; ++ep) {
+        const auto t0 = std::chrono::steady_clock::now();
+        dory_stats st{};
+        if (dory_epoch(e, &st) != DORY_OK) die(e, "dory_epoch");
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ep > 1) total_ms += ms;  // the reference skips the first epoch (pipeline.cpp:117)
+        const double denom = st.val_rows ? st.val_rows : 1;
+        std::printf("Epoch %u, acc: %.3f, loss: %.3f, time: %.3f ms\n", ep, st.acc_sum / denom, st.loss_sum / denom, ms);
+    }
+    if (epochs > 1) std::printf("<EM>: Average epoch time %.3f ms\n", total_ms / (epochs - 1));
+    dory_destroy(e);
+    return EXIT_SUCCESS;
+}

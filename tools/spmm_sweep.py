@@ -23,10 +23,9 @@ from dorylus_b200 import synth  # noqa: E402
 from dorylus_b200.engine import FORWARD, GCN, Engine  # noqa: E402
 
 SHAPES = {
-    0: [(0, 0, 0), (8, 4, 1), (8, 4, 2), (8, 4, 4), (4, 4, 2), (4, 4, 4), (16, 4, 2), (16, 2, 4), (16, 2, 8),
-        (16, 1, 8), (8, 2, 4), (8, 2, 8), (32, 1, 8), (32, 2, 4), (32, 4, 2), (32, 5, 2), (4, 2, 8), (8, 1, 8)],
-    1: [(0, 0, 0), (8, 4, 1), (8, 4, 2), (8, 4, 4), (4, 4, 2), (4, 4, 4), (16, 2, 4), (16, 2, 8), (32, 1, 8),
-        (4, 2, 8), (8, 2, 8)],
+    0: [(0, 0, 0), (8, 4, 1), (8, 4, 2), (8, 4, 9), (8, 2, 9), (8, 2, 4), (16, 2, 9), (16, 2, 4), (16, 1, 9),
+        (32, 1, 9), (32, 2, 9), (4, 4, 9), (4, 2, 9), (16, 4, 9)],
+    1: [(0, 0, 0), (8, 4, 1), (8, 4, 2), (8, 4, 9), (8, 2, 9), (16, 2, 9), (32, 1, 9), (4, 4, 9), (4, 2, 9)],
 }
 
 
@@ -57,7 +56,7 @@ def main():
             for layer in (0, 1):
                 c = e.whole_chunk(layer, FORWARD)
                 for lg, vec, un in SHAPES[layer]:
-                    if hi > 0 and (lg, vec, un) not in ((0, 0, 0), (8, 4, 2), (16, 2, 4)):
+                    if hi > 0 and (lg, vec, un) not in ((0, 0, 0), (8, 4, 9)):
                         continue
                     e.set_option("spmm_lg", lg)
                     e.set_option("spmm_vec", vec)
