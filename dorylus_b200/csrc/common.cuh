@@ -55,6 +55,7 @@ struct SpmmArgs {
     uint32_t low;           // first row when `light` is null
     int cfg_lg, cfg_vec;    // kernel shape override (0 = derive from nvec)
     int cfg_unroll;         // gather instructions in flight per lane group (0 = default)
+    int cfg_occ;            // CTAs per SM the kernel is compiled for (0 = default)
 };
 
 // Launches the aggregation; returns the number of kernels launched, or -1 on a launch error.

@@ -102,7 +102,7 @@ struct dory_engine {
     DevBuf rowstat, stats_dev;   // softmax-CE reduction scratch
     DevBuf flush;                // L2 flush target
     DevBuf stage;                // dense staging for host <-> padded-row copies
-    int spmm_lg = 0, spmm_vec = 0, spmm_unroll = 0;
+    int spmm_lg = 0, spmm_vec = 0, spmm_unroll = 0, spmm_occ = 0;
     int tensor_cores = 1;  // tcgen05 path for H.W (option "tensor_cores")
     uint32_t heavy_degree = kHeavyDegree;
 
@@ -383,6 +383,7 @@ SpmmArgs spmm_args(const dory_engine *e, const Adjacency &adj, const float *self
     a.cfg_lg = e->spmm_lg;
     a.cfg_vec = e->spmm_vec;
     a.cfg_unroll = e->spmm_unroll;
+    a.cfg_occ = e->spmm_occ;
     a.ptrs = adj.ptrs.as<uint64_t>();
     a.idx = adj.idx.as<uint32_t>();
     a.vals = adj.vals.as<float>();
@@ -777,8 +778,10 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
         if (v != 0 && v != 4 && v != 8 && v != 16 && v != 32) return fail(e, DORY_EINVAL, "spmm_lg must be 0, 4, 8, 16 or 32");
         e->spmm_lg = (int)v;
     } else if (std::strcmp(key, "spmm_vec") == 0) {
-        if (v > 5) return fail(e, DORY_EINVAL, "spmm_vec must be 0..5");
+        if (v > 4) return fail(e, DORY_EINVAL, "spmm_vec must be 0..4");
         e->spmm_vec = (int)v;
+    } else if (std::strcmp(key, "spmm_occ") == 0) {
+        e->spmm_occ = (int)v;
     } else if (std::strcmp(key, "tensor_cores") == 0) {
         e->tensor_cores = v != 0;
     } else if (std::strcmp(key, "spmm_unroll") == 0) {

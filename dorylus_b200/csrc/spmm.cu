@@ -82,8 +82,10 @@ __device__ __forceinline__ void add4(float4 &a, const float4 &b) {
 // VEC  : float4 per lane  -> a CTA column slab is LG*VEC float4 wide
 // TEAM : warps per destination row (1: warp-per-row, kWarpsPerCta: CTA-per-row)
 // U    : gather instructions issued back to back before their FMAs (each covers 32/LG edges)
-template <int LG, int VEC, int TEAM, int U>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, (U == 0 && VEC <= 4) ? 4 : 1)
+// OCC  : CTAs of 8 warps ptxas must fit per SM (register budget 65536 / (256 * OCC) per thread);
+//        the kernel is bound by bytes in flight, so resident warps are worth more than registers
+template <int LG, int VEC, int TEAM, int U, int OCC>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, OCC)
 spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nrows) {
     constexpr int EPW = 32 / LG;  // edges covered by one warp-wide gather instruction
     static_assert(U == 0 || LG % (U ? U : 1) == 0 || (U ? U : 1) % LG == 0,
@@ -286,32 +288,38 @@ void read_env_cfg() {
     }
 }
 
-template <int LG, int VEC, int U>
+template <int LG, int VEC, int U, int OCC>
 int launch_cfg(const SpmmArgs &a, cudaStream_t s) {
     int launches = 0;
     const uint32_t slab = LG * VEC;
     const uint32_t nslab = (a.nvec + slab - 1) / slab;
     if (a.n_heavy) {
         dim3 grid(a.n_heavy, nslab);
-        spmm_kernel<LG, VEC, kWarpsPerCta, U><<<grid, 32 * kWarpsPerCta, 0, s>>>(a, a.heavy, a.n_heavy);
+        spmm_kernel<LG, VEC, kWarpsPerCta, U, OCC><<<grid, 32 * kWarpsPerCta, 0, s>>>(a, a.heavy, a.n_heavy);
         ++launches;
     }
     if (a.n_light) {
         dim3 grid((a.n_light + kWarpsPerCta - 1) / kWarpsPerCta, nslab);
-        spmm_kernel<LG, VEC, 1, U><<<grid, 32 * kWarpsPerCta, 0, s>>>(a, a.light, a.n_light);
+        spmm_kernel<LG, VEC, 1, U, OCC><<<grid, 32 * kWarpsPerCta, 0, s>>>(a, a.light, a.n_light);
         ++launches;
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launches;
 }
 
+template <int LG, int VEC, int U>
+int launch_occ(const SpmmArgs &a, int occ, cudaStream_t s) {
+    if (occ >= 8) return launch_cfg<LG, VEC, U, 8>(a, s);
+    if (occ >= 6) return launch_cfg<LG, VEC, U, 6>(a, s);
+    if (occ >= 5) return launch_cfg<LG, VEC, U, 5>(a, s);
+    return launch_cfg<LG, VEC, U, 4>(a, s);
+}
+
 template <int LG, int VEC>
-int launch_unroll(const SpmmArgs &a, int unroll, cudaStream_t s) {
-    if (unroll == 9) return launch_cfg<LG, VEC, 0>(a, s);  // rotating two-deep pipeline
-    if (unroll >= 8 && VEC <= 2) return launch_cfg<LG, VEC, 8>(a, s);
-    if (unroll >= 4 && VEC <= 4) return launch_cfg<LG, VEC, 4>(a, s);
-    if (unroll >= 2) return launch_cfg<LG, VEC, 2>(a, s);
-    return launch_cfg<LG, VEC, 1>(a, s);
+int launch_unroll(const SpmmArgs &a, int unroll, int occ, cudaStream_t s) {
+    if (unroll == 9) return launch_occ<LG, VEC, 0>(a, occ, s);  // rotating two-deep pipeline
+    if (unroll >= 2) return launch_occ<LG, VEC, 2>(a, occ, s);
+    return launch_occ<LG, VEC, 1>(a, occ, s);
 }
 
 }  // namespace
@@ -323,7 +331,7 @@ void spmm_set_config(int lg, int vec) {
 }
 
 #define DORY_SPMM_CASE(LG_, VEC_) \
-    if (lg == LG_ && vec == VEC_) return launch_unroll<LG_, VEC_>(a, unroll, s)
+    if (lg == LG_ && vec == VEC_) return launch_unroll<LG_, VEC_>(a, unroll, occ, s)
 
 int launch_spmm(const SpmmArgs &a, cudaStream_t s) {
     read_env_cfg();
@@ -339,20 +347,18 @@ int launch_spmm(const SpmmArgs &a, cudaStream_t s) {
         else if (n <= 16) lg = 8, vec = 2;
         else lg = 8, vec = 4;
     }
-    if (unroll == 0) unroll = vec >= 4 ? 2 : (vec == 2 ? 4 : 8);
+    if (unroll == 0) unroll = 1;
+    const int occ = a.cfg_occ ? a.cfg_occ : 4;
     DORY_SPMM_CASE(4, 1);
     DORY_SPMM_CASE(4, 2);
-    DORY_SPMM_CASE(4, 4);
     DORY_SPMM_CASE(8, 1);
     DORY_SPMM_CASE(8, 2);
     DORY_SPMM_CASE(8, 4);
     DORY_SPMM_CASE(16, 1);
     DORY_SPMM_CASE(16, 2);
-    DORY_SPMM_CASE(16, 4);
     DORY_SPMM_CASE(32, 1);
     DORY_SPMM_CASE(32, 2);
     DORY_SPMM_CASE(32, 4);
-    DORY_SPMM_CASE(32, 5);
     return -1;
 }
 

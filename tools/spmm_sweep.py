@@ -3,9 +3,9 @@
 
     python tools/spmm_sweep.py [--workload reddit] [--out gpurun_out/spmm_sweep.json]
 
-For every (lanes-per-row LG, float4-per-lane VEC, gathers-in-flight U, heavy-degree) it times the
-layer-0 forward (F=602) and layer-1 forward (F=128) aggregations with CUDA events on the engine's
-stream.  Results feed the defaults in csrc/spmm.cu and DESIGN.md §5.
+For every (lanes-per-row LG, float4-per-lane VEC, gather mode U, CTAs/SM OCC, heavy-degree) it times
+the layer-0 forward (F=602) and layer-1 forward (F=128) aggregations with CUDA events on the
+engine's stream.  Results feed the defaults in csrc/spmm.cu and DESIGN.md §5.
 """
 import argparse
 import json
@@ -22,10 +22,14 @@ from dorylus_b200 import engine as dengine  # noqa: E402
 from dorylus_b200 import synth  # noqa: E402
 from dorylus_b200.engine import FORWARD, GCN, Engine  # noqa: E402
 
+# (lg, vec, unroll, occ)
 SHAPES = {
-    0: [(0, 0, 0), (8, 4, 1), (8, 4, 2), (8, 4, 9), (8, 2, 9), (8, 2, 4), (16, 2, 9), (16, 2, 4), (16, 1, 9),
-        (32, 1, 9), (32, 2, 9), (4, 4, 9), (4, 2, 9), (16, 4, 9)],
-    1: [(0, 0, 0), (8, 4, 1), (8, 4, 2), (8, 4, 9), (8, 2, 9), (16, 2, 9), (32, 1, 9), (4, 4, 9), (4, 2, 9)],
+    0: [(0, 0, 0, 0), (8, 4, 1, 4), (8, 4, 1, 5), (8, 4, 1, 6), (8, 4, 2, 4), (8, 4, 9, 4),
+        (8, 2, 1, 4), (8, 2, 1, 6), (8, 2, 1, 8), (8, 2, 2, 4), (8, 2, 2, 5), (8, 2, 2, 6), (8, 2, 9, 4), (8, 2, 9, 5),
+        (16, 2, 1, 4), (16, 2, 1, 6), (16, 2, 2, 5), (16, 1, 2, 6), (16, 1, 2, 8), (8, 1, 2, 8), (32, 1, 2, 8),
+        (32, 2, 2, 6), (32, 4, 1, 5), (4, 2, 2, 6)],
+    1: [(0, 0, 0, 0), (8, 4, 1, 4), (8, 4, 1, 5), (8, 4, 1, 6), (8, 4, 2, 4), (8, 2, 1, 6), (8, 2, 2, 5),
+        (8, 2, 2, 6), (16, 2, 1, 6), (16, 2, 2, 5), (32, 1, 2, 8), (4, 2, 2, 6)],
 }
 
 
@@ -34,7 +38,7 @@ def main():
     ap.add_argument("--workload", default="reddit")
     ap.add_argument("--out", default="gpurun_out/spmm_sweep.json")
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--heavy", default="1024,512,2048")
+    ap.add_argument("--heavy", default="1024")
     args = ap.parse_args()
     spec = synth.CONFIGS[args.workload]
     src, dst = synth.generate_edges(spec)
@@ -55,12 +59,13 @@ def main():
             e.set_tensor(0, "h", h)
             for layer in (0, 1):
                 c = e.whole_chunk(layer, FORWARD)
-                for lg, vec, un in SHAPES[layer]:
-                    if hi > 0 and (lg, vec, un) not in ((0, 0, 0), (8, 4, 9)):
+                for lg, vec, un, occ in SHAPES[layer]:
+                    if hi > 0 and lg not in (0,):
                         continue
                     e.set_option("spmm_lg", lg)
                     e.set_option("spmm_vec", vec)
                     e.set_option("spmm_unroll", un)
+                    e.set_option("spmm_occ", occ)
                     try:
                         e.aggregate(c)
                         e.aggregate(c)
@@ -72,8 +77,8 @@ def main():
                         ms = e.event_elapsed_ms(0, 1) / args.reps
                     except dengine.DoryError as ex:
                         ms = None
-                        print("skip", layer, lg, vec, un, ex, flush=True)
-                    r = dict(layer=layer, F=spec.dims[layer], lg=lg, vec=vec, unroll=un, heavy=heavy, ms=ms,
+                        print("skip", layer, lg, vec, un, occ, ex, flush=True)
+                    r = dict(layer=layer, F=spec.dims[layer], lg=lg, vec=vec, unroll=un, occ=occ, heavy=heavy, ms=ms,
                              gedges_per_s=None if ms is None else E / ms / 1e6)
                     results.append(r)
                     print(json.dumps(r), flush=True)
