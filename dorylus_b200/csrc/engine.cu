@@ -16,6 +16,7 @@
 #include <numeric>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dorylus_b200.h"
@@ -67,6 +68,10 @@ struct Adjacency {
     DevBuf ptrs, idx, vals, heavy, light;
     uint64_t nnz = 0;
     uint32_t n_heavy = 0, n_light = 0;
+    // Source-blocked copy (GCN): every row's edge list regrouped by source-row block so that one
+    // launch only gathers from a (V+G)/nb-row window of the feature block (an L2-sized working set).
+    DevBuf bptrs, bidx, bvals;  // [V*nb + 1], [E], [E]
+    uint32_t nb = 1;
 };
 
 struct WeightSet {
@@ -104,6 +109,7 @@ struct dory_engine {
     DevBuf stage;                // dense staging for host <-> padded-row copies
     int spmm_lg = 0, spmm_vec = 0, spmm_unroll = 0, spmm_occ = 0;
     int tensor_cores = 1;  // tcgen05 path for H.W (option "tensor_cores")
+    uint32_t src_blocks = 0;  // source windows per aggregation (0 = size from L2, 1 = off)
     uint32_t heavy_degree = kHeavyDegree;
 
     // Adam (AdamOptimizer.hpp:69-84)
@@ -214,6 +220,66 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
     if (!light.empty())
         CU(cudaMemcpyAsync(adj.light.p, light.data(), 4 * light.size(), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));  // host staging vectors die at scope exit
+
+    // ---- source-blocked copy.  A 128-float slab of the [V+G] x F block is (V+G) * 512 B; it only
+    // stays L2-resident when that is well below the 126 MB L2 (the two L2 halves mirror lines that
+    // both dies read, so the useful capacity for a chip-wide gather is about half).  Split the source
+    // rows into nb windows of <= kWindowBytes and regroup each row's edges by window.
+    uint32_t nb = e->src_blocks;
+    if (nb == 0) {
+        constexpr uint64_t kWindowBytes = 56ull << 20;
+        nb = (uint32_t)(((uint64_t)nSrcRows * 512 + kWindowBytes - 1) / kWindowBytes);
+    }
+    nb = std::max(1u, std::min(nb, 64u));
+    adj.nb = 1;
+    if (nb > 1 && nnz && e->cfg.gnn_type == DORY_GCN) {
+        const uint32_t rowsPerBlock = (nSrcRows + nb - 1) / nb;
+        std::vector<uint64_t> bp((size_t)V * nb + 1);
+        std::vector<uint32_t> bi(nnz);
+        std::vector<float> bv(nnz);
+        const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+        // every (row, block) segment stays inside the row's original [hp[v], hp[v+1]) range, so rows
+        // can be regrouped independently: stable counting sort by block id
+        auto work = [&](unsigned t) {
+            std::vector<uint64_t> cnt(nb);
+            for (uint32_t v = (uint32_t)((uint64_t)V * t / nt); v < (uint32_t)((uint64_t)V * (t + 1) / nt); ++v) {
+                std::fill(cnt.begin(), cnt.end(), 0);
+                for (uint64_t k = hp[v]; k < hp[v + 1]; ++k) {
+                    uint32_t s;
+                    std::memcpy(&s, idx + 4 * k, 4);
+                    ++cnt[s / rowsPerBlock];
+                }
+                uint64_t off = hp[v];
+                for (uint32_t b = 0; b < nb; ++b) {
+                    bp[(size_t)v * nb + b] = off;
+                    const uint64_t c = cnt[b];
+                    cnt[b] = off;  // becomes the write cursor
+                    off += c;
+                }
+                for (uint64_t k = hp[v]; k < hp[v + 1]; ++k) {
+                    uint32_t s;
+                    float w;
+                    std::memcpy(&s, idx + 4 * k, 4);
+                    std::memcpy(&w, vals + 4 * k, 4);
+                    const uint64_t pos = cnt[s / rowsPerBlock]++;
+                    bi[pos] = s;
+                    bv[pos] = w;
+                }
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+        bp[(size_t)V * nb] = nnz;
+        CU(adj.bptrs.alloc(8 * bp.size()));
+        CU(adj.bidx.alloc(4 * nnz));
+        CU(adj.bvals.alloc(4 * nnz));
+        CU(cudaMemcpyAsync(adj.bptrs.p, bp.data(), 8 * bp.size(), cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(adj.bidx.p, bi.data(), 4 * nnz, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(adj.bvals.p, bv.data(), 4 * nnz, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        adj.nb = nb;
+    }
     return DORY_OK;
 }
 
@@ -385,6 +451,8 @@ SpmmArgs spmm_args(const dory_engine *e, const Adjacency &adj, const float *self
     a.cfg_unroll = e->spmm_unroll;
     a.cfg_occ = e->spmm_occ;
     a.ptrs = adj.ptrs.as<uint64_t>();
+    a.ptr_stride = 1;
+    a.ptr_off = 0;
     a.idx = adj.idx.as<uint32_t>();
     a.vals = adj.vals.as<float>();
     a.selfw = selfw;
@@ -432,7 +500,21 @@ int aggregate_gcn(dory_engine *e, const dory_chunk *c) {
         adj = &e->bwd;
     }
     SpmmArgs a = spmm_args(e, *adj, e->norms.as<float>(), SELF_NORM, *src, *out, c->lowBound, c->upBound, e->V);
-    LAUNCHED(launch_spmm(a, e->stream));
+    if (adj->nb > 1 && src->ld >= 128) {
+        // one pass per source window; passes are separate launches (stream order) because they
+        // accumulate into the same output rows
+        a.ptrs = adj->bptrs.as<uint64_t>();
+        a.idx = adj->bidx.as<uint32_t>();
+        a.vals = adj->bvals.as<float>();
+        a.ptr_stride = adj->nb;
+        for (uint32_t b = 0; b < adj->nb; ++b) {
+            a.ptr_off = b;
+            a.self_mode = b == 0 ? SELF_NORM : SELF_ACCUM;
+            LAUNCHED(launch_spmm(a, e->stream));
+        }
+    } else {
+        LAUNCHED(launch_spmm(a, e->stream));
+    }
     e->stats.edges_aggregated += edges_in_range(e, *adj, c->lowBound, c->upBound);
     return DORY_OK;
 }
@@ -780,6 +862,9 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
     } else if (std::strcmp(key, "spmm_vec") == 0) {
         if (v > 4) return fail(e, DORY_EINVAL, "spmm_vec must be 0..4");
         e->spmm_vec = (int)v;
+    } else if (std::strcmp(key, "src_blocks") == 0) {
+        if (e->loaded) return fail(e, DORY_ESTATE, "src_blocks must be set before dory_load_partition");
+        e->src_blocks = (uint32_t)v;
     } else if (std::strcmp(key, "spmm_occ") == 0) {
         e->spmm_occ = (int)v;
     } else if (std::strcmp(key, "tensor_cores") == 0) {

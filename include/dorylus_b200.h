@@ -106,6 +106,10 @@ int dory_sync(dory_engine *e);
  *                           (0 = choose from the row width); a slab narrower than the row walks the
  *                           adjacency once per slab.
  *   "spmm_unroll"           gather instructions issued back to back per lane group (0 = default).
+ *   "spmm_occ"              CTAs per SM the aggregation kernel is compiled for (4, 5, 6 or 8).
+ *   "src_blocks"            source-row windows per aggregation: each pass gathers only from a
+ *                           (V+G)/n-row window so that it stays L2-resident (0 = size from the L2
+ *                           capacity, 1 = off; set before dory_load_partition; GCN only).
  *   "heavy_degree"          rows with at least this many edges get a whole CTA (set before
  *                           dory_load_partition).
  *   "tensor_cores"          1: run H.W on tcgen05 (3xTF32, fp32-level accuracy) when the shape

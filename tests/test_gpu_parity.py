@@ -83,6 +83,31 @@ def test_aggregate_is_bit_reproducible_and_linear():
         assert rel_err(e.get_tensor(0, "ah")[:, 0], rowsum) < TOL
 
 
+@pytest.mark.parametrize("nb", [2, 3, 7])
+def test_source_blocked_aggregation(oracle, nb):
+    """Forcing the L2-window path (several passes over source-row windows) on a small graph: same
+    result as the oracle for forward and backward, hub row included; chunk sub-ranges too."""
+    ds = random_dataset(V=1700, E_und=20000, dims=[200, 128, 9], seed=14, extra_edges=HUB)
+    g = ds.graphs[0]
+    e = Engine(ds.dims, GCN)
+    e.set_option("src_blocks", nb)
+    e.load_partition(ds.images[0])
+    e.set_tensor(0, "x", ds.feats)
+    with e:
+        e.aggregateGCN(e.whole_chunk(0, FORWARD))
+        want = oracle.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, ds.feats, None)
+        assert rel_err(e.get_tensor(0, "ah"), want) < TOL
+        grad = np.random.default_rng(2).standard_normal((ds.V, 128)).astype(np.float32)
+        e.set_tensor(1, "grad", grad)
+        e.aggregateGCN(e.whole_chunk(1, BACKWARD))
+        want_b = oracle.aggregate_gcn(g.row_ptrs, g.col_idxs, g.bwd_vals, g.norms, grad, None)
+        assert rel_err(e.get_tensor(0, "aTg"), want_b) < TOL
+        e.set_tensor(0, "ah", np.zeros_like(ds.feats))
+        e.aggregateGCN(Chunk(0, 0, 5, 900, 0, FORWARD, 1, True))
+        got = e.get_tensor(0, "ah")
+        assert rel_err(got[5:900], want[5:900]) < TOL and not got[900:].any() and not got[:5].any()
+
+
 def test_chunk_subrange_matches_reference_semantics(oracle):
     ds = random_dataset(V=500, E_und=4000, dims=[40, 8, 3], seed=12)
     g = ds.graphs[0]

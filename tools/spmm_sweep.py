@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/spmm_sweep.json")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--heavy", default="1024")
+    ap.add_argument("--src-blocks", default="1")
     args = ap.parse_args()
     spec = synth.CONFIGS[args.workload]
     src, dst = synth.generate_edges(spec)
@@ -50,17 +51,18 @@ def main():
     rng = np.random.default_rng(0)
     h = rng.standard_normal((spec.num_vertices, spec.dims[1])).astype(np.float32)
     results = []
-    heavies = [int(x) for x in args.heavy.split(",")]
-    for hi, heavy in enumerate(heavies):
+    combos = [(int(h), int(b)) for h in args.heavy.split(",") for b in args.src_blocks.split(",")]
+    for hi, (heavy, nblk) in enumerate(combos):
         with Engine(spec.dims, GCN) as e:
             e.set_option("heavy_degree", heavy)
+            e.set_option("src_blocks", nblk)
             e.load_partition(image)
             e.set_tensor(0, "x", feats)
             e.set_tensor(0, "h", h)
             for layer in (0, 1):
                 c = e.whole_chunk(layer, FORWARD)
                 for lg, vec, un, occ in SHAPES[layer]:
-                    if hi > 0 and lg not in (0,):
+                    if hi > 0 and (lg, vec, un, occ) not in ((0, 0, 0, 0), (8, 4, 1, 4), (8, 4, 2, 4), (16, 2, 1, 4), (8, 2, 2, 5)):
                         continue
                     e.set_option("spmm_lg", lg)
                     e.set_option("spmm_vec", vec)
@@ -78,7 +80,8 @@ def main():
                     except dengine.DoryError as ex:
                         ms = None
                         print("skip", layer, lg, vec, un, occ, ex, flush=True)
-                    r = dict(layer=layer, F=spec.dims[layer], lg=lg, vec=vec, unroll=un, occ=occ, heavy=heavy, ms=ms,
+                    r = dict(layer=layer, F=spec.dims[layer], lg=lg, vec=vec, unroll=un, occ=occ, heavy=heavy,
+                             src_blocks=nblk, ms=ms,
                              gedges_per_s=None if ms is None else E / ms / 1e6)
                     results.append(r)
                     print(json.dumps(r), flush=True)
