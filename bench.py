@@ -198,6 +198,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries exactly ONE JSON line: libraries that print banners to fd 1 (NCCL prints its
+    # version there) are sent to stderr; the result line goes to the saved descriptor.
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(result_fd, (json.dumps(obj) + "\n").encode())
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -223,7 +231,7 @@ def main():
                                 "sample": r["sample"]},
                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0}
-        print(json.dumps(out), flush=True)
+        emit(out)
         return 0
 
     import torch
@@ -373,7 +381,7 @@ def main():
         if cpu is not None:
             out["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"],
                                    "sample": cpu["sample"], "ms_per_step": cpu["ms_per_step"]}
-        print(json.dumps(out), flush=True)
+        emit(out)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
