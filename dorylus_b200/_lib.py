@@ -65,6 +65,8 @@ SYMBOLS = {
     "dory_set_tensor": (C.c_int, [_P, _u32, C.c_char_p, _f32p, _u64, _u32]),
     "dory_get_tensor": (C.c_int, [_P, _u32, C.c_char_p, _f32p, _u64, _u32]),
     "dory_tensor_shape": (C.c_int, [_P, _u32, C.c_char_p, _u64p, _u32p]),
+    "dory_prefetch_tensor": (C.c_int, [_P, _u32, C.c_char_p, _f32p, _u64, _u32]),
+    "dory_commit_prefetch": (C.c_int, [_P]),
     "dory_tensor_device": (C.c_int, [_P, _u32, C.c_char_p, C.POINTER(_P), _u64p, _u32p, _u32p]),
     "dory_init_weights": (C.c_int, [_P]),
     "dory_set_weights": (C.c_int, [_P, _u32, C.c_char_p, _f32p, _u32, _u32]),

@@ -107,6 +107,16 @@ struct dory_engine {
     DevBuf rowstat, stats_dev;   // softmax-CE reduction scratch
     DevBuf flush;                // L2 flush target
     DevBuf stage;                // dense staging for host <-> padded-row copies
+    // input pipeline (dory_prefetch_tensor / dory_commit_prefetch): DMA on its own stream into a
+    // per-tensor staging buffer, re-pitched into the tensor on the compute stream at commit time
+    struct Prefetch {
+        DevMat dst;
+        DevBuf stage;
+        cudaEvent_t staged = nullptr, consumed = nullptr;
+        bool pending = false, used = false;
+    };
+    cudaStream_t copy_stream = nullptr;
+    std::map<std::pair<uint32_t, std::string>, std::unique_ptr<Prefetch>> prefetch;
     int spmm_lg = 0, spmm_vec = 0, spmm_unroll = 0, spmm_occ = 0;
     int tensor_cores = 1;  // tcgen05 path for H.W (option "tensor_cores")
     uint32_t src_blocks = 0;  // source windows per aggregation (0 = size from L2, 1 = off)
@@ -834,12 +844,66 @@ int dory_create(dory_engine **out, const dory_config *cfg) {
 void dory_destroy(dory_engine *e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
+    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
     e->comm.reset();
+    for (auto &kv : e->prefetch) {
+        if (kv.second->staged) cudaEventDestroy(kv.second->staged);
+        if (kv.second->consumed) cudaEventDestroy(kv.second->consumed);
+    }
     for (auto &ev : e->events)
         if (ev) cudaEventDestroy(ev);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
+}
+
+int dory_prefetch_tensor(dory_engine *e, uint32_t layer, const char *name, const float *host, uint64_t rows,
+                         uint32_t cols) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!name || !host) return fail(e, DORY_EINVAL, "null argument");
+    const DevMat *m = find_tensor(e, layer, name);
+    if (!m) return fail(e, DORY_EINVAL, "no tensor '%s' at layer %u", name, layer);
+    if (m->rows != rows || m->cols != cols)
+        return fail(e, DORY_EINVAL, "tensor '%s'[%u] is %llu x %u, caller passed %llu x %u", name, layer,
+                    (unsigned long long)m->rows, m->cols, (unsigned long long)rows, cols);
+    if (rows == 0) return DORY_OK;
+    if (!e->copy_stream) CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    auto &slot = e->prefetch[{layer, std::string(name)}];
+    if (!slot) {
+        slot.reset(new dory_engine::Prefetch());
+        slot->dst = *m;
+        CU(slot->stage.alloc((size_t)rows * cols * 4));
+        CU(cudaEventCreateWithFlags(&slot->staged, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&slot->consumed, cudaEventDisableTiming));
+    }
+    if (slot->pending) return fail(e, DORY_ESTATE, "tensor '%s'[%u] already has an uncommitted prefetch", name, layer);
+    // the staging buffer may still be read by the previous commit's re-pitch kernel
+    if (slot->used) CU(cudaStreamWaitEvent(e->copy_stream, slot->consumed, 0));
+    CU(cudaMemcpyAsync(slot->stage.p, host, (size_t)rows * cols * 4, cudaMemcpyHostToDevice, e->copy_stream));
+    CU(cudaEventRecord(slot->staged, e->copy_stream));
+    slot->pending = true;
+    return DORY_OK;
+}
+
+int dory_commit_prefetch(dory_engine *e) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    for (auto &kv : e->prefetch) {
+        dory_engine::Prefetch &p = *kv.second;
+        if (!p.pending) continue;
+        CU(cudaStreamWaitEvent(e->stream, p.staged, 0));
+        if (is_edge_vector(p.dst) || p.dst.ld == p.dst.cols) {
+            CU(cudaMemcpyAsync(p.dst.p, p.stage.p, (size_t)p.dst.rows * p.dst.cols * 4, cudaMemcpyDeviceToDevice, e->stream));
+        } else {
+            LAUNCHED(launch_repitch(p.stage.as<float>(), p.dst.cols, p.dst.p, p.dst.ld, p.dst.rows, p.dst.cols, e->stream));
+        }
+        CU(cudaEventRecord(p.consumed, e->stream));
+        p.pending = false;
+        p.used = true;
+    }
+    return DORY_OK;
 }
 
 int dory_sync(dory_engine *e) {

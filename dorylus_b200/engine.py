@@ -158,6 +158,20 @@ class Engine:
         self._check(self._lib.dory_set_tensor(self._h, layer, name.encode(), host.ctypes.data_as(_f32p),
                                               host.shape[0], host.shape[1]))
 
+    def prefetch_tensor(self, layer: int, name: str, host: np.ndarray):
+        """Start the host->device DMA of a tensor on the copy stream (input pipeline).  `host` must be
+        a C-contiguous float32 array (pinned for a truly asynchronous copy) that the caller keeps alive
+        and unchanged until commit_prefetch() + sync()."""
+        if host.dtype != np.float32 or not host.flags.c_contiguous:
+            raise ValueError("prefetch_tensor needs a C-contiguous float32 array (no implicit copies)")
+        if host.ndim == 1:
+            host = host.reshape(-1, 1)
+        self._check(self._lib.dory_prefetch_tensor(self._h, layer, name.encode(), host.ctypes.data_as(_f32p),
+                                                   host.shape[0], host.shape[1]))
+
+    def commit_prefetch(self):
+        self._check(self._lib.dory_commit_prefetch(self._h))
+
     def get_tensor(self, layer: int, name: str) -> np.ndarray:
         """savedNNTensors[layer][name] -> host (synchronises)."""
         r, c = self.tensor_shape(layer, name)

@@ -148,6 +148,17 @@ int dory_get_tensor(dory_engine *e, uint32_t layer, const char *name, float *hos
                     uint32_t cols);
 int dory_tensor_shape(const dory_engine *e, uint32_t layer, const char *name, uint64_t *rows,
                       uint32_t *cols);
+/* Input pipeline.  The reference loads features once from disk (readFeaturesFile,
+ * engine/utils.cpp:486-552); a caller that streams new inputs every step can overlap the
+ * host->device DMA with the previous step's compute:
+ *   dory_prefetch_tensor  starts the DMA on the engine's copy stream and returns.  `host` should be
+ *                         pinned memory and must stay valid and unchanged until the matching
+ *                         dory_commit_prefetch has returned and dory_sync() has been called.
+ *   dory_commit_prefetch  makes every prefetched tensor visible to the operators enqueued after it
+ *                         (stream-ordered; operators enqueued before it still see the old values). */
+int dory_prefetch_tensor(dory_engine *e, uint32_t layer, const char *name, const float *host,
+                         uint64_t rows, uint32_t cols);
+int dory_commit_prefetch(dory_engine *e);
 /* Zero-copy view for callers that already hold data in HBM: device pointer + leading dimension
  * (in floats) of the padded row-major storage. */
 int dory_tensor_device(const dory_engine *e, uint32_t layer, const char *name, void **dptr,

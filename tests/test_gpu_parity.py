@@ -229,6 +229,35 @@ def test_partitions_with_ghosts_single_gpu(oracle):
             assert ei.value.code == _lib.ESTATE
 
 
+def test_prefetch_pipeline_semantics(oracle):
+    """dory_prefetch_tensor changes nothing until dory_commit_prefetch; afterwards the operators see the
+    new values; two prefetches of one tensor without a commit are refused."""
+    ds = random_dataset(V=3000, E_und=20000, dims=[602, 16, 4], seed=52)  # 7 MB: takes the staged path
+    g = ds.graphs[0]
+    with gcn_engine(ds) as e:
+        c = e.whole_chunk(0, FORWARD)
+        e.aggregateGCN(c)
+        a_old = e.get_tensor(0, "ah")
+        x2 = np.ascontiguousarray(ds.feats[::-1] * np.float32(0.5))
+        e.prefetch_tensor(0, "x", x2)
+        with pytest.raises(DoryError):
+            e.prefetch_tensor(0, "x", x2)
+        e.aggregateGCN(c)
+        assert np.array_equal(e.get_tensor(0, "ah"), a_old)  # not committed yet
+        e.commit_prefetch()
+        e.aggregateGCN(c)
+        want = oracle.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, x2, None)
+        assert rel_err(e.get_tensor(0, "ah"), want) < TOL
+        assert np.array_equal(e.get_tensor(0, "x"), x2)
+        for _ in range(3):  # steady-state reuse of the staging buffer
+            e.prefetch_tensor(0, "x", ds.feats)
+            e.commit_prefetch()
+        e.sync()
+        assert np.array_equal(e.get_tensor(0, "x"), ds.feats)
+        with pytest.raises(ValueError):
+            e.prefetch_tensor(0, "x", ds.feats.astype(np.float64))
+
+
 def test_shape_and_state_errors():
     ds = random_dataset(V=100, E_und=300, dims=[8, 4, 2], seed=61)
     e = Engine(ds.dims)
