@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--workload", default="reddit")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU baseline budget (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default=os.environ.get("DORY_EXCHANGE", "p2p"), choices=["p2p", "nccl"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # stdout carries exactly ONE JSON line: libraries that print banners to fd 1 (NCCL prints its
@@ -275,7 +276,9 @@ def main():
     upload_inputs()
     eng.init_weights()
     if world > 1:
-        ddist.setup_engine_comm(eng, graph, rank, world)
+        ddist.setup_engine_comm(eng, graph, rank, world, peer_memory=args.exchange == "p2p")
+        cfg_common["ghost_exchange"] = ("one store-through-NVLink kernel into peer ghost blocks (CUDA IPC) + 2 NCCL barriers"
+                                        if args.exchange == "p2p" else "pack -> NCCL all-to-all-v -> unpack")
 
     def barrier():
         eng.sync()

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libdorylus_b200.so")
 DORY_ABI_VERSION = 1
 DORY_MAX_LAYERS = 8
 DORY_UNIQUE_ID_BYTES = 128
+DORY_IPC_BLOB_BYTES = 80
 
 OK, EINVAL, ESTATE, ECUDA, ENOMEM, ECOMM, EFORMAT, ENODEV = 0, -1, -2, -3, -4, -5, -6, -7
 ERROR_NAMES = {EINVAL: "DORY_EINVAL", ESTATE: "DORY_ESTATE", ECUDA: "DORY_ECUDA", ENOMEM: "DORY_ENOMEM",
@@ -87,6 +88,9 @@ SYMBOLS = {
     "dory_comm_init": (C.c_int, [_P, _P]),
     "dory_comm_set_recv_slots": (C.c_int, [_P, _u32, _u32, _u32p, _u32]),
     "dory_comm_send_gvids": (C.c_int, [_P, _u32, _u32, _u32p, _u32p]),
+    "dory_comm_set_send_slots": (C.c_int, [_P, _u32, _u32, _u32p, _u32]),
+    "dory_comm_ipc_export": (C.c_int, [_P, _u32, C.c_char_p, _P]),
+    "dory_comm_ipc_import": (C.c_int, [_P, _u32, C.c_char_p, _u32, _P]),
     "dory_event_record": (C.c_int, [_P, _u32]),
     "dory_event_elapsed_ms": (C.c_int, [_P, _u32, _u32, _f32p]),
     "dory_flush_l2": (C.c_int, [_P, C.c_size_t]),

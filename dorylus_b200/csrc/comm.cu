@@ -90,7 +90,11 @@ Comm::~Comm() {
         if (p.dRecvSlots) cudaFree(p.dRecvSlots);
         if (p.sendStage) cudaFree(p.sendStage);
         if (p.recvStage) cudaFree(p.recvStage);
+        if (p.dSendSlots) cudaFree(p.dSendSlots);
+        if (p.dSendPeer) cudaFree(p.dSendPeer);
+        if (p.dSendOrder) cudaFree(p.dSendOrder);
     }
+    if (barrier_buf_) cudaFree(barrier_buf_);
     if (nccl_ && api().CommDestroy) api().CommDestroy(static_cast<ncclComm_t>(nccl_));
 }
 
@@ -217,6 +221,105 @@ std::string Comm::allreduce_sum(float *buf, size_t n, cudaStream_t s) {
     NcclApi &a = api();
     NC(a.AllReduce(buf, buf, n, ncclFloat, ncclSum, static_cast<ncclComm_t>(nccl_), s));
     return "";
+}
+
+// ------------------------------------------------------------------ peer-memory exchange
+namespace {
+
+constexpr int kMaxPeers = 16;
+struct PeerPtrs {
+    float4 *p[kMaxPeers];
+};
+
+// One warp per shipped row: read the local row once, store it into the owner-of-the-ghost's HBM
+// through the NVLink-mapped pointer.  `order` interleaves the peers so that all links are busy from
+// the first wave on.
+__global__ void __launch_bounds__(256)
+p2p_scatter_kernel(const float4 *__restrict__ local, const uint32_t *__restrict__ ids,
+                   const uint32_t *__restrict__ slots, const uint8_t *__restrict__ peer,
+                   const uint32_t *__restrict__ order, uint32_t n, PeerPtrs pp, uint32_t ld4) {
+    const uint32_t v = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (v >= n) return;
+    const uint32_t r = order[v];
+    const float4 *s = local + (size_t)ids[r] * ld4;
+    float4 *d = pp.p[peer[r]] + (size_t)slots[r] * ld4;
+    for (uint32_t c = threadIdx.x & 31; c < ld4; c += 32) d[c] = s[c];
+    __threadfence_system();
+}
+
+}  // namespace
+
+std::string Comm::set_send_slots(int dir, int peer, const uint32_t *slots, uint32_t n) {
+    Plan &p = plan_[dir];
+    if (p.sendSlots.size() != (size_t)nranks_) p.sendSlots.assign(nranks_, {});
+    if (n != p.sendCount[peer]) return "send slots: count differs from the send list of that peer";
+    p.sendSlots[peer].assign(slots, slots + n);
+    p.sendSlotsDirty = true;
+    return "";
+}
+
+bool Comm::p2p_ready(int dir) const {
+    const Plan &p = plan_[dir];
+    if (nranks_ > kMaxPeers || p.sendSlots.size() != (size_t)nranks_) return false;
+    for (int q = 0; q < nranks_; ++q)
+        if (q != rank_ && p.sendSlots[q].size() != p.sendCount[q]) return false;
+    return true;
+}
+
+std::string Comm::exchange_p2p(int dir, const float *local, float *const *peerGhost, uint32_t ld, cudaStream_t s,
+                               int &launches) {
+    Plan &p = plan_[dir];
+    launches = 0;
+    if (!p2p_ready(dir)) return "peer-memory exchange: send slots not installed";
+    if (p.sendSlotsDirty) {
+        std::vector<uint32_t> slots(p.sendTotal), order;
+        std::vector<uint8_t> peer(p.sendTotal);
+        uint32_t longest = 0;
+        for (int q = 0; q < nranks_; ++q) {
+            if (q == rank_) continue;
+            for (uint32_t i = 0; i < p.sendCount[q]; ++i) {
+                slots[p.sendOff[q] + i] = p.sendSlots[q][i];
+                peer[p.sendOff[q] + i] = (uint8_t)q;
+            }
+            longest = std::max(longest, p.sendCount[q]);
+        }
+        order.reserve(p.sendTotal);
+        for (uint32_t i = 0; i < longest; ++i)
+            for (int q = 0; q < nranks_; ++q)
+                if (q != rank_ && i < p.sendCount[q]) order.push_back(p.sendOff[q] + i);
+        if (p.dSendSlots) cudaFree(p.dSendSlots), p.dSendSlots = nullptr;
+        if (p.dSendPeer) cudaFree(p.dSendPeer), p.dSendPeer = nullptr;
+        if (p.dSendOrder) cudaFree(p.dSendOrder), p.dSendOrder = nullptr;
+        const size_t n = std::max<uint32_t>(p.sendTotal, 1);
+        CUS(cudaMalloc(&p.dSendSlots, n * 4));
+        CUS(cudaMalloc(&p.dSendPeer, n));
+        CUS(cudaMalloc(&p.dSendOrder, n * 4));
+        if (p.sendTotal) {
+            CUS(cudaMemcpyAsync(p.dSendSlots, slots.data(), n * 4, cudaMemcpyHostToDevice, s));
+            CUS(cudaMemcpyAsync(p.dSendPeer, peer.data(), n, cudaMemcpyHostToDevice, s));
+            CUS(cudaMemcpyAsync(p.dSendOrder, order.data(), n * 4, cudaMemcpyHostToDevice, s));
+        }
+        CUS(cudaStreamSynchronize(s));
+        p.sendSlotsDirty = false;
+    }
+    if (!barrier_buf_) {
+        CUS(cudaMalloc(&barrier_buf_, 16));
+        CUS(cudaMemsetAsync(barrier_buf_, 0, 16, s));
+    }
+    // barrier 1: every peer has finished reading the ghost block we are about to overwrite
+    std::string m = allreduce_sum(barrier_buf_, 1, s);
+    if (!m.empty()) return m;
+    if (p.sendTotal) {
+        PeerPtrs pp{};
+        for (int q = 0; q < nranks_; ++q) pp.p[q] = q == rank_ ? nullptr : reinterpret_cast<float4 *>(peerGhost[q]);
+        p2p_scatter_kernel<<<(p.sendTotal + 7) / 8, 256, 0, s>>>(
+            reinterpret_cast<const float4 *>(local), p.dSendIds, p.dSendSlots, p.dSendPeer,
+            p.dSendOrder, p.sendTotal, pp, ld / 4);
+        if (cudaGetLastError() != cudaSuccess) return "peer-memory scatter kernel launch failed";
+        ++launches;
+    }
+    // barrier 2: every peer's stores into OUR ghost block have been issued and fenced
+    return allreduce_sum(barrier_buf_ + 1, 1, s);
 }
 
 }  // namespace dory

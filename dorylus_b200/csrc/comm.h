@@ -33,6 +33,18 @@ public:
     std::string exchange(int dir, const float *local, float *ghost, uint32_t ld, cudaStream_t s, int &launches);
     std::string allreduce_sum(float *buf, size_t n, cudaStream_t s);
 
+    // ---- peer-memory path: pack + ship in ONE kernel that stores rows straight into the peers'
+    // ghost blocks over NVLink (no staging buffer, no unpack); NCCL only provides the two barriers.
+    // Send side additionally needs, per peer, the ghost slot each shipped row lands in.
+    std::string set_send_slots(int dir, int peer, const uint32_t *slots, uint32_t n);
+    // peerGhost[q]: device pointer (mapped with cudaIpcOpenMemHandle) to peer q's ghost block for
+    // this exchange; entries for q == rank are ignored.
+    std::string exchange_p2p(int dir, const float *local, float *const *peerGhost, uint32_t ld, cudaStream_t s,
+                             int &launches);
+    bool p2p_ready(int dir) const;
+    int rank() const { return rank_; }
+    int nranks() const { return nranks_; }
+
 private:
     struct Plan {
         std::vector<uint32_t> sendCount, sendOff;  // per peer, rows
@@ -45,7 +57,14 @@ private:
         size_t sendStageFloats = 0, recvStageFloats = 0;
         bool recvIdentity = false;  // concatenated slots == 0..G-1: receive straight into the ghost block
         bool recvDirty = true;
+        // peer-memory path
+        std::vector<std::vector<uint32_t>> sendSlots;  // per peer, ghost slot on that peer per shipped row
+        uint32_t *dSendSlots = nullptr;                // concatenated, same order as dSendIds
+        uint8_t *dSendPeer = nullptr;                  // peer id of every shipped row
+        uint32_t *dSendOrder = nullptr;                // issue order that interleaves the peers
+        bool sendSlotsDirty = true;
     };
+    float *barrier_buf_ = nullptr;
     std::string finalize_recv(Plan &p, uint32_t maxld, cudaStream_t s);
 
     void *nccl_ = nullptr;  // ncclComm_t

@@ -128,6 +128,11 @@ struct dory_engine {
 
     dory_stats stats{};
     std::unique_ptr<dory::Comm> comm;
+    // peer-memory exchange: local ghost tensor -> per-peer pointer to THEIR ghost tensor of the same
+    // (layer, name), mapped with cudaIpcOpenMemHandle; ipc_bases are the mappings to close
+    std::map<const float *, std::vector<float *>> peer_ghost;
+    std::vector<void *> ipc_bases;
+    int p2p = 1;
 
     uint32_t L() const { return cfg.n_layers; }
     uint32_t dim(uint32_t i) const { return cfg.dims[i]; }
@@ -630,7 +635,16 @@ int exchange(dory_engine *e, uint32_t dir, const DevMat &local, const DevMat &gh
     if (e->cfg.num_nodes <= 1) return DORY_OK;
     if (!e->comm) return fail(e, DORY_ESTATE, "scatter with %u partitions needs dory_comm_init", e->cfg.num_nodes);
     int launches = 0;
-    std::string msg = e->comm->exchange(dir, local.p, ghost.p, local.ld, e->stream, launches);
+    std::string msg;
+    auto pit = e->peer_ghost.find(ghost.p);
+    bool p2p = e->p2p && pit != e->peer_ghost.end() && e->comm->p2p_ready((int)dir);
+    if (p2p)
+        for (uint32_t q = 0; q < e->cfg.num_nodes; ++q)
+            if (q != e->cfg.node_id && !pit->second[q]) p2p = false;
+    if (p2p)
+        msg = e->comm->exchange_p2p((int)dir, local.p, pit->second.data(), local.ld, e->stream, launches);
+    else
+        msg = e->comm->exchange((int)dir, local.p, ghost.p, local.ld, e->stream, launches);
     if (!msg.empty()) return fail(e, DORY_ECOMM, "%s", msg.c_str());
     e->stats.kernel_launches += launches;
     return DORY_OK;
@@ -847,6 +861,7 @@ void dory_destroy(dory_engine *e) {
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
     e->comm.reset();
+    for (void *b : e->ipc_bases) cudaIpcCloseMemHandle(b);
     for (auto &kv : e->prefetch) {
         if (kv.second->staged) cudaEventDestroy(kv.second->staged);
         if (kv.second->consumed) cudaEventDestroy(kv.second->consumed);
@@ -926,6 +941,8 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
     } else if (std::strcmp(key, "spmm_vec") == 0) {
         if (v > 4) return fail(e, DORY_EINVAL, "spmm_vec must be 0..4");
         e->spmm_vec = (int)v;
+    } else if (std::strcmp(key, "p2p") == 0) {
+        e->p2p = v != 0;
     } else if (std::strcmp(key, "src_blocks") == 0) {
         if (e->loaded) return fail(e, DORY_ESTATE, "src_blocks must be set before dory_load_partition");
         e->src_blocks = (uint32_t)v;
@@ -1380,6 +1397,64 @@ int dory_comm_set_recv_slots(dory_engine *e, uint32_t dir, uint32_t peer, const 
     for (uint32_t l = 0; l <= e->L(); ++l) maxld = std::max(maxld, padded_ld(e->dim(l)));
     std::string msg = e->comm->set_recv_slots((int)dir, (int)peer, slots, n, maxld, e->stream);
     if (!msg.empty()) return fail(e, DORY_ECOMM, "%s", msg.c_str());
+    return DORY_OK;
+}
+
+int dory_comm_set_send_slots(dory_engine *e, uint32_t dir, uint32_t peer, const uint32_t *slots, uint32_t n) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!e->comm) return fail(e, DORY_ESTATE, "dory_comm_init first");
+    if (dir > 1 || peer >= e->cfg.num_nodes || peer == e->cfg.node_id || (n && !slots)) return fail(e, DORY_EINVAL, "bad argument");
+    std::string msg = e->comm->set_send_slots((int)dir, (int)peer, slots, n);
+    if (!msg.empty()) return fail(e, DORY_EINVAL, "%s", msg.c_str());
+    return DORY_OK;
+}
+
+namespace {
+struct IpcBlob {
+    cudaIpcMemHandle_t handle;
+    uint64_t ghost_offset_bytes;
+    uint64_t ghost_rows;
+};
+static_assert(sizeof(IpcBlob) <= DORY_IPC_BLOB_BYTES, "IPC blob does not fit DORY_IPC_BLOB_BYTES");
+
+bool is_ghost_name(const char *n) {
+    return !std::strcmp(n, "fg") || !std::strcmp(n, "bg") || !std::strcmp(n, "fg_z") || !std::strcmp(n, "bg_d");
+}
+}  // namespace
+
+int dory_comm_ipc_export(dory_engine *e, uint32_t layer, const char *ghost_name, void *blob80) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!ghost_name || !blob80 || !is_ghost_name(ghost_name)) return fail(e, DORY_EINVAL, "not a ghost tensor name");
+    const DevMat *m = find_tensor(e, layer, ghost_name);
+    if (!m) return fail(e, DORY_EINVAL, "no tensor '%s' at layer %u", ghost_name, layer);
+    // ghost rows follow the V local rows inside one allocation
+    IpcBlob b{};
+    b.ghost_offset_bytes = (uint64_t)e->V * m->ld * 4;
+    b.ghost_rows = m->rows;
+    void *base = reinterpret_cast<uint8_t *>(m->p) - b.ghost_offset_bytes;
+    CU(cudaIpcGetMemHandle(&b.handle, base));
+    std::memset(blob80, 0, DORY_IPC_BLOB_BYTES);
+    std::memcpy(blob80, &b, sizeof b);
+    return DORY_OK;
+}
+
+int dory_comm_ipc_import(dory_engine *e, uint32_t layer, const char *ghost_name, uint32_t peer, const void *blob80) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!ghost_name || !blob80 || !is_ghost_name(ghost_name)) return fail(e, DORY_EINVAL, "not a ghost tensor name");
+    if (peer >= e->cfg.num_nodes || peer == e->cfg.node_id) return fail(e, DORY_EINVAL, "bad peer");
+    const DevMat *m = find_tensor(e, layer, ghost_name);
+    if (!m) return fail(e, DORY_EINVAL, "no tensor '%s' at layer %u", ghost_name, layer);
+    IpcBlob b;
+    std::memcpy(&b, blob80, sizeof b);
+    void *base = nullptr;
+    CU(cudaIpcOpenMemHandle(&base, b.handle, cudaIpcMemLazyEnablePeerAccess));
+    e->ipc_bases.push_back(base);
+    auto &v = e->peer_ghost[m->p];
+    if (v.size() != e->cfg.num_nodes) v.assign(e->cfg.num_nodes, nullptr);
+    v[peer] = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(base) + b.ghost_offset_bytes);
     return DORY_OK;
 }
 

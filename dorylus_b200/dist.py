@@ -68,8 +68,11 @@ class GhostPlan:
             raise RuntimeError("ghost plan incomplete: partitions disagree about the edge cut")
 
 
-def setup_engine_comm(engine, graph: PartitionGraph, rank: int, world: int, group=None) -> GhostPlan:
-    """Create the engine's NCCL communicator and install the receive plan (GPU ranks only)."""
+def setup_engine_comm(engine, graph: PartitionGraph, rank: int, world: int, group=None,
+                      peer_memory: bool = True) -> GhostPlan:
+    """Create the engine's NCCL communicator and install the receive plan (GPU ranks only).
+    With `peer_memory` the ghost exchange runs as one store-through-NVLink kernel (csrc/comm.cu:
+    exchange_p2p); without it as pack -> NCCL all-to-all-v -> unpack."""
     import torch.distributed as dist
 
     box = [engine.comm_unique_id() if rank == 0 else None]
@@ -81,7 +84,30 @@ def setup_engine_comm(engine, graph: PartitionGraph, rank: int, world: int, grou
         for peer in range(world):
             if peer != rank:
                 engine.comm_set_recv_slots(dir, peer, plan.recv[dir][peer])
+    if peer_memory:
+        setup_peer_memory(engine, plan, rank, world, group)
     return plan
+
+
+def setup_peer_memory(engine, plan: GhostPlan, rank: int, world: int, group=None):
+    """Switch the exchanges to the peer-memory path: tell every sender where its rows land on the
+    receiver (the receiver's slot list, mirrored) and map every peer's ghost blocks (CUDA IPC)."""
+    import torch.distributed as dist
+
+    for dir in (FORWARD, BACKWARD):
+        everyone: List[Optional[list]] = [None] * world
+        dist.all_gather_object(everyone, plan.recv[dir], group=group)
+        for peer in range(world):
+            if peer != rank:
+                engine.comm_set_send_slots(dir, peer, everyone[peer][rank])  # where peer stores MY rows
+    mine = {key: engine.comm_ipc_export(*key) for key in engine.ghost_tensors()}
+    blobs: List[Optional[dict]] = [None] * world
+    dist.all_gather_object(blobs, mine, group=group)
+    for peer in range(world):
+        if peer == rank:
+            continue
+        for (layer, name), blob in blobs[peer].items():
+            engine.comm_ipc_import(layer, name, peer, blob)
 
 
 def host_exchange_rows(plan: GhostPlan, dir: int, local_rows: np.ndarray, ghost_rows: np.ndarray, group=None):

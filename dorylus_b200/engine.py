@@ -304,6 +304,27 @@ class Engine:
         self._check(self._lib.dory_comm_set_recv_slots(self._h, dir, peer, slots.ctypes.data_as(C.POINTER(C.c_uint32)),
                                                        slots.size))
 
+    def comm_set_send_slots(self, dir: int, peer: int, slots: np.ndarray):
+        slots = np.ascontiguousarray(slots, dtype=np.uint32)
+        self._check(self._lib.dory_comm_set_send_slots(self._h, dir, peer, slots.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                       slots.size))
+
+    def ghost_tensors(self):
+        """(layer, name) of every ghost block that takes part in an exchange."""
+        L = self.numLayers
+        if self.gnn_type == GCN:
+            return [(l, "fg") for l in range(1, L)] + [(l - 1, "bg") for l in range(1, L)]
+        return [(l, "fg_z") for l in range(L)] + [(l, "bg_d") for l in range(L)]
+
+    def comm_ipc_export(self, layer: int, name: str) -> bytes:
+        buf = C.create_string_buffer(_lib.DORY_IPC_BLOB_BYTES)
+        self._check(self._lib.dory_comm_ipc_export(self._h, layer, name.encode(), C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def comm_ipc_import(self, layer: int, name: str, peer: int, blob: bytes):
+        buf = C.create_string_buffer(blob, _lib.DORY_IPC_BLOB_BYTES)
+        self._check(self._lib.dory_comm_ipc_import(self._h, layer, name.encode(), peer, C.cast(buf, C.c_void_p)))
+
     # ------------------------------------------------------------------ timing helpers
     def event_record(self, slot: int):
         self._check(self._lib.dory_event_record(self._h, slot))

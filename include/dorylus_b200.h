@@ -225,6 +225,20 @@ int dory_comm_init(dory_engine *e, const void *id128);
  * in the order the peer sends them.  dorylus_b200.dist.GhostPlan computes it. */
 int dory_comm_set_recv_slots(dory_engine *e, uint32_t dir, uint32_t peer, const uint32_t *slots,
                              uint32_t n);
+/* Peer-memory exchange (optional, same-node ranks): instead of pack -> NCCL send/recv -> unpack,
+ * dory_scatter runs ONE kernel that reads each boundary row once and stores it straight into the
+ * owning peers' ghost blocks through NVLink-mapped pointers; NCCL is only used for the two barriers
+ * around it.  Set-up, once: (1) dory_comm_set_send_slots -- for each peer, the ghost slot on THAT
+ * peer of every row we ship (the peer's dory_comm_set_recv_slots list for us); (2) every rank
+ * exports each ghost-bearing tensor ("fg"/"bg", GAT "fg_z"/"bg_d") with dory_comm_ipc_export and
+ * imports its peers' blobs with dory_comm_ipc_import.  A (tensor, peer set) that is fully imported
+ * switches that exchange to the peer-memory path; option "p2p" = 0 forces NCCL. */
+#define DORY_IPC_BLOB_BYTES 80
+int dory_comm_set_send_slots(dory_engine *e, uint32_t dir, uint32_t peer, const uint32_t *slots,
+                             uint32_t n);
+int dory_comm_ipc_export(dory_engine *e, uint32_t layer, const char *ghost_name, void *blob80);
+int dory_comm_ipc_import(dory_engine *e, uint32_t layer, const char *ghost_name, uint32_t peer,
+                         const void *blob80);
 /* Global ids of the rows this partition sends to `peer` in direction `dir` (send-list order);
  * returns the count through *n; ids may be NULL to query the count. */
 int dory_comm_send_gvids(const dory_engine *e, uint32_t dir, uint32_t peer, uint32_t *ids,

@@ -23,6 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--parts", default="random")
     ap.add_argument("--epochs", type=int, default=2)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -53,7 +54,7 @@ def main():
         e.set_tensor(0, "fg", ds.feats[g.src_ghost_gvid])
     e.set_tensor(1, "lab", ds.onehot[g.local_to_global])
     e.init_weights()
-    ddist.setup_engine_comm(e, g, rank, world)
+    ddist.setup_engine_comm(e, g, rank, world, peer_memory=args.exchange == "p2p")
 
     worst = 0.0
     ok = True
@@ -83,7 +84,8 @@ def main():
     e.close()
     dist.destroy_process_group()
     if rank == 0:
-        print("MULTI_GPU_CHECK %s world=%d parts=%s worst_rel_err=%.2e" % ("PASS" if flag.item() == 0 else "FAIL", world, args.parts, worst), flush=True)
+        print("MULTI_GPU_CHECK %s world=%d parts=%s exchange=%s worst_rel_err=%.2e"
+              % ("PASS" if flag.item() == 0 else "FAIL", world, args.parts, args.exchange, worst), flush=True)
     sys.exit(0 if flag.item() == 0 else 1)
 
 
