@@ -394,7 +394,8 @@ def main():
             "per_layer_ms": agg_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "spmm_kernel (layer-0 forward aggregation, F=602; heavy + light launch)",
+                         "kernel": "spmm_kernel (layer-0 forward aggregation, F=602: per source window one "
+                                   "CTA-per-row launch + one warp-per-row launch)",
                          "algorithmic_bytes": b_alg,
                          "note": "min-traffic model; the gather itself moves E*F*4 bytes L2->SM (DESIGN.md §5)"},
             "e2e": {"value": n_spmm * E_global * args.steps / e2e_s, "unit": UNIT,

@@ -67,7 +67,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    build_host_driver()
     return LIB
+
+
+def build_host_driver() -> str:
+    """host/dorylus_b200_run: the C++ driver over the C ABI (plain g++, links the .so above)."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "host", "dorylus_b200_run.cpp")
+    out = os.path.join(root, "host", "dorylus_b200_run")
+    if os.path.exists(src) and _stale(out, [src, LIB, os.path.join(root, "include", "dorylus_b200.h")]):
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall", src, "-o", out, LIB, "-Wl,-rpath,$ORIGIN/../dorylus_b200"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("host driver build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return out
 
 
 if __name__ == "__main__":

@@ -10,6 +10,16 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # build artefacts are git-ignored: make sure they exist (no-op when up to date or when nvcc is absent
+    # and the prebuilt library travelled with the snapshot)
+    import shutil
+
+    from dorylus_b200 import build as product_build
+
+    if shutil.which("nvcc") or os.path.exists(product_build.NVCC):
+        product_build.build()
+    elif not os.path.exists(product_build.LIB):
+        raise pytest.UsageError("libdorylus_b200.so is missing and nvcc is not available to build it")
 
 
 @pytest.fixture(scope="session")
