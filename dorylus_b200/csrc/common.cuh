@@ -42,7 +42,8 @@ struct SpmmArgs {
     const uint64_t *ptrs;   // [V+1] columnPtrs (CSC, forward) or rowPtrs (CSR, backward); with source
                             // blocking [V*ptr_stride + 1]: row v, block b spans [ptrs[v*stride+b], ptrs[v*stride+b+1])
     uint32_t ptr_stride;    // number of source blocks the edge list of every row is grouped into (1 = none)
-    uint32_t ptr_off;       // the source block this launch walks
+    uint32_t ptr_off;       // first source block this launch walks
+    uint32_t ptr_span;      // number of consecutive source blocks it walks (>= 1)
     const uint32_t *idx;    // [E]   source row in `src` (local id, or V + ghost slot)
     const float *vals;      // [E]
     const float *selfw;     // [V]   vtxDataVec (SELF_NORM only)

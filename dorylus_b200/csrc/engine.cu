@@ -34,6 +34,9 @@ constexpr double kTrainPortion = 0.66;  // src/common/utils.hpp:60
 constexpr double kValPortion = 0.1;     // src/common/utils.hpp:61
 constexpr uint32_t kHeavyDegree = 1024; // default: rows with more edges get a whole CTA (spmm.cu)
 constexpr int kNumEvents = 64;
+// L2 budget of one aggregation pass (source rows x slab bytes).  Sweep on Reddit: 2 windows of 60 MB
+// beat 1, 3 and 4 (profiles/round1_spmm_sweep_v4_srcblocks.json).
+constexpr uint64_t kWindowBytes = 64ull << 20;
 
 thread_local std::string g_create_error;
 
@@ -134,6 +137,14 @@ struct dory_engine {
     std::vector<void *> ipc_bases;
     int p2p = 1;
 
+    // widest row slab (bytes, <= 512) any aggregation of this model gathers: GCN aggregates widths
+    // F_0 .. F_{L-1}, GAT the layer outputs F_1 .. F_L
+    uint32_t max_slab_bytes() const {
+        uint32_t m = 16;
+        const uint32_t lo = cfg.gnn_type == DORY_GCN ? 0 : 1, hi = cfg.gnn_type == DORY_GCN ? cfg.n_layers : cfg.n_layers + 1;
+        for (uint32_t l = lo; l < hi; ++l) m = std::max(m, std::min<uint32_t>(padded_ld(cfg.dims[l]) * 4, 512));
+        return m;
+    }
     uint32_t L() const { return cfg.n_layers; }
     uint32_t dim(uint32_t i) const { return cfg.dims[i]; }
 };
@@ -240,10 +251,12 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
     // stays L2-resident when that is well below the 126 MB L2 (the two L2 halves mirror lines that
     // both dies read, so the useful capacity for a chip-wide gather is about half).  Split the source
     // rows into nb windows of <= kWindowBytes and regroup each row's edges by window.
+    // Windows are sized for the WIDEST aggregated row slab of this model (<= 512 B); layers with
+    // narrower rows walk `span` consecutive windows per launch (aggregate_gcn), which works because a
+    // row's windows are stored back to back.
     uint32_t nb = e->src_blocks;
     if (nb == 0) {
-        constexpr uint64_t kWindowBytes = 64ull << 20;  // sweep: 2 windows of 60 MB beat 1, 3 and 4 on Reddit
-        nb = (uint32_t)(((uint64_t)nSrcRows * 512 + kWindowBytes - 1) / kWindowBytes);
+        nb = (uint32_t)(((uint64_t)nSrcRows * e->max_slab_bytes() + kWindowBytes - 1) / kWindowBytes);
     }
     nb = std::max(1u, std::min(nb, 64u));
     adj.nb = 1;
@@ -468,6 +481,7 @@ SpmmArgs spmm_args(const dory_engine *e, const Adjacency &adj, const float *self
     a.ptrs = adj.ptrs.as<uint64_t>();
     a.ptr_stride = 1;
     a.ptr_off = 0;
+    a.ptr_span = 1;
     a.idx = adj.idx.as<uint32_t>();
     a.vals = adj.vals.as<float>();
     a.selfw = selfw;
@@ -515,15 +529,19 @@ int aggregate_gcn(dory_engine *e, const dory_chunk *c) {
         adj = &e->bwd;
     }
     SpmmArgs a = spmm_args(e, *adj, e->norms.as<float>(), SELF_NORM, *src, *out, c->lowBound, c->upBound, e->V);
-    if (adj->nb > 1 && src->ld >= 128) {
-        // one pass per source window; passes are separate launches (stream order) because they
-        // accumulate into the same output rows
+    if (adj->nb > 1) {
+        // one pass per group of source windows; passes are separate launches (stream order) because
+        // they accumulate into the same output rows.  A group holds as many windows as keep
+        // rows x slab bytes within the L2 budget for THIS layer's row width.
+        const uint32_t slab = std::min<uint32_t>(src->ld * 4, 512);
+        const uint32_t span = e->src_blocks ? 1 : std::max(1u, e->max_slab_bytes() / slab);
         a.ptrs = adj->bptrs.as<uint64_t>();
         a.idx = adj->bidx.as<uint32_t>();
         a.vals = adj->bvals.as<float>();
         a.ptr_stride = adj->nb;
-        for (uint32_t b = 0; b < adj->nb; ++b) {
+        for (uint32_t b = 0; b < adj->nb; b += span) {
             a.ptr_off = b;
+            a.ptr_span = std::min(span, adj->nb - b);
             a.self_mode = b == 0 ? SELF_NORM : SELF_ACCUM;
             LAUNCHED(launch_spmm(a, e->stream));
         }

@@ -107,7 +107,7 @@ spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nro
     const uint32_t row = rowlist ? rowlist[rid] : a.low + rid;
     const uint32_t col0 = blockIdx.y * (LG * VEC);  // slab start, float4 units
     const uint64_t pbase = (uint64_t)row * a.ptr_stride + a.ptr_off;
-    const uint64_t e_begin = a.ptrs[pbase], e_end = a.ptrs[pbase + 1];
+    const uint64_t e_begin = a.ptrs[pbase], e_end = a.ptrs[pbase + a.ptr_span];
     const float4 *__restrict__ src4 = reinterpret_cast<const float4 *>(a.src);
     const uint32_t ld4 = a.ld >> 2;
     const uint64_t pol_stream = policy_evict_first();

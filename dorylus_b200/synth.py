@@ -80,6 +80,8 @@ def generate_edges(spec: GraphSpec):
     rng = np.random.default_rng(spec.seed)
     V = spec.num_vertices
     n_und = spec.num_edges // 2
+    if V > 2_000_000 and spec.locality == 0:
+        return _configuration_model(rng, V, n_und, spec.sigma)
     w = np.exp(spec.sigma * rng.standard_normal(V)).astype(np.float64)
     prob, alias = _alias_table(w)
     u = _alias_sample(rng, prob, alias, n_und)
@@ -94,6 +96,25 @@ def generate_edges(spec: GraphSpec):
     # remove self loops by nudging the second endpoint (keeps the edge count exact)
     same = u == v
     v = np.where(same, (v + 1) % V, v).astype(np.uint32)
+    src = np.empty(2 * n_und, dtype=np.uint32)
+    dst = np.empty(2 * n_und, dtype=np.uint32)
+    src[0::2], dst[0::2] = u, v
+    src[1::2], dst[1::2] = v, u
+    return src, dst
+
+
+def _configuration_model(rng, V: int, n_und: int, sigma: float):
+    """Large graphs: log-normal degree sequence + random stub matching (O(E), no per-vertex Python
+    loop).  Same statistics as the Chung-Lu sampler above up to the exactness of the degrees."""
+    w = np.exp(sigma * rng.standard_normal(V))
+    deg = np.floor(w * (2.0 * n_und / w.sum())).astype(np.int64)
+    short = 2 * n_und - int(deg.sum())
+    bump = rng.integers(0, V, size=short)
+    np.add.at(deg, bump, 1)
+    stubs = np.repeat(np.arange(V, dtype=np.uint32), deg)
+    rng.shuffle(stubs)
+    u, v = stubs[:n_und], stubs[n_und:2 * n_und]
+    v = np.where(u == v, (v + 1) % V, v).astype(np.uint32)
     src = np.empty(2 * n_und, dtype=np.uint32)
     dst = np.empty(2 * n_und, dtype=np.uint32)
     src[0::2], dst[0::2] = u, v
