@@ -257,6 +257,12 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
     uint32_t nb = e->src_blocks;
     if (nb == 0) {
         nb = (uint32_t)(((uint64_t)nSrcRows * e->max_slab_bytes() + kWindowBytes - 1) / kWindowBytes);
+        // every window costs one more pass over the rows (offsets, read-modify-write of `out`, a
+        // partly filled 32-edge batch): only worth it while a (row, window) still holds ~64 edges.
+        // Reddit (degree 492): 2 windows; Amazon / Friendster shapes (degree ~25): none
+        // (tools/shape_bench.py: 10 windows made the Amazon-shape aggregation 4x slower).
+        const uint64_t avgDeg = V ? nnz / V : 0;
+        nb = (uint32_t)std::min<uint64_t>(nb, std::max<uint64_t>(1, avgDeg / 64));
     }
     nb = std::max(1u, std::min(nb, 64u));
     adj.nb = 1;

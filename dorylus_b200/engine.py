@@ -62,7 +62,11 @@ def preprocess_edges(src: np.ndarray, dst: np.ndarray, parts: np.ndarray, num_ve
     if rc != 0:
         raise DoryError(rc, lib.dory_last_error(None).decode())
     try:
-        return C.string_at(img, n.value)
+        if n.value < (1 << 31):
+            return C.string_at(img, n.value)
+        # images beyond 2 GiB (e.g. one eighth of the Friendster shape) do not fit a bytes object built
+        # through ctypes: hand back a uint8 array (load_partition and parse_graph_bin accept both)
+        return np.ctypeslib.as_array((C.c_ubyte * n.value).from_address(img.value)).copy()
     finally:
         lib.dory_free(img)
 
