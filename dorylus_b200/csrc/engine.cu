@@ -209,7 +209,13 @@ void build_row_lists(const std::vector<uint64_t> &ptrs, uint32_t heavyDegree, st
     });
     heavy.clear();
     light.clear();
-    for (uint32_t v : order) ((ptrs[v + 1] - ptrs[v]) >= heavyDegree ? heavy : light).push_back(v);
+    // heavy rows (a CTA each): heaviest first, so the hubs start early and the tail back-fills;
+    // light rows (a warp each, < heavyDegree edges): natural id order, which keeps whatever source
+    // locality the vertex numbering has (community-ordered graphs re-use neighbours' rows in L2)
+    for (uint32_t v : order)
+        if ((ptrs[v + 1] - ptrs[v]) >= heavyDegree) heavy.push_back(v);
+    for (uint32_t v = 0; v < V; ++v)
+        if ((ptrs[v + 1] - ptrs[v]) < heavyDegree) light.push_back(v);
 }
 
 int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const uint8_t *idx,

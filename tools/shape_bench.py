@@ -32,10 +32,13 @@ def main():
     ap.add_argument("--gnn", default="GCN")
     ap.add_argument("--sigma", type=float, default=0.9)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--locality", type=float, default=0.0, help="fraction of edges kept inside a community block")
+    ap.add_argument("--communities", type=int, default=1)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     if args.V:
-        spec = synth.GraphSpec(args.name, args.V, args.E, [int(x) for x in args.dims.split(",")], seed=77, sigma=args.sigma)
+        spec = synth.GraphSpec(args.name, args.V, args.E, [int(x) for x in args.dims.split(",")], seed=77, sigma=args.sigma,
+                               locality=args.locality, communities=args.communities)
     else:
         spec = synth.CONFIGS[args.name]
     t0 = time.time()
