@@ -60,6 +60,8 @@ struct SpmmArgs {
     int cfg_lg, cfg_vec;    // kernel shape override (0 = derive from nvec)
     int cfg_unroll;         // gather instructions in flight per lane group (0 = default)
     int cfg_occ;            // CTAs per SM the kernel is compiled for (0 = default)
+    int cfg_light;          // light rows: 0 auto, 1 a warp per row, 2 a lane group per row
+    uint32_t light_avg_degree;  // mean edges per light row (picks the light-row kernel)
 };
 
 // Launches the aggregation; returns the number of kernels launched, or -1 on a launch error.

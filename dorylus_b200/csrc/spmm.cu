@@ -272,6 +272,99 @@ spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nro
     }
 }
 
+// Low-degree rows (Amazon / Friendster shapes: ~25 edges per vertex).  A warp that owns ONE such row
+// spends its life in three dependent latencies (offsets -> ids -> rows) for a single 32-edge batch.
+// Here every LANE GROUP of LG lanes owns its own row (32/LG rows per warp) and walks it edge by edge,
+// U edges in flight, with no cross-group reduction at all -- and in the reference's own summation
+// order (self term, then edges in file order).  The row must fit one slab: nvec <= LG * VEC.
+template <int LG, int VEC, int U>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, 4)
+spmm_group_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nrows) {
+    constexpr int G = 32 / LG;  // rows per warp
+    const int lane = threadIdx.x & 31;
+    const int g = lane / LG, l = lane % LG;
+    const uint32_t rid = (blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * G + g;
+    const bool live = rid < nrows;
+    const uint32_t row = live ? (rowlist ? rowlist[rid] : a.low + rid) : 0;
+    const float4 *__restrict__ src4 = reinterpret_cast<const float4 *>(a.src);
+    const uint32_t ld4 = a.ld >> 2;
+    const uint64_t pol_keep = policy_evict_last();
+    uint64_t e = 0, e_end = 0;
+    if (live) {
+        const uint64_t pbase = (uint64_t)row * a.ptr_stride + a.ptr_off;
+        e = a.ptrs[pbase];
+        e_end = a.ptrs[pbase + a.ptr_span];
+    }
+    bool act[VEC];
+    float4 acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        act[j] = live && (uint32_t)(l + j * LG) < a.nvec;
+        acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // self term first, like the reference (gcn_ops.cpp:166-171)
+    if (a.self_mode != SELF_ZERO) {
+        const float sw = a.self_mode == SELF_NORM ? a.selfw[row] : 1.f;
+        const float4 *base = a.self_mode == SELF_ACCUM ? reinterpret_cast<const float4 *>(a.out) : src4;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+            if (act[j]) {
+                const float4 x = base[(size_t)row * ld4 + l + j * LG];
+                acc[j] = make_float4(x.x * sw, x.y * sw, x.z * sw, x.w * sw);
+            }
+    }
+    // groups of one warp have different trip counts: the loop runs to the longest row of the warp
+    // (rows are issued in degree classes, so the spread is < 2x)
+    while (__any_sync(kFull, e < e_end)) {
+        float4 x[U][VEC];
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool ev = e + u < e_end;
+            uint32_t s = 0;
+            w[u] = 0.f;
+            if (ev) {  // the LG lanes of a group read the same word: one sector per group
+                s = __ldg(a.idx + e + u);
+                w[u] = __ldg(a.vals + e + u);
+            }
+            const float4 *rp = src4 + (size_t)s * ld4 + l;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                x[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (act[j] && ev) x[u][j] = ld_row_f4(rp + j * LG, pol_keep);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) fma4(acc[j], x[u][j], w[u]);
+        e += U;
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+        if (act[j]) reinterpret_cast<float4 *>(a.out)[(size_t)row * ld4 + l + j * LG] = acc[j];
+}
+
+template <int LG, int VEC, int U>
+int launch_group(const SpmmArgs &a, cudaStream_t s) {
+    constexpr int G = 32 / LG;
+    const uint32_t rowsPerCta = kWarpsPerCta * G;
+    spmm_group_kernel<LG, VEC, U><<<(a.n_light + rowsPerCta - 1) / rowsPerCta, 32 * kWarpsPerCta, 0, s>>>(
+        a, a.light, a.n_light);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// Light rows through the lane-group kernel; returns 0 when the row is too wide for it.
+int launch_light_groups(const SpmmArgs &a, cudaStream_t s) {
+    const uint32_t n = a.nvec;
+    if (n <= 4) return launch_group<4, 1, 4>(a, s);
+    if (n <= 8) return launch_group<4, 2, 4>(a, s);
+    if (n <= 12) return launch_group<4, 3, 2>(a, s);
+    if (n <= 16) return launch_group<4, 4, 2>(a, s);
+    if (n <= 32) return launch_group<8, 4, 2>(a, s);
+    return 0;
+}
+
 int g_cfg_lg = 0, g_cfg_vec = 0, g_cfg_unroll = 0;
 bool g_cfg_read = false;
 
@@ -334,7 +427,25 @@ void spmm_set_config(int lg, int vec) {
 #define DORY_SPMM_CASE(LG_, VEC_) \
     if (lg == LG_ && vec == VEC_) return launch_unroll<LG_, VEC_>(a, unroll, occ, s)
 
+int launch_spmm_rows(const SpmmArgs &a, cudaStream_t s);
+
 int launch_spmm(const SpmmArgs &a, cudaStream_t s) {
+    // low-degree light rows that fit one slab: a lane group per row (cfg_light: 0 auto, 1 warp, 2 group)
+    const bool fits = a.nvec <= 32;
+    const bool groups = a.n_light && fits && (a.cfg_light == 2 || (a.cfg_light == 0 && a.light_avg_degree < 96));
+    if (!groups) return launch_spmm_rows(a, s);
+    int launches = 0;
+    if (a.n_heavy) {
+        SpmmArgs h = a;
+        h.n_light = 0;
+        launches = launch_spmm_rows(h, s);
+        if (launches < 0) return -1;
+    }
+    const int n = launch_light_groups(a, s);
+    return n < 0 ? -1 : launches + n;
+}
+
+int launch_spmm_rows(const SpmmArgs &a, cudaStream_t s) {
     read_env_cfg();
     int lg = a.cfg_lg ? a.cfg_lg : g_cfg_lg, vec = a.cfg_vec ? a.cfg_vec : g_cfg_vec;
     int unroll = a.cfg_unroll ? a.cfg_unroll : g_cfg_unroll;

@@ -107,6 +107,8 @@ int dory_sync(dory_engine *e);
  *                           adjacency once per slab.
  *   "spmm_unroll"           gather instructions issued back to back per lane group (0 = default).
  *   "spmm_occ"              CTAs per SM the aggregation kernel is compiled for (4, 5, 6 or 8).
+ *   "spmm_light"            rows below the heavy threshold: 1 = a warp per row, 2 = a lane group per
+ *                           row (several rows per warp; rows up to 128 floats), 0 = choose by degree.
  *   "src_blocks"            source-row windows per aggregation: each pass gathers only from a
  *                           (V+G)/n-row window so that it stays L2-resident (0 = size from the L2
  *                           capacity, 1 = off; set before dory_load_partition; GCN only).

@@ -83,6 +83,28 @@ def test_aggregate_is_bit_reproducible_and_linear():
         assert rel_err(e.get_tensor(0, "ah")[:, 0], rowsum) < TOL
 
 
+@pytest.mark.parametrize("light", [1, 2], ids=["warp-per-row", "lane-group-per-row"])
+@pytest.mark.parametrize("F", [16, 48, 64, 100, 128])
+def test_light_row_kernels(oracle, F, light):
+    """Both light-row kernels, forced, on a low-degree graph with ragged degrees (isolated vertices,
+    degree-1 vertices, a hub that goes to the CTA-per-row kernel) and a chunk sub-range."""
+    ds = random_dataset(V=1600, E_und=9000, dims=[F, 8, 3], seed=15, sigma=1.3, extra_edges=HUB)
+    g = ds.graphs[0]
+    with gcn_engine(ds) as e:
+        e.set_option("spmm_light", light)
+        e.aggregateGCN(e.whole_chunk(0, FORWARD))
+        want = oracle.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, ds.feats, None)
+        got = e.get_tensor(0, "ah")
+        assert rel_err(got, want) < TOL
+        assert (np.diff(g.col_ptrs) == 0).any()  # the graph does contain isolated vertices
+        iso = np.diff(g.col_ptrs) == 0
+        assert np.array_equal(got[iso], (ds.feats[iso] * g.norms[iso][:, None]).astype(np.float32))
+        e.set_tensor(0, "ah", np.zeros_like(ds.feats))
+        e.aggregateGCN(Chunk(0, 0, 37, 1203, 0, FORWARD, 1, True))
+        got = e.get_tensor(0, "ah")
+        assert rel_err(got[37:1203], want[37:1203]) < TOL and not got[:37].any() and not got[1203:].any()
+
+
 @pytest.mark.parametrize("nb", [2, 3, 7])
 def test_source_blocked_aggregation(oracle, nb):
     """Forcing the L2-window path (several passes over source-row windows) on a small graph: same
