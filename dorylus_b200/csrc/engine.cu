@@ -122,6 +122,7 @@ struct dory_engine {
     cudaStream_t copy_stream = nullptr;
     std::map<std::pair<uint32_t, std::string>, std::unique_ptr<Prefetch>> prefetch;
     int spmm_lg = 0, spmm_vec = 0, spmm_unroll = 0, spmm_occ = 0, spmm_light = 0;
+    int row_order = 0;  // light-row issue order: 0 = decide from the graph, 1 = degree-descending, 2 = degree classes
     int tensor_cores = 1;  // tcgen05 path for H.W (option "tensor_cores")
     uint32_t src_blocks = 0;  // source windows per aggregation (0 = size from L2, 1 = off)
     uint32_t heavy_degree = kHeavyDegree;
@@ -200,8 +201,8 @@ const DevMat *find_tensor(const dory_engine *e, uint32_t layer, const char *name
 }
 
 // Degree-descending row lists (longest-processing-time-first issue order for spmm.cu).
-void build_row_lists(const std::vector<uint64_t> &ptrs, uint32_t heavyDegree, std::vector<uint32_t> &heavy,
-                     std::vector<uint32_t> &light) {
+void build_row_lists(const std::vector<uint64_t> &ptrs, uint32_t heavyDegree, bool keepLocality,
+                     std::vector<uint32_t> &heavy, std::vector<uint32_t> &light) {
     const uint32_t V = (uint32_t)ptrs.size() - 1;
     std::vector<uint32_t> order(V);
     std::iota(order.begin(), order.end(), 0u);
@@ -211,13 +212,20 @@ void build_row_lists(const std::vector<uint64_t> &ptrs, uint32_t heavyDegree, st
     heavy.clear();
     light.clear();
     // heavy rows (a CTA each): heaviest first, so the hubs start early and the tail back-fills.
-    // light rows (a warp, or a lane group, each): grouped into power-of-two degree classes, heaviest
-    // class first, natural id order inside a class.  Rows that share a CTA / warp then have similar
-    // trip counts (a CTA's registers are held until its longest row ends: fully natural order cost
-    // 13 % on Reddit), while a class still walks the vertex numbering in order, which keeps the
-    // source locality of community-ordered graphs (-30 % on the Amazon / Friendster shapes).
+    // light rows (a warp, or a lane group, each):
+    //  - graph without locality in its vertex numbering: plain degree-descending order -- rows that
+    //    share a CTA / warp then have near-equal trip counts (a CTA's registers are held until its
+    //    longest row ends: natural order cost 13 % on the Reddit shape, degree classes 5 %);
+    //  - graph WITH locality (most edges stay near the diagonal, e.g. community-ordered ids):
+    //    power-of-two degree classes, heaviest class first, natural id order inside a class, which
+    //    keeps neighbours' source rows hot in L2 (-30 % on the Amazon / Friendster shapes).
     for (uint32_t v : order)
         if ((ptrs[v + 1] - ptrs[v]) >= heavyDegree) heavy.push_back(v);
+    if (!keepLocality) {
+        for (uint32_t v : order)
+            if ((ptrs[v + 1] - ptrs[v]) < heavyDegree) light.push_back(v);
+        return;
+    }
     auto cls = [&](uint32_t v) {
         uint64_t d = ptrs[v + 1] - ptrs[v];
         int c = 0;
@@ -254,7 +262,24 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
         CU(cudaMemcpyAsync(adj.vals.p, vals, 4 * nnz, cudaMemcpyHostToDevice, e->stream));
     }
     std::vector<uint32_t> heavy, light;
-    build_row_lists(hp, e->heavy_degree, heavy, light);
+    // locality of the vertex numbering: share of edges whose source is within 1/64 of the row space
+    // of its destination (a uniformly random graph has ~3 %)
+    bool keepLocality = e->row_order == 2;
+    if (e->row_order == 0 && nnz) {
+        const uint64_t band = std::max<uint64_t>(1, nSrcRows / 64);
+        const uint64_t stride = std::max<uint64_t>(1, nnz / (1u << 22));  // sample ~4 M edges
+        uint64_t near = 0, seen = 0;
+        uint32_t v = 0;
+        for (uint64_t k = 0; k < nnz; k += stride) {
+            while (hp[v + 1] <= k) ++v;
+            uint32_t s;
+            std::memcpy(&s, idx + 4 * k, 4);
+            near += (s > v ? s - v : v - s) < band;
+            ++seen;
+        }
+        keepLocality = near * 4 >= seen;  // >= 25 % of the edges are near-diagonal
+    }
+    build_row_lists(hp, e->heavy_degree, keepLocality, heavy, light);
     adj.n_heavy = (uint32_t)heavy.size();
     adj.n_light = (uint32_t)light.size();
     {
@@ -995,6 +1020,10 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
     } else if (std::strcmp(key, "src_blocks") == 0) {
         if (e->loaded) return fail(e, DORY_ESTATE, "src_blocks must be set before dory_load_partition");
         e->src_blocks = (uint32_t)v;
+    } else if (std::strcmp(key, "row_order") == 0) {
+        if (e->loaded) return fail(e, DORY_ESTATE, "row_order must be set before dory_load_partition");
+        if (v > 2) return fail(e, DORY_EINVAL, "row_order must be 0 (auto), 1 (degree-descending) or 2 (degree classes)");
+        e->row_order = (int)v;
     } else if (std::strcmp(key, "spmm_light") == 0) {
         if (v > 2) return fail(e, DORY_EINVAL, "spmm_light must be 0 (auto), 1 (warp per row) or 2 (lane group per row)");
         e->spmm_light = (int)v;

@@ -114,6 +114,9 @@ int dory_sync(dory_engine *e);
  *                           capacity, 1 = off; set before dory_load_partition; GCN only).
  *   "heavy_degree"          rows with at least this many edges get a whole CTA (set before
  *                           dory_load_partition).
+ *   "row_order"             issue order of the remaining rows: 1 = degree-descending, 2 = power-of-two
+ *                           degree classes in vertex-id order (keeps the numbering's locality),
+ *                           0 = decide from the share of near-diagonal edges (set before load).
  *   "tensor_cores"          1: run H.W on tcgen05 (3xTF32, fp32-level accuracy) when the shape
  *                           qualifies; 0: always the fp32 CUDA-core GEMM. */
 int dory_set_option(dory_engine *e, const char *key, const char *value);
