@@ -180,13 +180,28 @@ spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nro
             }
         }
     }
+    // ids / weights of the NEXT 32-edge batch are requested before the current batch is walked, so
+    // their (HBM-streamed) latency is off the dependent chain id -> shuffle -> gather
+    uint32_t s_n = 0;
+    float w_n = 0.f;
+    {
+        const uint64_t my = e_begin + (uint64_t)team_rank * 32 + lane;
+        if (U > 0 && my < e_end) {
+            s_n = ld_stream_u32(a.idx + my, pol_stream);
+            w_n = ld_stream_f32(a.vals + my, pol_stream);
+        }
+    }
     for (uint64_t e0 = e_begin + (uint64_t)team_rank * 32; U > 0 && e0 < e_end; e0 += 32 * TEAM) {
-        const uint64_t my = e0 + lane;
-        uint32_t s_l = 0;
-        float w_l = 0.f;
-        if (my < e_end) {
-            s_l = ld_stream_u32(a.idx + my, pol_stream);
-            w_l = ld_stream_f32(a.vals + my, pol_stream);
+        const uint32_t s_l = s_n;
+        const float w_l = w_n;
+        {
+            const uint64_t nx = e0 + 32 * TEAM + lane;
+            s_n = 0;
+            w_n = 0.f;
+            if (nx < e_end) {
+                s_n = ld_stream_u32(a.idx + nx, pol_stream);
+                w_n = ld_stream_f32(a.vals + nx, pol_stream);
+            }
         }
         const int n = (int)min((uint64_t)32, e_end - e0);
 #pragma unroll 1
