@@ -66,8 +66,6 @@ struct SpmmArgs {
 
 // Launches the aggregation; returns the number of kernels launched, or -1 on a launch error.
 int launch_spmm(const SpmmArgs &a, cudaStream_t s);
-// Tuning override read once from DORY_SPMM_CFG="LG,VEC" (lanes per row, float4 per lane).
-void spmm_set_config(int lg, int vec);
 
 // ---- dense apply (dense.cu) ----------------------------------------------------------------
 enum GemmEpilogue : int { EPI_NONE = 0, EPI_TANH = 1 };

@@ -1032,7 +1032,7 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
     } else if (std::strcmp(key, "tensor_cores") == 0) {
         e->tensor_cores = v != 0;
     } else if (std::strcmp(key, "spmm_unroll") == 0) {
-        if (v > 9) return fail(e, DORY_EINVAL, "spmm_unroll must be 0..8, or 9 for the rotating pipeline");
+        if (v > 2) return fail(e, DORY_EINVAL, "spmm_unroll must be 0 (default), 1 or 2");
         e->spmm_unroll = (int)v;
     } else if (std::strcmp(key, "heavy_degree") == 0) {
         if (e->loaded) return fail(e, DORY_ESTATE, "heavy_degree must be set before dory_load_partition");

@@ -16,15 +16,14 @@
 //   * edge ids / weights are read once per 32 edges with one coalesced 128 B load each and
 //     distributed by warp shuffles; they bypass L1 and are marked evict-first in L2 (streamed
 //     once per slab) while feature rows are marked evict-last, so that L2 keeps the slab;
-//   * rows are issued in degree-descending order (longest-processing-time-first), so the
-//     power-law tail fills in behind the hubs instead of stretching the last wave;
-//   * wide rows are cut into column slabs (gridDim.y): a slab of the source block (V x 128
-//     floats = 119 MB on Reddit) is what L2 has to hold while the adjacency is walked once per
-//     slab.  Without slabs the 561 MB layer-0 block misses L2 78 % of the time and the kernel is
-//     bound by 193 GB of DRAM re-reads (profiles/round1_spmm_ncu.md).
-#include <cstdio>
-#include <cstdlib>
-
+//   * rows are issued heaviest first (longest-processing-time-first), so the power-law tail
+//     fills in behind the hubs instead of stretching the last wave (engine.cu: build_row_lists);
+//   * wide rows are cut into 128-float column slabs (gridDim.y) and the source rows into windows
+//     (ptr_stride / ptr_off / ptr_span, one launch per window group): a pass gathers from
+//     rows x 512 B ~ 60 MB, which is what stays resident in L2.  Walking whole 2.4 KB rows of the
+//     561 MB layer-0 block instead misses L2 78 % of the time and is bound by 193 GB of DRAM
+//     re-reads per aggregation (profiles/round1_spmm_v1_full.md vs round1_final_full.md);
+//   * low-degree rows take spmm_group_kernel (a lane group per row) instead of a warp per row.
 #include "common.cuh"
 
 namespace dory {
@@ -88,9 +87,8 @@ template <int LG, int VEC, int TEAM, int U, int OCC>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, OCC)
 spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nrows) {
     constexpr int EPW = 32 / LG;  // edges covered by one warp-wide gather instruction
-    static_assert(U == 0 || LG % (U ? U : 1) == 0 || (U ? U : 1) % LG == 0,
-                  "U must divide the number of steps per 32-edge batch");
-    constexpr int UU = U == 0 ? 1 : (U < LG ? U : LG);  // steps per inner block (LG steps per 32 edges)
+    static_assert(U >= 1 && (LG % U == 0 || U % LG == 0), "U must divide the number of steps per 32-edge batch");
+    constexpr int UU = U < LG ? U : LG;  // steps per inner block (a batch of 32 edges has LG steps)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / LG, l = lane % LG;
 
@@ -120,78 +118,18 @@ spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nro
 #pragma unroll
     for (int j = 0; j < VEC; ++j) act[j] = (col0 + l + j * LG) < a.nvec;
 
-    if constexpr (U == 0) {
-        // Rotating two-deep software pipeline: the gather of step t+1 (or of the first step of the
-        // NEXT 32-edge batch, whose ids were prefetched one batch ahead) is always in flight while
-        // step t is consumed, so the dependent chain id-load -> shuffle -> gather never drains.
-        const uint64_t stride = 32 * TEAM;
-        uint64_t e0 = e_begin + (uint64_t)team_rank * 32;
-        uint32_t s_cur = 0, s_nxt = 0;
-        float w_cur = 0.f, w_nxt = 0.f;
-        auto fetch_ids = [&](uint64_t eb, uint32_t &s, float &w) {
-            s = 0;
-            w = 0.f;
-            const uint64_t my = eb + lane;
-            if (my < e_end) {
-                s = ld_stream_u32(a.idx + my, pol_stream);
-                w = ld_stream_f32(a.vals + my, pol_stream);
-            }
-        };
-        float4 x[2][VEC];
-        float wv[2];
-        auto issue = [&](int slot, uint32_t s_l, float w_l, int step, int n) {
-            const int sl = step * EPW + g;
-            const uint32_t s = __shfl_sync(kFull, s_l, sl);
-            wv[slot] = __shfl_sync(kFull, w_l, sl);
-            const bool ev = sl < n;
-            const float4 *rp = src4 + (size_t)s * ld4 + col0 + l;
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                x[slot][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (act[j] && ev) x[slot][j] = ld_row_f4(rp + j * LG, pol_keep);
-            }
-        };
-        if (e0 < e_end) {
-            fetch_ids(e0, s_cur, w_cur);
-            fetch_ids(e0 + stride, s_nxt, w_nxt);
-            int n = (int)min((uint64_t)32, e_end - e0);
-            issue(0, s_cur, w_cur, 0, n);
-            while (true) {
-                const uint64_t e1 = e0 + stride;
-                const bool more = e1 < e_end;
-                const int n1 = more ? (int)min((uint64_t)32, e_end - e1) : 0;
-#pragma unroll 1
-                for (int k = 0; k < LG; k += 2) {  // two steps per trip: slots alternate 0, 1
-                    issue(1, s_cur, w_cur, k + 1, n);
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) fma4(acc[j], x[0][j], wv[0]);
-                    // next step: same batch, or step 0 of the next batch
-                    if (k + 2 < LG) issue(0, s_cur, w_cur, k + 2, n);
-                    else issue(0, s_nxt, w_nxt, 0, n1);
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) fma4(acc[j], x[1][j], wv[1]);
-                }
-                if (!more) break;
-                e0 = e1;
-                n = n1;
-                s_cur = s_nxt;
-                w_cur = w_nxt;
-                fetch_ids(e0 + stride, s_nxt, w_nxt);
-            }
-        }
-    }
     // ids / weights of the NEXT 32-edge batch are requested before the current batch is walked, so
     // their (HBM-streamed) latency is off the dependent chain id -> shuffle -> gather
     uint32_t s_n = 0;
     float w_n = 0.f;
     {
         const uint64_t my = e_begin + (uint64_t)team_rank * 32 + lane;
-        if (U > 0 && my < e_end) {
+        if (my < e_end) {
             s_n = ld_stream_u32(a.idx + my, pol_stream);
             w_n = ld_stream_f32(a.vals + my, pol_stream);
         }
     }
-    for (uint64_t e0 = e_begin + (uint64_t)team_rank * 32; U > 0 && e0 < e_end; e0 += 32 * TEAM) {
+    for (uint64_t e0 = e_begin + (uint64_t)team_rank * 32; e0 < e_end; e0 += 32 * TEAM) {
         const uint32_t s_l = s_n;
         const float w_l = w_n;
         {
@@ -380,23 +318,6 @@ int launch_light_groups(const SpmmArgs &a, cudaStream_t s) {
     return 0;
 }
 
-int g_cfg_lg = 0, g_cfg_vec = 0, g_cfg_unroll = 0;
-bool g_cfg_read = false;
-
-void read_env_cfg() {
-    if (g_cfg_read) return;
-    g_cfg_read = true;
-    if (const char *s = std::getenv("DORY_SPMM_CFG")) {
-        int lg = 0, vec = 0, u = 0;
-        const int got = std::sscanf(s, "%d,%d,%d", &lg, &vec, &u);
-        if (got >= 2) {
-            g_cfg_lg = lg;
-            g_cfg_vec = vec;
-        }
-        if (got == 3) g_cfg_unroll = u;
-    }
-}
-
 template <int LG, int VEC, int U, int OCC>
 int launch_cfg(const SpmmArgs &a, cudaStream_t s) {
     int launches = 0;
@@ -426,18 +347,11 @@ int launch_occ(const SpmmArgs &a, int occ, cudaStream_t s) {
 
 template <int LG, int VEC>
 int launch_unroll(const SpmmArgs &a, int unroll, int occ, cudaStream_t s) {
-    if (unroll == 9) return launch_occ<LG, VEC, 0>(a, occ, s);  // rotating two-deep pipeline
     if (unroll >= 2) return launch_occ<LG, VEC, 2>(a, occ, s);
     return launch_occ<LG, VEC, 1>(a, occ, s);
 }
 
 }  // namespace
-
-void spmm_set_config(int lg, int vec) {
-    g_cfg_read = true;
-    g_cfg_lg = lg;
-    g_cfg_vec = vec;
-}
 
 #define DORY_SPMM_CASE(LG_, VEC_) \
     if (lg == LG_ && vec == VEC_) return launch_unroll<LG_, VEC_>(a, unroll, occ, s)
@@ -461,9 +375,7 @@ int launch_spmm(const SpmmArgs &a, cudaStream_t s) {
 }
 
 int launch_spmm_rows(const SpmmArgs &a, cudaStream_t s) {
-    read_env_cfg();
-    int lg = a.cfg_lg ? a.cfg_lg : g_cfg_lg, vec = a.cfg_vec ? a.cfg_vec : g_cfg_vec;
-    int unroll = a.cfg_unroll ? a.cfg_unroll : g_cfg_unroll;
+    int lg = a.cfg_lg, vec = a.cfg_vec, unroll = a.cfg_unroll;
     if (lg == 0 || vec == 0) {
         // Default (tools/spmm_sweep.py on the Reddit shape, profiles/): 8 lanes x 4 float4 per
         // gathered row = 128-float slabs, 4 edges per gather instruction.  Narrow rows use fewer
