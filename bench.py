@@ -263,22 +263,26 @@ def main():
     onehot = formats.one_hot(labels[graph.local_to_global], dims[-1])
     # pinned host staging (the e2e leg copies from here every step)
     pin_x = torch.from_numpy(np.ascontiguousarray(x_loc)).pin_memory()
-    pin_g = torch.from_numpy(np.ascontiguousarray(x_gh)).pin_memory() if graph.src_ghost_cnt else None
     pin_l = torch.from_numpy(onehot).pin_memory()
     del feats, x_loc, x_gh
+    chunk0 = eng.whole_chunk(0, FORWARD)
 
+    # Every rank uploads the feature rows it OWNS; the layer-0 ghost rows travel GPU to GPU
+    # (dory_scatter of a layer-0 FORWARD chunk) instead of crossing PCIe once per partition that
+    # needs them -- at 8 ranks that would be 8 x 0.49 GB of host reads per step for 0.56 GB of input.
     def upload_inputs():
         eng.set_tensor(0, "x", pin_x.numpy())
-        if pin_g is not None:
-            eng.set_tensor(0, "fg", pin_g.numpy())
+        if world > 1:
+            eng.scatter(chunk0)
         eng.set_tensor(L - 1, "lab", pin_l.numpy())
 
-    upload_inputs()
     eng.init_weights()
     if world > 1:
         ddist.setup_engine_comm(eng, graph, rank, world, peer_memory=args.exchange == "p2p")
         cfg_common["ghost_exchange"] = ("one store-through-NVLink kernel into peer ghost blocks (CUDA IPC) + 2 NCCL barriers"
                                         if args.exchange == "p2p" else "pack -> NCCL all-to-all-v -> unpack")
+        cfg_common["layer0_ghost_rows"] = "shipped over NVLink from the owning rank every step (not uploaded)"
+    upload_inputs()
 
     def barrier():
         eng.sync()
@@ -321,7 +325,7 @@ def main():
 
     # ---- end to end through the public API: H2D of the step's inputs + epoch + D2H of the result
     eng.sync()
-    h2d = pin_x.numel() * 4 + (pin_g.numel() * 4 if pin_g is not None else 0) + pin_l.numel() * 4
+    h2d = pin_x.numel() * 4 + pin_l.numel() * 4  # this rank's bytes; the JSON line reports the sum over ranks
     for _ in range(2):
         upload_inputs()
         eng.epoch()
@@ -337,21 +341,24 @@ def main():
     # The timed region still contains K host->device copies of every input and K loss read-backs.
     def prefetch_inputs():
         eng.prefetch_tensor(0, "x", pin_x.numpy())
-        if pin_g is not None:
-            eng.prefetch_tensor(0, "fg", pin_g.numpy())
         eng.prefetch_tensor(L - 1, "lab", pin_l.numpy())
 
+    def commit_inputs():
+        eng.commit_prefetch()
+        if world > 1:
+            eng.scatter(chunk0)
+
     prefetch_inputs()
-    eng.commit_prefetch()
+    commit_inputs()
     eng.epoch()
     prefetch_inputs()  # inputs of the first timed step are in flight when the clock starts
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        eng.commit_prefetch()
+        commit_inputs()
         prefetch_inputs()
         res = eng.epoch()
-    eng.commit_prefetch()  # drain: the K-th copy issued inside the region completes inside it
+    commit_inputs()  # drain: the K-th copy issued inside the region completes inside it
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -366,6 +373,11 @@ def main():
     e2e_s = allmax(e2e_s)
     e2e_sync_s = allmax(e2e_sync_s)
     agg_ms = {k: allmax(v) for k, v in agg_ms.items()}
+    h2d_all = h2d
+    if dist is not None:
+        t = torch.tensor([h2d], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        h2d_all = int(t.item())
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -399,7 +411,7 @@ def main():
                          "algorithmic_bytes": b_alg,
                          "note": "min-traffic model; the gather itself moves E*F*4 bytes L2->SM (DESIGN.md §5)"},
             "e2e": {"value": n_spmm * E_global * args.steps / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+                    "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": 8 * n_gpus,
                     "ms_per_step": 1e3 * e2e_s / args.steps,
                     "input_pipeline": "dory_prefetch_tensor/dory_commit_prefetch (DMA of step i+1 overlaps step i)",
                     "unpipelined_value": n_spmm * E_global * args.steps / e2e_sync_s,

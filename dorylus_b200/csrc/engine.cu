@@ -727,7 +727,11 @@ int exchange(dory_engine *e, uint32_t dir, const DevMat &local, const DevMat &gh
 int scatter_gcn(dory_engine *e, const dory_chunk *c) {
     const uint32_t L = e->L();
     if (c->dir == DORY_FORWARD) {  // gcn_ops.cpp:207-209: h[layer-1] -> fg[layer]
-        if (c->layer == 0 || c->layer >= L) return fail(e, DORY_EINVAL, "scatter: forward layer %u out of range", c->layer);
+        // layer 0 (no reference counterpart): the reference fills the layer-0 ghost rows of EVERY
+        // partition from the feature file (readFeaturesFile, engine/utils.cpp:486-552).  A caller that
+        // streams features uploads only the rows it owns and ships x -> the peers' fg[0] over NVLink.
+        if (c->layer == 0) return exchange(e, DORY_FORWARD, *find_tensor(e, 0, "x"), *find_tensor(e, 0, "fg"));
+        if (c->layer >= L) return fail(e, DORY_EINVAL, "scatter: forward layer %u out of range", c->layer);
         return exchange(e, DORY_FORWARD, *find_tensor(e, c->layer - 1, "h"), *find_tensor(e, c->layer, "fg"));
     }
     if (c->layer == 0 || c->layer >= L) return fail(e, DORY_EINVAL, "scatter: backward layer %u out of range", c->layer);

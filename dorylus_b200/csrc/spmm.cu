@@ -227,12 +227,18 @@ spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nro
 
 // Low-degree rows (Amazon / Friendster shapes: ~25 edges per vertex).  A warp that owns ONE such row
 // spends its life in three dependent latencies (offsets -> ids -> rows) for a single 32-edge batch.
-// Here every LANE GROUP of LG lanes owns its own row (32/LG rows per warp) and walks it edge by edge,
-// U edges in flight, with no cross-group reduction at all -- and in the reference's own summation
-// order (self term, then edges in file order).  The row must fit one slab: nvec <= LG * VEC.
-template <int LG, int VEC, int U>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, 4)
+// Here every LANE GROUP of LG lanes owns its own row (32/LG rows per warp) and walks it edge by edge
+// with no cross-group reduction at all -- and in the reference's own summation order (self term,
+// then edges in file order).  The row must fit one slab: nvec <= LG * VEC.
+//   * ids / weights: the LG lanes of a group read LG consecutive edges with one load each (a
+//     contiguous 4*LG-byte piece per group) and hand them round by shuffles inside the group; the
+//     NEXT batch of LG is requested before the current one is gathered, so the id latency is off the
+//     dependent chain id -> address -> row;
+//   * U gathers are in flight per group before their FMAs.
+template <int LG, int VEC, int U, int OCC>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, OCC)
 spmm_group_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nrows) {
+    static_assert(LG % U == 0, "U must divide the id batch");
     constexpr int G = 32 / LG;  // rows per warp
     const int lane = threadIdx.x & 31;
     const int g = lane / LG, l = lane % LG;
@@ -242,11 +248,18 @@ spmm_group_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32
     const float4 *__restrict__ src4 = reinterpret_cast<const float4 *>(a.src);
     const uint32_t ld4 = a.ld >> 2;
     const uint64_t pol_keep = policy_evict_last();
+    const uint64_t pol_stream = policy_evict_first();
     uint64_t e = 0, e_end = 0;
     if (live) {
         const uint64_t pbase = (uint64_t)row * a.ptr_stride + a.ptr_off;
         e = a.ptrs[pbase];
         e_end = a.ptrs[pbase + a.ptr_span];
+    }
+    uint32_t s_n = 0;
+    float w_n = 0.f;
+    if (e + l < e_end) {
+        s_n = ld_stream_u32(a.idx + e + l, pol_stream);
+        w_n = ld_stream_f32(a.vals + e + l, pol_stream);
     }
     bool act[VEC];
     float4 acc[VEC];
@@ -269,40 +282,48 @@ spmm_group_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32
     // groups of one warp have different trip counts: the loop runs to the longest row of the warp
     // (rows are issued in degree classes, so the spread is < 2x)
     while (__any_sync(kFull, e < e_end)) {
-        float4 x[U][VEC];
-        float w[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const bool ev = e + u < e_end;
-            uint32_t s = 0;
-            w[u] = 0.f;
-            if (ev) {  // the LG lanes of a group read the same word: one sector per group
-                s = __ldg(a.idx + e + u);
-                w[u] = __ldg(a.vals + e + u);
-            }
-            const float4 *rp = src4 + (size_t)s * ld4 + l;
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                x[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (act[j] && ev) x[u][j] = ld_row_f4(rp + j * LG, pol_keep);
-            }
+        const uint32_t s_c = s_n;
+        const float w_c = w_n;
+        s_n = 0;
+        w_n = 0.f;
+        if (e + LG + l < e_end) {
+            s_n = ld_stream_u32(a.idx + e + LG + l, pol_stream);
+            w_n = ld_stream_f32(a.vals + e + LG + l, pol_stream);
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u)
+        for (int k0 = 0; k0 < LG; k0 += U) {
+            float4 x[U][VEC];
+            float w[U];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) fma4(acc[j], x[u][j], w[u]);
-        e += U;
+            for (int u = 0; u < U; ++u) {
+                const int from = g * LG + k0 + u;
+                const uint32_t s = __shfl_sync(kFull, s_c, from);
+                w[u] = __shfl_sync(kFull, w_c, from);
+                const bool ev = e + (k0 + u) < e_end;  // a padding edge never touches memory
+                const float4 *rp = src4 + (size_t)s * ld4 + l;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    x[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (act[j] && ev) x[u][j] = ld_row_f4(rp + j * LG, pol_keep);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) fma4(acc[j], x[u][j], w[u]);
+        }
+        e += LG;
     }
 #pragma unroll
     for (int j = 0; j < VEC; ++j)
         if (act[j]) reinterpret_cast<float4 *>(a.out)[(size_t)row * ld4 + l + j * LG] = acc[j];
 }
 
-template <int LG, int VEC, int U>
+template <int LG, int VEC, int U, int OCC>
 int launch_group(const SpmmArgs &a, cudaStream_t s) {
     constexpr int G = 32 / LG;
     const uint32_t rowsPerCta = kWarpsPerCta * G;
-    spmm_group_kernel<LG, VEC, U><<<(a.n_light + rowsPerCta - 1) / rowsPerCta, 32 * kWarpsPerCta, 0, s>>>(
+    spmm_group_kernel<LG, VEC, U, OCC><<<(a.n_light + rowsPerCta - 1) / rowsPerCta, 32 * kWarpsPerCta, 0, s>>>(
         a, a.light, a.n_light);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -310,11 +331,11 @@ int launch_group(const SpmmArgs &a, cudaStream_t s) {
 // Light rows through the lane-group kernel; returns 0 when the row is too wide for it.
 int launch_light_groups(const SpmmArgs &a, cudaStream_t s) {
     const uint32_t n = a.nvec;
-    if (n <= 4) return launch_group<4, 1, 4>(a, s);
-    if (n <= 8) return launch_group<4, 2, 4>(a, s);
-    if (n <= 12) return launch_group<4, 3, 2>(a, s);
-    if (n <= 16) return launch_group<4, 4, 2>(a, s);
-    if (n <= 32) return launch_group<8, 4, 2>(a, s);
+    if (n <= 4) return launch_group<4, 1, 4, 6>(a, s);
+    if (n <= 8) return launch_group<4, 2, 4, 4>(a, s);
+    if (n <= 12) return launch_group<4, 3, 2, 4>(a, s);
+    if (n <= 16) return launch_group<4, 4, 2, 4>(a, s);
+    if (n <= 32) return launch_group<8, 4, 2, 4>(a, s);
     return 0;
 }
 

@@ -317,7 +317,8 @@ class Engine:
         """(layer, name) of every ghost block that takes part in an exchange."""
         L = self.numLayers
         if self.gnn_type == GCN:
-            return [(l, "fg") for l in range(1, L)] + [(l - 1, "bg") for l in range(1, L)]
+            # (0, "fg") takes part in the layer-0 input exchange (scatter of a layer-0 FORWARD chunk)
+            return [(l, "fg") for l in range(0, L)] + [(l - 1, "bg") for l in range(1, L)]
         return [(l, "fg_z") for l in range(L)] + [(l, "bg_d") for l in range(L)]
 
     def comm_ipc_export(self, layer: int, name: str) -> bytes:

@@ -196,6 +196,11 @@ int dory_apply_update(dory_engine *e, uint32_t layer);
  *                      Like CPUComm it always processes the whole partition.
  * dory_scatter      == Engine::scatterGCN/GAT + ghostReceiver* + the scatter barrier
  *                      (gcn_ops.cpp:204-362, gat_ops.cpp:277-435, ops/pipeline.cpp:256-342).
+ *                      Extension (GCN): a FORWARD chunk at layer 0 ships the owned rows of "x" into the
+ *                      peers' "fg"[0] blocks.  The reference has no such step -- every partition reads
+ *                      its layer-0 ghost rows from the feature file (engine/utils.cpp:486-552); with it
+ *                      a caller that streams inputs uploads each feature row over PCIe once per box
+ *                      instead of once per partition that has it as a ghost.
  * dory_apply_edge   == Engine::applyEdgeGCN/GAT -> NNCompute(vertex=false)
  *                      -> CPUComm::edgNNForwardGAT/edgNNBackwardGAT (CPU_comm.cpp:190-242); GCN: no-op.
  * dory_predict      == Engine::predictGAT (gat_ops.cpp:247-265).

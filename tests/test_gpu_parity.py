@@ -251,6 +251,41 @@ def test_partitions_with_ghosts_single_gpu(oracle):
             assert ei.value.code == _lib.ESTATE
 
 
+def test_empty_graph_and_tiny_widths(oracle):
+    """No edges at all (every vertex isolated: ah = norm * x = x), and widths of 1 / 3 / 5 floats
+    (row pitch 4 / 4 / 8) on a small ragged graph with duplicate edges."""
+    from dorylus_b200 import engine as dengine
+    from dorylus_b200 import formats
+
+    V = 77
+    img = dengine.preprocess_edges(np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(V, np.int32), V, 0, 1)
+    x = np.random.default_rng(0).standard_normal((V, 9)).astype(np.float32)
+    with Engine([9, 4, 2], GCN) as e:
+        e.load_partition(img)
+        e.set_tensor(0, "x", x)
+        e.aggregateGCN(e.whole_chunk(0, FORWARD))
+        assert np.array_equal(e.get_tensor(0, "ah"), x)
+        lab = np.zeros((V, 2), np.float32)
+        lab[:, 0] = 1
+        e.set_tensor(1, "lab", lab)
+        e.init_weights()
+        e.epoch()  # a whole epoch on an edgeless graph is well defined
+    for F in (1, 3, 5):
+        ds = random_dataset(V=211, E_und=900, dims=[F, 3, 2], seed=100 + F, sigma=1.0)
+        src2 = np.concatenate([ds.src, ds.src[:50]])  # duplicates are kept and counted (quirk Q2)
+        dst2 = np.concatenate([ds.dst, ds.dst[:50]])
+        img = dengine.preprocess_edges(src2, dst2, np.zeros(ds.V, np.int32), ds.V, 0, 1)
+        g = formats.parse_graph_bin(img)
+        with Engine(ds.dims, GCN) as e:
+            e.load_partition(img)
+            e.set_tensor(0, "x", ds.feats)
+            e.aggregateGCN(e.whole_chunk(0, FORWARD))
+            want = oracle.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, ds.feats, None)
+            assert rel_err(e.get_tensor(0, "ah"), want) < TOL
+            A = dense_normalized_adjacency(ds.V, src2, dst2)
+            assert rel_err(e.get_tensor(0, "ah"), A @ ds.feats.astype(np.float64)) < TOL
+
+
 def test_prefetch_pipeline_semantics(oracle):
     """dory_prefetch_tensor changes nothing until dory_commit_prefetch; afterwards the operators see the
     new values; two prefetches of one tensor without a commit are refused."""

@@ -50,14 +50,19 @@ def main():
     e = Engine(dims, GCN, node_id=rank, num_nodes=world, device=local)
     e.load_partition(ds.images[rank])
     e.set_tensor(0, "x", ds.feats[g.local_to_global])
-    if g.src_ghost_cnt:
-        e.set_tensor(0, "fg", ds.feats[g.src_ghost_gvid])
     e.set_tensor(1, "lab", ds.onehot[g.local_to_global])
     e.init_weights()
     ddist.setup_engine_comm(e, g, rank, world, peer_memory=args.exchange == "p2p")
+    # layer-0 ghost rows are NOT uploaded: every rank ships the rows it owns (scatter of a layer-0
+    # FORWARD chunk); ghost rows are copies, so they must equal the owner's rows to the bit
+    from dorylus_b200.engine import FORWARD
+    e.scatter(e.whole_chunk(0, FORWARD))
+    ok = True
+    if g.src_ghost_cnt:
+        ok = np.array_equal(e.get_tensor(0, "fg"), ds.feats[g.src_ghost_gvid])
+        print("[rank %d] layer-0 input exchange %s (%d ghost rows)" % (rank, "OK" if ok else "FAIL", g.src_ghost_cnt), flush=True)
 
     worst = 0.0
-    ok = True
     for ep in range(args.epochs):
         want = orc.epoch()
         st = e.epoch()

@@ -24,8 +24,8 @@ from dorylus_b200.engine import FORWARD, GCN, Engine  # noqa: E402
 
 # (lg, vec, unroll, occ)
 SHAPES = {
-    0: [(0, 0, 0, 0), (8, 4, 1, 4), (8, 4, 1, 5), (8, 4, 1, 6), (8, 4, 2, 4), (8, 4, 9, 4),
-        (8, 2, 1, 4), (8, 2, 1, 6), (8, 2, 1, 8), (8, 2, 2, 4), (8, 2, 2, 5), (8, 2, 2, 6), (8, 2, 9, 4), (8, 2, 9, 5),
+    0: [(0, 0, 0, 0), (8, 4, 1, 4), (8, 4, 1, 5), (8, 4, 1, 6), (8, 4, 2, 4),
+        (8, 2, 1, 4), (8, 2, 1, 6), (8, 2, 1, 8), (8, 2, 2, 4), (8, 2, 2, 5), (8, 2, 2, 6),
         (16, 2, 1, 4), (16, 2, 1, 6), (16, 2, 2, 5), (16, 1, 2, 6), (16, 1, 2, 8), (8, 1, 2, 8), (32, 1, 2, 8),
         (32, 2, 2, 6), (32, 4, 1, 5), (4, 2, 2, 6)],
     1: [(0, 0, 0, 0), (8, 4, 1, 4), (8, 4, 1, 5), (8, 4, 1, 6), (8, 4, 2, 4), (8, 2, 1, 6), (8, 2, 2, 5),
