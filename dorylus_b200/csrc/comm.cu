@@ -233,11 +233,46 @@ struct PeerPtrs {
 
 // One warp per shipped row: read the local row once, store it into the owner-of-the-ghost's HBM
 // through the NVLink-mapped pointer.  `order` interleaves the peers so that all links are busy from
-// the first wave on.
+// the first wave on.  RPW rows per warp: all their loads are issued before the first remote store
+// (a 512 B row is one float4 per lane, so RPW rows = RPW independent loads in flight per lane).
+// No fence inside the kernel: the stores only have to be visible to the peer once the collective
+// that follows the kernel on this stream has completed, and kernel completion orders them before it.
+template <int RPW>
 __global__ void __launch_bounds__(256)
 p2p_scatter_kernel(const float4 *__restrict__ local, const uint32_t *__restrict__ ids,
                    const uint32_t *__restrict__ slots, const uint8_t *__restrict__ peer,
                    const uint32_t *__restrict__ order, uint32_t n, PeerPtrs pp, uint32_t ld4) {
+    const uint32_t v0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW;
+    const uint32_t lane = threadIdx.x & 31;
+    const float4 *s[RPW];
+    float4 *d[RPW];
+#pragma unroll
+    for (int k = 0; k < RPW; ++k) {
+        s[k] = nullptr;
+        d[k] = nullptr;
+        if (v0 + k < n) {
+            const uint32_t r = order[v0 + k];
+            s[k] = local + (size_t)ids[r] * ld4;
+            d[k] = pp.p[peer[r]] + (size_t)slots[r] * ld4;
+        }
+    }
+    for (uint32_t c = lane; c < ld4; c += 32) {
+        float4 x[RPW];
+#pragma unroll
+        for (int k = 0; k < RPW; ++k)
+            if (s[k]) x[k] = __ldg(s[k] + c);
+#pragma unroll
+        for (int k = 0; k < RPW; ++k)
+            if (s[k]) d[k][c] = x[k];
+    }
+}
+
+// A warp per shipped row with a system-scope fence per warp (the first version; kept selectable
+// for the comparison in profiles/).
+__global__ void __launch_bounds__(256)
+p2p_scatter_fenced_kernel(const float4 *__restrict__ local, const uint32_t *__restrict__ ids,
+                          const uint32_t *__restrict__ slots, const uint8_t *__restrict__ peer,
+                          const uint32_t *__restrict__ order, uint32_t n, PeerPtrs pp, uint32_t ld4) {
     const uint32_t v = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (v >= n) return;
     const uint32_t r = order[v];
@@ -267,7 +302,7 @@ bool Comm::p2p_ready(int dir) const {
 }
 
 std::string Comm::exchange_p2p(int dir, const float *local, float *const *peerGhost, uint32_t ld, cudaStream_t s,
-                               int &launches) {
+                               int &launches, bool pre_barrier) {
     Plan &p = plan_[dir];
     launches = 0;
     if (!p2p_ready(dir)) return "peer-memory exchange: send slots not installed";
@@ -306,19 +341,29 @@ std::string Comm::exchange_p2p(int dir, const float *local, float *const *peerGh
         CUS(cudaMalloc(&barrier_buf_, 16));
         CUS(cudaMemsetAsync(barrier_buf_, 0, 16, s));
     }
-    // barrier 1: every peer has finished reading the ghost block we are about to overwrite
-    std::string m = allreduce_sum(barrier_buf_, 1, s);
-    if (!m.empty()) return m;
+    // barrier 1: every peer has finished reading the ghost block we are about to overwrite.  The
+    // caller elides it when a collective already separates those reads from this call (every rank
+    // runs the same operator sequence, so a collective that follows MY reads follows the peers' too).
+    if (pre_barrier) {
+        std::string m = allreduce_sum(barrier_buf_, 1, s);
+        if (!m.empty()) return m;
+    }
     if (p.sendTotal) {
         PeerPtrs pp{};
         for (int q = 0; q < nranks_; ++q) pp.p[q] = q == rank_ ? nullptr : reinterpret_cast<float4 *>(peerGhost[q]);
-        p2p_scatter_kernel<<<(p.sendTotal + 7) / 8, 256, 0, s>>>(
-            reinterpret_cast<const float4 *>(local), p.dSendIds, p.dSendSlots, p.dSendPeer,
-            p.dSendOrder, p.sendTotal, pp, ld / 4);
+        const float4 *l4 = reinterpret_cast<const float4 *>(local);
+        const uint32_t n = p.sendTotal;
+        auto grid = [n](uint32_t rpw) { return (n + 8 * rpw - 1) / (8 * rpw); };
+        switch (p2p_variant_) {
+        case 1: p2p_scatter_kernel<1><<<grid(1), 256, 0, s>>>(l4, p.dSendIds, p.dSendSlots, p.dSendPeer, p.dSendOrder, n, pp, ld / 4); break;
+        case 2: p2p_scatter_kernel<2><<<grid(2), 256, 0, s>>>(l4, p.dSendIds, p.dSendSlots, p.dSendPeer, p.dSendOrder, n, pp, ld / 4); break;
+        case 9: p2p_scatter_fenced_kernel<<<grid(1), 256, 0, s>>>(l4, p.dSendIds, p.dSendSlots, p.dSendPeer, p.dSendOrder, n, pp, ld / 4); break;
+        default: p2p_scatter_kernel<4><<<grid(4), 256, 0, s>>>(l4, p.dSendIds, p.dSendSlots, p.dSendPeer, p.dSendOrder, n, pp, ld / 4); break;
+        }
         if (cudaGetLastError() != cudaSuccess) return "peer-memory scatter kernel launch failed";
         ++launches;
     }
-    // barrier 2: every peer's stores into OUR ghost block have been issued and fenced
+    // barrier 2: every peer's stores into OUR ghost block are complete (their kernels have finished)
     return allreduce_sum(barrier_buf_ + 1, 1, s);
 }
 

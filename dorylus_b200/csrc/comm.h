@@ -39,8 +39,11 @@ public:
     std::string set_send_slots(int dir, int peer, const uint32_t *slots, uint32_t n);
     // peerGhost[q]: device pointer (mapped with cudaIpcOpenMemHandle) to peer q's ghost block for
     // this exchange; entries for q == rank are ignored.
+    // pre_barrier = false skips the barrier in front of the stores (see exchange_p2p).
     std::string exchange_p2p(int dir, const float *local, float *const *peerGhost, uint32_t ld, cudaStream_t s,
-                             int &launches);
+                             int &launches, bool pre_barrier = true);
+    // 0: 4 rows per warp (default), 1 / 2: that many rows per warp, 9: one row + system fence per warp
+    void set_p2p_variant(int v) { p2p_variant_ = v; }
     bool p2p_ready(int dir) const;
     int rank() const { return rank_; }
     int nranks() const { return nranks_; }
@@ -65,6 +68,7 @@ private:
         bool sendSlotsDirty = true;
     };
     float *barrier_buf_ = nullptr;
+    int p2p_variant_ = 0;
     std::string finalize_recv(Plan &p, uint32_t maxld, cudaStream_t s);
 
     void *nccl_ = nullptr;  // ncclComm_t

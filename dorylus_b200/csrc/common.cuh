@@ -54,6 +54,7 @@ struct SpmmArgs {
     int self_mode;
     const uint32_t *heavy;  // row ids with degree >= heavy threshold, degree-descending (may be null)
     uint32_t n_heavy;
+    uint32_t n_vheavy;      // the first n_vheavy entries of `heavy` are hub rows: a cluster of CTAs each
     const uint32_t *light;  // remaining row ids, degree-descending; null => rows low..low+n_light-1
     uint32_t n_light;
     uint32_t low;           // first row when `light` is null

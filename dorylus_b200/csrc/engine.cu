@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <set>
 #include <memory>
 #include <numeric>
 #include <random>
@@ -71,6 +72,7 @@ struct Adjacency {
     DevBuf ptrs, idx, vals, heavy, light;
     uint64_t nnz = 0;
     uint32_t n_heavy = 0, n_light = 0;
+    uint32_t n_vheavy = 0;  // leading entries of `heavy` with degree >= hub_degree (a CTA cluster each)
     uint32_t light_avg_degree = 0;
     // Source-blocked copy (GCN): every row's edge list regrouped by source-row block so that one
     // launch only gathers from a (V+G)/nb-row window of the feature block (an L2-sized working set).
@@ -126,6 +128,7 @@ struct dory_engine {
     int tensor_cores = 1;  // tcgen05 path for H.W (option "tensor_cores")
     uint32_t src_blocks = 0;  // source windows per aggregation (0 = size from L2, 1 = off)
     uint32_t heavy_degree = kHeavyDegree;
+    uint32_t hub_degree = 0;  // rows with more edges get a cluster of 8 CTAs (0 = from the partition's size)
 
     // Adam (AdamOptimizer.hpp:69-84)
     float beta1 = .9f, beta2 = .999f, eps = 1e-07f, lr_t = 0.f;
@@ -138,6 +141,11 @@ struct dory_engine {
     std::map<const float *, std::vector<float *>> peer_ghost;
     std::vector<void *> ipc_bases;
     int p2p = 1;
+    int p2p_variant = 0;        // option "p2p_rows": rows per warp of the store kernel (comm.cu)
+    int elide_pre_barrier = 1;  // option "p2p_elide_barrier"
+    // ghost blocks an aggregation has read since this engine last took part in a collective: only
+    // those need the barrier in front of a peer-memory exchange that overwrites them
+    std::set<const float *> ghost_reads_pending;
 
     // widest row slab (bytes, <= 512) any aggregation of this model gathers: GCN aggregates widths
     // F_0 .. F_{L-1}, GAT the layer outputs F_1 .. F_L
@@ -282,6 +290,13 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
     build_row_lists(hp, e->heavy_degree, keepLocality, heavy, light);
     adj.n_heavy = (uint32_t)heavy.size();
     adj.n_light = (uint32_t)light.size();
+    // Hub rows.  The heavy launch keeps ~600 CTAs resident (148 SMs x 4); a row that holds more than
+    // ~1/600 of the launch's edges cannot finish inside the launch's ideal duration even when it is
+    // issued first, so rows above nnz / 2048 are split over a cluster of 8 CTAs.  The whole Reddit
+    // shape has none (27 K < 114.6 M / 2048); one eighth of it has a few dozen per partition.
+    const uint64_t hubDegree = e->hub_degree ? e->hub_degree : std::max<uint64_t>(2048, nnz / 2048);
+    adj.n_vheavy = 0;  // `heavy` is degree-descending: the hubs are its prefix
+    while (adj.n_vheavy < adj.n_heavy && hp[heavy[adj.n_vheavy] + 1] - hp[heavy[adj.n_vheavy]] >= hubDegree) ++adj.n_vheavy;
     {
         uint64_t lightEdges = 0;
         for (uint32_t v : light) lightEdges += hp[v + 1] - hp[v];
@@ -549,6 +564,7 @@ SpmmArgs spmm_args(const dory_engine *e, const Adjacency &adj, const float *self
     if (low == 0 && up == V) {
         a.heavy = adj.heavy.as<uint32_t>();
         a.n_heavy = adj.n_heavy;
+        a.n_vheavy = adj.n_vheavy;
         a.light = adj.light.as<uint32_t>();
         a.n_light = adj.n_light;
         a.low = 0;
@@ -584,6 +600,8 @@ int aggregate_gcn(dory_engine *e, const dory_chunk *c) {
         out = find_tensor(e, c->layer - 1, "aTg");
         adj = &e->bwd;
     }
+    if (const DevMat *gh = c->dir == DORY_FORWARD ? find_tensor(e, c->layer, "fg") : find_tensor(e, c->layer - 1, "bg"))
+        e->ghost_reads_pending.insert(gh->p);
     SpmmArgs a = spmm_args(e, *adj, e->norms.as<float>(), SELF_NORM, *src, *out, c->lowBound, c->upBound, e->V);
     if (adj->nb > 1) {
         // one pass per group of source windows; passes are separate launches (stream order) because
@@ -715,11 +733,15 @@ int exchange(dory_engine *e, uint32_t dir, const DevMat &local, const DevMat &gh
     if (p2p)
         for (uint32_t q = 0; q < e->cfg.num_nodes; ++q)
             if (q != e->cfg.node_id && !pit->second[q]) p2p = false;
-    if (p2p)
-        msg = e->comm->exchange_p2p((int)dir, local.p, pit->second.data(), local.ld, e->stream, launches);
-    else
+    if (p2p) {
+        const bool pre = !e->elide_pre_barrier || e->ghost_reads_pending.count(ghost.p) != 0;
+        e->comm->set_p2p_variant(e->p2p_variant);
+        msg = e->comm->exchange_p2p((int)dir, local.p, pit->second.data(), local.ld, e->stream, launches, pre);
+    } else {
         msg = e->comm->exchange((int)dir, local.p, ghost.p, local.ld, e->stream, launches);
+    }
     if (!msg.empty()) return fail(e, DORY_ECOMM, "%s", msg.c_str());
+    e->ghost_reads_pending.clear();  // both paths end in a collective
     e->stats.kernel_launches += launches;
     return DORY_OK;
 }
@@ -772,6 +794,9 @@ int aggregate_gat(dory_engine *e, const dory_chunk *c) {
     if (c->upBound > e->V || c->lowBound > c->upBound) return fail(e, DORY_EINVAL, "chunk bounds out of range");
     const uint32_t fl = c->layer - 1;
     const DevMat &z = *find_tensor(e, fl, "z");
+    if (const DevMat *gh = find_tensor(e, fl, "fg_z")) e->ghost_reads_pending.insert(gh->p);
+    if (c->dir == DORY_BACKWARD)
+        if (const DevMat *gh = find_tensor(e, fl, "bg_d")) e->ghost_reads_pending.insert(gh->p);
     if (c->dir == DORY_FORWARD) {  // gat_ops.cpp:201-220: ah = z + sum A[e] z_src
         SpmmArgs a = spmm_args(e, e->fwd, nullptr, SELF_ONE, z, *find_tensor(e, fl, "ah"), c->lowBound, c->upBound, e->V);
         LAUNCHED(launch_spmm(a, e->stream));
@@ -873,6 +898,7 @@ int apply_update_impl(dory_engine *e, uint32_t layer) {
     if (e->comm && e->cfg.num_nodes > 1) {  // weighttensor.cpp:263-267: local + ghost updates summed
         std::string msg = e->comm->allreduce_sum(W.dw.as<float>(), W.floats(), e->stream);
         if (!msg.empty()) return fail(e, DORY_ECOMM, "%s", msg.c_str());
+        e->ghost_reads_pending.clear();
     }
     if (e->cfg.gnn_type == DORY_GAT) return DORY_OK;  // tryApplyUpdateFake, weightserver.cpp:112-116 (Q10)
     LAUNCHED(launch_adam(W.w.as<float>(), W.dw.as<float>(), W.m.as<float>(), W.v.as<float>(), W.floats(),
@@ -1021,9 +1047,16 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
         e->spmm_vec = (int)v;
     } else if (std::strcmp(key, "p2p") == 0) {
         e->p2p = v != 0;
+    } else if (std::strcmp(key, "p2p_rows") == 0) {
+        e->p2p_variant = (int)v;
+    } else if (std::strcmp(key, "p2p_elide_barrier") == 0) {
+        e->elide_pre_barrier = v != 0;
     } else if (std::strcmp(key, "src_blocks") == 0) {
         if (e->loaded) return fail(e, DORY_ESTATE, "src_blocks must be set before dory_load_partition");
         e->src_blocks = (uint32_t)v;
+    } else if (std::strcmp(key, "hub_degree") == 0) {
+        if (e->loaded) return fail(e, DORY_ESTATE, "hub_degree must be set before dory_load_partition");
+        e->hub_degree = (uint32_t)v;
     } else if (std::strcmp(key, "row_order") == 0) {
         if (e->loaded) return fail(e, DORY_ESTATE, "row_order must be set before dory_load_partition");
         if (v > 2) return fail(e, DORY_EINVAL, "row_order must be 0 (auto), 1 (degree-descending) or 2 (degree classes)");

@@ -24,7 +24,13 @@
 //     561 MB layer-0 block instead misses L2 78 % of the time and is bound by 193 GB of DRAM
 //     re-reads per aggregation (profiles/round1_spmm_v1_full.md vs round1_final_full.md);
 //   * low-degree rows take spmm_group_kernel (a lane group per row) instead of a warp per row.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace dory {
 namespace {
@@ -80,12 +86,24 @@ __device__ __forceinline__ void add4(float4 &a, const float4 &b) {
 // LG   : lanes cooperating on one source row (power of two, 4..32)
 // VEC  : float4 per lane  -> a CTA column slab is LG*VEC float4 wide
 // TEAM : warps per destination row (1: warp-per-row, kWarpsPerCta: CTA-per-row)
+// CL   : CL > 1 (TEAM == kWarpsPerCta only) is launched as thread-block clusters of CL CTAs.  The
+//        first a.n_vheavy clusters each own ONE hub row: the CL * 8 warps split its edge list, every
+//        CTA reduces its warps in shared memory and rank 0 then adds the CTA partials through
+//        distributed shared memory in rank order -- still no atomics, still the same bits every run.
+//        The remaining clusters are just CL independent CTA-per-row rows.  A hub row's edge list is
+//        the longest dependent chain of the launch (a warp retires ~4 edges per L2 round trip); at 8
+//        partitions a 27 K-edge row on one CTA outlasted the rest of its launch
+//        (profiles/round1_ops_n8.md).  Hubs and ordinary heavy rows share one launch so that the few
+//        hub clusters do not run alone on an otherwise idle chip.
 // U    : gather instructions issued back to back before their FMAs (each covers 32/LG edges)
 // OCC  : CTAs of 8 warps ptxas must fit per SM (register budget 65536 / (256 * OCC) per thread);
 //        the kernel is bound by bytes in flight, so resident warps are worth more than registers
-template <int LG, int VEC, int TEAM, int U, int OCC>
+template <int LG, int VEC, int TEAM, int U, int OCC, int CL = 1>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, OCC)
 spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nrows) {
+    static_assert(CL == 1 || TEAM == kWarpsPerCta, "clusters split CTA-per-row rows only");
+    int warps = TEAM;  // warps walking this row
+    bool hub = false;
     constexpr int EPW = 32 / LG;  // edges covered by one warp-wide gather instruction
     static_assert(U >= 1 && (LG % U == 0 || U % LG == 0), "U must divide the number of steps per 32-edge batch");
     constexpr int UU = U < LG ? U : LG;  // steps per inner block (a batch of 32 edges has LG steps)
@@ -98,9 +116,21 @@ spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nro
         rid = blockIdx.x * kWarpsPerCta + warp;
         team_rank = 0;
         if (rid >= nrows) return;
-    } else {
+    } else if (CL == 1) {
         rid = blockIdx.x;
         team_rank = warp;
+    } else {
+        const uint32_t cid = blockIdx.x / CL, crank = cg::this_cluster().block_rank();
+        hub = cid < a.n_vheavy;
+        if (hub) {
+            rid = cid;
+            team_rank = (int)crank * TEAM + warp;
+            warps = TEAM * CL;
+        } else {
+            rid = a.n_vheavy + (cid - a.n_vheavy) * CL + crank;
+            team_rank = warp;
+            if (rid >= nrows) return;  // padding CTA of the last non-hub cluster (never cluster-syncs)
+        }
     }
     const uint32_t row = rowlist ? rowlist[rid] : a.low + rid;
     const uint32_t col0 = blockIdx.y * (LG * VEC);  // slab start, float4 units
@@ -129,11 +159,11 @@ spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nro
             w_n = ld_stream_f32(a.vals + my, pol_stream);
         }
     }
-    for (uint64_t e0 = e_begin + (uint64_t)team_rank * 32; e0 < e_end; e0 += 32 * TEAM) {
+    for (uint64_t e0 = e_begin + (uint64_t)team_rank * 32; e0 < e_end; e0 += 32 * (uint64_t)warps) {
         const uint32_t s_l = s_n;
         const float w_l = w_n;
         {
-            const uint64_t nx = e0 + 32 * TEAM + lane;
+            const uint64_t nx = e0 + 32 * (uint64_t)warps + lane;
             s_n = 0;
             w_n = 0.f;
             if (nx < e_end) {
@@ -202,16 +232,40 @@ spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nro
             for (int j = 0; j < VEC; ++j) part[warp][l + j * LG] = acc[j];
         }
         __syncthreads();
-        // every thread of the CTA finishes a strided share of the slab's columns
-        for (int c = threadIdx.x; c < LG * VEC; c += 32 * TEAM) {
-            if (col0 + c >= a.nvec) continue;
-            float4 t = part[0][c];
+        if (CL == 1 || !hub) {
+            // every thread of the CTA finishes a strided share of the slab's columns
+            for (int c = threadIdx.x; c < LG * VEC; c += 32 * TEAM) {
+                if (col0 + c >= a.nvec) continue;
+                float4 t = part[0][c];
 #pragma unroll
-            for (int wv = 1; wv < TEAM; ++wv) add4(t, part[wv][c]);
-            const size_t o = (size_t)row * ld4 + col0 + c;
-            float4 self = self_term(o);
-            add4(self, t);
-            st_stream_f4(reinterpret_cast<float4 *>(a.out) + o, self, pol_stream);
+                for (int wv = 1; wv < TEAM; ++wv) add4(t, part[wv][c]);
+                const size_t o = (size_t)row * ld4 + col0 + c;
+                float4 self = self_term(o);
+                add4(self, t);
+                st_stream_f4(reinterpret_cast<float4 *>(a.out) + o, self, pol_stream);
+            }
+        } else {
+            // CTA partial -> part[0]; rank 0 adds the peers' partials over DSMEM in rank order
+            cg::cluster_group cl = cg::this_cluster();
+            for (int c = threadIdx.x; c < LG * VEC; c += 32 * TEAM) {
+                float4 t = part[0][c];
+#pragma unroll
+                for (int wv = 1; wv < TEAM; ++wv) add4(t, part[wv][c]);
+                part[0][c] = t;  // column c is read and written by this thread only
+            }
+            cl.sync();
+            if (cl.block_rank() == 0) {
+                for (int c = threadIdx.x; c < LG * VEC; c += 32 * TEAM) {
+                    if (col0 + c >= a.nvec) continue;
+                    float4 t = part[0][c];
+                    for (int r = 1; r < CL; ++r) add4(t, cl.map_shared_rank(&part[0][0], r)[c]);
+                    const size_t o = (size_t)row * ld4 + col0 + c;
+                    float4 self = self_term(o);
+                    add4(self, t);
+                    st_stream_f4(reinterpret_cast<float4 *>(a.out) + o, self, pol_stream);
+                }
+            }
+            cl.sync();  // peers keep their shared memory alive until rank 0 has read it
         }
     } else if (g == 0) {
 #pragma unroll
@@ -339,12 +393,35 @@ int launch_light_groups(const SpmmArgs &a, cudaStream_t s) {
     return 0;
 }
 
+constexpr int kClusterCtas = 8;  // CTAs sharing one very heavy row (portable cluster size limit)
+
 template <int LG, int VEC, int U, int OCC>
 int launch_cfg(const SpmmArgs &a, cudaStream_t s) {
     int launches = 0;
     const uint32_t slab = LG * VEC;
     const uint32_t nslab = (a.nvec + slab - 1) / slab;
-    if (a.n_heavy) {
+    const uint32_t n_vheavy = a.heavy ? std::min(a.n_vheavy, a.n_heavy) : 0;
+    if (n_vheavy) {  // hub rows present: the whole heavy launch goes out as clusters of 8 CTAs
+        SpmmArgs h = a;
+        h.n_vheavy = n_vheavy;
+        const uint32_t clusters = n_vheavy + (a.n_heavy - n_vheavy + kClusterCtas - 1) / kClusterCtas;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(clusters * kClusterCtas, nslab);
+        cfg.blockDim = dim3(32 * kWarpsPerCta);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = s;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = kClusterCtas;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, spmm_kernel<LG, VEC, kWarpsPerCta, U, OCC, kClusterCtas>, h, a.heavy, a.n_heavy) !=
+            cudaSuccess)
+            return -1;
+        ++launches;
+    } else if (a.n_heavy) {
         dim3 grid(a.n_heavy, nslab);
         spmm_kernel<LG, VEC, kWarpsPerCta, U, OCC><<<grid, 32 * kWarpsPerCta, 0, s>>>(a, a.heavy, a.n_heavy);
         ++launches;

@@ -114,6 +114,13 @@ int dory_sync(dory_engine *e);
  *                           capacity, 1 = off; set before dory_load_partition; GCN only).
  *   "heavy_degree"          rows with at least this many edges get a whole CTA (set before
  *                           dory_load_partition).
+ *   "hub_degree"            rows with at least this many edges get a thread-block cluster of 8 CTAs
+ *                           (partials combined through distributed shared memory); 0 = E_p / 2048,
+ *                           at least 2048 (set before dory_load_partition).
+ *   "p2p_rows"              rows per warp of the peer-memory store kernel (0 = default 4, 1, 2;
+ *                           9 = one row per warp with a system fence, the first version).
+ *   "p2p_elide_barrier"     1 (default): skip the barrier in front of a peer-memory exchange when a
+ *                           collective already separates it from the last read of that ghost block.
  *   "row_order"             issue order of the remaining rows: 1 = degree-descending, 2 = power-of-two
  *                           degree classes in vertex-id order (keeps the numbering's locality),
  *                           0 = decide from the share of near-diagonal edges (set before load).

@@ -130,6 +130,34 @@ def test_source_blocked_aggregation(oracle, nb):
         assert rel_err(got[5:900], want[5:900]) < TOL and not got[900:].any() and not got[:5].any()
 
 
+@pytest.mark.parametrize("nb,hub", [(1, 64), (3, 64), (1, 1499), (2, 100000)])
+def test_hub_rows_on_thread_block_clusters(oracle, nb, hub):
+    """Rows at or above "hub_degree" are walked by a cluster of 8 CTAs whose partial sums meet in
+    distributed shared memory (spmm.cu, CL = 8).  Lowering the threshold sends most rows of a small
+    graph down that path: forward and backward, with and without source windows, every row width
+    class (one slab, several slabs, a partial last slab), bit-reproducible."""
+    ds = random_dataset(V=1700, E_und=60000, dims=[300, 128, 9], seed=19, extra_edges=HUB)
+    g = ds.graphs[0]
+    e = Engine(ds.dims, GCN)
+    e.set_option("src_blocks", nb)
+    e.set_option("heavy_degree", 32)
+    e.set_option("hub_degree", hub)
+    e.load_partition(ds.images[0])
+    e.set_tensor(0, "x", ds.feats)
+    with e:
+        e.aggregateGCN(e.whole_chunk(0, FORWARD))
+        got = e.get_tensor(0, "ah")
+        want = oracle.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, ds.feats, None)
+        assert rel_err(got, want) < TOL
+        e.aggregateGCN(e.whole_chunk(0, FORWARD))
+        assert np.array_equal(got, e.get_tensor(0, "ah"))  # fixed summation order
+        grad = np.random.default_rng(2).standard_normal((ds.V, 128)).astype(np.float32)
+        e.set_tensor(1, "grad", grad)
+        e.aggregateGCN(e.whole_chunk(1, BACKWARD))
+        want_b = oracle.aggregate_gcn(g.row_ptrs, g.col_idxs, g.bwd_vals, g.norms, grad, None)
+        assert rel_err(e.get_tensor(0, "aTg"), want_b) < TOL
+
+
 def test_chunk_subrange_matches_reference_semantics(oracle):
     ds = random_dataset(V=500, E_und=4000, dims=[40, 8, 3], seed=12)
     g = ds.graphs[0]
