@@ -143,18 +143,19 @@ __global__ void tanh_backward_kernel(const float4 *__restrict__ aTg, const float
                        a.w * (1.f - t.w * t.w));
 }
 
-// One warp per vertex row; C <= 32 * kMaxPerLane classes.
+// One warp per vertex row; PER classes per lane (C <= 32 * PER <= 32 * kMaxPerLane).
 constexpr int kMaxPerLane = 8;
+template <int PER>
 __global__ void __launch_bounds__(256) softmax_ce_kernel(const SoftmaxCEArgs a) {
     const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= a.V) return;
     const float *z = a.z + (size_t)row * a.ld;
     const float *lab = a.lab + (size_t)row * a.ld;
-    float v[kMaxPerLane], lb[kMaxPerLane];
+    float v[PER], lb[PER];
     float mx = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < kMaxPerLane; ++j) {
+    for (int j = 0; j < PER; ++j) {
         const uint32_t c = lane + 32 * j;
         v[j] = c < a.C ? z[c] : -INFINITY;
         lb[j] = c < a.C ? lab[c] : 0.f;
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const SoftmaxCEArgs a) 
     for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < kMaxPerLane; ++j) {
+    for (int j = 0; j < PER; ++j) {
         const uint32_t c = lane + 32 * j;
         v[j] = c < a.C ? expf(v[j] - mx) : 0.f;
         sum += v[j];
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const SoftmaxCEArgs a) 
     float pbest = -INFINITY, lbest = -INFINITY;
     uint32_t pidx = 0, lidx = 0;
 #pragma unroll
-    for (int j = 0; j < kMaxPerLane; ++j) {
+    for (int j = 0; j < PER; ++j) {
         const uint32_t c = lane + 32 * j;
         v[j] = v[j] / denom;
         if (c < a.C) {
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const SoftmaxCEArgs a) 
         // acc += label[argmax(pred)];  loss -= log(pred[argmax(label)])
         float accv = 0.f, lossv = 0.f;
 #pragma unroll
-        for (int j = 0; j < kMaxPerLane; ++j) {
+        for (int j = 0; j < PER; ++j) {
             const uint32_t c = lane + 32 * j;
             if (c == pidx) accv = lb[j];
             if (c == lidx) lossv = -logf(v[j]);
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const SoftmaxCEArgs a) 
     // maskout + hadamardSub + scale (CPU_comm.cpp:118-121, 464-471)
     const uint64_t maskBeg = (uint64_t)a.trainEnd * a.C;
 #pragma unroll
-    for (int j = 0; j < kMaxPerLane; ++j) {
+    for (int j = 0; j < PER; ++j) {
         const uint32_t c = lane + 32 * j;
         if (c >= a.C) continue;
         if (a.pred) a.pred[(size_t)row * a.ld + c] = v[j];
@@ -302,9 +303,11 @@ int launch_gemm(const GemmArgs &g, cudaStream_t s) {
     dim3 grid((unsigned)((g.M + BM - 1) / BM), (g.N + BN - 1) / BN, 1);
     int launches = 0;
     if (g.transA) {
-        // split the vertex dimension so that ~4 CTAs per SM are in flight; partials reduced in order
+        // split the vertex dimension so that ~4 CTAs per SM are in flight (chunks of >= 256 vertices:
+        // one eighth of the Reddit shape got 15 CTAs for its 128 x 41 product with 2048-vertex chunks,
+        // 185 us for 29 K rows); partials reduced in ascending order
         const size_t cfloats = (size_t)g.M * g.ldc;
-        int nsplit = (int)std::min<uint64_t>((g.K + 2047) / 2048, 592 / std::max(1u, grid.x * grid.y));
+        int nsplit = (int)std::min<uint64_t>((g.K + 255) / 256, 592 / std::max(1u, grid.x * grid.y));
         nsplit = std::max(1, std::min<int>(nsplit, (int)(g.ws_floats / std::max<size_t>(cfloats, 1))));
         uint64_t kchunk = (g.K + nsplit - 1) / nsplit;
         kchunk = (kchunk + BK - 1) / BK * BK;
@@ -348,7 +351,11 @@ int launch_tanh_backward(const float *aTg, const float *h, float *g, uint64_t n,
 int launch_softmax_ce(const SoftmaxCEArgs &a, cudaStream_t s) {
     if (a.C > 32 * kMaxPerLane) return -1;
     if (a.V == 0) return 0;
-    softmax_ce_kernel<<<(a.V + 7) / 8, 256, 0, s>>>(a);
+    const unsigned grid = (a.V + 7) / 8;
+    if (a.C <= 32) softmax_ce_kernel<1><<<grid, 256, 0, s>>>(a);
+    else if (a.C <= 64) softmax_ce_kernel<2><<<grid, 256, 0, s>>>(a);
+    else if (a.C <= 128) softmax_ce_kernel<4><<<grid, 256, 0, s>>>(a);
+    else softmax_ce_kernel<kMaxPerLane><<<grid, 256, 0, s>>>(a);
     stat_reduce_kernel<<<1, 1024, 0, s>>>(a.rowstat, a.V, a.valEnd - a.trainEnd, a.stats);
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }

@@ -26,6 +26,7 @@
 #include "gat.cuh"
 #include "gemm_tc.cuh"
 #include "loader.h"
+#include "partition.h"
 
 using namespace dory;
 
@@ -1147,6 +1148,25 @@ int dory_preprocess_dir(const char *dir, uint32_t part, uint32_t n_parts, int un
     const bool ok = std::fwrite(img.data(), 1, img.size(), of) == img.size();
     std::fclose(of);
     return ok ? DORY_OK : fail(e, DORY_EFORMAT, "short write on %s%s", dir, name);
+}
+
+int dory_partition_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_edges, uint32_t n_vertices,
+                         uint32_t n_parts, uint32_t passes, int32_t *parts, uint64_t *edge_cut) {
+    const std::string m = dory::partition_edges(src, dst, n_edges, n_vertices, n_parts, passes ? passes : 8, parts, edge_cut);
+    if (m.empty()) return DORY_OK;
+    g_create_error = m;
+    return DORY_EINVAL;
+}
+
+int dory_partition_file(const char *bsnap_path, uint32_t n_parts, const char *out_dir) {
+    if (!bsnap_path || !n_parts) {
+        g_create_error = "dory_partition_file: bad argument";
+        return DORY_EINVAL;
+    }
+    const std::string m = dory::partition_file(bsnap_path, n_parts, out_dir, 8);
+    if (m.empty()) return DORY_OK;
+    g_create_error = m;
+    return DORY_EFORMAT;
 }
 
 int dory_load_partition(dory_engine *e, const void *graph_bin, size_t len) {

@@ -8,6 +8,7 @@ point of include/dorylus_b200.h -- no arithmetic happens in Python.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -78,6 +79,31 @@ def preprocess_dir(dataset_dir: str, part: int, num_parts: int, undirected: bool
     if rc != 0:
         raise DoryError(rc, lib.dory_last_error(None).decode())
     return d + "graph.%d.bin" % part
+
+
+def partition_edges(src: np.ndarray, dst: np.ndarray, num_vertices: int, num_parts: int, passes: int = 0):
+    """== inputs/partitioner.cpp without METIS: owner per global vertex (int32) and the edge cut
+    (records whose endpoints have different owners).  Host only."""
+    lib = _lib.load()
+    src = np.ascontiguousarray(src, dtype=np.uint32)
+    dst = np.ascontiguousarray(dst, dtype=np.uint32)
+    parts = np.empty(num_vertices, dtype=np.int32)
+    cut = C.c_uint64()
+    rc = lib.dory_partition_edges(src.ctypes.data_as(C.POINTER(C.c_uint32)), dst.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                  src.size, num_vertices, num_parts, passes,
+                                  parts.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(cut))
+    if rc != 0:
+        raise DoryError(rc, lib.dory_last_error(None).decode())
+    return parts, int(cut.value)
+
+
+def partition_file(bsnap_path: str, num_parts: int, out_dir: str) -> str:
+    """Reads graph.bsnap, writes <out_dir>/<name>.parts and .comm like the reference's partitioner."""
+    lib = _lib.load()
+    rc = lib.dory_partition_file(bsnap_path.encode(), num_parts, out_dir.encode())
+    if rc != 0:
+        raise DoryError(rc, lib.dory_last_error(None).decode())
+    return os.path.join(out_dir, os.path.basename(bsnap_path) + ".parts")
 
 
 class Engine:

@@ -141,6 +141,20 @@ int dory_preprocess_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_e
 int dory_preprocess_dir(const char *dir, uint32_t part, uint32_t n_parts, int undirected);
 void dory_free(void *p);
 
+/* ---- partitioning (host only) ------------------------------------------------------------------
+ * dory_partition_edges == inputs/partitioner.cpp:63-111 (symmetrise the edge list, k-way edge-cut
+ * partition with unit vertex weights) with METIS_PartGraphKway replaced by a deterministic
+ * restreaming greedy partitioner that balances vertices AND in-edges per partition
+ * (csrc/partition.cpp).  parts[v] receives the owner of global vertex v; *edge_cut (may be NULL) the
+ * number of edge records whose endpoints have different owners.  passes = 0 picks the default.
+ * dory_partition_file  == the whole tool: reads <bsnap_path> (graph.bsnap), writes
+ * <out_dir>/<basename>.parts (one id per line, partitioner.cpp:123-128, read back by
+ * DataLoader::readPartsFile, graph/dataloader.cpp:53-87) and <basename>.comm ("Communication cost: N").
+ * Errors of these two calls are reported through dory_last_error(NULL). */
+int dory_partition_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_edges, uint32_t n_vertices,
+                         uint32_t n_parts, uint32_t passes, int32_t *parts, uint64_t *edge_cut);
+int dory_partition_file(const char *bsnap_path, uint32_t n_parts, const char *out_dir);
+
 /* ---- partition + tensors --------------------------------------------------------------------
  * dory_load_partition == Graph::init (graph/graph.cpp:7-115) + Engine::preallocateGCN/GAT
  * (gcn_ops.cpp:27-93, gat_ops.cpp:27-115): parses a graph.<id>.bin image, uploads CSC/CSR/norms/

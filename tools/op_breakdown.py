@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--out", default="")
+    ap.add_argument("--emulate-parts", type=int, default=0,
+                    help="single GPU: run partition 0 of P (ghost rows filled with noise, no exchange) -- the "
+                         "per-rank kernel shapes of a P-GPU run, e.g. under ncu")
     ap.add_argument("--sustain", type=int, default=150, help="epochs of the sustained (clock-sampled) run")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
     args = ap.parse_args()
@@ -47,16 +50,22 @@ def main():
     from dorylus_b200 import formats
     from dorylus_b200.engine import BACKWARD, FORWARD, GCN, Engine
 
-    spec, image, graph, feats, labels, n_edges, cut = bench.build_workload(args.workload, world, rank)
+    emu = args.emulate_parts if world == 1 else 0
+    spec, image, graph, feats, labels, n_edges, cut = bench.build_workload(args.workload, emu or world, rank)
     dims = spec.dims
     L = len(dims) - 1
-    e = Engine(dims, GCN, node_id=rank, num_nodes=world, device=local)
+    e = Engine(dims, GCN, node_id=rank, num_nodes=emu or world, device=local)
     for kv in args.opt:
         k, v = kv.split("=", 1)
         e.set_option(k, v)
     e.load_partition(image)
-    x_loc, _ = formats.partition_rows(graph, feats)
+    x_loc, x_gh = formats.partition_rows(graph, feats)
     e.set_tensor(0, "x", np.ascontiguousarray(x_loc))
+    if emu:
+        e.set_tensor(0, "fg", np.ascontiguousarray(x_gh))
+        rng = np.random.default_rng(1)
+        e.set_tensor(1, "fg", rng.standard_normal((graph.src_ghost_cnt, dims[1])).astype(np.float32))
+        e.set_tensor(0, "bg", rng.standard_normal((graph.dst_ghost_cnt, dims[1])).astype(np.float32))
     e.set_tensor(L - 1, "lab", formats.one_hot(labels[graph.local_to_global], dims[-1]))
     e.init_weights()
     if world > 1:
@@ -70,13 +79,14 @@ def main():
         ops.append(("GA fwd L%d (F=%d)" % (l, dims[l]), e.aggregate, c))
         ops.append(("AV fwd L%d" % l, e.applyVertex, c))
         n = e.incLayer(c)
-        ops.append(("SC %s L%d" % ("fwd" if n.dir == FORWARD else "bwd", n.layer), e.scatter, n))
+        if not emu:
+            ops.append(("SC %s L%d" % ("fwd" if n.dir == FORWARD else "bwd", n.layer), e.scatter, n))
     for l in range(L - 1, 0, -1):
         c = e.whole_chunk(l, BACKWARD)
         ops.append(("GA bwd L%d (F=%d)" % (l, dims[l]), e.aggregate, c))
         ops.append(("AV bwd L%d" % (l - 1), e.applyVertex, c))
         n = e.incLayer(c)
-        if n.layer != 0:
+        if n.layer != 0 and not emu:
             ops.append(("SC bwd L%d" % n.layer, e.scatter, n))
     for l in range(L - 1, -1, -1):
         ops.append(("update W%d" % l, lambda layer, _l=l: e.apply_update(_l), l))
@@ -110,11 +120,13 @@ def main():
     # whole epochs back to back (what bench.py times)
     barrier()
     e.event_record(60)
-    for _ in range(args.reps):
+    for _ in range(0 if emu else args.reps):
         e.epoch_async()
     e.event_record(61)
     barrier()
     plain = e.event_elapsed_ms(60, 61) / args.reps
+    if emu:
+        plain = tot
     vec = np.concatenate([acc, [tot, plain]])
     # ghost exchange alone, store-kernel variants (option "p2p_rows"), back to back: ranks stay in
     # lockstep through the barriers, so this is the cost of the exchange itself
@@ -155,7 +167,7 @@ def main():
             sampler = None
     barrier()
     e.event_record(56)
-    for _ in range(args.sustain):
+    for _ in range(0 if emu else args.sustain):
         e.epoch_async()
     e.event_record(57)
     barrier()
