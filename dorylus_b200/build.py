@@ -76,7 +76,8 @@ def build_host_driver() -> str:
     root = os.path.dirname(HERE)
     src = os.path.join(root, "host", "dorylus_b200_run.cpp")
     out = os.path.join(root, "host", "dorylus_b200_run")
-    if os.path.exists(src) and _stale(out, [src, LIB, os.path.join(root, "include", "dorylus_b200.h")]):
+    if os.path.exists(src) and _stale(out, [src, LIB, os.path.join(root, "include", "dorylus_b200.h"),
+                                            os.path.join(root, "host", "saga_pipeline.hpp")]):
         cmd = ["g++", "-std=c++17", "-O2", "-Wall", src, "-o", out, LIB, "-Wl,-rpath,$ORIGIN/../dorylus_b200"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -8,10 +8,16 @@
 //
 //   dorylus_b200_run --datasetdir D/ --featuresfile F --labelsfile L --layerfile C
 //                    [--numepochs 10] [--lr 0.01] [--gnn GCN|GAT] [--undirected 0]
+//                    [--pipeline 1 [--numlambdas N] [--targetacc A] [--switchthreshold T]]
+//
+// --pipeline 1 drives the epochs through host/saga_pipeline.hpp -- the reference's chunk queues,
+// priority order, barriers, early-stop state machine and <EM> report (engine/ops/pipeline.cpp) --
+// instead of dory_epoch; --numlambdas is the number of chunks per partition (numLambdasForward).
 //
 // Prints one line per epoch in the weight server's format (weightserver.cpp:258-262:
 // "Epoch %u, acc: %.3f, loss: %.3f") plus the epoch time the graph server reports
 // (ops/pipeline.cpp:117-136).
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +27,7 @@
 #include <vector>
 
 #include "../include/dorylus_b200.h"
+#include "saga_pipeline.hpp"
 
 namespace {
 
@@ -42,8 +49,8 @@ bool read_file(const std::string &path, std::vector<char> &out) {
 
 int main(int argc, char **argv) {
     std::string dir, featuresFile, labelsFile, layerFile, gnn = "GCN";
-    unsigned epochs = 10, undirected = 0;
-    float lr = 0.01f;
+    unsigned epochs = 10, undirected = 0, pipeline = 0, numLambdas = 1;
+    float lr = 0.01f, targetAcc = 1.1f, switchThreshold = 0.02f;
     for (int i = 1; i + 1 < argc; i += 2) {
         const std::string k = argv[i], v = argv[i + 1];
         if (k == "--datasetdir") dir = v;
@@ -54,6 +61,10 @@ int main(int argc, char **argv) {
         else if (k == "--lr") lr = (float)std::atof(v.c_str());
         else if (k == "--gnn") gnn = v;
         else if (k == "--undirected") undirected = (unsigned)std::atoi(v.c_str());
+        else if (k == "--pipeline") pipeline = (unsigned)std::atoi(v.c_str());
+        else if (k == "--numlambdas") numLambdas = (unsigned)std::max(1, std::atoi(v.c_str()));
+        else if (k == "--targetacc") targetAcc = (float)std::atof(v.c_str());
+        else if (k == "--switchthreshold") switchThreshold = (float)std::atof(v.c_str());
         else {
             std::fprintf(stderr, "unknown flag %s\n", k.c_str());
             return EXIT_FAILURE;
@@ -136,6 +147,25 @@ int main(int argc, char **argv) {
     }
     if (dory_set_tensor(e, cfg.n_layers - 1, "lab", onehot.data(), V, C) != DORY_OK) die(e, "dory_set_tensor(labels)");
     if (dory_init_weights(e) != DORY_OK) die(e, "dory_init_weights");
+
+    if (pipeline) {
+        saga::Config pc;
+        pc.gnn = cfg.gnn_type;
+        pc.numLayers = cfg.n_layers;
+        pc.numChunks = numLambdas;
+        pc.numEpochs = epochs;
+        pc.localVtxCnt = (uint32_t)V;
+        pc.nodeId = 0;
+        pc.targetAcc = targetAcc;
+        pc.switchThreshold = switchThreshold;
+        saga::Pipeline pipe(pc, saga::engine_ops(e));
+        if (pipe.run() != DORY_OK) die(e, "pipeline");
+        pipe.report();
+        std::printf("Final: epochs %u, state %s, acc: %.3f, loss: %.3f\n", pipe.epochs_run(),
+                    saga::converge_name(pipe.converge_state()), pipe.last_acc(), pipe.last_loss());
+        dory_destroy(e);
+        return EXIT_SUCCESS;
+    }
 
     double total_ms = 0;
     for (unsigned ep = 1; ep <= epochs; ++ep) {

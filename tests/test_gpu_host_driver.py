@@ -21,6 +21,67 @@ def test_driver_is_built():
     assert os.path.exists(BIN), "run `python -m dorylus_b200.build`"
 
 
+def test_pipeline_shell_unit_checks(tmp_path):
+    """host/saga_pipeline.hpp with recording stubs (no GPU): queue priority == Chunk::operator<,
+    operator order of GCN (2 and 3 layers, 2 chunks) and GAT epochs, barriers, early stop."""
+    exe = str(tmp_path / "test_saga_pipeline")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", os.path.join(ROOT, "host", "test_saga_pipeline.cpp"),
+                        "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def write_dataset(ds):
+    root = tempfile.mkdtemp()
+    d = os.path.join(root, "parts_1") + "/"
+    os.makedirs(d)
+    formats.write_bsnap_edges(d + "graph.bsnap.edges", ds.V, ds.src, ds.dst)
+    formats.write_parts(d + "graph.bsnap.parts", np.zeros(ds.V, np.int32))
+    formats.write_features(os.path.join(root, "features.bsnap"), ds.feats)
+    formats.write_labels(os.path.join(root, "labels.bsnap"), ds.labels, ds.dims[-1])
+    formats.write_layer_config(os.path.join(root, "layers.config"), ds.dims)
+    return [BIN, "--datasetdir", d, "--featuresfile", os.path.join(root, "features.bsnap"),
+            "--labelsfile", os.path.join(root, "labels.bsnap"), "--layerfile", os.path.join(root, "layers.config")]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lambdas", [1, 3])
+def test_pipeline_mode_matches_oracle(oracle, lambdas):
+    """--pipeline 1: the reference's chunk queues drive the engine (several chunks per partition
+    aggregate their own destination ranges); accuracy / loss per epoch as the weight server logs
+    them, the epoch and <EM> lines of the graph server, early stop at the target accuracy."""
+    from oracle.driver import OracleGCN
+
+    ds = random_dataset(V=900, E_und=7000, dims=[50, 16, 6], seed=78)
+    cmd = write_dataset(ds)
+    r = subprocess.run(cmd + ["--numepochs", "5", "--pipeline", "1", "--numlambdas", str(lambdas)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = [(int(m.group(1)), float(m.group(2)), float(m.group(3)))
+           for m in re.finditer(r"Epoch (\d+), acc: ([0-9.]+), loss: ([0-9.]+)", r.stderr)]
+    assert [g[0] for g in got] == [1, 2, 3, 4, 5]
+    orc = OracleGCN(oracle, ds.graphs, ds.dims)
+    orc.load_features(ds.feats, ds.onehot)
+    val = int(ds.V * 0.1)
+    accs = []
+    for ep, acc, loss in got:
+        w = orc.epoch()
+        accs.append(w["acc"][0] / val)
+        assert abs(acc - w["acc"][0] / val) < 2e-4 and abs(loss - w["loss"][0] / val) < 2e-4  # 4 decimals
+    assert len(re.findall(r"Sync Epoch \d+ starts", r.stderr)) == 5
+    assert len(re.findall(r"Time for epoch \d+: [0-9.]+ms", r.stderr)) == 5
+    assert "<EM>: Using %d lambdas" % lambdas in r.stderr and "<EM>: Average  sync epoch time" in r.stderr
+    assert "Final: epochs 5, state EARLY" in r.stdout
+    # early stop: a target the third epoch reaches -> DONE, no fourth epoch
+    target = accs[2]
+    if target > max(accs[:2]) and target > 0:
+        r = subprocess.run(cmd + ["--numepochs", "5", "--pipeline", "1", "--targetacc", "%.6f" % (target - 1e-4),
+                                  "--switchthreshold", "0.0"], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        assert "Final: epochs 3, state DONE" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.gpu
 def test_driver_epochs_match_oracle(oracle):
     from oracle.driver import OracleGCN
