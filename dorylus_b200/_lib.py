@@ -86,6 +86,8 @@ SYMBOLS = {
     "dory_backward": (C.c_int, [_P, _u32]),
     "dory_epoch": (C.c_int, [_P, C.POINTER(DoryStats)]),
     "dory_get_stats": (C.c_int, [_P, C.POINTER(DoryStats)]),
+    "dory_stats_enqueue": (C.c_int, [_P, _u32]),
+    "dory_stats_collect": (C.c_int, [_P, _u32, C.POINTER(DoryStats)]),
     "dory_comm_unique_id": (C.c_int, [_P]),
     "dory_comm_init": (C.c_int, [_P, _P]),
     "dory_comm_set_recv_slots": (C.c_int, [_P, _u32, _u32, _u32p, _u32]),

@@ -136,6 +136,13 @@ struct dory_engine {
     unsigned adam_epochs = 0;
 
     dory_stats stats{};
+    // stream-ordered statistics read-back (dory_stats_enqueue / dory_stats_collect): pinned host
+    // slots, one event each
+    static constexpr uint32_t kStatSlots = 4;
+    float *stats_host = nullptr;  // [kStatSlots][2], cudaHostAlloc
+    cudaEvent_t stats_ready[kStatSlots] = {};
+    dory_stats stats_snap[kStatSlots] = {};
+    bool stats_pending[kStatSlots] = {};
     std::unique_ptr<dory::Comm> comm;
     // peer-memory exchange: local ghost tensor -> per-peer pointer to THEIR ghost tensor of the same
     // (layer, name), mapped with cudaIpcOpenMemHandle; ipc_bases are the mappings to close
@@ -662,6 +669,15 @@ int gemm_nt(dory_engine *e, const float *G, uint32_t ldg, uint64_t rows, const W
 
 // dW = A^T . G   (A: V x Fin, G: V x Fout -> dW: Fin x Fout), deterministic split over vertices
 int gemm_tn(dory_engine *e, const DevMat &A, const float *G, uint32_t ldg, WeightSet &W, float *out) {
+    if (use_tensor_cores(e)) {
+        int n = launch_gemm_tn_tc(A.p, A.ld, W.prows, G, ldg, A.rows, out, W.ld, e->gemm_ws.as<float>(),
+                                  e->gemm_ws.bytes / 4, e->stream);
+        if (n > 0) {
+            e->stats.kernel_launches += n;
+            return DORY_OK;
+        }
+        if (n < 0) return fail(e, DORY_ECUDA, "tcgen05 dW GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     GemmArgs g{};
     g.A = A.p; g.lda = A.ld; g.B = G; g.ldb = ldg; g.C = out; g.ldc = W.ld;
     g.M = W.prows; g.N = W.ld; g.K = A.rows;
@@ -973,6 +989,9 @@ void dory_destroy(dory_engine *e) {
     }
     for (auto &ev : e->events)
         if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->stats_ready)
+        if (ev) cudaEventDestroy(ev);
+    if (e->stats_host) cudaFreeHost(e->stats_host);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -1494,6 +1513,34 @@ int dory_get_stats(dory_engine *e, dory_stats *stats) {
     if (!stats) return fail(e, DORY_EINVAL, "null argument");
     if ((rc = fetch_stats(e))) return rc;
     *stats = e->stats;
+    return DORY_OK;
+}
+
+int dory_stats_enqueue(dory_engine *e, uint32_t slot) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (slot >= dory_engine::kStatSlots) return fail(e, DORY_EINVAL, "stats slot %u out of range", slot);
+    if (e->stats_pending[slot]) return fail(e, DORY_ESTATE, "stats slot %u has an uncollected read-back", slot);
+    if (!e->stats_host) CU(cudaHostAlloc(reinterpret_cast<void **>(&e->stats_host), sizeof(float) * 2 * dory_engine::kStatSlots, cudaHostAllocDefault));
+    if (!e->stats_ready[slot]) CU(cudaEventCreateWithFlags(&e->stats_ready[slot], cudaEventDisableTiming));
+    CU(cudaMemcpyAsync(e->stats_host + 2 * slot, e->stats_dev.p, 2 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaEventRecord(e->stats_ready[slot], e->stream));
+    e->stats_snap[slot] = e->stats;  // host-side counters as of this point of the stream
+    e->stats_pending[slot] = true;
+    return DORY_OK;
+}
+
+int dory_stats_collect(dory_engine *e, uint32_t slot, dory_stats *stats) {
+    int rc = check_loaded(e);
+    if (rc) return rc;
+    if (!stats) return fail(e, DORY_EINVAL, "null argument");
+    if (slot >= dory_engine::kStatSlots || !e->stats_pending[slot])
+        return fail(e, DORY_ESTATE, "stats slot %u has no read-back in flight", slot);
+    CU(cudaEventSynchronize(e->stats_ready[slot]));
+    *stats = e->stats_snap[slot];
+    stats->acc_sum = e->stats_host[2 * slot];
+    stats->loss_sum = e->stats_host[2 * slot + 1];
+    e->stats_pending[slot] = false;
     return DORY_OK;
 }
 

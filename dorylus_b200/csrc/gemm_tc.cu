@@ -21,6 +21,7 @@
 // stage and finally signals the epilogue.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <map>
 #include <mutex>
@@ -299,6 +300,228 @@ __global__ void split_transpose_kernel(const float *__restrict__ W, uint32_t ldw
     lo[(size_t)n * Kpad + k] = w - h;
 }
 
+// ------------------------------------------------------------------ dW = A^T . G  (split over the vertices)
+//
+// Weight gradient of ApplyVertex: dW[Fin x Fout] = AH^T . G with AH [V x Fin] and G [V x Fout] both
+// row-major, i.e. the contraction runs over the ROWS of both operands (CPUComm::vtxNNBackwardGCN,
+// CPU_comm.cpp:146-151: ah.dot(interGrad, true, false); cublasSgemm with CUBLAS_OP_T in the
+// reference GPU backend).  For the tensor core that makes both operands MN-major: a TMA box of
+// 32 vertices x 32 floats is 32 rows of 128 B (row = one vertex, the K index).  The only shared-memory
+// layout tcgen05 accepts for MN-major 32-bit operands is the 128-byte swizzle with 32-byte atomicity
+// (layout type SWIZZLE_128B_BASE32B; the four 32 B chunks of a row are XOR-ed with row & 3, TMA mode
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): its canonical form is 4-row (K) groups 512 B apart and 32-float
+// (M / N) blocks one box (4096 B) apart, which is what the boxes are -- so no transpose is ever
+// materialised; the instruction descriptor just says "A and B are MN-major".
+//   grid = (M tiles of 128, splits): a CTA reduces its vertex range into one 128 x BN fp32 tile
+//   (3xTF32: hi.hi -> D0, hi.lo + lo.hi -> D1, as above, both operands split in shared memory by the
+//   converter warps) and writes the partial to ws[split]; splitk_reduce adds the partials in
+//   ascending order (deterministic dW).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(4096 >> 4) << 16;  // leading byte offset: next 32-element block along M / N
+    d |= (uint64_t)(512 >> 4) << 32;   // stride byte offset: next 4-row group along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;            // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+template <int BN>
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_mn() {
+    return umma_idesc_tf32<BN>() | (1u << 15) | (1u << 16);  // a_major = b_major = MN
+}
+
+template <int BN>
+struct SmemLayoutTN {
+    static constexpr int kStages = BN == 128 ? 3 : 4;
+    static constexpr uint32_t kBox = 32 * BK * 4;        // one TMA box: 32 floats x 32 vertices = 4 KB
+    static constexpr uint32_t kABytes = BM * BK * 4;     // 4 boxes
+    static constexpr uint32_t kBBytes = BN * BK * 4;     // BN / 32 boxes
+    static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;  // hi and lo of both operands
+    static constexpr uint32_t kTxBytes = kABytes + kBBytes;
+    static constexpr uint32_t kBarOffset = kStages * kStageBytes;
+    static constexpr uint32_t kTotal = kBarOffset + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapG,
+                  float *__restrict__ ws, uint32_t ldc, uint32_t Mpad, uint64_t K, uint64_t kchunk,
+                  size_t split_stride) {
+    using L = SmemLayoutTN<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    auto stage_a_hi = [&](int s) { return base + s * L::kStageBytes; };
+    auto stage_a_lo = [&](int s) { return base + s * L::kStageBytes + L::kABytes; };
+    auto stage_b_hi = [&](int s) { return base + s * L::kStageBytes + 2 * L::kABytes; };
+    auto stage_b_lo = [&](int s) { return base + s * L::kStageBytes + 2 * L::kABytes + L::kBBytes; };
+    const uint32_t bar0 = base + L::kBarOffset;
+    auto bar_full = [&](int s) { return bar0 + 8 * s; };
+    auto bar_conv = [&](int s) { return bar0 + 8 * (L::kStages + s); };
+    auto bar_empty = [&](int s) { return bar0 + 8 * (2 * L::kStages + s); };
+    const uint32_t bar_done = bar0 + 8 * (3 * L::kStages);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen_base + L::kBarOffset + 8 * (3 * L::kStages + 1));
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapG);
+        for (int s = 0; s < L::kStages; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_conv(s), kConvThreads);
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(2 * BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int m0 = blockIdx.x * BM;
+    const uint64_t kbeg = (uint64_t)blockIdx.y * kchunk;
+    const uint64_t kend = kbeg + kchunk < K ? kbeg + kchunk : K;
+    const uint32_t nkb = (uint32_t)((kend - kbeg + BK - 1) / BK);  // rows past K are zero-filled by TMA
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+                const int s = kb % L::kStages;
+                const uint32_t ph = (kb / L::kStages) & 1;
+                mbar_wait(bar_empty(s), ph ^ 1);
+                mbar_expect_tx(bar_full(s), L::kTxBytes);
+                const int k0 = (int)(kbeg + (uint64_t)kb * BK);
+#pragma unroll
+                for (int i = 0; i < BM / 32; ++i) tma_load_2d(stage_a_hi(s) + i * L::kBox, &mapA, m0 + 32 * i, k0, bar_full(s));
+#pragma unroll
+                for (int j = 0; j < BN / 32; ++j) tma_load_2d(stage_b_hi(s) + j * L::kBox, &mapG, 32 * j, k0, bar_full(s));
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc_tf32_mn<BN>();
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+            const int s = kb % L::kStages;
+            const uint32_t ph = (kb / L::kStages) & 1;
+            mbar_wait(bar_full(s), ph);
+            mbar_wait(bar_conv(s), ph);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint32_t koff = k * 1024;  // one 8-vertex group of every box
+                    const uint64_t a_hi = umma_desc_mn_sw128(stage_a_hi(s) + koff);
+                    const uint64_t a_lo = umma_desc_mn_sw128(stage_a_lo(s) + koff);
+                    const uint64_t b_hi = umma_desc_mn_sw128(stage_b_hi(s) + koff);
+                    const uint64_t b_lo = umma_desc_mn_sw128(stage_b_lo(s) + koff);
+                    const uint32_t acc = (kb | (uint32_t)k) ? 1u : 0u;
+                    tc_mma_tf32(tmem, a_hi, b_hi, idesc, acc);
+                    tc_mma_tf32(tmem + BN, a_hi, b_lo, idesc, acc);
+                    tc_mma_tf32(tmem + BN, a_lo, b_hi, idesc, 1u);
+                }
+                tc_commit(bar_empty(s));
+                if (kb + 1 == nkb) tc_commit(bar_done);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int t = threadIdx.x - 64;
+        auto split = [](const float4 v, float4 &h, float4 &l) {
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+            l.x = v.x - h.x;
+            l.y = v.y - h.y;
+            l.z = v.z - h.z;
+            l.w = v.w - h.w;
+        };
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+            const int s = kb % L::kStages;
+            const uint32_t ph = (kb / L::kStages) & 1;
+            mbar_wait(bar_full(s), ph);
+            float4 *ahi = reinterpret_cast<float4 *>(gen_base + s * L::kStageBytes);
+            float4 *alo = reinterpret_cast<float4 *>(gen_base + s * L::kStageBytes + L::kABytes);
+            float4 *bhi = reinterpret_cast<float4 *>(gen_base + s * L::kStageBytes + 2 * L::kABytes);
+            float4 *blo = reinterpret_cast<float4 *>(gen_base + s * L::kStageBytes + 2 * L::kABytes + L::kBBytes);
+#pragma unroll
+            for (int i = 0; i < (BM * BK / 4) / kConvThreads; ++i) {
+                const int idx = t + i * kConvThreads;
+                float4 h, l;
+                split(ahi[idx], h, l);
+                ahi[idx] = h;
+                alo[idx] = l;
+            }
+#pragma unroll
+            for (int i = 0; i < (BN * BK / 4) / kConvThreads; ++i) {
+                const int idx = t + i * kConvThreads;
+                float4 h, l;
+                split(bhi[idx], h, l);
+                bhi[idx] = h;
+                blo[idx] = l;
+            }
+            fence_proxy_async();
+            mbar_arrive(bar_conv(s));
+        }
+        float *out = ws + (size_t)blockIdx.y * split_stride;
+        const int q = warp & 3;
+        const uint32_t m = (uint32_t)m0 + q * 32 + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        if (nkb) {
+            mbar_wait(bar_done, 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            float d0[32], d1[32];
+            if (nkb) {
+                tc_ld_32x32(lane_base + c * 32, d0);
+                tc_ld_32x32(lane_base + BN + c * 32, d1);
+                tc_wait_ld();
+            } else {  // empty vertex range (more splits than 32-vertex blocks): contributes zero
+#pragma unroll
+                for (int j = 0; j < 32; ++j) d0[j] = d1[j] = 0.f;
+            }
+            if (m < Mpad) {
+                float4 *o = reinterpret_cast<float4 *>(out + (size_t)m * ldc + c * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    o[j] = make_float4(d0[4 * j] + d1[4 * j], d0[4 * j + 1] + d1[4 * j + 1], d0[4 * j + 2] + d1[4 * j + 2],
+                                       d0[4 * j + 3] + d1[4 * j + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN) : "memory");
+    }
+}
+
+// C[i] = sum_z ws[z][i], ascending z
+__global__ void tn_reduce_kernel(const float4 *__restrict__ ws, float4 *__restrict__ C, size_t n4, size_t stride4,
+                                 int nsplit) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 s = ws[i];
+    for (int z = 1; z < nsplit; ++z) {
+        const float4 v = ws[(size_t)z * stride4 + i];
+        s.x += v.x;
+        s.y += v.y;
+        s.z += v.z;
+        s.w += v.w;
+    }
+    C[i] = s;
+}
+
 // ------------------------------------------------------------------ host side
 using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -318,7 +541,8 @@ EncodeFn encode_fn() {
     return fn;
 }
 
-bool make_map(CUtensorMap *map, const float *ptr, uint64_t rows, uint32_t cols, uint32_t ld, uint32_t boxRows) {
+bool make_map(CUtensorMap *map, const float *ptr, uint64_t rows, uint32_t cols, uint32_t ld, uint32_t boxRows,
+              CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeFn fn = encode_fn();
     if (!fn) return false;
     const cuuint64_t dims[2] = {cols, rows};
@@ -326,7 +550,7 @@ bool make_map(CUtensorMap *map, const float *ptr, uint64_t rows, uint32_t cols, 
     const cuuint32_t box[2] = {(cuuint32_t)BK, boxRows};
     const cuuint32_t estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -383,6 +607,66 @@ int launch_bn(const float *A, uint32_t lda, uint64_t M, const float *W, uint32_t
 }
 
 }  // namespace
+
+namespace {
+
+template <int BN>
+int launch_tn_bn(const float *A, uint32_t lda, uint32_t Mpad, const float *G, uint64_t K, float *C, float *ws,
+                 size_t ws_floats, cudaStream_t s) {
+    using L = SmemLayoutTN<BN>;
+    const uint32_t mtiles = (Mpad + BM - 1) / BM;
+    const size_t cfloats = (size_t)Mpad * BN;
+    // enough splits for one CTA per SM (each holds 192 KB of shared memory), chunks of >= 256 vertices
+    uint64_t nsplit = std::min<uint64_t>(std::max<uint64_t>(1, 148 / mtiles), (K + 255) / 256);
+    nsplit = std::max<uint64_t>(1, std::min<uint64_t>(nsplit, ws_floats / cfloats));
+    uint64_t kchunk = (K + nsplit - 1) / nsplit;
+    kchunk = (kchunk + BK - 1) / BK * BK;
+    nsplit = (K + kchunk - 1) / kchunk;
+    if (ws_floats < cfloats * nsplit) return 0;
+    Cache &c = cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto get_map = [&](const float *p, uint32_t cols, uint32_t ld) -> const CUtensorMap * {
+        auto key = std::make_tuple(p, ld | 0x80000000u, K);  // high bit: 32 x 32 boxes (transposed use)
+        auto it = c.amaps.find(key);
+        if (it == c.amaps.end()) {
+            CUtensorMap m;
+            if (!make_map(&m, p, K, cols, ld, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return nullptr;
+            it = c.amaps.emplace(key, m).first;
+        }
+        return &it->second;
+    };
+    const CUtensorMap *ma = get_map(A, Mpad, lda), *mg = get_map(G, BN, BN);
+    if (!ma || !mg) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_tn_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kTotal) != cudaSuccess)
+            return -1;
+        attr_set = true;
+    }
+    dim3 grid(mtiles, (unsigned)nsplit);
+    gemm_tn_tc_kernel<BN><<<grid, kThreads, L::kTotal, s>>>(*ma, *mg, nsplit > 1 ? ws : C, BN, Mpad, K, kchunk, cfloats);
+    int launches = 1;
+    if (nsplit > 1) {
+        const size_t n4 = cfloats / 4;
+        tn_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4 *>(ws),
+                                                                     reinterpret_cast<float4 *>(C), n4, n4, (int)nsplit);
+        ++launches;
+    }
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return launches;
+}
+
+}  // namespace
+
+int launch_gemm_tn_tc(const float *A, uint32_t lda, uint32_t Mpad, const float *G, uint32_t ldg, uint64_t K, float *C,
+                      uint32_t ldc, float *ws, size_t ws_floats, cudaStream_t s) {
+    // Supported: output pitch == G's pitch == 64 or 128, M (padded) a multiple of 32 within A's pitch,
+    // a vertex range worth splitting.  Anything else takes the fp32 SIMT path (dense.cu).
+    if (ldg != ldc || Mpad % 32 != 0 || Mpad == 0 || Mpad > lda || K < 1024 || !ws) return 0;
+    if (ldg == 128) return launch_tn_bn<128>(A, lda, Mpad, G, K, C, ws, ws_floats, s);
+    if (ldg == 64) return launch_tn_bn<64>(A, lda, Mpad, G, K, C, ws, ws_floats, s);
+    return 0;
+}
 
 int launch_gemm_tc(const float *A, uint32_t lda, uint64_t M, const float *W, uint32_t ldw, uint32_t Kpad, float *C,
                    float *C2, uint32_t ldc, int epilogue, cudaStream_t s) {

@@ -298,6 +298,16 @@ class Engine:
         """Enqueue one epoch without reading the statistics back (no synchronisation)."""
         self._check(self._lib.dory_epoch(self._h, None))
 
+    def stats_enqueue(self, slot: int = 0):
+        """Start the device->host copy of the statistics behind everything enqueued so far."""
+        self._check(self._lib.dory_stats_enqueue(self._h, slot))
+
+    def stats_collect(self, slot: int = 0) -> dict:
+        """Wait for that copy (not for later work) and return it."""
+        s = DoryStats()
+        self._check(self._lib.dory_stats_collect(self._h, slot, C.byref(s)))
+        return self._stats(s)
+
     def stats(self) -> dict:
         s = DoryStats()
         self._check(self._lib.dory_get_stats(self._h, C.byref(s)))

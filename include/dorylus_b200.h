@@ -242,6 +242,12 @@ int dory_forward(dory_engine *e, uint32_t layer);
 int dory_backward(dory_engine *e, uint32_t layer);
 int dory_epoch(dory_engine *e, dory_stats *stats /* may be NULL */);
 int dory_get_stats(dory_engine *e, dory_stats *stats);
+/* Stream-ordered read-back for callers that keep several steps in flight (dory_epoch(e, NULL) only
+ * enqueues): dory_stats_enqueue copies the statistics of everything enqueued so far into pinned host
+ * memory BEHIND that work and returns at once; dory_stats_collect waits for that copy alone (not for
+ * later work) and returns it.  slot in 0..3; a slot must be collected before it is enqueued again. */
+int dory_stats_enqueue(dory_engine *e, uint32_t slot);
+int dory_stats_collect(dory_engine *e, uint32_t slot, dory_stats *stats);
 
 /* ---- multi-GPU (replaces CommManager / NodeManager, commmanager/commmanager.cpp:11-279) -------
  * One process per GPU.  Rank 0 calls dory_comm_unique_id, the host distributes the 128 bytes

@@ -343,6 +343,30 @@ def test_prefetch_pipeline_semantics(oracle):
             e.prefetch_tensor(0, "x", ds.feats.astype(np.float64))
 
 
+def test_stream_ordered_stats_readback(oracle):
+    """dory_stats_enqueue / dory_stats_collect: the statistics of step i, read without waiting for
+    step i+1 that is already enqueued; equal to what the blocking dory_epoch returns."""
+    ds = random_dataset(V=700, E_und=5000, dims=[40, 16, 5], seed=41)
+    with gcn_engine(ds) as a, gcn_engine(ds) as b:
+        want = [a.epoch() for _ in range(4)]
+        got = []
+        for i in range(4):
+            b.epoch_async()
+            b.stats_enqueue(i & 1)
+            if i:
+                got.append(b.stats_collect((i - 1) & 1))
+        got.append(b.stats_collect(1))
+        for w, g in zip(want, got):
+            assert g["acc_sum"] == w["acc_sum"] and g["loss_sum"] == w["loss_sum"]
+            assert g["epochs_done"] == w["epochs_done"]
+        with pytest.raises(DoryError):
+            b.stats_collect(0)  # nothing in flight
+        b.stats_enqueue(2)
+        with pytest.raises(DoryError):
+            b.stats_enqueue(2)  # must be collected first
+        b.stats_collect(2)
+
+
 def test_shape_and_state_errors():
     ds = random_dataset(V=100, E_und=300, dims=[8, 4, 2], seed=61)
     e = Engine(ds.dims)

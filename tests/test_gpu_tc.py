@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from helpers import random_dataset, rel_err
-from dorylus_b200.engine import FORWARD, GCN, Engine
+from dorylus_b200.engine import BACKWARD, FORWARD, GCN, Engine
 
 pytestmark = pytest.mark.gpu
 
@@ -36,6 +36,34 @@ def test_forward_apply_tensor_core_path(dims, V):
     assert err_tc < 1e-5 and err_simt < 1e-5
     assert rel_err(out[1][1], np.tanh(z64)) < 1e-5
     assert rel_err(out[1][0], out[0][0]) < 1e-5
+
+
+@pytest.mark.parametrize("dims,V", [([602, 128, 41], 5003), ([128, 64, 64, 25], 4099), ([96, 128, 7], 1025),
+                                    ([602, 128, 41], 40000)],
+                         ids=["reddit", "amazon", "odd", "reddit-40k"])
+def test_weight_gradient_tensor_core_path(dims, V):
+    """dW = AH^T . (aTg * (1 - h^2)): the contraction over the vertices on tcgen05 with MN-major
+    operands (gemm_tn_tc_kernel), vertex counts that are not a multiple of the 32-vertex TMA box and
+    that need several splits, against float64 and against the fp32 CUDA-core path."""
+    ds = random_dataset(V=V, E_und=2 * V, dims=dims, seed=92)
+    rng = np.random.default_rng(6)
+    ah = rng.standard_normal((V, dims[0])).astype(np.float32)
+    aTg = rng.standard_normal((V, dims[1])).astype(np.float32)
+    h = np.tanh(rng.standard_normal((V, dims[1]))).astype(np.float32)
+    out = {}
+    for tc in (0, 1):
+        with _engine(ds, tc) as e:
+            e.set_tensor(0, "ah", ah)
+            e.set_tensor(0, "aTg", aTg)
+            e.set_tensor(0, "h", h)
+            e.applyVertexGCN(e.whole_chunk(1, BACKWARD))  # NNCompute on the incremented chunk: layer 0
+            out[tc] = e.get_weight_grad(0)
+    g64 = aTg.astype(np.float64) * (1.0 - h.astype(np.float64) ** 2)
+    dw64 = ah.astype(np.float64).T @ g64
+    err_simt, err_tc = rel_err(out[0], dw64), rel_err(out[1], dw64)
+    print("dims", dims, "V", V, "dW rel err vs float64: simt %.2e  tcgen05 3xTF32 %.2e" % (err_simt, err_tc))
+    assert err_tc < 1e-5 and err_simt < 1e-5
+    assert rel_err(out[1], out[0]) < 1e-5
 
 
 def test_epochs_with_tensor_cores_match_oracle(oracle):
