@@ -50,7 +50,7 @@ struct SpmmArgs {
     const float *src;       // [(V+G) x ld] local rows then ghost rows
     float *out;             // [V x ld]
     uint32_t ld;            // common row pitch of src and out, in floats
-    uint32_t nvec;          // row width in float4 units to process (= ld / 4)
+    uint32_t nvec;          // row width in float4 units to process (data columns only, <= ld / 4)
     int self_mode;
     const uint32_t *heavy;  // row ids with degree >= heavy threshold, degree-descending (may be null)
     uint32_t n_heavy;

@@ -130,6 +130,7 @@ struct dory_engine {
     uint32_t src_blocks = 0;  // source windows per aggregation (0 = size from L2, 1 = off)
     uint32_t heavy_degree = kHeavyDegree;
     uint32_t hub_degree = 0;  // rows with more edges get a cluster of 8 CTAs (0 = from the partition's size)
+    uint32_t locality_block = 0;  // rows per block of the locality-preserving row order (0 = from L2)
 
     // Adam (AdamOptimizer.hpp:69-84)
     float beta1 = .9f, beta2 = .999f, eps = 1e-07f, lr_t = 0.f;
@@ -217,7 +218,7 @@ const DevMat *find_tensor(const dory_engine *e, uint32_t layer, const char *name
 }
 
 // Degree-descending row lists (longest-processing-time-first issue order for spmm.cu).
-void build_row_lists(const std::vector<uint64_t> &ptrs, uint32_t heavyDegree, bool keepLocality,
+void build_row_lists(const std::vector<uint64_t> &ptrs, uint32_t heavyDegree, bool keepLocality, uint32_t blockRows,
                      std::vector<uint32_t> &heavy, std::vector<uint32_t> &light) {
     const uint32_t V = (uint32_t)ptrs.size() - 1;
     std::vector<uint32_t> order(V);
@@ -232,9 +233,13 @@ void build_row_lists(const std::vector<uint64_t> &ptrs, uint32_t heavyDegree, bo
     //  - graph without locality in its vertex numbering: plain degree-descending order -- rows that
     //    share a CTA / warp then have near-equal trip counts (a CTA's registers are held until its
     //    longest row ends: natural order cost 13 % on the Reddit shape, degree classes 5 %);
-    //  - graph WITH locality (most edges stay near the diagonal, e.g. community-ordered ids):
-    //    power-of-two degree classes, heaviest class first, natural id order inside a class, which
-    //    keeps neighbours' source rows hot in L2 (-30 % on the Amazon / Friendster shapes).
+    //  - graph WITH locality (most edges stay near the diagonal, e.g. community-ordered ids): blocks
+    //    of `blockRows` consecutive vertices, inside a block power-of-two degree classes (heaviest
+    //    first), inside a class natural id order.  The classes keep the trip counts of a warp's rows
+    //    within 2x; the blocks keep a community's rows together in TIME: with classes over the whole
+    //    graph a community's source rows were fetched from HBM once per class (7.1 GB of DRAM reads
+    //    for 1.5 GB of compulsory bytes on the Friendster shape, profiles/round1_lowdeg.md), with
+    //    blocks the source rows of a block (<= 24 MB) are still in L2 when its next class runs.
     for (uint32_t v : order)
         if ((ptrs[v + 1] - ptrs[v]) >= heavyDegree) heavy.push_back(v);
     if (!keepLocality) {
@@ -248,10 +253,15 @@ void build_row_lists(const std::vector<uint64_t> &ptrs, uint32_t heavyDegree, bo
         while (d >>= 1) ++c;
         return c;
     };
+    blockRows = std::max(blockRows, 1u);
     std::vector<std::vector<uint32_t>> byClass(64);
-    for (uint32_t v = 0; v < V; ++v)
-        if ((ptrs[v + 1] - ptrs[v]) < heavyDegree) byClass[cls(v)].push_back(v);
-    for (int c = 63; c >= 0; --c) light.insert(light.end(), byClass[c].begin(), byClass[c].end());
+    for (uint32_t b0 = 0; b0 < V; b0 += blockRows) {
+        const uint32_t b1 = (uint32_t)std::min<uint64_t>((uint64_t)b0 + blockRows, V);
+        for (auto &c : byClass) c.clear();
+        for (uint32_t v = b0; v < b1; ++v)
+            if ((ptrs[v + 1] - ptrs[v]) < heavyDegree) byClass[cls(v)].push_back(v);
+        for (int c = 63; c >= 0; --c) light.insert(light.end(), byClass[c].begin(), byClass[c].end());
+    }
 }
 
 int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const uint8_t *idx,
@@ -295,7 +305,10 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
         }
         keepLocality = near * 4 >= seen;  // >= 25 % of the edges are near-diagonal
     }
-    build_row_lists(hp, e->heavy_degree, keepLocality, heavy, light);
+    // rows per locality block: their widest gathered slab must fit L2 with room to spare (24 MB)
+    const uint32_t blockRows = e->locality_block ? e->locality_block
+                                                 : std::max<uint32_t>(32768u, (24u << 20) / std::max(16u, e->max_slab_bytes()));
+    build_row_lists(hp, e->heavy_degree, keepLocality, blockRows, heavy, light);
     adj.n_heavy = (uint32_t)heavy.size();
     adj.n_light = (uint32_t)light.size();
     // Hub rows.  The heavy launch keeps ~600 CTAs resident (148 SMs x 4); a row that holds more than
@@ -567,7 +580,9 @@ SpmmArgs spmm_args(const dory_engine *e, const Adjacency &adj, const float *self
     a.src = src.p;
     a.out = out.p;
     a.ld = src.ld;
-    a.nvec = src.ld / 4;
+    // float4 columns that carry data: the padding columns of a row (zero on both sides, never written)
+    // are not gathered -- a quarter of every row at F = 48 / 41 / 100 (pitches 64 / 64 / 128)
+    a.nvec = std::min<uint32_t>(src.ld / 4, (std::max(src.cols, out.cols) + 3) / 4);
     a.self_mode = mode;
     if (low == 0 && up == V) {
         a.heavy = adj.heavy.as<uint32_t>();
@@ -1079,6 +1094,9 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
     } else if (std::strcmp(key, "src_blocks") == 0) {
         if (e->loaded) return fail(e, DORY_ESTATE, "src_blocks must be set before dory_load_partition");
         e->src_blocks = (uint32_t)v;
+    } else if (std::strcmp(key, "locality_block") == 0) {
+        if (e->loaded) return fail(e, DORY_ESTATE, "locality_block must be set before dory_load_partition");
+        e->locality_block = (uint32_t)v;
     } else if (std::strcmp(key, "hub_degree") == 0) {
         if (e->loaded) return fail(e, DORY_ESTATE, "hub_degree must be set before dory_load_partition");
         e->hub_degree = (uint32_t)v;

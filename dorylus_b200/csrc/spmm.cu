@@ -287,7 +287,10 @@ spmm_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32_t nro
 //   * ids / weights: the LG lanes of a group read LG consecutive edges with one load each (a
 //     contiguous 4*LG-byte piece per group) and hand them round by shuffles inside the group; the
 //     NEXT batch of LG is requested before the current one is gathered, so the id latency is off the
-//     dependent chain id -> address -> row;
+//     dependent chain id -> address -> row.  These loads allocate in L1 with the default L2 policy:
+//     a group consumes its row's 128 B line of ids 16 B at a time over several iterations, and with
+//     the streaming (no-allocate, evict-first) loads of the warp-per-row kernel every piece went back
+//     to HBM -- 7.1 GB of DRAM reads for 1.5 GB of compulsory bytes (profiles/round1_lowdeg.md);
 //   * U gathers are in flight per group before their FMAs.
 template <int LG, int VEC, int U, int OCC>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, OCC)
@@ -302,7 +305,6 @@ spmm_group_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32
     const float4 *__restrict__ src4 = reinterpret_cast<const float4 *>(a.src);
     const uint32_t ld4 = a.ld >> 2;
     const uint64_t pol_keep = policy_evict_last();
-    const uint64_t pol_stream = policy_evict_first();
     uint64_t e = 0, e_end = 0;
     if (live) {
         const uint64_t pbase = (uint64_t)row * a.ptr_stride + a.ptr_off;
@@ -312,8 +314,8 @@ spmm_group_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32
     uint32_t s_n = 0;
     float w_n = 0.f;
     if (e + l < e_end) {
-        s_n = ld_stream_u32(a.idx + e + l, pol_stream);
-        w_n = ld_stream_f32(a.vals + e + l, pol_stream);
+        s_n = __ldg(a.idx + e + l);
+        w_n = __ldg(a.vals + e + l);
     }
     bool act[VEC];
     float4 acc[VEC];
@@ -341,8 +343,8 @@ spmm_group_kernel(const SpmmArgs a, const uint32_t *__restrict__ rowlist, uint32
         s_n = 0;
         w_n = 0.f;
         if (e + LG + l < e_end) {
-            s_n = ld_stream_u32(a.idx + e + LG + l, pol_stream);
-            w_n = ld_stream_f32(a.vals + e + LG + l, pol_stream);
+            s_n = __ldg(a.idx + e + LG + l);
+            w_n = __ldg(a.vals + e + LG + l);
         }
 #pragma unroll
         for (int k0 = 0; k0 < LG; k0 += U) {

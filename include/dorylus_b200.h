@@ -124,6 +124,10 @@ int dory_sync(dory_engine *e);
  *   "row_order"             issue order of the remaining rows: 1 = degree-descending, 2 = power-of-two
  *                           degree classes in vertex-id order (keeps the numbering's locality),
  *                           0 = decide from the share of near-diagonal edges (set before load).
+ *   "locality_block"        rows per block of the locality-preserving order (row_order 2): degree
+ *                           classes are formed inside blocks of this many consecutive vertices so that
+ *                           a block's source rows stay in L2 across its classes (0 = 24 MB worth of
+ *                           the widest gathered slab; set before load).
  *   "tensor_cores"          1: run H.W on tcgen05 (3xTF32, fp32-level accuracy) when the shape
  *                           qualifies; 0: always the fp32 CUDA-core GEMM. */
 int dory_set_option(dory_engine *e, const char *key, const char *value);

@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--locality", type=float, default=0.0, help="fraction of edges kept inside a community block")
     ap.add_argument("--communities", type=int, default=1)
     ap.add_argument("--out", default="")
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value set before load (repeatable)")
     args = ap.parse_args()
     if args.V:
         spec = synth.GraphSpec(args.name, args.V, args.E, [int(x) for x in args.dims.split(",")], seed=77, sigma=args.sigma,
@@ -56,7 +57,11 @@ def main():
         peak = float(json.load(open(p))["hbm_gbs"])
     rng = np.random.default_rng(0)
     out = dict(name=spec.name, gnn=args.gnn, V=V, E=E, dims=dims, hbm_peak_gbs=peak, layers=[])
+    out["options"] = args.opt
     with Engine(dims, gnn, flags=flags) as e:
+        for kv in args.opt:
+            k, v = kv.split("=", 1)
+            e.set_option(k, v)
         e.load_partition(image)
         del image
         feats = synth.generate_features(V, dims[0], 3)
