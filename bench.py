@@ -279,7 +279,7 @@ def main():
     eng.init_weights()
     if world > 1:
         ddist.setup_engine_comm(eng, graph, rank, world, peer_memory=args.exchange == "p2p")
-        cfg_common["ghost_exchange"] = ("one store-through-NVLink kernel into peer ghost blocks (CUDA IPC) + 2 NCCL barriers"
+        cfg_common["ghost_exchange"] = ("one store-through-NVLink kernel into peer ghost blocks (CUDA IPC) + 1 NCCL barrier"
                                         if args.exchange == "p2p" else "pack -> NCCL all-to-all-v -> unpack")
         cfg_common["layer0_ghost_rows"] = "shipped over NVLink from the owning rank every step (not uploaded)"
     upload_inputs()
