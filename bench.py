@@ -58,6 +58,11 @@ def build_workload(name: str, world: int, rank: int):
     return spec, image, graph, feats, labels, n_edges, cut
 
 
+def alg_flops_spmm(V_p, E_p, F):
+    """fp32 flops of one aggregation: one FMA per (edge, feature) plus the self term."""
+    return 2 * F * (E_p + V_p)
+
+
 def alg_bytes_spmm(V_p, G_p, E_p, F):
     """ALGORITHMIC (compulsory) bytes of one aggregation: every distinct source
     row read once, output written once, fp32 values + u32 indices, u64 offsets, fp32 self norm."""
@@ -383,6 +388,7 @@ def main():
         dist.all_reduce(t)
         h2d_all = int(t.item())
 
+    fma_peak = eng.measure_fma_peak() if rank == 0 else None  # TFLOP/s, non-tensor fp32 (a few ms)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         feats_again = synth.generate_features(spec.num_vertices, dims[0], spec.seed + 1, dense=True)
@@ -392,6 +398,7 @@ def main():
         peak, peak_src = measured_peaks()
         V_p, G_p, E_p = graph.local_vtx_cnt, graph.src_ghost_cnt, graph.local_in_edge_cnt
         b_alg = alg_bytes_spmm(V_p, G_p, E_p, dims[0])
+        f_alg = alg_flops_spmm(V_p, E_p, dims[0])
         achieved = b_alg / (agg_ms["L0_fwd"] * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
@@ -413,6 +420,14 @@ def main():
                          "kernel": "spmm_kernel (layer-0 forward aggregation, F=602: per source window one "
                                    "CTA-per-row launch + one warp-per-row launch)",
                          "algorithmic_bytes": b_alg,
+                         # t_roof = max(B_alg / BW_hbm, F_alg / P_fp32); this aggregation's
+                         # arithmetic intensity (68 flop/B) puts it on the fp32-FMA side of the classic roofline
+                         "algorithmic_flops": f_alg, "fp32_fma_peak_tflops": fma_peak,
+                         "t_roof_ms": 1e3 * max(b_alg / (peak * 1e9), f_alg / (fma_peak * 1e12)),
+                         "frac_of_t_roof": max(b_alg / (peak * 1e9), f_alg / (fma_peak * 1e12)) / (agg_ms["L0_fwd"] * 1e-3),
+                         "gathered_tb_per_s": 4.0 * dims[0] * E_p / (agg_ms["L0_fwd"] * 1e-3) / 1e12,
+                         "binding": "L2->SM gather bandwidth: E*F*4 bytes cross it whatever HBM does "
+                                    "(lts__throughput 76-80 % of peak on every launch, profiles/round1_final2_full.md)",
                          "note": "min-traffic model; the gather itself moves E*F*4 bytes L2->SM (DESIGN.md §5)"},
             "e2e": {"value": n_spmm * E_global * args.steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": 8 * n_gpus,

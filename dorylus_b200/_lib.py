@@ -98,6 +98,7 @@ SYMBOLS = {
     "dory_event_record": (C.c_int, [_P, _u32]),
     "dory_event_elapsed_ms": (C.c_int, [_P, _u32, _u32, _f32p]),
     "dory_flush_l2": (C.c_int, [_P, C.c_size_t]),
+    "dory_measure_fma_peak": (C.c_int, [_P, _f32p]),
 }
 
 _lib = None

@@ -120,6 +120,8 @@ int launch_adam(float *w, const float *grad, float *m, float *v, size_t n, float
                 float beta2, float eps, cudaStream_t s);
 
 int launch_fill(float *p, size_t n, float value, cudaStream_t s);
+// fp32 FMA micro-benchmark (bench.py's compute roof): blocks x 256 threads x iters x 8 FMAs
+int launch_fma_peak(float *sink, int iters, unsigned blocks, cudaStream_t s);
 // dst[r*ldd + c] = src[r*lds + c] for c < cols (changes the row pitch; either side may be dense).
 int launch_repitch(const float *src, uint32_t lds, float *dst, uint32_t ldd, uint64_t rows, uint32_t cols,
                    cudaStream_t s);

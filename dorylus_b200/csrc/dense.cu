@@ -271,6 +271,23 @@ __global__ void adam_kernel(float *__restrict__ w, const float *__restrict__ gra
     w[i] -= delta;
 }
 
+// fp32 FMA micro-benchmark: 8 independent accumulator chains per thread, `iters` x 8 FMAs each;
+// the result is stored so that the loop cannot be removed.  2 * 8 * iters * threads flops.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float *__restrict__ sink, int iters, float a, float b) {
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (float)(threadIdx.x + k) * 1e-3f;
+#pragma unroll 16  // 128 FFMA per trip: loop control is ~2 % of the issue slots
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = fmaf(x[k], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += x[k];
+    if (s == 123.456f) sink[0] = s;  // practically never true; keeps the chains alive
+}
+
 __global__ void fill_kernel(float *__restrict__ p, size_t n, float value) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = value;
@@ -364,6 +381,11 @@ int launch_adam(float *w, const float *grad, float *m, float *v, size_t n, float
                 float beta2, float eps, cudaStream_t s) {
     if (n == 0) return 0;
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, grad, m, v, n, lr_t, beta1, beta2, eps);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_fma_peak(float *sink, int iters, unsigned blocks, cudaStream_t s) {
+    fma_peak_kernel<<<blocks, 256, 0, s>>>(sink, iters, 0.999f, 1e-3f);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

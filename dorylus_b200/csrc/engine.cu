@@ -1700,4 +1700,33 @@ int dory_flush_l2(dory_engine *e, size_t bytes) {
     return DORY_OK;
 }
 
+int dory_measure_fma_peak(dory_engine *e, float *tflops) {
+    if (!e || !tflops) return DORY_EINVAL;
+    if (e->flush.bytes < 256) CU(e->flush.alloc(256));
+    int dev = 0, sms = 148;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const unsigned blocks = (unsigned)sms * 8;  // 8 CTAs of 256 threads per SM: all 64 warp slots
+    const int iters = 1 << 16;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    LAUNCHED(launch_fma_peak(e->flush.as<float>(), 1 << 10, blocks, e->stream));  // warm-up
+    float best = 0.f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CU(cudaEventRecord(a, e->stream));
+        LAUNCHED(launch_fma_peak(e->flush.as<float>(), iters, blocks, e->stream));
+        CU(cudaEventRecord(b, e->stream));
+        CU(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        const double flops = 2.0 * 8.0 * iters * 256.0 * blocks;
+        best = std::max(best, (float)(flops / (ms * 1e-3) / 1e12));
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops = best;
+    return DORY_OK;
+}
+
 }  // extern "C"

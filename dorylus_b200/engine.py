@@ -375,5 +375,11 @@ class Engine:
         self._check(self._lib.dory_event_elapsed_ms(self._h, a, b, C.byref(ms)))
         return float(ms.value)
 
+    def measure_fma_peak(self) -> float:
+        """Non-tensor fp32 FMA throughput of this GPU in TFLOP/s (register-only FMA loop)."""
+        t = C.c_float()
+        self._check(self._lib.dory_measure_fma_peak(self._h, C.byref(t)))
+        return float(t.value)
+
     def flush_l2(self, nbytes: int = 256 << 20):
         self._check(self._lib.dory_flush_l2(self._h, nbytes))

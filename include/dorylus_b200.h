@@ -292,6 +292,9 @@ int dory_event_elapsed_ms(dory_engine *e, uint32_t slot_start, uint32_t slot_sto
 /* Writes `bytes` of HBM on the engine's stream (bench.py flushes the 126 MB L2 between timed
  * iterations with this). */
 int dory_flush_l2(dory_engine *e, size_t bytes);
+/* Non-tensor fp32 FMA throughput of this GPU (TFLOP/s), measured with a register-only FMA loop on
+ * every SM: the compute roof bench.py quotes beside the HBM roof. */
+int dory_measure_fma_peak(dory_engine *e, float *tflops);
 
 #ifdef __cplusplus
 }
