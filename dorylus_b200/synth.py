@@ -30,6 +30,11 @@ CONFIGS = {
     "cora": GraphSpec("cora", 2708, 10556, [1433, 16, 7], seed=1, sigma=0.6),
     # BASELINE.json configs[1]/[2]: Reddit (232K verts, 114M edges, 602 feat), dims run/reddit.config
     "reddit": GraphSpec("reddit", 232965, 114615892, [602, 128, 41], seed=11, sigma=1.0),
+    # the same degree sequence with community structure (not a BASELINE config; DESIGN.md section 11:
+    # what a tile-reuse aggregation kernel would be measured on): 80 % of the edges stay inside one
+    # of 1,024 contiguous communities of ~227 vertices
+    "reddit-communities": GraphSpec("reddit-communities", 232965, 114615892, [602, 128, 41], seed=11, sigma=1.0,
+                                    locality=0.8, communities=1024),
     # scaled-down Reddit shape for parity tests that run the CPU oracle in seconds
     "reddit-small": GraphSpec("reddit-small", 8192, 8192 * 96, [602, 128, 41], seed=21, sigma=1.0),
     "reddit-tiny": GraphSpec("reddit-tiny", 600, 600 * 24, [602, 128, 41], seed=31, sigma=0.8),
