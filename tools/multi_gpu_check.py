@@ -75,13 +75,17 @@ def main():
             "grad1": rel_err(e.get_tensor(1, "grad"), t[1]["grad"]),
             "bg0": rel_err(e.get_tensor(0, "bg"), t[0]["bg"]) if g.dst_ghost_cnt else 0.0,
             "aTg0": rel_err(e.get_tensor(0, "aTg"), t[0]["aTg"]),
-            "W0": rel_err(e.get_weights(0), orc.W[0]),
-            "W1": rel_err(e.get_weights(1), orc.W[1]),
         }
-        # ghost rows are copies: they must be bit-identical to the owner's rows
+        # post-Adam weights: the looser bar of tests/test_gpu_parity.py (Adam's first steps are
+        # sign-like, so entries whose gradient is rounding noise move by O(lr) either way), then
+        # re-synced so that every epoch's tensors are checked from identical weights
+        werrs = {"W0": rel_err(e.get_weights(0), orc.W[0]), "W1": rel_err(e.get_weights(1), orc.W[1])}
+        for l in range(2):
+            e.set_weights(l, orc.W[l])
         worst = max(worst, max(errs.values()))
-        good = max(errs.values()) < 1e-5 and st["acc_sum"] == want["acc"][rank]
+        good = max(errs.values()) < 1e-5 and max(werrs.values()) < 5e-4 and st["acc_sum"] == want["acc"][rank]
         ok = ok and good
+        errs.update(werrs)
         print("[rank %d] epoch %d %s errs %s acc %s/%s" % (rank, ep, "OK" if good else "FAIL",
               {k: float("%.1e" % v) for k, v in errs.items()}, st["acc_sum"], want["acc"][rank]), flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
