@@ -1192,6 +1192,34 @@ int dory_preprocess_dir(const char *dir, uint32_t part, uint32_t n_parts, int un
     return ok ? DORY_OK : fail(e, DORY_EFORMAT, "short write on %s%s", dir, name);
 }
 
+int dory_read_features(const char *dataset_dir, const char *features_file, const void *graph_bin, size_t len,
+                       uint32_t node_id, uint32_t n_features, float *local_rows, float *ghost_rows) {
+    if (!dataset_dir || !features_file || !graph_bin || !local_rows) {
+        g_create_error = "dory_read_features: null argument";
+        return DORY_EINVAL;
+    }
+    dory::PartitionView g;
+    std::string m = dory::parse_partition(graph_bin, len, g);
+    if (m.empty() && g.srcGhostCnt && !ghost_rows) m = "dory_read_features: partition has ghost rows but ghost_rows is null";
+    if (m.empty()) m = dory::read_features(dataset_dir, features_file, g, node_id, n_features, local_rows, ghost_rows);
+    if (m.empty()) return DORY_OK;
+    g_create_error = m;
+    return DORY_EFORMAT;
+}
+
+int dory_read_labels(const char *labels_file, const void *graph_bin, size_t len, uint32_t kinds, float *onehot) {
+    if (!labels_file || !graph_bin || !onehot) {
+        g_create_error = "dory_read_labels: null argument";
+        return DORY_EINVAL;
+    }
+    dory::PartitionView g;
+    std::string m = dory::parse_partition(graph_bin, len, g);
+    if (m.empty()) m = dory::read_labels(labels_file, g, kinds, onehot);
+    if (m.empty()) return DORY_OK;
+    g_create_error = m;
+    return DORY_EFORMAT;
+}
+
 int dory_partition_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_edges, uint32_t n_vertices,
                          uint32_t n_parts, uint32_t passes, int32_t *parts, uint64_t *edge_cut) {
     const std::string m = dory::partition_edges(src, dst, n_edges, n_vertices, n_parts, passes ? passes : 8, parts, edge_cut);

@@ -11,6 +11,8 @@
 // high-water mark is the image itself plus O(V_global) integers.
 #include "loader.h"
 
+#include <fstream>
+
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
@@ -342,6 +344,86 @@ std::string preprocess_partition(const EdgeList &el, const int32_t *parts, uint3
             if (undirected) place(d, s);
         }
     });
+    return "";
+}
+
+// == Engine::readFeaturesFile (engine/utils.cpp:486-552) for the partition in `g`: the per-partition
+// cache <dir>feats<F0>.<id>.bin (local rows, then source-ghost rows) wins when it exists; otherwise
+// the global features file is streamed once (header {uint32 numFeatures}, rows in global-vertex
+// order), rows of local vertices and of source ghosts are picked out, and the cache is written.
+std::string read_features(const std::string &dir, const std::string &featuresFile, const PartitionView &g,
+                          uint32_t nodeId, uint32_t F, float *local, float *ghost) {
+    const size_t V = g.localVtxCnt, Gs = g.srcGhostCnt;
+    const std::string cache = dir + "feats" + std::to_string(F) + "." + std::to_string(nodeId) + ".bin";
+    {
+        std::ifstream in(cache, std::ios::binary);
+        if (in.good()) {
+            in.read(reinterpret_cast<char *>(local), (std::streamsize)(sizeof(float) * V * F));
+            if (Gs) in.read(reinterpret_cast<char *>(ghost), (std::streamsize)(sizeof(float) * Gs * F));
+            if (!in.good()) return "feature cache " + cache + " is shorter than the partition needs";
+            return "";
+        }
+    }
+    std::ifstream in(featuresFile, std::ios::binary);
+    if (!in.good()) return "cannot open features file " + featuresFile;
+    uint32_t nf = 0;
+    in.read(reinterpret_cast<char *>(&nf), 4);
+    if (!in.good() || nf != F) return "features file: numFeatures does not match the layer config";
+    // where does global vertex v go?  local id, or V + ghost slot (graph.srcGhostVtcs), or nowhere
+    std::vector<uint32_t> where(g.globalVtxCnt, kNone);
+    for (size_t l = 0; l < V; ++l) {
+        const uint32_t gv = rd<uint32_t>(g.localToGlobal + 4 * l);
+        if (gv >= g.globalVtxCnt) return "graph image: local vertex id out of range";
+        where[gv] = (uint32_t)l;
+    }
+    for (size_t k = 0; k < Gs; ++k) {
+        const uint32_t gv = rd<uint32_t>(g.srcGhostPairs + 8 * k), lv = rd<uint32_t>(g.srcGhostPairs + 8 * k + 4);
+        if (gv >= g.globalVtxCnt || lv < V || lv - V >= Gs) return "graph image: ghost vertex id out of range";
+        where[gv] = lv;  // the ghost test comes first in the reference (utils.cpp:520); ids are disjoint anyway
+    }
+    std::vector<float> row(F);
+    uint32_t gvid = 0;
+    while (in.read(reinterpret_cast<char *>(row.data()), (std::streamsize)(sizeof(float) * F))) {
+        if (gvid >= g.globalVtxCnt) return "features file has more rows than the graph has vertices";
+        const uint32_t w = where[gvid];
+        if (w != kNone) std::memcpy((w < V ? local + (size_t)w * F : ghost + (size_t)(w - V) * F), row.data(), sizeof(float) * F);
+        ++gvid;
+    }
+    if (gvid != g.globalVtxCnt) return "features file has fewer rows than the graph has vertices";
+    std::ofstream out(cache, std::ios::binary);  // utils.cpp:537-551 (a failure to write is only logged there)
+    if (out.good()) {
+        out.write(reinterpret_cast<const char *>(local), (std::streamsize)(sizeof(float) * V * F));
+        if (Gs) out.write(reinterpret_cast<const char *>(ghost), (std::streamsize)(sizeof(float) * Gs * F));
+    }
+    return "";
+}
+
+// == Engine::readLabelsFile (engine/utils.cpp:559-596): header {uint32 labelKinds}, one uint32 per
+// global vertex; local vertices get a one-hot row of `kinds` floats.
+std::string read_labels(const std::string &labelsFile, const PartitionView &g, uint32_t kinds, float *onehot) {
+    std::ifstream in(labelsFile, std::ios::binary);
+    if (!in.good()) return "cannot open labels file " + labelsFile;
+    uint32_t k = 0;
+    in.read(reinterpret_cast<char *>(&k), 4);
+    if (!in.good() || k != kinds) return "labels file: labelKinds does not match the layer config";
+    const size_t V = g.localVtxCnt;
+    std::vector<uint32_t> g2l(g.globalVtxCnt, kNone);
+    for (size_t l = 0; l < V; ++l) {
+        const uint32_t gv = rd<uint32_t>(g.localToGlobal + 4 * l);
+        if (gv >= g.globalVtxCnt) return "graph image: local vertex id out of range";
+        g2l[gv] = (uint32_t)l;
+    }
+    std::memset(onehot, 0, sizeof(float) * V * kinds);
+    uint32_t gvid = 0, cur = 0;
+    while (in.read(reinterpret_cast<char *>(&cur), 4)) {
+        if (gvid >= g.globalVtxCnt) return "labels file has more entries than the graph has vertices";
+        if (g2l[gvid] != kNone) {
+            if (cur >= kinds) return "label " + std::to_string(cur) + " out of range at vertex " + std::to_string(gvid);
+            onehot[(size_t)g2l[gvid] * kinds + cur] = 1.f;
+        }
+        ++gvid;
+    }
+    if (gvid != g.globalVtxCnt) return "labels file has fewer entries than the graph has vertices";
     return "";
 }
 

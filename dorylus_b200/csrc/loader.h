@@ -40,4 +40,10 @@ std::string preprocess_partition(const EdgeList &edges, const int32_t *parts, ui
                                  uint32_t part, uint32_t nParts, bool undirected,
                                  std::vector<uint8_t> &image);
 
+// == Engine::readFeaturesFile incl. the feats<F0>.<id>.bin cache / Engine::readLabelsFile
+// (engine/utils.cpp:486-596) for one partition.  local: [V x F], ghost: [Gs x F], onehot: [V x kinds].
+std::string read_features(const std::string &dir, const std::string &featuresFile, const PartitionView &g,
+                          uint32_t nodeId, uint32_t F, float *local, float *ghost);
+std::string read_labels(const std::string &labelsFile, const PartitionView &g, uint32_t kinds, float *onehot);
+
 }  // namespace dory

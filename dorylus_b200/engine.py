@@ -81,6 +81,46 @@ def preprocess_dir(dataset_dir: str, part: int, num_parts: int, undirected: bool
     return d + "graph.%d.bin" % part
 
 
+def _image_buffer(image):
+    if isinstance(image, np.ndarray):
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        return image, image.ctypes.data_as(C.c_void_p), image.size
+    buf = (C.c_char * len(image)).from_buffer_copy(image)
+    return buf, C.cast(buf, C.c_void_p), len(image)
+
+
+def read_features(dataset_dir: str, features_file: str, image, node_id: int, num_features: int):
+    """== Engine::readFeaturesFile for the partition `image` (graph.<id>.bin bytes): (local rows,
+    source-ghost rows); reads / writes the reference's feats<F0>.<id>.bin cache.  Host only."""
+    from .formats import parse_graph_bin
+
+    lib = _lib.load()
+    g = parse_graph_bin(image)
+    keep, ptr, n = _image_buffer(image)
+    local = np.empty((g.local_vtx_cnt, num_features), dtype=np.float32)
+    ghost = np.empty((g.src_ghost_cnt, num_features), dtype=np.float32)
+    d = dataset_dir if dataset_dir.endswith("/") else dataset_dir + "/"
+    rc = lib.dory_read_features(d.encode(), features_file.encode(), ptr, n, node_id, num_features,
+                                local.ctypes.data_as(_f32p), ghost.ctypes.data_as(_f32p) if ghost.size else None)
+    if rc != 0:
+        raise DoryError(rc, lib.dory_last_error(None).decode())
+    return local, ghost
+
+
+def read_labels(labels_file: str, image, kinds: int) -> np.ndarray:
+    """== Engine::readLabelsFile: one-hot [V_p x kinds] for the partition `image`.  Host only."""
+    from .formats import parse_graph_bin
+
+    lib = _lib.load()
+    g = parse_graph_bin(image)
+    keep, ptr, n = _image_buffer(image)
+    onehot = np.empty((g.local_vtx_cnt, kinds), dtype=np.float32)
+    rc = lib.dory_read_labels(labels_file.encode(), ptr, n, kinds, onehot.ctypes.data_as(_f32p))
+    if rc != 0:
+        raise DoryError(rc, lib.dory_last_error(None).decode())
+    return onehot
+
+
 def partition_edges(src: np.ndarray, dst: np.ndarray, num_vertices: int, num_parts: int, passes: int = 0):
     """== inputs/partitioner.cpp without METIS: owner per global vertex (int32) and the edge cut
     (records whose endpoints have different owners).  Host only."""

@@ -8,11 +8,13 @@
 //
 //   dorylus_b200_run --datasetdir D/ --featuresfile F --labelsfile L --layerfile C
 //                    [--numepochs 10] [--lr 0.01] [--gnn GCN|GAT] [--undirected 0]
-//                    [--pipeline 1 [--numlambdas N] [--targetacc A] [--switchthreshold T]]
+//                    [--pipeline 1 [--numlambdas N] [--targetacc A] [--switchthreshold T]] [--dry-run 1]
 //
 // --pipeline 1 drives the epochs through host/saga_pipeline.hpp -- the reference's chunk queues,
 // priority order, barriers, early-stop state machine and <EM> report (engine/ops/pipeline.cpp) --
 // instead of dory_epoch; --numlambdas is the number of chunks per partition (numLambdasForward).
+// --dry-run 1 stops after the host-side half (preprocess, features / labels incl. the reference's
+// feats<F0>.<id>.bin cache) and prints what it read: no GPU needed.
 //
 // Prints one line per epoch in the weight server's format (weightserver.cpp:258-262:
 // "Epoch %u, acc: %.3f, loss: %.3f") plus the epoch time the graph server reports
@@ -49,7 +51,7 @@ bool read_file(const std::string &path, std::vector<char> &out) {
 
 int main(int argc, char **argv) {
     std::string dir, featuresFile, labelsFile, layerFile, gnn = "GCN";
-    unsigned epochs = 10, undirected = 0, pipeline = 0, numLambdas = 1;
+    unsigned epochs = 10, undirected = 0, pipeline = 0, numLambdas = 1, dryRun = 0;
     float lr = 0.01f, targetAcc = 1.1f, switchThreshold = 0.02f;
     for (int i = 1; i + 1 < argc; i += 2) {
         const std::string k = argv[i], v = argv[i + 1];
@@ -62,6 +64,7 @@ int main(int argc, char **argv) {
         else if (k == "--gnn") gnn = v;
         else if (k == "--undirected") undirected = (unsigned)std::atoi(v.c_str());
         else if (k == "--pipeline") pipeline = (unsigned)std::atoi(v.c_str());
+        else if (k == "--dry-run") dryRun = (unsigned)std::atoi(v.c_str());
         else if (k == "--numlambdas") numLambdas = (unsigned)std::max(1, std::atoi(v.c_str()));
         else if (k == "--targetacc") targetAcc = (float)std::atof(v.c_str());
         else if (k == "--switchthreshold") switchThreshold = (float)std::atof(v.c_str());
@@ -101,50 +104,41 @@ int main(int argc, char **argv) {
     cfg.device = 0;
     cfg.learning_rate = lr;
 
-    dory_engine *e = nullptr;
-    if (dory_create(&e, &cfg) != DORY_OK) die(nullptr, "dory_create");
-
+    // Engine::init order (engine/engine.cpp:62-100): partition image (preprocess when absent), then
+    // features and labels.  Everything up to dory_create is host-only.
     std::vector<char> image;
     if (!read_file(dir + "graph.0.bin", image)) {
         std::fprintf(stderr, "[ Node   0 ]  Preprocessing... Output to %sgraph.0.bin\n", dir.c_str());
         if (dory_preprocess_dir(dir.c_str(), 0, 1, (int)undirected) != DORY_OK) die(nullptr, "dory_preprocess_dir");
         if (!read_file(dir + "graph.0.bin", image)) die(nullptr, "cannot read graph.0.bin");
     }
-    if (dory_load_partition(e, image.data(), image.size()) != DORY_OK) die(e, "dory_load_partition");
-    uint64_t cnt[7];
-    dory_graph_counts(e, cnt);
-    const uint64_t V = cnt[0];
+    if (image.size() < 16) die(nullptr, "graph.0.bin is too short");
+    uint32_t hdr[4];  // localVtxCnt, globalVtxCnt, srcGhostCnt, dstGhostCnt (graph/graph.cpp:204-207)
+    std::memcpy(hdr, image.data(), sizeof hdr);
+    const uint64_t V = hdr[0], Gs = hdr[2];
+    const uint32_t F0 = cfg.dims[0], C = cfg.dims[cfg.n_layers];
 
-    // readFeaturesFile / readLabelsFile, engine/utils.cpp:486-596 (single partition: local order == global order)
-    std::vector<char> raw;
-    if (!read_file(featuresFile, raw) || raw.size() < 4) die(nullptr, "cannot read features file");
-    uint32_t nf;
-    std::memcpy(&nf, raw.data(), 4);
-    if (nf != cfg.dims[0] || raw.size() != 4 + (size_t)V * nf * 4) {
-        std::fprintf(stderr, "features file does not match layer config / vertex count\n");
-        return EXIT_FAILURE;
+    // readFeaturesFile (with its feats<F0>.<id>.bin cache) / readLabelsFile, engine/utils.cpp:486-596
+    std::vector<float> feats(V * F0), ghostFeats(Gs * F0), onehot(V * C);
+    if (dory_read_features(dir.c_str(), featuresFile.c_str(), image.data(), image.size(), 0, F0, feats.data(),
+                           Gs ? ghostFeats.data() : nullptr) != DORY_OK)
+        die(nullptr, "dory_read_features");
+    if (dory_read_labels(labelsFile.c_str(), image.data(), image.size(), C, onehot.data()) != DORY_OK)
+        die(nullptr, "dory_read_labels");
+    if (dryRun) {  // host-side half only: what was read, without touching a GPU
+        double fs = 0, ls = 0;
+        for (float x : feats) fs += x;
+        for (size_t i = 0; i < onehot.size(); ++i) ls += onehot[i] * (double)(i % C);
+        std::printf("dry run: V %llu ghosts %llu F0 %u classes %u feature_sum %.6f label_sum %.1f\n",
+                    (unsigned long long)V, (unsigned long long)Gs, F0, C, fs, ls);
+        return EXIT_SUCCESS;
     }
+
+    dory_engine *e = nullptr;
+    if (dory_create(&e, &cfg) != DORY_OK) die(nullptr, "dory_create");
+    if (dory_load_partition(e, image.data(), image.size()) != DORY_OK) die(e, "dory_load_partition");
     const char *in_name = cfg.gnn_type == DORY_GCN ? "x" : "h";
-    if (dory_set_tensor(e, 0, in_name, reinterpret_cast<const float *>(raw.data() + 4), V, nf) != DORY_OK)
-        die(e, "dory_set_tensor(features)");
-    if (!read_file(labelsFile, raw) || raw.size() < 4) die(nullptr, "cannot read labels file");
-    uint32_t kinds;
-    std::memcpy(&kinds, raw.data(), 4);
-    const uint32_t C = cfg.dims[cfg.n_layers];
-    if (kinds != C || raw.size() != 4 + (size_t)V * 4) {
-        std::fprintf(stderr, "labels file does not match layer config / vertex count\n");
-        return EXIT_FAILURE;
-    }
-    std::vector<float> onehot((size_t)V * C, 0.f);
-    for (uint64_t v = 0; v < V; ++v) {
-        uint32_t c;
-        std::memcpy(&c, raw.data() + 4 + 4 * v, 4);
-        if (c >= C) {
-            std::fprintf(stderr, "label %u out of range at vertex %llu\n", c, (unsigned long long)v);
-            return EXIT_FAILURE;
-        }
-        onehot[v * C + c] = 1.f;
-    }
+    if (dory_set_tensor(e, 0, in_name, feats.data(), V, F0) != DORY_OK) die(e, "dory_set_tensor(features)");
     if (dory_set_tensor(e, cfg.n_layers - 1, "lab", onehot.data(), V, C) != DORY_OK) die(e, "dory_set_tensor(labels)");
     if (dory_init_weights(e) != DORY_OK) die(e, "dory_init_weights");
 

@@ -145,6 +145,19 @@ int dory_preprocess_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_e
 int dory_preprocess_dir(const char *dir, uint32_t part, uint32_t n_parts, int undirected);
 void dory_free(void *p);
 
+/* ---- dataset inputs (host only) ----------------------------------------------------------------
+ * dory_read_features == Engine::readFeaturesFile (engine/utils.cpp:486-552) for the partition whose
+ * graph.<id>.bin image is passed: if <dataset_dir>feats<F0>.<node_id>.bin exists it is read (local rows,
+ * then source-ghost rows -- the reference's per-partition cache); otherwise the global features file
+ * (uint32 numFeatures, then one row per global vertex) is streamed, the partition's local and ghost
+ * rows are picked out and the cache file is written.  local_rows: [V_p x F0], ghost_rows: [Gs_p x F0]
+ * (may be NULL when the partition has no source ghosts) -- what dory_set_tensor(e, 0, "x" / "fg") takes.
+ * dory_read_labels   == Engine::readLabelsFile (engine/utils.cpp:559-596): one-hot [V_p x kinds] for
+ * dory_set_tensor(e, L-1, "lab").  `dataset_dir` ends with '/'.  Errors: dory_last_error(NULL). */
+int dory_read_features(const char *dataset_dir, const char *features_file, const void *graph_bin, size_t len,
+                       uint32_t node_id, uint32_t n_features, float *local_rows, float *ghost_rows);
+int dory_read_labels(const char *labels_file, const void *graph_bin, size_t len, uint32_t kinds, float *onehot);
+
 /* ---- partitioning (host only) ------------------------------------------------------------------
  * dory_partition_edges == inputs/partitioner.cpp:63-111 (symmetrise the edge list, k-way edge-cut
  * partition with unit vertex weights) with METIS_PartGraphKway replaced by a deterministic

@@ -45,6 +45,27 @@ def write_dataset(ds):
             "--labelsfile", os.path.join(root, "labels.bsnap"), "--layerfile", os.path.join(root, "layers.config")]
 
 
+def test_driver_dry_run_reads_the_dataset_directory():
+    """--dry-run 1: the host-side half of the driver without a GPU -- preprocess graph.0.bin, read
+    features / labels through dory_read_features / dory_read_labels, write the feats<F0>.0.bin cache."""
+    ds = random_dataset(V=300, E_und=1500, dims=[11, 6, 4], seed=79)
+    cmd = write_dataset(ds)
+    d = cmd[2]
+    r = subprocess.run(cmd + ["--dry-run", "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    m = re.search(r"dry run: V (\d+) ghosts (\d+) F0 (\d+) classes (\d+) feature_sum ([-0-9.]+) label_sum ([0-9.]+)", r.stdout)
+    assert m, r.stdout
+    assert (int(m.group(1)), int(m.group(2)), int(m.group(3)), int(m.group(4))) == (300, 0, 11, 4)
+    assert abs(float(m.group(5)) - float(ds.feats.astype(np.float64).sum())) < 1e-3
+    assert float(m.group(6)) == float(ds.labels.sum())
+    assert open(d + "graph.0.bin", "rb").read() == ds.images[0]
+    assert np.array_equal(np.fromfile(d + "feats11.0.bin", dtype=np.float32), ds.feats.ravel())
+    # a second run takes the cache (the features file may be gone, engine/utils.cpp:488-501)
+    r = subprocess.run([c if c != cmd[4] else cmd[4] + ".gone" for c in cmd] + ["--dry-run", "1"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "dry run: V 300" in r.stdout, r.stderr
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("lambdas", [1, 3])
 def test_pipeline_mode_matches_oracle(oracle, lambdas):

@@ -86,3 +86,48 @@ def test_bad_inputs_raise():
         dengine.preprocess_edges(np.array([0], np.uint32), np.array([1], np.uint32), np.array([0, 5, 0, 0], np.int32), 4, 0, 2)
     with pytest.raises(ValueError):
         formats.parse_graph_bin(b"\x00" * 10)
+
+
+def test_read_features_and_labels_like_the_reference(tmp_path):
+    """dory_read_features / dory_read_labels == Engine::readFeaturesFile / readLabelsFile
+    (engine/utils.cpp:486-596): rows of local vertices and of source ghosts picked out of the global
+    files, the feats<F0>.<id>.bin cache written in the reference's layout (local rows, then ghost
+    rows) and -- like the reference -- preferred over the features file once it exists."""
+    from helpers import random_dataset
+    from dorylus_b200.engine import DoryError, read_features, read_labels
+
+    ds = random_dataset(V=700, E_und=4000, dims=[13, 8, 5], P=3, seed=12)
+    d = str(tmp_path) + "/"
+    ffile, lfile = d + "features.bsnap", d + "labels.bsnap"
+    formats.write_features(ffile, ds.feats)
+    formats.write_labels(lfile, ds.labels, 5)
+    for p in range(3):
+        g = ds.graphs[p]
+        loc, gh = read_features(d, ffile, ds.images[p], p, 13)
+        assert np.array_equal(loc, ds.feats[g.local_to_global])
+        assert np.array_equal(gh, ds.feats[g.src_ghost_gvid])
+        cache = d + "feats13.%d.bin" % p
+        raw = np.fromfile(cache, dtype=np.float32)
+        assert raw.size == (g.local_vtx_cnt + g.src_ghost_cnt) * 13
+        assert np.array_equal(raw, np.concatenate([loc.ravel(), gh.ravel()]))
+        assert np.array_equal(read_labels(lfile, ds.images[p], 5), ds.onehot[g.local_to_global])
+    # the cache wins: change it, the features file is no longer consulted (utils.cpp:488-501)
+    g = ds.graphs[1]
+    fake = np.arange((g.local_vtx_cnt + g.src_ghost_cnt) * 13, dtype=np.float32)
+    fake.tofile(d + "feats13.1.bin")
+    loc, gh = read_features(d, d + "does-not-exist", ds.images[1], 1, 13)
+    assert np.array_equal(np.concatenate([loc.ravel(), gh.ravel()]), fake)
+    # error paths return codes, not asserts
+    with pytest.raises(DoryError):
+        read_features(d, ffile, ds.images[0], 0, 12)  # width differs from the file's header, no cache for 12
+    with pytest.raises(DoryError):
+        read_labels(lfile, ds.images[0], 4)  # labelKinds mismatch
+    short = d + "short.bsnap"
+    formats.write_features(short, ds.feats[:-1])
+    with pytest.raises(DoryError):
+        read_features(d + "nocache/", short, ds.images[0], 0, 13)
+    bad = ds.labels.copy()
+    bad[ds.graphs[0].local_to_global[0]] = 9
+    formats.write_labels(d + "bad.bsnap", bad, 5)
+    with pytest.raises(DoryError):
+        read_labels(d + "bad.bsnap", ds.images[0], 5)
