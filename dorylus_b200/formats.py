@@ -12,6 +12,8 @@ Layouts follow SURVEY.md §10:
   (graph/graph.cpp:200-273) and read by ``Graph::init`` (graph/graph.cpp:7-115).
 * ``feats<F0>.<id>.bin`` -- local rows then src-ghost rows (engine/utils.cpp:487-501).
 * layer config -- text, one width per line (engine/utils.cpp:460-479).
+* text inputs -- the converters of the reference's inputs/ directory (graphToBinary.cpp,
+  featuresToBinary.cpp, labelsToBinary.cpp) as ``convert_*_text``.
 """
 from __future__ import annotations
 
@@ -98,6 +100,90 @@ def write_layer_config(path: str, dims: List[int]) -> None:
 def read_layer_config(path: str) -> List[int]:
     with open(path) as f:
         return [int(line.strip()) for line in f if line.strip()]
+
+
+# --------------------------------------------------------------------------- text -> binary converters
+def convert_graph_text(snap_path: str, out_path: str, undirected: bool = False, with_header: bool = True):
+    """== inputs/graphToBinary.cpp: a text edge list ("src dst" per line, lines starting with '#' or
+    '%' skipped, reading stops at the first line that does not parse) -> graph.bsnap.  Self loops
+    are dropped; with `undirected` every record is followed by its reverse.  Like the reference the
+    header counts the non-loop LINES (graphToBinary.cpp:36-53), not the doubled records.
+    Returns (numVertices, numEdges as written in the header)."""
+    src, dst = [], []
+    with open(snap_path) as f:
+        for line in f:
+            if line[:1] in ("#", "%"):
+                continue
+            tok = line.split()
+            try:
+                a, b = int(tok[0]), int(tok[1])
+            except (IndexError, ValueError):
+                break  # `if (!(iss >> src >> dst)) break;`
+            if a < 0 or b < 0:
+                break
+            if a == b:
+                continue
+            src.append(a)
+            dst.append(b)
+    s = np.asarray(src, dtype=np.uint32)
+    d = np.asarray(dst, dtype=np.uint32)
+    nv = int(max(s.max(initial=0), d.max(initial=0))) + 1
+    ne = int(s.size)
+    rec = np.empty((s.size, 4 if undirected else 2), dtype=np.uint32)
+    rec[:, 0], rec[:, 1] = s, d
+    if undirected:
+        rec[:, 2], rec[:, 3] = d, s
+    with open(out_path, "wb") as f:
+        if with_header:
+            f.write(BS_HEADER.pack(4, nv, ne))
+        rec.tofile(f)
+    return nv, ne
+
+
+def _leading_digit(line: str) -> bool:
+    return bool(line) and "0" <= line[0] <= "9"
+
+
+def convert_features_text(path: str, num_features: int):
+    """== inputs/featuresToBinary.cpp: one comma / space separated row per line -> <path>.bsnap.
+    Faithful to the reference's filter: a (trimmed) line whose first character is not a digit is
+    SKIPPED -- that includes rows whose first value is negative (featuresToBinary.cpp:51-52).
+    Returns (rows written, lines skipped)."""
+    import re
+
+    rows, skipped = [], 0
+    with open(path) as f:
+        for line in f:
+            line = line.strip()
+            if not _leading_digit(line):
+                skipped += bool(line)
+                continue
+            vals = [v for v in re.split(r"[, ]+", line) if v != ""]
+            if len(vals) != num_features:
+                raise ValueError("row with %d values, header says %d" % (len(vals), num_features))
+            rows.append(np.asarray([float(v) for v in vals], dtype=np.float32))
+    feats = np.stack(rows) if rows else np.zeros((0, num_features), np.float32)
+    write_features(path + ".bsnap", feats)
+    return feats.shape[0], skipped
+
+
+def convert_labels_text(path: str, label_kinds: int):
+    """== inputs/labelsToBinary.cpp: one class id per line -> <path>.bsnap (same leading-digit filter)."""
+    out, skipped = [], 0
+    with open(path) as f:
+        for line in f:
+            line = line.strip()
+            if not line:
+                continue
+            if not _leading_digit(line):
+                skipped += 1
+                continue
+            m = 0
+            while m < len(line) and line[m].isdigit():  # std::stoul stops at the first non-digit
+                m += 1
+            out.append(int(line[:m]))
+    write_labels(path + ".bsnap", np.asarray(out, dtype=np.uint32), label_kinds)
+    return len(out), skipped
 
 
 def one_hot(labels: np.ndarray, kinds: int) -> np.ndarray:
