@@ -6,6 +6,8 @@ Sources of truth (all under /root/reference, never copied as source code):
   * miscs/dgl-non-sampling/data/raw0, raw1  -- text dumps of WeightServer::xavierInitializer
     (602x128 and 128x41, seed 8888) that the reference authors used to make DGL "computationally the
     same"; we keep raw1 whole and a row subsample of raw0.
+  * miscs/check-correctness/weights-602-1000-41 -- an older weight dump: 643,000 consecutive draws of
+    the same seeded generator, scaled by 1.5 (a known-answer test for the RNG stream).
   * miscs/dgl-non-sampling/data/{tm,vm,sm}.pt + gendata.py -- the 66/10/24 % mask layout.
   * the reference's own loader / Matrix::dot / AdamOptimizer compiled in oracle/_ref and run on
     small seeded inputs (graph.<id>.bin images, sgemm results, Adam trajectories).
@@ -34,6 +36,32 @@ def xavier_fixture():
     rows0 = np.unique(np.concatenate([np.arange(4), np.arange(0, 602, 13), [601]]))
     np.savez_compressed(os.path.join(HERE, "xavier.npz"), raw0_rows=rows0, raw0=raw0[rows0], raw1=raw1,
                         raw0_sum=raw0.sum(), raw0_abs_sum=np.abs(raw0).sum())
+
+
+def weight_dump_fixture():
+    """miscs/check-correctness/weights-602-1000-41: a 602x1000 and a 1000x41 matrix in the
+    "Matrix Dims: (r, c)" text format (parsed by miscs/numpy-gnn/load_data.py:84-107), 6 significant
+    digits.  It predates the per-matrix re-seeding: both matrices are 1.5 x consecutive draws of ONE
+    std::default_random_engine(8888) + uniform_real_distribution<float>(-1, 1) stream -- a known-answer
+    test for 643,000 draws of the generator WeightServer::xavierInitializer still uses.  We keep a
+    subsample (flat positions in the concatenated stream + values)."""
+    import re
+
+    txt = open(os.path.join(REF, "miscs/check-correctness/weights-602-1000-41")).read()
+    blocks = re.split(r"Matrix Dims: \((\d+), (\d+)\)\n", txt)
+    dims, vals = [], []
+    for i in range(1, len(blocks), 3):
+        r, c = int(blocks[i]), int(blocks[i + 1])
+        v = np.array(blocks[i + 2].split(), dtype=np.float64)
+        assert v.size == r * c, (r, c, v.size)
+        dims.append((r, c))
+        vals.append(v)
+    assert dims == [(602, 1000), (1000, 41)], dims
+    stream = np.concatenate(vals)
+    pos = np.unique(np.concatenate([np.arange(64), np.arange(0, stream.size, 997), np.arange(602000 - 32, 602000 + 64),
+                                    np.arange(stream.size - 64, stream.size)]))
+    np.savez_compressed(os.path.join(HERE, "weight_dump.npz"), dims=np.array(dims), pos=pos, vals=stream[pos],
+                        total=stream.size, abs_sum=np.abs(stream).sum())
 
 
 def mask_fixture():
@@ -106,6 +134,7 @@ def ref_fixture():
 
 if __name__ == "__main__":
     xavier_fixture()
+    weight_dump_fixture()
     mask_fixture()
     ref_fixture()
     for f in sorted(os.listdir(HERE)):

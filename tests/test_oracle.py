@@ -18,6 +18,22 @@ def test_xavier_matches_reference_dumps(oracle, golden):
     assert abs(float(w0.astype(np.float64).sum()) - float(g["raw0_sum"])) < 1e-4
 
 
+def test_rng_stream_matches_reference_weight_dump(oracle, golden):
+    """miscs/check-correctness/weights-602-1000-41 (6 significant digits): 602x1000 then 1000x41
+    values = 1.5 x consecutive draws of one default_random_engine(8888) / uniform(-1, 1) stream -- the
+    generator xavierInitializer uses.  643,000 draws of the oracle's stream must reproduce it."""
+    g = golden["weight_dump"]
+    total = int(g["total"])
+    assert total == 602 * 1000 + 1000 * 41
+    rows = (total + 999) // 1000
+    w = oracle.xavier(rows, 1000).astype(np.float64) / np.sqrt(6.0 / (rows + 1000))  # undo the Xavier scale
+    stream = 1.5 * w.ravel()[:total]
+    want = g["vals"]
+    got = stream[g["pos"]]
+    assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-2)) < 2e-5  # printed with 6 digits
+    assert abs(np.abs(stream).sum() - float(g["abs_sum"])) < 1e-5 * float(g["abs_sum"])
+
+
 def test_mask_layout_matches_gendata(golden):
     """gendata.py: per block of V/60 vertices, first int(blk*0.66) train, next int(blk*0.1) val."""
     m = golden["masks"]
