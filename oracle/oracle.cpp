@@ -23,12 +23,16 @@
  * CblasRowMajor and beta = 0 (src/common/matrix.cpp:263-315); the OpenBLAS build is the one
  * inside scipy.libs (the reference pins no OpenBLAS version: gnnman/helpers/blas.install:13).
  *
- * Parity pinning: the reference ships NO golden vector for aggregation / apply outputs
- *  — those are "parity unpinned by the reference".  What IS pinned:
- *   - xavier():   against miscs/dgl-non-sampling/data/raw0, raw1 (tests/golden/xavier_*.json)
+ * Parity pinning (tests/test_oracle.py, fixtures under tests/golden/ written by make_golden.py):
+ *   - xavier():   against miscs/dgl-non-sampling/data/raw0, raw1 (xavier.npz), and the seeded RNG
+ *                 stream over 643,000 draws against miscs/check-correctness/weights-602-1000-41
  *   - adam, sgemm wrapper, graph arrays: against the compiled reference (oracle/_ref)
- *   - aggregate:  against the dense statement  (D^-1/2 A D^-1/2 + D^-1) X  built from the
- *                 compiled reference loader's own arrays (numpy-gnn/layers.py:199-210)
+ *   - aggregate / apply (ah, z, h, soft-max, grad, aTg, dW): against the reference's dense-numpy GCN
+ *                 miscs/numpy-gnn, IMPORTED and run by make_golden.py on a small symmetric graph
+ *                 (numpy_gnn.npz), and against the dense statement (D^-1/2 A D^-1/2 + D^-1) X built
+ *                 from the compiled reference loader's own arrays
+ *   - still unpinned by the reference (nothing that states them runs here): the loss scale, the
+ *                 float-wise maskout (Q6) and CPUComm's validation statistics.
  */
 #include <algorithm>
 #include <cmath>

@@ -8,6 +8,8 @@ Sources of truth (all under /root/reference, never copied as source code):
     same"; we keep raw1 whole and a row subsample of raw0.
   * miscs/check-correctness/weights-602-1000-41 -- an older weight dump: 643,000 consecutive draws of
     the same seeded generator, scaled by 1.5 (a known-answer test for the RNG stream).
+  * miscs/numpy-gnn (load_data.py, layers.py, loss.py) -- the reference's dense-numpy GCN, imported and
+    run on a small graph: forward tensors, soft-max and backward chain of a 2-layer model.
   * miscs/dgl-non-sampling/data/{tm,vm,sm}.pt + gendata.py -- the 66/10/24 % mask layout.
   * the reference's own loader / Matrix::dot / AdamOptimizer compiled in oracle/_ref and run on
     small seeded inputs (graph.<id>.bin images, sgemm results, Adam trajectories).
@@ -62,6 +64,62 @@ def weight_dump_fixture():
                                     np.arange(stream.size - 64, stream.size)]))
     np.savez_compressed(os.path.join(HERE, "weight_dump.npz"), dims=np.array(dims), pos=pos, vals=stream[pos],
                         total=stream.size, abs_sum=np.abs(stream).sum())
+
+
+def numpy_gnn_fixture():
+    """The reference's dense-numpy GCN (miscs/numpy-gnn: load_data.py builds A_hat, layers.py holds
+    Aggregate / Linear / Tanh, loss.py the soft-max) is a Python reference: it is imported here and run
+    on a small symmetric, duplicate-free graph (where its column-sum normalisation equals the C++
+    loader's) written in the reference's own binary formats.  Stored: inputs, the
+    forward tensors of a 2-layer GCN (A X W0 -> tanh -> A H W1), the soft-max, and numpy-gnn's
+    backward chain (Linear / Tanh / Aggregate .backward) driven by an upstream gradient."""
+    import contextlib
+    import io
+
+    sys.path.insert(0, os.path.join(REF, "miscs/numpy-gnn"))
+    import layers as nl  # noqa: E402  (the reference's module)
+    import load_data as nld  # noqa: E402
+    import loss as nloss  # noqa: E402
+
+    rng = np.random.default_rng(2024)
+    V, dims = 90, [12, 8, 5]
+    pairs = set()
+    while len(pairs) < 400:
+        a, b = (int(x) for x in rng.integers(0, V, 2))
+        if a != b:
+            pairs.add((min(a, b), max(a, b)))
+    und = np.array(sorted(pairs), dtype=np.uint32)
+    src = np.concatenate([und[:, 0], und[:, 1]])
+    dst = np.concatenate([und[:, 1], und[:, 0]])
+    feats = (rng.random((V, dims[0]), dtype=np.float32) * 2 - 1).astype(np.float32)
+    labels = rng.integers(0, dims[2], V).astype(np.uint32)
+    W0 = (rng.standard_normal((dims[0], dims[1])) * 0.4).astype(np.float32)
+    W1 = (rng.standard_normal((dims[1], dims[2])) * 0.4).astype(np.float32)
+    upstream = (rng.standard_normal((V, dims[2])) * 1e-2).astype(np.float32)  # d handed to the backward chain
+    d = tempfile.mkdtemp() + "/"
+    formats.write_bsnap_edges(d + "graph.bsnap", V, src, dst)
+    formats.write_features(d + "features.bsnap", feats)
+    formats.write_labels(d + "labels.bsnap", labels, dims[2])
+    with contextlib.redirect_stdout(io.StringIO()):
+        A_hat, X, y = nld.load_data(d, "t", binary=True)
+    assert A_hat.shape == (V, V) and np.array_equal(X, feats) and np.array_equal(y, labels.astype(np.int32))
+    net = [nl.Aggregate("A0", A_hat), nl.Linear("W0", dims[0], dims[1], "uniform").set_W(W0.astype(np.float64)),
+           nl.Tanh("t0"), nl.Aggregate("A1", A_hat), nl.Linear("W1", dims[1], dims[2], "uniform").set_W(W1.astype(np.float64))]
+    acts = [X.astype(np.float64)]
+    for layer in net:
+        acts.append(layer.forward(acts[-1]))
+    ah0, z0, h0, ah1, logits = acts[1:]
+    target = np.eye(dims[2])[y]
+    prob = nloss.SoftmaxCrossEntropyLoss("l").backward(logits, target) + target  # backward() returns prob - target
+    g = upstream.astype(np.float64)
+    grads = {}
+    for layer in reversed(net):
+        g = layer.backward(g)
+        grads[layer.name] = g
+    np.savez_compressed(os.path.join(HERE, "numpy_gnn.npz"), V=V, dims=np.array(dims), src=src, dst=dst, feats=feats,
+                        labels=labels, W0=W0, W1=W1, upstream=upstream, A_hat=A_hat, ah0=ah0, z0=z0, h0=h0, ah1=ah1,
+                        logits=logits, prob=prob, dW1=net[4].grad_W, grad1=grads["W1"], aTg0=grads["A1"],
+                        g0=grads["t0"], dW0=net[1].grad_W)
 
 
 def mask_fixture():
@@ -135,6 +193,7 @@ def ref_fixture():
 if __name__ == "__main__":
     xavier_fixture()
     weight_dump_fixture()
+    numpy_gnn_fixture()
     mask_fixture()
     ref_fixture()
     for f in sorted(os.listdir(HERE)):

@@ -34,6 +34,45 @@ def test_rng_stream_matches_reference_weight_dump(oracle, golden):
     assert abs(np.abs(stream).sum() - float(g["abs_sum"])) < 1e-5 * float(g["abs_sum"])
 
 
+def test_oracle_matches_numpy_gnn_reference_run(oracle, golden):
+    """tests/golden/numpy_gnn.npz was produced by IMPORTING the reference's dense-numpy GCN
+    (miscs/numpy-gnn) and running it on a small symmetric graph in the reference's file formats.
+    The oracle's restatement of aggregateGCN / vtxNNForwardGCN / vtxNNBackwardGCN must reproduce its
+    forward tensors, its soft-max and -- fed the same upstream gradient -- its backward chain."""
+    from dorylus_b200 import engine as dengine
+    from dorylus_b200 import formats
+
+    g = golden["numpy_gnn"]
+    V, dims = int(g["V"]), [int(x) for x in g["dims"]]
+    image = dengine.preprocess_edges(g["src"], g["dst"], np.zeros(V, np.int32), V, 0, 1)
+    pg = formats.parse_graph_bin(image)
+    feats, W0, W1 = g["feats"], g["W0"], g["W1"]
+    tol = 2e-6
+    # the loader's arrays realise numpy-gnn's A_hat (symmetric graph: Q2 does not bite)
+    A = dense_normalized_adjacency(V, g["src"], g["dst"])
+    assert np.max(np.abs(A - g["A_hat"])) < 1e-12
+    # forward
+    ah0 = oracle.aggregate_gcn(pg.col_ptrs, pg.row_idxs, pg.fwd_vals, pg.norms, feats, None)
+    assert rel_err(ah0, g["ah0"]) < tol
+    z0, h0 = oracle.vtx_forward_gcn_hidden(ah0, W0)
+    assert rel_err(z0, g["z0"]) < tol and rel_err(h0, g["h0"]) < tol
+    ah1 = oracle.aggregate_gcn(pg.col_ptrs, pg.row_idxs, pg.fwd_vals, pg.norms, h0, None)
+    assert rel_err(ah1, g["ah1"]) < tol
+    onehot = formats.one_hot(g["labels"], dims[2])
+    r = oracle.vtx_forward_gcn_last(ah1, W1, onehot, V)
+    assert rel_err(r["pred"], g["prob"]) < tol  # un-masked soft-max of A H W1
+    # backward chain from numpy-gnn's upstream gradient d: dW1 = ah1^T d, grad1 = d W1^T,
+    # aTg0 = A^T grad1, g0 = aTg0 * (1 - h0^2), dW0 = ah0^T g0
+    d = g["upstream"]
+    dW1 = oracle.dot(ah1, d, True, False)
+    grad1 = oracle.dot(d, W1, False, True)
+    assert rel_err(dW1, g["dW1"]) < tol and rel_err(grad1, g["grad1"]) < tol
+    aTg0 = oracle.aggregate_gcn(pg.row_ptrs, pg.col_idxs, pg.bwd_vals, pg.norms, grad1, None)
+    assert rel_err(aTg0, g["aTg0"]) < tol
+    dW0, _ = oracle.vtx_backward_gcn(aTg0, z0, ah0, W0, False)
+    assert rel_err(dW0, g["dW0"]) < tol
+
+
 def test_mask_layout_matches_gendata(golden):
     """gendata.py: per block of V/60 vertices, first int(blk*0.66) train, next int(blk*0.1) val."""
     m = golden["masks"]
