@@ -33,6 +33,13 @@ REF_SOURCES = [
     "src/graph-server/utils/utils.cpp",
     "src/weight-server/AdamOptimizer.cpp",
 ]
+# #included (inside namespaces) by ref_driver.cpp: the Lambda functions' tensor ops
+REF_INCLUDED = [
+    "src/funcs/gcn/ops/forward_ops.cpp",
+    "src/funcs/gcn/ops/backward_ops.cpp",
+    "src/funcs/gat/ops/forward_ops.cpp",
+    "src/funcs/gat/ops/backward_ops.cpp",
+]
 
 
 def openblas_path() -> str:
@@ -81,7 +88,7 @@ def build_ref(force: bool = False) -> str | None:
     os.makedirs(REF_DIR, exist_ok=True)
     srcs = [os.path.join(REF_ROOT, s) for s in REF_SOURCES]
     drv = os.path.join(HERE, "ref_driver.cpp")
-    if force or _newer(out, srcs + [drv, __file__]):
+    if force or _newer(out, srcs + [drv, __file__] + [os.path.join(REF_ROOT, s) for s in REF_INCLUDED]):
         blas = openblas_path()
         objs = []
         for i, s in enumerate(srcs + [drv]):

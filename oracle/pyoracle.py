@@ -308,3 +308,72 @@ class Ref:
 
     def adam(self, lr, dims):
         return _Adam(self.lib, "ref", lr, dims)
+
+    # ---- the Lambda functions' own tensor ops (src/funcs/{gcn,gat}/ops), sequenced as their main.cpp does
+    def funcs_gcn_forward(self, ah, W):
+        """forwardLayer, funcs/gcn/main.cpp:244-250 -> (z, h)."""
+        ah, W = _c32(ah), _c32(W)
+        V, Fin = ah.shape
+        z = np.empty((V, W.shape[1]), np.float32)
+        h = np.empty_like(z)
+        self.lib.ref_funcs_gcn_forward(_f(ah), _f(W), C.c_uint(V), C.c_uint(Fin), C.c_uint(W.shape[1]), _f(z), _f(h))
+        return z, h
+
+    def funcs_gcn_final(self, ah, W, lab, scale: float):
+        """finalLayer, funcs/gcn/main.cpp:83-108.  `correct` / `loss` are checkAccuracy / checkLoss over
+        ALL rows (forward_ops.cpp), `masked` the predictions after maskout()."""
+        ah, W, lab = _c32(ah), _c32(W), _c32(lab)
+        V, Fin = ah.shape
+        Cc = W.shape[1]
+        o = dict(pred=np.empty((V, Cc), np.float32), masked=np.empty((V, Cc), np.float32),
+                 d=np.empty((V, Cc), np.float32), grad=np.empty((V, Fin), np.float32),
+                 dW=np.empty((Fin, Cc), np.float32))
+        correct, loss = C.c_uint(), C.c_float()
+        self.lib.ref_funcs_gcn_final(_f(ah), _f(W), _f(lab), C.c_uint(V), C.c_uint(Fin), C.c_uint(Cc),
+                                     C.c_float(scale), _f(o["pred"]), C.byref(correct), C.byref(loss),
+                                     _f(o["masked"]), _f(o["d"]), _f(o["grad"]), _f(o["dW"]))
+        o["correct"], o["loss"] = int(correct.value), float(loss.value)
+        return o
+
+    def funcs_gcn_backward(self, ah, z, aTg, W):
+        """backwardLayer, funcs/gcn/main.cpp:176-189 -> (resultGrad, d_weights)."""
+        ah, z, aTg, W = _c32(ah), _c32(z), _c32(aTg), _c32(W)
+        V, Fin = ah.shape
+        Fout = W.shape[1]
+        grad = np.empty((V, Fin), np.float32)
+        dW = np.empty((Fin, Fout), np.float32)
+        self.lib.ref_funcs_gcn_backward(_f(ah), _f(z), _f(aTg), _f(W), C.c_uint(V), C.c_uint(Fin), C.c_uint(Fout),
+                                        _f(grad), _f(dW))
+        return grad, dW
+
+    def funcs_gat_edge_forward(self, z, a, col_ptrs):
+        """funcs/gat/main.cpp:84-94: az = edgeMatMul(eInfo, Z, a); A = leakyReLU(az)."""
+        z, a = _c32(z), _c32(a).reshape(-1)
+        V, F = z.shape
+        ptrs = np.ascontiguousarray(col_ptrs, dtype=np.uint64)
+        nnz = int(ptrs[V])
+        az = np.zeros(max(nnz, 1), np.float32)
+        A = np.zeros(max(nnz, 1), np.float32)
+        self.lib.ref_funcs_gat_edge_forward(_f(z), _f(a), _q(ptrs), C.c_uint(V), C.c_uint(F), C.c_uint(nnz), _f(az), _f(A))
+        return az[:nnz], A[:nnz]
+
+    def funcs_gat_edge_backward(self, grad, az, z, a, col_ptrs):
+        """funcs/gat/main.cpp:150-160: dA = expandHadamardMul(grad, leakyReLUDerivative(az)) . a -> (dA, dAct)."""
+        grad, az, z, a = _c32(grad), _c32(az), _c32(z), _c32(a).reshape(-1)
+        V, F = z.shape
+        ptrs = np.ascontiguousarray(col_ptrs, dtype=np.uint64)
+        nnz = int(ptrs[V])
+        dA = np.zeros(max(nnz, 1), np.float32)
+        dAct = np.zeros((max(nnz, 1), F), np.float32)
+        self.lib.ref_funcs_gat_edge_backward(_f(grad), _f(az), _f(z), _f(a), _q(ptrs), C.c_uint(V), C.c_uint(F),
+                                             C.c_uint(nnz), _f(dA), _f(dAct))
+        return dA[:nnz], dAct[:nnz]
+
+    def funcs_gat_expand_dot(self, m, v, col_ptrs):
+        m, v = _c32(m), _c32(v).reshape(-1)
+        V, F = m.shape
+        ptrs = np.ascontiguousarray(col_ptrs, dtype=np.uint64)
+        nnz = int(ptrs[V])
+        out = np.zeros(max(nnz, 1), np.float32)
+        self.lib.ref_funcs_gat_expand_dot(_f(m), _f(v), _q(ptrs), C.c_uint(V), C.c_uint(F), C.c_uint(nnz), _f(out))
+        return out[:nnz]

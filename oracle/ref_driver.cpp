@@ -9,6 +9,14 @@
  *   Graph::init              src/graph-server/graph/graph.cpp:7-115
  *   Matrix::dot              src/common/matrix.cpp:263-315   (-> cblas_sgemm)
  *   AdamOptimizer            src/weight-server/AdamOptimizer.cpp:3-51
+ *   the Lambda functions' tensor ops (the reference's SECOND statement of the apply step):
+ *     src/funcs/gcn/ops/forward_ops.cpp, backward_ops.cpp   softmax, tanh, tanhDerivative, maskout,
+ *                                                            checkAccuracy, checkLoss
+ *     src/funcs/gat/ops/forward_ops.cpp, backward_ops.cpp   leakyReLU(+Derivative), edgeMatMul,
+ *                                                            expandDot, expandHadamardMul, reduce
+ *   sequenced exactly as src/funcs/gcn/main.cpp:83-108 (finalLayer), :176-189 (backwardLayer),
+ *   :244-250 (forwardLayer) and src/funcs/gat/main.cpp:84-101, :130-170 do -- main.cpp itself needs
+ *   ZeroMQ and the AWS SDK and does not build here.
  *
  * Output: oracle/_ref/libdoryref.so (git-ignored, travels to the GPU box).
  */
@@ -21,6 +29,24 @@
 #include "graph-server/graph/graph.hpp"
 #include "common/matrix.hpp"
 #include "weight-server/AdamOptimizer.hpp"
+
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+
+/* The two Lambda functions define the same global names (softmax, tanh, ...), so each pair of
+ * translation units is compiled inside its own namespace, from the files where they lie.  Their
+ * headers only pull common/matrix.hpp and common/utils.hpp, which are already included above. */
+namespace ref_funcs_gcn {
+#include "funcs/gcn/ops/forward_ops.cpp"
+#include "funcs/gcn/ops/backward_ops.cpp"
+}  // namespace ref_funcs_gcn
+#undef __FWD_OPS_HPP__
+#undef __BKWD_OPS_HPP__
+namespace ref_funcs_gat {
+#include "funcs/gat/ops/forward_ops.cpp"
+#include "funcs/gat/ops/backward_ops.cpp"
+}  // namespace ref_funcs_gat
 
 extern "C" {
 
@@ -105,5 +131,125 @@ void ref_adam_update(void *h, unsigned layer, float *weight, float *grad) {
     static_cast<AdamOptimizer *>(h)->update(layer, weight, grad);
 }
 void ref_adam_destroy(void *h) { delete static_cast<AdamOptimizer *>(h); }
+
+
+/* ---------------------------------------------------------------- src/funcs (Lambda) tensor ops
+ * Inputs are copied into new[] buffers because the reference ops return freshly allocated
+ * matrices and some (maskout, operator/=) write in place. */
+static Matrix own_copy(const float *p, unsigned r, unsigned c) {
+    float *d = new float[(size_t)r * c];
+    std::memcpy(d, p, sizeof(float) * (size_t)r * c);
+    return Matrix(r, c, d);
+}
+static void take(Matrix &m, float *out) {
+    if (out) std::memcpy(out, m.getData(), m.getDataSize());
+    delete[] m.getData();
+}
+
+/* forwardLayer, funcs/gcn/main.cpp:244-250: Z = AH.dot(W); H = tanh(Z). */
+void ref_funcs_gcn_forward(const float *ah, const float *w, unsigned V, unsigned Fin, unsigned Fout,
+                           float *z, float *h) {
+    Matrix AH = own_copy(ah, V, Fin), W = own_copy(w, Fin, Fout);
+    Matrix Z = AH.dot(W);
+    Matrix H = ref_funcs_gcn::tanh(Z);
+    take(H, h);
+    take(Z, z);
+    take(AH, nullptr);
+    take(W, nullptr);
+}
+
+/* finalLayer, funcs/gcn/main.cpp:83-108: softmax, (accuracy / loss over all rows), maskout,
+ * d_out = (preds - labels) / trainset_size, interGrad = d_out . W^T, d_weights = AH^T . d_out.
+ * `scale` is what the caller divides by: the Lambda payload carries the integer
+ * globalVtxCnt * TRAIN_PORTION (lambda_comm.cpp:156), CPUComm the float product (CPU_comm.cpp:121). */
+void ref_funcs_gcn_final(const float *ah, const float *w, const float *lab, unsigned V, unsigned Fin,
+                         unsigned C, float scale, float *preds_out, unsigned *correct_out, float *loss_out,
+                         float *masked_out, float *d_out_out, float *grad, float *dW) {
+    Matrix AH = own_copy(ah, V, Fin), W = own_copy(w, Fin, C), labels = own_copy(lab, V, C);
+    Matrix Z = AH.dot(W);
+    Matrix preds = ref_funcs_gcn::softmax(Z);
+    take(Z, nullptr);
+    if (preds_out) std::memcpy(preds_out, preds.getData(), preds.getDataSize());
+    if (correct_out) *correct_out = ref_funcs_gcn::checkAccuracy(preds, labels);
+    if (loss_out) *loss_out = ref_funcs_gcn::checkLoss(preds, labels);
+    ref_funcs_gcn::maskout(preds, labels);
+    if (masked_out) std::memcpy(masked_out, preds.getData(), preds.getDataSize());
+    Matrix d_out = preds - labels;
+    d_out /= scale;
+    Matrix interGrad = d_out.dot(W, false, true);
+    Matrix d_weights = AH.dot(d_out, true, false);
+    take(interGrad, grad);
+    take(d_weights, dW);
+    take(d_out, d_out_out);
+    take(preds, nullptr);
+    take(labels, nullptr);
+    take(AH, nullptr);
+    take(W, nullptr);
+}
+
+/* backwardLayer, funcs/gcn/main.cpp:176-189. */
+void ref_funcs_gcn_backward(const float *ah, const float *z, const float *aTg, const float *w, unsigned V,
+                            unsigned Fin, unsigned Fout, float *resultGrad, float *dW) {
+    Matrix AH = own_copy(ah, V, Fin), Z = own_copy(z, V, Fout), grad = own_copy(aTg, V, Fout),
+           W = own_copy(w, Fin, Fout);
+    Matrix actDeriv = ref_funcs_gcn::tanhDerivative(Z);
+    Matrix interGrad = grad * actDeriv;
+    Matrix result = interGrad.dot(W, false, true);
+    Matrix d_weights = AH.dot(interGrad, true, false);
+    take(result, resultGrad);
+    take(d_weights, dW);
+    take(interGrad, nullptr);
+    take(actDeriv, nullptr);
+    take(AH, nullptr);
+    take(Z, nullptr);
+    take(grad, nullptr);
+    take(W, nullptr);
+}
+
+/* GAT edge forward, funcs/gat/main.cpp:84-94: az = edgeMatMul(eInfo, Z, a); A = leakyReLU(az). */
+void ref_funcs_gat_edge_forward(const float *z, const float *a, const unsigned long long *edgePtrs, unsigned V,
+                                unsigned F, unsigned nEdges, float *az, float *A) {
+    Matrix Z = own_copy(z, V, F), av = own_copy(a, F, 1);
+    EdgeInfo eInfo{V, nEdges, const_cast<unsigned long long *>(edgePtrs)};
+    Matrix edgeValInputs = ref_funcs_gat::edgeMatMul(eInfo, Z, av);
+    Matrix edgeVals = ref_funcs_gat::leakyReLU(edgeValInputs);
+    take(edgeVals, A);
+    take(edgeValInputs, az);
+    take(Z, nullptr);
+    take(av, nullptr);
+}
+
+/* GAT edge backward, funcs/gat/main.cpp:150-170: dLRelu = leakyReLUDerivative(az);
+ * dAct = expandHadamardMul(grad, dLRelu); dA = dAct . a; da = (z^T z) . reduce(dAct)^T.
+ * reduce() accumulates into an uninitialised new[] buffer in the reference (quirk Q11); the driver
+ * cannot change that, so it is only safe for small dAct -- the caller passes small cases and the
+ * result is checked for finiteness before it is used. */
+void ref_funcs_gat_edge_backward(const float *grad, const float *az, const float *z, const float *a,
+                                 const unsigned long long *edgePtrs, unsigned V, unsigned F, unsigned nEdges,
+                                 float *dA, float *dAct_out) {
+    Matrix G = own_copy(grad, V, F), AZ = own_copy(az, nEdges, 1), av = own_copy(a, F, 1);
+    (void)z;
+    EdgeInfo eInfo{V, nEdges, const_cast<unsigned long long *>(edgePtrs)};
+    Matrix dLRelu = ref_funcs_gat::leakyReLUDerivative(AZ);
+    Matrix dAct = ref_funcs_gat::expandHadamardMul(G, dLRelu, eInfo);
+    Matrix dAm = dAct.dot(av);
+    take(dAm, dA);
+    take(dAct, dAct_out);
+    take(dLRelu, nullptr);
+    take(G, nullptr);
+    take(AZ, nullptr);
+    take(av, nullptr);
+}
+
+/* expandDot, funcs/gat/ops/backward_ops.cpp (same body as CPU_comm.cpp:299-319). */
+void ref_funcs_gat_expand_dot(const float *m, const float *v, const unsigned long long *edgePtrs, unsigned V,
+                              unsigned F, unsigned nEdges, float *out) {
+    Matrix M = own_copy(m, V, F), vv = own_copy(v, F, 1);
+    EdgeInfo eInfo{V, nEdges, const_cast<unsigned long long *>(edgePtrs)};
+    Matrix r = ref_funcs_gat::expandDot(M, vv, eInfo);
+    take(r, out);
+    take(M, nullptr);
+    take(vv, nullptr);
+}
 
 }  // extern "C"

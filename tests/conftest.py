@@ -43,4 +43,4 @@ def golden():
     import numpy as np
 
     d = os.path.join(ROOT, "tests", "golden")
-    return {n: np.load(os.path.join(d, n + ".npz")) for n in ("xavier", "masks", "reference_runs", "weight_dump", "numpy_gnn")}
+    return {n: np.load(os.path.join(d, n + ".npz")) for n in ("xavier", "masks", "reference_runs", "weight_dump", "numpy_gnn", "funcs_ops")}

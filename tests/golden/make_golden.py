@@ -13,6 +13,10 @@ Sources of truth (all under /root/reference, never copied as source code):
   * miscs/dgl-non-sampling/data/{tm,vm,sm}.pt + gendata.py -- the 66/10/24 % mask layout.
   * the reference's own loader / Matrix::dot / AdamOptimizer compiled in oracle/_ref and run on
     small seeded inputs (graph.<id>.bin images, sgemm results, Adam trajectories).
+  * src/funcs/{gcn,gat}/ops/{forward,backward}_ops.cpp -- the Lambda functions' tensor ops (the
+    reference's second statement of ApplyVertex / ApplyEdge), compiled into oracle/_ref and sequenced as
+    funcs/gcn/main.cpp and funcs/gat/main.cpp do: soft-max, the float-wise maskout (quirk Q6), the scaled
+    output gradient, tanh / tanh', weight gradients, GAT edge scores and their backward (funcs_ops.npz).
 The GPU box has no /root/reference: tests read only the .npz files written here.
 """
 import os
@@ -190,7 +194,48 @@ def ref_fixture():
     np.savez_compressed(os.path.join(HERE, "reference_runs.npz"), **out)
 
 
+def funcs_fixture():
+    """Real runs of the Lambda functions' ops on seeded inputs.  V = 53 makes the maskout quirk bite in
+    the middle of a row: stt = 34, (end - stt) = 19 floats = 2 rows of C = 7 plus 5 floats."""
+    ref = Ref()
+    rng = np.random.default_rng(77)
+    out = {}
+    V, Fin, Fhid, C, gV = 53, 10, 6, 7, 53  # one partition: globalVtxCnt == V
+    ah0 = rng.standard_normal((V, Fin)).astype(np.float32)
+    W0 = (rng.standard_normal((Fin, Fhid)) * 0.5).astype(np.float32)
+    z0, h0 = ref.funcs_gcn_forward(ah0, W0)
+    out.update(gcn_ah0=ah0, gcn_W0=W0, gcn_z0=z0, gcn_h0=h0)
+    ah1 = rng.standard_normal((V, Fhid)).astype(np.float32)
+    W1 = (rng.standard_normal((Fhid, C)) * 0.5).astype(np.float32)
+    labels = rng.integers(0, C, V)
+    lab = np.zeros((V, C), np.float32)
+    lab[np.arange(V), labels] = 1
+    scale = np.float32(gV * 0.66)  # CPU_comm.cpp:121 (float); the Lambda payload truncates it to an integer
+    fin = ref.funcs_gcn_final(ah1, W1, lab, float(scale))
+    out.update(gcn_ah1=ah1, gcn_W1=W1, gcn_lab=lab, gcn_gV=gV, gcn_scale=scale, gcn_pred=fin["pred"],
+               gcn_masked=fin["masked"], gcn_d=fin["d"], gcn_grad1=fin["grad"], gcn_dW1=fin["dW"],
+               gcn_correct_all_rows=fin["correct"], gcn_loss_all_rows=fin["loss"])
+    aTg = (rng.standard_normal((V, Fhid)) * 0.1).astype(np.float32)
+    rgrad, dW0 = ref.funcs_gcn_backward(ah0, z0, aTg, W0)
+    out.update(gcn_aTg0=aTg, gcn_resultGrad0=rgrad, gcn_dW0=dW0)
+    # ---- GAT edge ops on a ragged adjacency (empty rows included)
+    Vg, Fg = 17, 5
+    deg = rng.integers(0, 6, Vg)
+    deg[3] = 0
+    ptrs = np.concatenate([[0], np.cumsum(deg)]).astype(np.uint64)
+    z = rng.standard_normal((Vg, Fg)).astype(np.float32)
+    a = rng.standard_normal((Fg, 1)).astype(np.float32)
+    az, A = ref.funcs_gat_edge_forward(z, a, ptrs)
+    grad = rng.standard_normal((Vg, Fg)).astype(np.float32)
+    dA, dAct = ref.funcs_gat_edge_backward(grad, az, z, a, ptrs)
+    ed = ref.funcs_gat_expand_dot(z, a, ptrs)
+    out.update(gat_ptrs=ptrs, gat_z=z, gat_a=a, gat_az=az, gat_A=A, gat_grad=grad, gat_dA=dA, gat_dAct=dAct,
+               gat_expand_dot=ed)
+    np.savez_compressed(os.path.join(HERE, "funcs_ops.npz"), **out)
+
+
 if __name__ == "__main__":
+    funcs_fixture()
     xavier_fixture()
     weight_dump_fixture()
     numpy_gnn_fixture()

@@ -205,6 +205,82 @@ def test_vtx_backward(oracle):
     assert none is None and np.array_equal(dW0, dW)
 
 
+# ---------------------------------------------------------------- the Lambda functions' own ops
+def test_oracle_matches_lambda_gcn_ops_golden(oracle, golden):
+    """tests/golden/funcs_ops.npz holds REAL runs of src/funcs/gcn/ops (softmax, maskout, tanh,
+    tanhDerivative) sequenced as funcs/gcn/main.cpp does -- the reference's second statement of
+    ApplyVertex.  The oracle's restatement of CPUComm::vtxNN{Forward,Backward}GCN must agree with it,
+    including the float-wise maskout (quirk Q6) and the 1/(V * 0.66) scale."""
+    g = golden["funcs_ops"]
+    z0, h0 = oracle.vtx_forward_gcn_hidden(g["gcn_ah0"], g["gcn_W0"])
+    assert rel_err(z0, g["gcn_z0"]) < 1e-6 and rel_err(h0, g["gcn_h0"]) < 1e-6
+    r = oracle.vtx_forward_gcn_last(g["gcn_ah1"], g["gcn_W1"], g["gcn_lab"], int(g["gcn_gV"]))
+    assert rel_err(r["pred"], g["gcn_pred"]) < 1e-6
+    assert rel_err(r["d"], g["gcn_d"]) < 1e-6
+    assert rel_err(r["grad"], g["gcn_grad1"]) < 1e-6
+    assert rel_err(r["dW"], g["gcn_dW1"]) < 1e-6
+    dW0, grad0 = oracle.vtx_backward_gcn(g["gcn_aTg0"], g["gcn_z0"], g["gcn_ah0"], g["gcn_W0"], True)
+    assert rel_err(dW0, g["gcn_dW0"]) < 1e-6
+    assert rel_err(grad0, g["gcn_resultGrad0"]) < 1e-6
+
+
+def test_lambda_maskout_quirk_shape(golden):
+    """What the reference's maskout() really overwrites: (end - stt) FLOATS from row stt on, i.e. two
+    rows and five floats of a third at V = 53, C = 7 -- not the 19 non-training rows."""
+    g = golden["funcs_ops"]
+    pred, masked, lab = g["gcn_pred"], g["gcn_masked"], g["gcn_lab"]
+    V, C = pred.shape
+    stt = int(V * 0.66)
+    want = pred.copy().reshape(-1)
+    want[stt * C: stt * C + (V - stt)] = lab.reshape(-1)[stt * C: stt * C + (V - stt)]
+    assert np.array_equal(masked.reshape(-1), want)
+    assert (V - stt) % C != 0  # the fixture ends mid-row on purpose
+    d = (masked - lab) / g["gcn_scale"]
+    assert rel_err(g["gcn_d"], d) < 1e-6
+    # checkAccuracy / checkLoss (forward_ops.cpp) run over all rows
+    assert int(g["gcn_correct_all_rows"]) == int((pred.argmax(1) == lab.argmax(1)).sum())
+    loss = float(-np.log(pred[np.arange(V), lab.argmax(1)].astype(np.float64)).sum())
+    assert abs(float(g["gcn_loss_all_rows"]) - loss) < 1e-3
+
+
+def test_oracle_matches_lambda_gat_ops_golden(oracle, golden):
+    """src/funcs/gat/ops: edgeMatMul + leakyReLU (edge forward), leakyReLUDerivative +
+    expandHadamardMul + dAct . a (edge backward), expandDot -- on a ragged adjacency with empty rows."""
+    g = golden["funcs_ops"]
+    az, A = oracle.edg_forward_gat(g["gat_z"], g["gat_a"], g["gat_ptrs"])
+    assert rel_err(az, g["gat_az"]) < 1e-6 and rel_err(A, g["gat_A"]) < 1e-6
+    assert rel_err(az, g["gat_expand_dot"]) < 1e-6  # expandDot == edgeMatMul (quirk Q8: one-sided score)
+    dA, _da = oracle.edg_backward_gat(g["gat_grad"], g["gat_az"], g["gat_z"], g["gat_a"], g["gat_ptrs"])
+    assert rel_err(dA, g["gat_dA"]) < 1e-6
+    # dAct is the E x F' tensor the reference materialises: grad[dst(e)] * leaky'(az[e])
+    ptrs = g["gat_ptrs"].astype(np.int64)
+    dst = np.repeat(np.arange(len(ptrs) - 1), np.diff(ptrs))
+    want = g["gat_grad"][dst] * np.where(g["gat_az"] > 0, 1.0, 0.01)[:, None].astype(np.float32)
+    assert rel_err(g["gat_dAct"], want) < 1e-6
+
+
+@pytest.mark.parametrize("V,Fin,Fout,C", [(200, 33, 17, 5), (1, 4, 3, 2), (97, 602, 128, 41)])
+def test_oracle_matches_lambda_ops_live(oracle, ref, V, Fin, Fout, C):
+    """Same comparison against the compiled reference ops on fresh inputs (needs oracle/_ref)."""
+    rng = np.random.default_rng(V)
+    ah = rng.standard_normal((V, Fin)).astype(np.float32)
+    W = (rng.standard_normal((Fin, Fout)) * 0.3).astype(np.float32)
+    z, h = ref.funcs_gcn_forward(ah, W)
+    oz, oh = oracle.vtx_forward_gcn_hidden(ah, W)
+    assert rel_err(oz, z) < 1e-6 and rel_err(oh, h) < 1e-6
+    aTg = rng.standard_normal((V, Fout)).astype(np.float32)
+    rgrad, rdW = ref.funcs_gcn_backward(ah, z, aTg, W)
+    odW, ograd = oracle.vtx_backward_gcn(aTg, z, ah, W, True)
+    assert rel_err(odW, rdW) < 1e-6 and rel_err(ograd, rgrad) < 1e-6
+    W1 = (rng.standard_normal((Fout, C)) * 0.3).astype(np.float32)
+    lab = np.zeros((V, C), np.float32)
+    lab[np.arange(V), rng.integers(0, C, V)] = 1
+    fin = ref.funcs_gcn_final(h, W1, lab, float(np.float32(V * 0.66)))
+    o = oracle.vtx_forward_gcn_last(h, W1, lab, V)
+    for k in ("pred", "d", "grad", "dW"):
+        assert rel_err(o[k], fin[k]) < 1e-6, k
+
+
 # ---------------------------------------------------------------- whole epoch: partitions agree
 def test_epoch_partitioned_equals_single_partition(oracle):
     """The per-partition state machine with ghost exchange reproduces the 1-partition run
