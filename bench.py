@@ -202,6 +202,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU baseline budget (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default=os.environ.get("DORY_EXCHANGE", "p2p"), choices=["p2p", "nccl"])
+    ap.add_argument("--apply-first", action="store_true",
+                    help="opt-in schedule: layers that narrow run A_hat.(in.W) instead of the reference's "
+                         "(A_hat.in).W (DORY_FLAG_APPLY_FIRST); the default keeps the reference's operator order")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # stdout carries exactly ONE JSON line: libraries that print banners to fd 1 (NCCL prints its
@@ -252,6 +255,7 @@ def main():
 
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
 
+    from dorylus_b200 import _lib as dlib
     from dorylus_b200 import dist as ddist
     from dorylus_b200.engine import BACKWARD, FORWARD, GCN, Engine
 
@@ -261,9 +265,16 @@ def main():
     E_global = n_edges
     n_spmm = 2 * L - 1
 
-    eng = Engine(dims, GCN, node_id=rank, num_nodes=world, device=local_rank)
+    eng = Engine(dims, GCN, node_id=rank, num_nodes=world, device=local_rank,
+                 flags=dlib.FLAG_APPLY_FIRST if args.apply_first else 0)
     eng.load_partition(image)
     del image
+    sched = [eng.apply_first(l) for l in range(L)]
+    # an apply-first layer 0 gathers t = x . W, computed from the rows each rank owns: x needs no ghost rows
+    ship_x_ghosts = world > 1 and not sched[0]
+    cfg_common["schedule"] = ("reference order (aggregate, then apply) on every layer" if not any(sched) else
+                              "apply-first on layers %s (A_hat.(in.W)); reference order elsewhere"
+                              % [l for l in range(L) if sched[l]])
     x_loc, x_gh = formats.partition_rows(graph, feats)
     onehot = formats.one_hot(labels[graph.local_to_global], dims[-1])
     # pinned host staging (the e2e leg copies from here every step)
@@ -277,7 +288,7 @@ def main():
     # needs them -- at 8 ranks that would be 8 x 0.49 GB of host reads per step for 0.56 GB of input.
     def upload_inputs():
         eng.set_tensor(0, "x", pin_x.numpy())
-        if world > 1:
+        if ship_x_ghosts:
             eng.scatter(chunk0)
         eng.set_tensor(L - 1, "lab", pin_l.numpy())
 
@@ -286,7 +297,8 @@ def main():
         ddist.setup_engine_comm(eng, graph, rank, world, peer_memory=args.exchange == "p2p")
         cfg_common["ghost_exchange"] = ("one store-through-NVLink kernel into peer ghost blocks (CUDA IPC) + 1 NCCL barrier"
                                         if args.exchange == "p2p" else "pack -> NCCL all-to-all-v -> unpack")
-        cfg_common["layer0_ghost_rows"] = "shipped over NVLink from the owning rank every step (not uploaded)"
+        cfg_common["layer0_ghost_rows"] = ("shipped over NVLink from the owning rank every step (not uploaded)"
+                                           if ship_x_ghosts else "not needed (layer 0 gathers t = x.W)")
     upload_inputs()
 
     def barrier():
@@ -315,8 +327,13 @@ def main():
     launches = st["kernel_launches"] - launches0
 
     # ---- per-aggregation timings (CUDA events on the engine's stream), same warm state
+    # the reference order aggregates forward at every layer and backward at layers >= 1; an apply-first
+    # layer aggregates F_out-wide rows in both directions (its forward launch includes the activation)
+    agg_list = [("L%d_fwd" % l, l, FORWARD) for l in range(L)] + \
+               [("L%d_bwd" % l, l, BACKWARD) for l in range(L - 1, -1, -1) if l > 0 or sched[0]]
+    agg_width = {"L%d_%s" % (l, d): (dims[l + 1] if sched[l] else dims[l]) for l in range(L) for d in ("fwd", "bwd")}
     agg_ms = {}
-    for name, layer, d in (("L0_fwd", 0, FORWARD), ("L1_fwd", 1, FORWARD), ("L1_bwd", 1, BACKWARD)):
+    for name, layer, d in agg_list:
         c = eng.whole_chunk(layer, d)
         for _ in range(2):
             eng.aggregate(c)
@@ -350,7 +367,7 @@ def main():
 
     def commit_inputs():
         eng.commit_prefetch()
-        if world > 1:
+        if ship_x_ghosts:
             eng.scatter(chunk0)
 
     prefetch_inputs()
@@ -397,17 +414,19 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peaks()
         V_p, G_p, E_p = graph.local_vtx_cnt, graph.src_ghost_cnt, graph.local_in_edge_cnt
-        b_alg = alg_bytes_spmm(V_p, G_p, E_p, dims[0])
-        f_alg = alg_flops_spmm(V_p, E_p, dims[0])
+        F0 = agg_width["L0_fwd"]
+        b_alg = alg_bytes_spmm(V_p, G_p, E_p, F0)
+        f_alg = alg_flops_spmm(V_p, E_p, F0)
         achieved = b_alg / (agg_ms["L0_fwd"] * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and not sched[0]:  # the capture is of the F = dims[0] aggregation
             with open(tpath) as f:
                 traffic = json.load(f).get("dram_bytes_per_aggregate_L0_fwd")
         value = n_spmm * E_global * args.steps / (ms_total * 1e-3)
         cfg_common.update(V=spec.num_vertices, E=E_global, dims=dims, edge_cut=cut,
-                          aggregations_per_step=n_spmm)
+                          aggregations_per_step=n_spmm, aggregations_launched_per_step=len(agg_list),
+                          aggregated_row_widths=agg_width if any(sched) else None)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -417,15 +436,15 @@ def main():
             "per_layer_ms": agg_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "spmm_kernel (layer-0 forward aggregation, F=602: per source window one "
-                                   "CTA-per-row launch + one warp-per-row launch)",
+                         "kernel": "spmm_kernel (layer-0 forward aggregation, F=%d: per source window one "
+                                   "CTA-per-row launch + one warp-per-row launch)" % F0,
                          "algorithmic_bytes": b_alg,
                          # t_roof = max(B_alg / BW_hbm, F_alg / P_fp32); this aggregation's
                          # arithmetic intensity (68 flop/B) puts it on the fp32-FMA side of the classic roofline
                          "algorithmic_flops": f_alg, "fp32_fma_peak_tflops": fma_peak,
                          "t_roof_ms": 1e3 * max(b_alg / (peak * 1e9), f_alg / (fma_peak * 1e12)),
                          "frac_of_t_roof": max(b_alg / (peak * 1e9), f_alg / (fma_peak * 1e12)) / (agg_ms["L0_fwd"] * 1e-3),
-                         "gathered_tb_per_s": 4.0 * dims[0] * E_p / (agg_ms["L0_fwd"] * 1e-3) / 1e12,
+                         "gathered_tb_per_s": 4.0 * F0 * E_p / (agg_ms["L0_fwd"] * 1e-3) / 1e12,
                          "binding": "L2->SM gather bandwidth: E*F*4 bytes cross it whatever HBM does "
                                     "(lts__throughput 76-80 % of peak on every launch, profiles/round1_final2_full.md)",
                          "note": "min-traffic model; the gather itself moves E*F*4 bytes L2->SM (DESIGN.md §5)"},

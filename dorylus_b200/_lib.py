@@ -22,7 +22,7 @@ ERROR_NAMES = {EINVAL: "DORY_EINVAL", ESTATE: "DORY_ESTATE", ECUDA: "DORY_ECUDA"
 
 FORWARD, BACKWARD = 0, 1
 GCN, GAT = 0, 1
-FLAG_STRICT_MASK, FLAG_GAT_PREDICT_AH, FLAG_NO_TENSOR_CORES = 0x1, 0x2, 0x4
+FLAG_STRICT_MASK, FLAG_GAT_PREDICT_AH, FLAG_NO_TENSOR_CORES, FLAG_APPLY_FIRST = 0x1, 0x2, 0x4, 0x8
 
 
 class DoryChunk(C.Structure):
@@ -84,6 +84,7 @@ SYMBOLS = {
     "dory_apply_edge": (C.c_int, [_P, _chunkp]),
     "dory_predict": (C.c_int, [_P, _chunkp]),
     "dory_inc_layer": (C.c_int, [_P, _chunkp]),
+    "dory_layer_schedule": (C.c_int, [_P, _u32, C.POINTER(C.c_int)]),
     "dory_forward": (C.c_int, [_P, _u32]),
     "dory_backward": (C.c_int, [_P, _u32]),
     "dory_epoch": (C.c_int, [_P, C.POINTER(DoryStats)]),

@@ -94,6 +94,8 @@ int launch_gemm(const GemmArgs &g, cudaStream_t s);
 
 // g = aTg (*) (1 - h^2)                              (CPU_comm.cpp:142-143)
 int launch_tanh_backward(const float *aTg, const float *h, float *g, uint64_t n, cudaStream_t s);
+// h = tanh(z) over n floats (n a multiple of 4)     (activate, CPU_comm.cpp:265-274)
+int launch_tanh_forward(const float *z, float *h, uint64_t n, cudaStream_t s);
 
 // Last-layer fused softmax / validation statistics / maskout / gradient scale
 // (CPU_comm.cpp:108-121).  Writes d = (maskout(softmax(z)) - lab) / denom into `d`,

@@ -143,6 +143,15 @@ __global__ void tanh_backward_kernel(const float4 *__restrict__ aTg, const float
                        a.w * (1.f - t.w * t.w));
 }
 
+// h = tanh(z): activate(), CPU_comm.cpp:265-274, as its own pass -- the apply-first schedule applies
+// the activation to the OUTPUT of the aggregation instead of in the GEMM epilogue.
+__global__ void tanh_forward_kernel(const float4 *__restrict__ z, float4 *__restrict__ h, size_t n4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = z[i];
+    h[i] = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
+}
+
 // One warp per vertex row; PER classes per lane (C <= 32 * PER <= 32 * kMaxPerLane).
 constexpr int kMaxPerLane = 8;
 template <int PER>
@@ -362,6 +371,14 @@ int launch_tanh_backward(const float *aTg, const float *h, float *g, uint64_t n,
     tanh_backward_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(
         reinterpret_cast<const float4 *>(aTg), reinterpret_cast<const float4 *>(h),
         reinterpret_cast<float4 *>(g), n4);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_tanh_forward(const float *z, float *h, uint64_t n, cudaStream_t s) {
+    const size_t n4 = n / 4;
+    if (n4 == 0) return 0;
+    tanh_forward_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4 *>(z),
+                                                                     reinterpret_cast<float4 *>(h), n4);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -131,6 +131,11 @@ struct dory_engine {
     uint32_t heavy_degree = kHeavyDegree;
     uint32_t hub_degree = 0;  // rows with more edges get a cluster of 8 CTAs (0 = from the partition's size)
     uint32_t locality_block = 0;  // rows per block of the locality-preserving row order (0 = from L2)
+    // apply-first schedule (DORY_FLAG_APPLY_FIRST, include/dorylus_b200.h): af[l] != 0 -> layer l runs
+    // A_hat . (in . W); decided in dory_load_partition from the flag / the "apply_first_mask" option
+    std::vector<uint8_t> af;
+    long af_mask = -1;
+    bool apply_first(uint32_t l) const { return l < af.size() && af[l]; }
 
     // Adam (AdamOptimizer.hpp:69-84)
     float beta1 = .9f, beta2 = .999f, eps = 1e-07f, lr_t = 0.f;
@@ -157,11 +162,14 @@ struct dory_engine {
     std::set<const float *> ghost_reads_pending;
 
     // widest row slab (bytes, <= 512) any aggregation of this model gathers: GCN aggregates widths
-    // F_0 .. F_{L-1}, GAT the layer outputs F_1 .. F_L
+    // F_0 .. F_{L-1} (an apply-first layer l: F_{l+1}), GAT the layer outputs F_1 .. F_L
     uint32_t max_slab_bytes() const {
         uint32_t m = 16;
         const uint32_t lo = cfg.gnn_type == DORY_GCN ? 0 : 1, hi = cfg.gnn_type == DORY_GCN ? cfg.n_layers : cfg.n_layers + 1;
-        for (uint32_t l = lo; l < hi; ++l) m = std::max(m, std::min<uint32_t>(padded_ld(cfg.dims[l]) * 4, 512));
+        for (uint32_t l = lo; l < hi; ++l) {
+            const uint32_t w = apply_first(l) ? cfg.dims[l + 1] : cfg.dims[l];
+            m = std::max(m, std::min<uint32_t>(padded_ld(w) * 4, 512));
+        }
         return m;
     }
     uint32_t L() const { return cfg.n_layers; }
@@ -425,9 +433,31 @@ int preallocate_gcn(dory_engine *e) {
     T(0, "x", x.rows_from(0, V));
     T(0, "fg", x.rows_from(V, e->Gs));
     for (uint32_t l = 0; l < L; ++l) {
-        DevMat ah = new_tensor(e, V, e->dim(l), ce);
-        CU(ce);
-        T(l, "ah", ah);
+        if (e->apply_first(l)) {
+            // apply-first layer: t = in . W with its ghost block, dL/dz with ITS ghost block, and the
+            // two aggregation outputs (z, u); "ah" / "grad" / "bg" of this layer are never formed
+            const uint32_t nf = e->dim(l + 1);
+            DevMat t = new_tensor(e, (uint64_t)V + e->Gs, nf, ce);
+            CU(ce);
+            T(l, "t", t.rows_from(0, V));
+            T(l, "fg_t", t.rows_from(V, e->Gs));
+            DevMat g = new_tensor(e, (uint64_t)V + e->Gd, nf, ce);
+            CU(ce);
+            T(l, "g", g.rows_from(0, V));
+            T(l, "bg_g", g.rows_from(V, e->Gd));
+            DevMat u = new_tensor(e, V, nf, ce);
+            CU(ce);
+            T(l, "u", u);
+            if (l + 1 == L) {  // logits of the last layer (the reference order keeps them in scratch)
+                DevMat z = new_tensor(e, V, nf, ce);
+                CU(ce);
+                T(l, "z", z);
+            }
+        } else {
+            DevMat ah = new_tensor(e, V, e->dim(l), ce);
+            CU(ce);
+            T(l, "ah", ah);
+        }
         if (l + 1 < L) {
             DevMat z = new_tensor(e, V, e->dim(l + 1), ce);
             CU(ce);
@@ -442,10 +472,12 @@ int preallocate_gcn(dory_engine *e) {
     CU(ce);
     T(L - 1, "lab", lab);
     for (uint32_t l = L - 1; l > 0; --l) {
-        DevMat grad = new_tensor(e, (uint64_t)V + e->Gd, e->dim(l), ce);
-        CU(ce);
-        T(l, "grad", grad.rows_from(0, V));
-        T(l - 1, "bg", grad.rows_from(V, e->Gd));
+        if (!e->apply_first(l)) {
+            DevMat grad = new_tensor(e, (uint64_t)V + e->Gd, e->dim(l), ce);
+            CU(ce);
+            T(l, "grad", grad.rows_from(0, V));
+            T(l - 1, "bg", grad.rows_from(V, e->Gd));
+        }
         DevMat aTg = new_tensor(e, V, e->dim(l), ce);
         CU(ce);
         T(l - 1, "aTg", aTg);
@@ -607,25 +639,9 @@ uint64_t edges_in_range(dory_engine *e, const Adjacency &adj, uint32_t low, uint
 }
 
 // ------------------------------------------------------------------ GCN operators
-int aggregate_gcn(dory_engine *e, const dory_chunk *c) {
-    const uint32_t L = e->L();
-    if (c->upBound > e->V || c->lowBound > c->upBound) return fail(e, DORY_EINVAL, "chunk bounds out of range");
-    const DevMat *src, *out;
-    const Adjacency *adj;
-    if (c->dir == DORY_FORWARD) {
-        if (c->layer >= L) return fail(e, DORY_EINVAL, "aggregate: forward layer %u out of range", c->layer);
-        src = c->layer == 0 ? find_tensor(e, 0, "x") : find_tensor(e, c->layer - 1, "h");
-        out = find_tensor(e, c->layer, "ah");
-        adj = &e->fwd;
-    } else {
-        if (c->layer == 0 || c->layer >= L) return fail(e, DORY_EINVAL, "aggregate: backward layer %u out of range", c->layer);
-        src = find_tensor(e, c->layer, "grad");
-        out = find_tensor(e, c->layer - 1, "aTg");
-        adj = &e->bwd;
-    }
-    if (const DevMat *gh = c->dir == DORY_FORWARD ? find_tensor(e, c->layer, "fg") : find_tensor(e, c->layer - 1, "bg"))
-        e->ghost_reads_pending.insert(gh->p);
-    SpmmArgs a = spmm_args(e, *adj, e->norms.as<float>(), SELF_NORM, *src, *out, c->lowBound, c->upBound, e->V);
+// One GCN aggregation out = self + A . src over `adj` (all source windows), rows [low, up).
+int run_gcn_spmm(dory_engine *e, const Adjacency *adj, const DevMat *src, const DevMat *out, uint32_t low, uint32_t up) {
+    SpmmArgs a = spmm_args(e, *adj, e->norms.as<float>(), SELF_NORM, *src, *out, low, up, e->V);
     if (adj->nb > 1) {
         // one pass per group of source windows; passes are separate launches (stream order) because
         // they accumulate into the same output rows.  A group holds as many windows as keep
@@ -645,8 +661,54 @@ int aggregate_gcn(dory_engine *e, const dory_chunk *c) {
     } else {
         LAUNCHED(launch_spmm(a, e->stream));
     }
-    e->stats.edges_aggregated += edges_in_range(e, *adj, c->lowBound, c->upBound);
+    e->stats.edges_aggregated += edges_in_range(e, *adj, low, up);
     return DORY_OK;
+}
+
+int softmax_ce_gcn(dory_engine *e, const float *logits, const DevMat &lab, float *d);
+
+int aggregate_gcn(dory_engine *e, const dory_chunk *c) {
+    const uint32_t L = e->L();
+    if (c->upBound > e->V || c->lowBound > c->upBound) return fail(e, DORY_EINVAL, "chunk bounds out of range");
+    const DevMat *src, *out, *ghost;
+    const Adjacency *adj;
+    const bool af = e->apply_first(c->layer);
+    if (c->dir == DORY_FORWARD) {
+        if (c->layer >= L) return fail(e, DORY_EINVAL, "aggregate: forward layer %u out of range", c->layer);
+        if (af) {  // z = A_hat [t; fg_t], then the activation (include/dorylus_b200.h: apply-first schedule)
+            if (c->lowBound != 0 || c->upBound != e->V)
+                return fail(e, DORY_EINVAL, "aggregate: layer %u runs apply-first, which takes whole-partition chunks", c->layer);
+            src = find_tensor(e, c->layer, "t");
+            out = find_tensor(e, c->layer, "z");
+            ghost = find_tensor(e, c->layer, "fg_t");
+        } else {
+            src = c->layer == 0 ? find_tensor(e, 0, "x") : find_tensor(e, c->layer - 1, "h");
+            out = find_tensor(e, c->layer, "ah");
+            ghost = find_tensor(e, c->layer, "fg");
+        }
+        adj = &e->fwd;
+    } else {
+        if (c->layer >= L || (c->layer == 0 && !af)) return fail(e, DORY_EINVAL, "aggregate: backward layer %u out of range", c->layer);
+        if (af) {  // u = A_hat^T [g; bg_g]
+            src = find_tensor(e, c->layer, "g");
+            out = find_tensor(e, c->layer, "u");
+            ghost = find_tensor(e, c->layer, "bg_g");
+        } else {
+            src = find_tensor(e, c->layer, "grad");
+            out = find_tensor(e, c->layer - 1, "aTg");
+            ghost = find_tensor(e, c->layer - 1, "bg");
+        }
+        adj = &e->bwd;
+    }
+    if (ghost) e->ghost_reads_pending.insert(ghost->p);
+    int rc = run_gcn_spmm(e, adj, src, out, c->lowBound, c->upBound);
+    if (rc || !af || c->dir != DORY_FORWARD) return rc;
+    if (c->layer + 1 < L) {  // h = tanh(z), activate(): CPU_comm.cpp:265-274
+        const DevMat &h = *find_tensor(e, c->layer, "h");
+        LAUNCHED(launch_tanh_forward(out->p, h.p, (uint64_t)e->V * out->ld, e->stream));
+        return DORY_OK;
+    }
+    return softmax_ce_gcn(e, out->p, *find_tensor(e, c->layer, "lab"), find_tensor(e, c->layer, "g")->p);
 }
 
 bool use_tensor_cores(const dory_engine *e) { return e->tensor_cores && !(e->cfg.flags & DORY_FLAG_NO_TENSOR_CORES); }
@@ -702,12 +764,37 @@ int gemm_tn(dory_engine *e, const DevMat &A, const float *G, uint32_t ldg, Weigh
     return DORY_OK;
 }
 
+// Last-layer soft-max, validation statistics, maskout and gradient scale (CPU_comm.cpp:108-121):
+// d = (maskout(softmax(logits)) - lab) / (V_global * 0.66).
+int softmax_ce_gcn(dory_engine *e, const float *logits, const DevMat &lab, float *d) {
+    SoftmaxCEArgs s{};
+    s.z = logits; s.lab = lab.p; s.d = d; s.pred = nullptr;
+    s.ld = lab.ld; s.C = lab.cols; s.V = e->V;
+    s.trainEnd = (unsigned)(e->V * kTrainPortion);
+    s.valEnd = s.trainEnd + (unsigned)(e->V * kValPortion);
+    s.maskFloats = e->V - s.trainEnd;  // CPU_comm.cpp:470: sizeof(FeatType) * (end - stt)
+    s.strictMask = (e->cfg.flags & DORY_FLAG_STRICT_MASK) != 0;
+    s.denom = (float)(e->gV * kTrainPortion);  // CPU_comm.cpp:121
+    s.rowstat = e->rowstat.as<float>();
+    s.stats = e->stats_dev.as<float>();
+    LAUNCHED(launch_softmax_ce(s, e->stream));
+    e->stats.val_rows = s.valEnd - s.trainEnd;
+    return DORY_OK;
+}
+
+// The rows a layer's dense product reads: "x" (layer 0) or the previous layer's "h", local rows.
+const DevMat &gcn_layer_input(dory_engine *e, uint32_t layer) {
+    return layer == 0 ? *find_tensor(e, 0, "x") : *find_tensor(e, layer - 1, "h");
+}
+
 // CPUComm::vtxNNForwardGCN, CPU_comm.cpp:98-135
 int vtx_forward_gcn(dory_engine *e, uint32_t layer) {
     const uint32_t L = e->L();
     if (layer >= L) return fail(e, DORY_EINVAL, "apply_vertex: layer %u out of range", layer);
-    const DevMat &ah = *find_tensor(e, layer, "ah");
     WeightSet &W = e->W[layer];
+    if (e->apply_first(layer))  // t = in . W; aggregation and activation follow (aggregate_gcn)
+        return gemm_nn(e, gcn_layer_input(e, layer), W, *find_tensor(e, layer, "t"), nullptr);
+    const DevMat &ah = *find_tensor(e, layer, "ah");
     if (layer + 1 < L) {
         return gemm_nn(e, ah, W, *find_tensor(e, layer, "z"), find_tensor(e, layer, "h"));
     }
@@ -719,18 +806,7 @@ int vtx_forward_gcn(dory_engine *e, uint32_t layer) {
     d.p = e->scratchB.as<float>();
     int rc = gemm_nn(e, ah, W, logits, nullptr);
     if (rc) return rc;
-    SoftmaxCEArgs s{};
-    s.z = logits.p; s.lab = lab.p; s.d = d.p; s.pred = nullptr;
-    s.ld = lab.ld; s.C = lab.cols; s.V = e->V;
-    s.trainEnd = (unsigned)(e->V * kTrainPortion);
-    s.valEnd = s.trainEnd + (unsigned)(e->V * kValPortion);
-    s.maskFloats = e->V - s.trainEnd;  // CPU_comm.cpp:470: sizeof(FeatType) * (end - stt)
-    s.strictMask = (e->cfg.flags & DORY_FLAG_STRICT_MASK) != 0;
-    s.denom = (float)(e->gV * kTrainPortion);  // CPU_comm.cpp:121
-    s.rowstat = e->rowstat.as<float>();
-    s.stats = e->stats_dev.as<float>();
-    LAUNCHED(launch_softmax_ce(s, e->stream));
-    e->stats.val_rows = s.valEnd - s.trainEnd;
+    if ((rc = softmax_ce_gcn(e, logits.p, lab, d.p))) return rc;
     if (layer > 0) {
         rc = gemm_nt(e, d.p, d.ld, e->V, W, *find_tensor(e, layer, "grad"));
         if (rc) return rc;
@@ -744,6 +820,10 @@ int vtx_backward_gcn(dory_engine *e, uint32_t layer) {
     if (layer + 1 >= L) return fail(e, DORY_EINVAL, "apply_vertex backward: layer %u out of range", layer);
     const DevMat &aTg = *find_tensor(e, layer, "aTg");
     const DevMat &h = *find_tensor(e, layer, "h");
+    if (e->apply_first(layer)) {  // dL/dz into "g"; its aggregation and dW follow in this layer's backward pass
+        LAUNCHED(launch_tanh_backward(aTg.p, h.p, find_tensor(e, layer, "g")->p, (uint64_t)e->V * aTg.ld, e->stream));
+        return DORY_OK;
+    }
     const DevMat &ah = *find_tensor(e, layer, "ah");
     WeightSet &W = e->W[layer];
     float *g = e->scratchA.as<float>();
@@ -752,6 +832,15 @@ int vtx_backward_gcn(dory_engine *e, uint32_t layer) {
     if (rc) return rc;
     if (layer != 0) rc = gemm_nt(e, g, aTg.ld, e->V, W, *find_tensor(e, layer, "grad"));
     return rc;
+}
+
+// Backward apply of an apply-first layer: dW = in^T . u; l > 0: aTg[l-1] = u . W^T (= dL/dh[l-1]).
+int vtx_backward_apply_first(dory_engine *e, uint32_t layer) {
+    const DevMat &u = *find_tensor(e, layer, "u");
+    WeightSet &W = e->W[layer];
+    int rc = gemm_tn(e, gcn_layer_input(e, layer), u.p, u.ld, W, W.dw.as<float>());
+    if (rc || layer == 0) return rc;
+    return gemm_nt(e, u.p, u.ld, e->V, W, *find_tensor(e, layer - 1, "aTg"));
 }
 
 // Engine::scatterGCN + ghostReceiverGCN: rows of `name`[srcLayer] -> peers' ghost block.
@@ -780,15 +869,19 @@ int exchange(dory_engine *e, uint32_t dir, const DevMat &local, const DevMat &gh
 
 int scatter_gcn(dory_engine *e, const dory_chunk *c) {
     const uint32_t L = e->L();
+    const bool af = e->apply_first(c->layer);
     if (c->dir == DORY_FORWARD) {  // gcn_ops.cpp:207-209: h[layer-1] -> fg[layer]
+        if (c->layer >= L) return fail(e, DORY_EINVAL, "scatter: forward layer %u out of range", c->layer);
+        // apply-first layer: what its aggregation gathers is t = in . W
+        if (af) return exchange(e, DORY_FORWARD, *find_tensor(e, c->layer, "t"), *find_tensor(e, c->layer, "fg_t"));
         // layer 0 (no reference counterpart): the reference fills the layer-0 ghost rows of EVERY
         // partition from the feature file (readFeaturesFile, engine/utils.cpp:486-552).  A caller that
         // streams features uploads only the rows it owns and ships x -> the peers' fg[0] over NVLink.
         if (c->layer == 0) return exchange(e, DORY_FORWARD, *find_tensor(e, 0, "x"), *find_tensor(e, 0, "fg"));
-        if (c->layer >= L) return fail(e, DORY_EINVAL, "scatter: forward layer %u out of range", c->layer);
         return exchange(e, DORY_FORWARD, *find_tensor(e, c->layer - 1, "h"), *find_tensor(e, c->layer, "fg"));
     }
-    if (c->layer == 0 || c->layer >= L) return fail(e, DORY_EINVAL, "scatter: backward layer %u out of range", c->layer);
+    if (c->layer >= L || (c->layer == 0 && !af)) return fail(e, DORY_EINVAL, "scatter: backward layer %u out of range", c->layer);
+    if (af) return exchange(e, DORY_BACKWARD, *find_tensor(e, c->layer, "g"), *find_tensor(e, c->layer, "bg_g"));
     return exchange(e, DORY_BACKWARD, *find_tensor(e, c->layer, "grad"), *find_tensor(e, c->layer - 1, "bg"));
 }
 
@@ -1114,6 +1207,11 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
     } else if (std::strcmp(key, "spmm_unroll") == 0) {
         if (v > 2) return fail(e, DORY_EINVAL, "spmm_unroll must be 0 (default), 1 or 2");
         e->spmm_unroll = (int)v;
+    } else if (std::strcmp(key, "apply_first_mask") == 0) {
+        if (e->loaded) return fail(e, DORY_ESTATE, "apply_first_mask must be set before dory_load_partition");
+        if (e->cfg.gnn_type != DORY_GCN) return fail(e, DORY_EINVAL, "apply_first_mask is a GCN option");
+        if (v >= (1L << e->cfg.n_layers)) return fail(e, DORY_EINVAL, "apply_first_mask has bits beyond layer %u", e->cfg.n_layers - 1);
+        e->af_mask = v;
     } else if (std::strcmp(key, "heavy_degree") == 0) {
         if (e->loaded) return fail(e, DORY_ESTATE, "heavy_degree must be set before dory_load_partition");
         e->heavy_degree = (uint32_t)std::max<long>(v, 1);
@@ -1264,6 +1362,12 @@ int dory_load_partition(dory_engine *e, const void *graph_bin, size_t len) {
                 if (id >= e->V) return fail(e, DORY_EFORMAT, "send list references vertex %u >= %u", id, e->V);
         }
     }
+    e->af.assign(e->L(), 0);
+    if (e->cfg.gnn_type == DORY_GCN)
+        for (uint32_t l = 0; l < e->L(); ++l) {
+            if (e->af_mask >= 0) e->af[l] = (e->af_mask >> l) & 1;
+            else if (e->cfg.flags & DORY_FLAG_APPLY_FIRST) e->af[l] = padded_ld(e->dim(l + 1)) < padded_ld(e->dim(l));
+        }
     int rc = upload_adjacency(e, e->fwd, pv.colPtrs, pv.rowIdxs, pv.fwdVals, pv.fwdNnz, e->V, e->V + e->Gs);
     if (rc) return rc;
     rc = upload_adjacency(e, e->bwd, pv.rowPtrs, pv.colIdxs, pv.bwdVals, pv.bwdNnz, e->V, e->V + e->Gd);
@@ -1437,6 +1541,12 @@ int dory_apply_update(dory_engine *e, uint32_t layer) {
     return apply_update_impl(e, layer);
 }
 
+int dory_layer_schedule(const dory_engine *e, uint32_t layer, int *apply_first) {
+    if (!e || !apply_first || !e->loaded || layer >= e->L()) return DORY_EINVAL;
+    *apply_first = e->apply_first(layer) ? 1 : 0;
+    return DORY_OK;
+}
+
 int dory_inc_layer(const dory_engine *e, dory_chunk *c) {
     if (!e || !c) return DORY_EINVAL;
     if (e->cfg.gnn_type == DORY_GCN) inc_layer_gcn(e, c); else inc_layer_gat(e, c);
@@ -1456,6 +1566,10 @@ int dory_apply_vertex(dory_engine *e, const dory_chunk *c) {
     if (!c) return fail(e, DORY_EINVAL, "null chunk");
     if (e->cfg.gnn_type == DORY_GCN) {
         if (c->dir == DORY_FORWARD) return vtx_forward_gcn(e, c->layer);
+        if (c->layer >= e->L()) return fail(e, DORY_EINVAL, "apply_vertex: backward layer %u out of range", c->layer);
+        if (e->apply_first(c->layer)) {  // this layer's own dense products come after ITS aggregation
+            if ((rc = vtx_backward_apply_first(e, c->layer)) || c->layer == 0) return rc;
+        }
         dory_chunk n = *c;  // applyVertexGCN, gcn_ops.cpp:198-200: inc layer first
         inc_layer_gcn(e, &n);
         if (n.dir != DORY_BACKWARD) return fail(e, DORY_EINVAL, "apply_vertex: backward chunk at layer 0 has nothing to apply");
@@ -1496,10 +1610,18 @@ int dory_forward(dory_engine *e, uint32_t layer) {
     int rc = check_loaded(e);
     if (rc) return rc;
     dory_chunk c{0, e->cfg.node_id, 0, e->V, layer, DORY_FORWARD, 0, 1};
-    if (e->cfg.gnn_type == DORY_GCN) {  // GA -> AV -> SC -> AE
-        if ((rc = dory_aggregate(e, &c))) return rc;
-        if ((rc = dory_apply_vertex(e, &c))) return rc;
+    if (e->cfg.gnn_type == DORY_GCN) {
+        if (e->apply_first(layer)) {  // AV -> SC -> GA (+ activation)
+            if ((rc = dory_apply_vertex(e, &c))) return rc;
+            if ((rc = dory_scatter(e, &c))) return rc;
+            if ((rc = dory_aggregate(e, &c))) return rc;
+        } else {  // GA -> AV
+            if ((rc = dory_aggregate(e, &c))) return rc;
+            if ((rc = dory_apply_vertex(e, &c))) return rc;
+        }
         inc_layer_gcn(e, &c);
+        // -> SC -> AE for the next chunk; an apply-first layer ships its own t after its dense product
+        if (c.dir == DORY_FORWARD && e->apply_first(c.layer)) return DORY_OK;
         if ((rc = dory_scatter(e, &c))) return rc;
         return dory_apply_edge(e, &c);
     }
@@ -1521,8 +1643,10 @@ int dory_backward(dory_engine *e, uint32_t layer) {
     if (e->cfg.gnn_type == DORY_GCN) {  // GA -> AV(B) -> SC -> AE for the next backward layer
         if ((rc = dory_aggregate(e, &c))) return rc;
         if ((rc = dory_apply_vertex(e, &c))) return rc;
+        if (layer == 0) return DORY_OK;  // only reached when layer 0 is apply-first (dW[0] is done)
         inc_layer_gcn(e, &c);
-        if (c.layer == 0) return DORY_OK;  // vtxNNBackward(0) ended the epoch
+        // vtxNNBackward(0) ended the epoch -- unless layer 0 is apply-first and still owes dW[0]
+        if (c.layer == 0 && !e->apply_first(0)) return DORY_OK;
         if ((rc = dory_scatter(e, &c))) return rc;
         return dory_apply_edge(e, &c);
     }
@@ -1544,6 +1668,7 @@ int dory_epoch(dory_engine *e, dory_stats *stats) {
             if ((rc = dory_forward(e, l))) return rc;
         for (uint32_t l = L - 1; l > 0; --l)
             if ((rc = dory_backward(e, l))) return rc;
+        if (e->apply_first(0) && (rc = dory_backward(e, 0))) return rc;
     } else {
         for (uint32_t l = 0; l < L; ++l)
             if ((rc = dory_forward(e, l))) return rc;
@@ -1660,7 +1785,8 @@ struct IpcBlob {
 static_assert(sizeof(IpcBlob) <= DORY_IPC_BLOB_BYTES, "IPC blob does not fit DORY_IPC_BLOB_BYTES");
 
 bool is_ghost_name(const char *n) {
-    return !std::strcmp(n, "fg") || !std::strcmp(n, "bg") || !std::strcmp(n, "fg_z") || !std::strcmp(n, "bg_d");
+    return !std::strcmp(n, "fg") || !std::strcmp(n, "bg") || !std::strcmp(n, "fg_z") || !std::strcmp(n, "bg_d") ||
+           !std::strcmp(n, "fg_t") || !std::strcmp(n, "bg_g");
 }
 }  // namespace
 

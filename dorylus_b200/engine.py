@@ -389,12 +389,23 @@ class Engine:
         self._check(self._lib.dory_comm_set_send_slots(self._h, dir, peer, slots.ctypes.data_as(C.POINTER(C.c_uint32)),
                                                        slots.size))
 
+    def apply_first(self, layer: int) -> bool:
+        """True when `layer` runs the apply-first schedule (DORY_FLAG_APPLY_FIRST, dory_layer_schedule)."""
+        v = C.c_int(0)
+        self._check(self._lib.dory_layer_schedule(self._h, layer, C.byref(v)))
+        return bool(v.value)
+
     def ghost_tensors(self):
         """(layer, name) of every ghost block that takes part in an exchange."""
         L = self.numLayers
         if self.gnn_type == GCN:
-            # (0, "fg") takes part in the layer-0 input exchange (scatter of a layer-0 FORWARD chunk)
-            return [(l, "fg") for l in range(0, L)] + [(l - 1, "bg") for l in range(1, L)]
+            out = [(0, "fg")]  # the layer-0 input exchange (scatter of a layer-0 FORWARD chunk)
+            for l in range(L):
+                if self.apply_first(l):  # ghosts of t = in . W (forward) and of dL/dz (backward)
+                    out += [(l, "fg_t"), (l, "bg_g")]
+                elif l > 0:
+                    out += [(l, "fg"), (l - 1, "bg")]
+            return out
         return [(l, "fg_z") for l in range(L)] + [(l, "bg_d") for l in range(L)]
 
     def comm_ipc_export(self, layer: int, name: str) -> bytes:

@@ -9,10 +9,13 @@
 //   dorylus_b200_run --datasetdir D/ --featuresfile F --labelsfile L --layerfile C
 //                    [--numepochs 10] [--lr 0.01] [--gnn GCN|GAT] [--undirected 0]
 //                    [--pipeline 1 [--numlambdas N] [--targetacc A] [--switchthreshold T]] [--dry-run 1]
+//                    [--apply-first 1]
 //
 // --pipeline 1 drives the epochs through host/saga_pipeline.hpp -- the reference's chunk queues,
 // priority order, barriers, early-stop state machine and <EM> report (engine/ops/pipeline.cpp) --
 // instead of dory_epoch; --numlambdas is the number of chunks per partition (numLambdasForward).
+// --apply-first 1 sets DORY_FLAG_APPLY_FIRST (GCN layers that narrow run A_hat.(in.W)); that schedule is
+// driven by dory_epoch, not by the reference's queue order, so it excludes --pipeline 1.
 // --dry-run 1 stops after the host-side half (preprocess, features / labels incl. the reference's
 // feats<F0>.<id>.bin cache) and prints what it read: no GPU needed.
 //
@@ -51,7 +54,7 @@ bool read_file(const std::string &path, std::vector<char> &out) {
 
 int main(int argc, char **argv) {
     std::string dir, featuresFile, labelsFile, layerFile, gnn = "GCN";
-    unsigned epochs = 10, undirected = 0, pipeline = 0, numLambdas = 1, dryRun = 0;
+    unsigned epochs = 10, undirected = 0, pipeline = 0, numLambdas = 1, dryRun = 0, applyFirst = 0;
     float lr = 0.01f, targetAcc = 1.1f, switchThreshold = 0.02f;
     for (int i = 1; i + 1 < argc; i += 2) {
         const std::string k = argv[i], v = argv[i + 1];
@@ -65,6 +68,7 @@ int main(int argc, char **argv) {
         else if (k == "--undirected") undirected = (unsigned)std::atoi(v.c_str());
         else if (k == "--pipeline") pipeline = (unsigned)std::atoi(v.c_str());
         else if (k == "--dry-run") dryRun = (unsigned)std::atoi(v.c_str());
+        else if (k == "--apply-first") applyFirst = (unsigned)std::atoi(v.c_str());
         else if (k == "--numlambdas") numLambdas = (unsigned)std::max(1, std::atoi(v.c_str()));
         else if (k == "--targetacc") targetAcc = (float)std::atof(v.c_str());
         else if (k == "--switchthreshold") switchThreshold = (float)std::atof(v.c_str());
@@ -103,6 +107,13 @@ int main(int argc, char **argv) {
     cfg.num_nodes = 1;
     cfg.device = 0;
     cfg.learning_rate = lr;
+    if (applyFirst) {
+        if (pipeline || cfg.gnn_type != DORY_GCN) {
+            std::fprintf(stderr, "--apply-first 1 is a GCN schedule driven by dory_epoch (not with --pipeline 1 / GAT)\n");
+            return EXIT_FAILURE;
+        }
+        cfg.flags |= DORY_FLAG_APPLY_FIRST;
+    }
 
     // Engine::init order (engine/engine.cpp:62-100): partition image (preprocess when absent), then
     // features and labels.  Everything up to dory_create is host-only.

@@ -66,6 +66,14 @@ typedef struct dory_chunk {
 #define DORY_FLAG_GAT_PREDICT_AH 0x2u /* predictGAT reads "ah" instead of replicating quirk Q9
                                        (gat_ops.cpp:252 reads "az") */
 #define DORY_FLAG_NO_TENSOR_CORES 0x4u /* force the fp32 SIMT GEMM path for H.W */
+#define DORY_FLAG_APPLY_FIRST 0x8u    /* GCN: run every layer whose output rows are narrower than its
+                                       input rows as  A_hat . (in . W)  instead of the reference's
+                                       (A_hat . in) . W  (gcn_ops.cpp:130-191 then CPU_comm.cpp:98-159).
+                                       Same z / h / weight gradients up to fp32 rounding, F_out-wide
+                                       gathers instead of F_in-wide ones (Reddit layer 0: 128 instead of
+                                       602 floats per edge).  "ah", "grad" and "bg" of such a layer are not
+                                       materialised; see "apply-first schedule" below.  Off by default:
+                                       the default path keeps the reference's operator order. */
 
 /* What Engine::init gathers from its CLI + layer config file (engine/utils.cpp:313-479). */
 typedef struct dory_config {
@@ -129,7 +137,9 @@ int dory_sync(dory_engine *e);
  *                           a block's source rows stay in L2 across its classes (0 = 24 MB worth of
  *                           the widest gathered slab; set before load).
  *   "tensor_cores"          1: run H.W on tcgen05 (3xTF32, fp32-level accuracy) when the shape
- *                           qualifies; 0: always the fp32 CUDA-core GEMM. */
+ *                           qualifies; 0: always the fp32 CUDA-core GEMM.
+ *   "apply_first_mask"      bit l = 1: layer l runs apply-first (overrides the width rule of
+ *                           DORY_FLAG_APPLY_FIRST; GCN only; set before dory_load_partition). */
 int dory_set_option(dory_engine *e, const char *key, const char *value);
 
 /* ---- dataset preprocessing (host only, no GPU needed) --------------------------------------
@@ -249,6 +259,25 @@ int dory_scatter(dory_engine *e, const dory_chunk *c);
 int dory_apply_edge(dory_engine *e, const dory_chunk *c);
 int dory_predict(dory_engine *e, const dory_chunk *c);
 int dory_inc_layer(const dory_engine *e, dory_chunk *c);
+
+/* Apply-first schedule (DORY_FLAG_APPLY_FIRST / option "apply_first_mask"; GCN).  For a layer l that
+ * runs apply-first the operators keep their names but the order inside dory_forward / dory_backward
+ * is AV -> SC -> GA (the order the reference's GAT uses), on these tensors:
+ *   forward   dory_apply_vertex  "t"[l] = in . W[l]          (in = "x" or "h"[l-1], local rows only)
+ *             dory_scatter       "t"[l] -> peers' "fg_t"[l]  (chunk.layer = l: fills the ghost block the
+ *                                                             aggregation of layer l reads)
+ *             dory_aggregate     "z"[l] = A_hat ["t"; "fg_t"], then "h"[l] = tanh("z"[l]); last layer:
+ *                                soft-max / statistics / maskout / scale on "z" -> "g"[l]
+ *                                (whole-partition chunks only)
+ *   backward  dory_scatter       "g"[l] -> peers' "bg_g"[l]  ("g"[l] = dL/dz[l], chunk.layer = l)
+ *             dory_aggregate     "u"[l] = A_hat^T ["g"; "bg_g"]
+ *             dory_apply_vertex  dW[l] = in^T . "u"[l];  l > 0: "aTg"[l-1] = "u"[l] . W[l]^T, followed by
+ *                                the activation derivative of layer l-1 exactly as in the reference order
+ *                                (into "g"[l-1] when that layer is apply-first too)
+ * "aTg"[l-1] is dL/dh[l-1] under either schedule.  A BACKWARD chunk at layer 0 is valid when layer 0 is
+ * apply-first (its weight gradient needs one aggregation the reference order does not have).
+ * dory_layer_schedule reports what a layer runs: *apply_first = 1 or 0. */
+int dory_layer_schedule(const dory_engine *e, uint32_t layer, int *apply_first);
 
 /* Coarser granularity named by BASELINE.json ("per-layer forward()/backward()"):
  * dory_forward(l)  = one chunk's GA->AV->SC->AE pass with dir == FORWARD at layer l,

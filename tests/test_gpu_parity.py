@@ -95,47 +95,6 @@ def test_engine_matches_numpy_gnn_golden(golden):
         assert rel_err(e.get_weight_grad(0), g["dW0"]) < TOL
 
 
-def test_engine_matches_lambda_ops_golden(golden):
-    """ApplyVertex of the CUDA path against tests/golden/funcs_ops.npz -- REAL runs of the reference's
-    Lambda tensor ops (src/funcs/gcn/ops, sequenced as funcs/gcn/main.cpp: forwardLayer, finalLayer,
-    backwardLayer): z / h, then grad and dW of the last layer (soft-max, the float-wise maskout of quirk
-    Q6 ending mid-row, the 1/(V * 0.66) scale), then the hidden layer's backward apply."""
-    from dorylus_b200 import engine as dengine
-
-    g = golden["funcs_ops"]
-    V, Fin = g["gcn_ah0"].shape
-    dims = [Fin, g["gcn_W0"].shape[1], g["gcn_W1"].shape[1]]
-    assert int(g["gcn_gV"]) == V
-    ring = np.arange(V, dtype=np.uint32)
-    src, dst = np.concatenate([ring, (ring + 1) % V]), np.concatenate([(ring + 1) % V, ring])
-    image = dengine.preprocess_edges(src.astype(np.uint32), dst.astype(np.uint32), np.zeros(V, np.int32), V, 0, 1)
-    e = Engine(dims, GCN)
-    e.load_partition(image)
-    with e:
-        e.set_weights(0, g["gcn_W0"])
-        e.set_weights(1, g["gcn_W1"])
-        e.set_tensor(1, "lab", g["gcn_lab"])
-        e.set_tensor(0, "ah", g["gcn_ah0"])
-        e.applyVertexGCN(e.whole_chunk(0, FORWARD))
-        assert rel_err(e.get_tensor(0, "z"), g["gcn_z0"]) < TOL
-        assert rel_err(e.get_tensor(0, "h"), g["gcn_h0"]) < TOL
-        e.set_tensor(1, "ah", g["gcn_ah1"])
-        e.applyVertexGCN(e.whole_chunk(1, FORWARD))
-        assert rel_err(e.get_tensor(1, "grad"), g["gcn_grad1"]) < TOL
-        assert rel_err(e.get_weight_grad(1), g["gcn_dW1"]) < TOL
-        # validation statistics (getTrainStat) recomputed from the reference's soft-max output
-        pred, lab = g["gcn_pred"], g["gcn_lab"]
-        stt = int(V * 0.66)
-        val = slice(stt, stt + int(V * 0.1))
-        st = e.stats()
-        assert st["acc_sum"] == float((pred[val].argmax(1) == lab[val].argmax(1)).sum())
-        want_loss = float(-np.log(pred[val][np.arange(val.stop - val.start), lab[val].argmax(1)].astype(np.float64)).sum())
-        assert abs(st["loss_sum"] - want_loss) < 1e-3
-        e.set_tensor(0, "aTg", g["gcn_aTg0"])
-        e.applyVertexGCN(e.whole_chunk(1, BACKWARD))  # NNCompute on the incremented chunk: layer 0
-        assert rel_err(e.get_weight_grad(0), g["gcn_dW0"]) < TOL
-
-
 def test_aggregate_is_bit_reproducible_and_linear():
     ds = random_dataset(V=1600, E_und=30000, dims=[128, 32, 8], seed=8, extra_edges=HUB)
     with gcn_engine(ds) as e:
