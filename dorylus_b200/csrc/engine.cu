@@ -128,6 +128,7 @@ struct dory_engine {
     int row_order = 0;  // light-row issue order: 0 = decide from the graph, 1 = degree-descending, 2 = degree classes
     int tensor_cores = 1;  // tcgen05 path for H.W (option "tensor_cores")
     uint32_t src_blocks = 0;  // source windows per aggregation (0 = size from L2, 1 = off)
+    int gat_windows = 0;      // option "gat_windows": source windows for the GAT aggregations too
     uint32_t heavy_degree = kHeavyDegree;
     uint32_t hub_degree = 0;  // rows with more edges get a cluster of 8 CTAs (0 = from the partition's size)
     uint32_t locality_block = 0;  // rows per block of the locality-preserving row order (0 = from L2)
@@ -358,7 +359,7 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
     }
     nb = std::max(1u, std::min(nb, 64u));
     adj.nb = 1;
-    if (nb > 1 && nnz && e->cfg.gnn_type == DORY_GCN) {
+    if (nb > 1 && nnz && (e->cfg.gnn_type == DORY_GCN || e->gat_windows)) {
         const uint32_t rowsPerBlock = (nSrcRows + nb - 1) / nb;
         std::vector<uint64_t> bp((size_t)V * nb + 1);
         std::vector<uint32_t> bi(nnz);
@@ -639,9 +640,14 @@ uint64_t edges_in_range(dory_engine *e, const Adjacency &adj, uint32_t low, uint
 }
 
 // ------------------------------------------------------------------ GCN operators
-// One GCN aggregation out = self + A . src over `adj` (all source windows), rows [low, up).
-int run_gcn_spmm(dory_engine *e, const Adjacency *adj, const DevMat *src, const DevMat *out, uint32_t low, uint32_t up) {
-    SpmmArgs a = spmm_args(e, *adj, e->norms.as<float>(), SELF_NORM, *src, *out, low, up, e->V);
+// One aggregation out = self(mode) + A . src over `adj`, rows [low, up), walking the source windows of
+// the adjacency when it has them.  `vals` overrides the adjacency's edge values; with windows that is
+// only valid for values that are constant along a destination row (the regrouped copy permutes a row's
+// edges inside the row's own range) -- true of the GAT attention values and their gradients (quirk Q8).
+int run_spmm(dory_engine *e, const Adjacency *adj, const float *selfw, int mode, const DevMat *src, const DevMat *out,
+             uint32_t low, uint32_t up, const float *vals = nullptr) {
+    SpmmArgs a = spmm_args(e, *adj, selfw, mode, *src, *out, low, up, e->V);
+    if (vals) a.vals = vals;
     if (adj->nb > 1) {
         // one pass per group of source windows; passes are separate launches (stream order) because
         // they accumulate into the same output rows.  A group holds as many windows as keep
@@ -650,12 +656,12 @@ int run_gcn_spmm(dory_engine *e, const Adjacency *adj, const DevMat *src, const 
         const uint32_t span = e->src_blocks ? 1 : std::max(1u, e->max_slab_bytes() / slab);
         a.ptrs = adj->bptrs.as<uint64_t>();
         a.idx = adj->bidx.as<uint32_t>();
-        a.vals = adj->bvals.as<float>();
+        a.vals = vals ? vals : adj->bvals.as<float>();
         a.ptr_stride = adj->nb;
         for (uint32_t b = 0; b < adj->nb; b += span) {
             a.ptr_off = b;
             a.ptr_span = std::min(span, adj->nb - b);
-            a.self_mode = b == 0 ? SELF_NORM : SELF_ACCUM;
+            a.self_mode = b == 0 ? mode : SELF_ACCUM;
             LAUNCHED(launch_spmm(a, e->stream));
         }
     } else {
@@ -663,6 +669,10 @@ int run_gcn_spmm(dory_engine *e, const Adjacency *adj, const DevMat *src, const 
     }
     e->stats.edges_aggregated += edges_in_range(e, *adj, low, up);
     return DORY_OK;
+}
+
+int run_gcn_spmm(dory_engine *e, const Adjacency *adj, const DevMat *src, const DevMat *out, uint32_t low, uint32_t up) {
+    return run_spmm(e, adj, e->norms.as<float>(), SELF_NORM, src, out, low, up);
 }
 
 int softmax_ce_gcn(dory_engine *e, const float *logits, const DevMat &lab, float *d);
@@ -922,22 +932,17 @@ int aggregate_gat(dory_engine *e, const dory_chunk *c) {
     if (const DevMat *gh = find_tensor(e, fl, "fg_z")) e->ghost_reads_pending.insert(gh->p);
     if (c->dir == DORY_BACKWARD)
         if (const DevMat *gh = find_tensor(e, fl, "bg_d")) e->ghost_reads_pending.insert(gh->p);
-    if (c->dir == DORY_FORWARD) {  // gat_ops.cpp:201-220: ah = z + sum A[e] z_src
-        SpmmArgs a = spmm_args(e, e->fwd, nullptr, SELF_ONE, z, *find_tensor(e, fl, "ah"), c->lowBound, c->upBound, e->V);
-        LAUNCHED(launch_spmm(a, e->stream));
-        e->stats.edges_aggregated += edges_in_range(e, e->fwd, c->lowBound, c->upBound);
-        return DORY_OK;
-    }
+    // The edge values of both forward-adjacency terms live in arrays of the ORIGINAL edge order ("A"
+    // aliases forwardAdj.values, "dA"); they are passed explicitly so that the windowed walk (option
+    // "gat_windows") can use them with the regrouped ids.
+    if (c->dir == DORY_FORWARD)  // gat_ops.cpp:201-220: ah = z + sum A[e] z_src
+        return run_spmm(e, &e->fwd, nullptr, SELF_ONE, &z, find_tensor(e, fl, "ah"), c->lowBound, c->upBound,
+                        e->fwd.vals.as<float>());
     // gat_ops.cpp:221-241: aTg = sum_out bvals * grad_dst  +  sum_in dA * z_src   (zero-initialised, Q11)
     const DevMat &aTg = *find_tensor(e, fl, "aTg");
-    SpmmArgs a1 = spmm_args(e, e->bwd, nullptr, SELF_ZERO, *find_tensor(e, fl, "grad"), aTg, c->lowBound, c->upBound, e->V);
-    LAUNCHED(launch_spmm(a1, e->stream));
-    SpmmArgs a2 = spmm_args(e, e->fwd, nullptr, SELF_ACCUM, z, aTg, c->lowBound, c->upBound, e->V);
-    a2.vals = find_tensor(e, fl, "dA")->p;
-    LAUNCHED(launch_spmm(a2, e->stream));
-    e->stats.edges_aggregated += edges_in_range(e, e->bwd, c->lowBound, c->upBound) +
-                                 edges_in_range(e, e->fwd, c->lowBound, c->upBound);
-    return DORY_OK;
+    int rc = run_spmm(e, &e->bwd, nullptr, SELF_ZERO, find_tensor(e, fl, "grad"), &aTg, c->lowBound, c->upBound);
+    if (rc) return rc;
+    return run_spmm(e, &e->fwd, nullptr, SELF_ACCUM, &z, &aTg, c->lowBound, c->upBound, find_tensor(e, fl, "dA")->p);
 }
 
 const DevMat &gat_layer_input(dory_engine *e, uint32_t layer) {  // CPU_comm.cpp:162-164
@@ -1187,6 +1192,9 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
     } else if (std::strcmp(key, "src_blocks") == 0) {
         if (e->loaded) return fail(e, DORY_ESTATE, "src_blocks must be set before dory_load_partition");
         e->src_blocks = (uint32_t)v;
+    } else if (std::strcmp(key, "gat_windows") == 0) {
+        if (e->loaded) return fail(e, DORY_ESTATE, "gat_windows must be set before dory_load_partition");
+        e->gat_windows = v != 0;
     } else if (std::strcmp(key, "locality_block") == 0) {
         if (e->loaded) return fail(e, DORY_ESTATE, "locality_block must be set before dory_load_partition");
         e->locality_block = (uint32_t)v;

@@ -120,6 +120,12 @@ int dory_sync(dory_engine *e);
  *   "src_blocks"            source-row windows per aggregation: each pass gathers only from a
  *                           (V+G)/n-row window so that it stays L2-resident (0 = size from the L2
  *                           capacity, 1 = off; set before dory_load_partition; GCN only).
+ *   "gat_windows"           1: the GAT aggregations walk the source windows too (the attention values
+ *                           "A" and their gradients "dA" are constant along a destination row -- quirk
+ *                           Q8, one-sided score -- so the regrouped edge ids can be used with value
+ *                           arrays kept in the original edge order; a caller that overwrites "A" / "dA"
+ *                           with values that vary inside a row must leave this off).  Default 0; set
+ *                           before dory_load_partition.
  *   "heavy_degree"          rows with at least this many edges get a whole CTA (set before
  *                           dory_load_partition).
  *   "hub_degree"            rows with at least this many edges get a thread-block cluster of 8 CTAs

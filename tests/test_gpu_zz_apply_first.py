@@ -14,8 +14,8 @@ import pytest
 from apply_first_model import ApplyFirstGCN, choose_apply_first
 from helpers import random_dataset, rel_err
 from dorylus_b200 import _lib
-from dorylus_b200.engine import BACKWARD, FORWARD, GCN, DoryError, Engine
-from oracle.driver import OracleGCN
+from dorylus_b200.engine import BACKWARD, FORWARD, GAT, GCN, DoryError, Engine
+from oracle.driver import OracleGAT, OracleGCN
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("DORY_TEST_UNVERIFIED") != "1",
@@ -143,3 +143,29 @@ def test_apply_first_two_partitions_on_one_gpu(oracle):
     finally:
         for e in eng:
             e.close()
+
+
+@pytest.mark.parametrize("nb", [2, 5])
+def test_gat_source_windows_match_oracle(oracle, nb):
+    """Option "gat_windows": the GAT aggregations on the source-windowed adjacency (regrouped ids, value
+    arrays in the original edge order) reproduce the oracle like the un-windowed walk does."""
+    ds = random_dataset(V=300, E_und=1500, dims=[24, 12, 5], seed=71)
+    orc = OracleGAT(oracle, ds.graphs, ds.dims, predict_from="ah")
+    orc.load_features(ds.feats, ds.onehot)
+    orc.epoch()
+    e = Engine(ds.dims, GAT, flags=_lib.FLAG_GAT_PREDICT_AH)
+    e.set_option("gat_windows", 1)
+    e.set_option("src_blocks", nb)
+    e.load_partition(ds.images[0])
+    with e:
+        e.set_tensor(0, "h", ds.feats)
+        e.set_tensor(len(ds.dims) - 2, "lab", ds.onehot)
+        e.init_weights()
+        for l in range(2):
+            e.set_weights(l, orc.a[l], "a_i")
+        e.epoch()
+        t = orc.saved[0]
+        for l in range(2):
+            for name in ("z", "ah", "grad", "aTg"):
+                assert rel_err(e.get_tensor(l, name), t[l][name]) < TOL, (l, name)
+            assert rel_err(e.get_weight_grad(l), orc.dW[0][l]) < TOL
