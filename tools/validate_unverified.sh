@@ -1,0 +1,25 @@
+#!/bin/bash
+# First GPU call of the next session: run everything that was written without hardware access
+# (tests gated by DORY_TEST_UNVERIFIED, the apply-first bench arm, GAT source windows) and leave the
+# results under gpurun_out/.  Usage (≈6 GPU-minutes):
+#   gpurun --timeout 900 -- 'bash tools/validate_unverified.sh'
+set -x
+mkdir -p gpurun_out
+DORY_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_zz_apply_first.py tests/test_gpu_zz_lambda_golden.py \
+    -q -m gpu 2>&1 | tail -40 > gpurun_out/unverified_tests.log
+cat gpurun_out/unverified_tests.log
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_reference_order.json 2> gpurun_out/bench_reference_order.log
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --apply-first > gpurun_out/bench_apply_first.json 2> gpurun_out/bench_apply_first.log
+cat gpurun_out/bench_reference_order.json gpurun_out/bench_apply_first.json
+# Reddit GAT (configs[2]) with and without source windows
+timeout 600 python tools/shape_bench.py --name reddit --gnn GAT --out gpurun_out/shape_reddit_gat.json > /dev/null 2> gpurun_out/shape_gat.log
+timeout 600 python tools/shape_bench.py --name reddit --gnn GAT --opt gat_windows=1 --out gpurun_out/shape_reddit_gat_windows.json > /dev/null 2>> gpurun_out/shape_gat.log
+python - <<'PY'
+import json
+for n in ("shape_reddit_gat", "shape_reddit_gat_windows"):
+    try:
+        d = json.load(open("gpurun_out/%s.json" % n))
+        print(n, "epoch_ms", d["epoch_ms"], [(l["layer"], l["dir"], round(l["ms"], 3)) for l in d["layers"]])
+    except Exception as ex:
+        print(n, "missing:", ex)
+PY
