@@ -95,6 +95,7 @@ SYMBOLS = {
     "dory_comm_init": (C.c_int, [_P, _P]),
     "dory_comm_set_recv_slots": (C.c_int, [_P, _u32, _u32, _u32p, _u32]),
     "dory_comm_send_gvids": (C.c_int, [_P, _u32, _u32, _u32p, _u32p]),
+    "dory_ghost_slots": (C.c_int, [_P, C.c_size_t, _u32, _P, C.c_size_t, _u32, _u32p, _u32p]),
     "dory_comm_set_send_slots": (C.c_int, [_P, _u32, _u32, _u32p, _u32]),
     "dory_comm_ipc_export": (C.c_int, [_P, _u32, C.c_char_p, _P]),
     "dory_comm_ipc_import": (C.c_int, [_P, _u32, C.c_char_p, _u32, _P]),

@@ -1774,6 +1774,43 @@ int dory_comm_set_recv_slots(dory_engine *e, uint32_t dir, uint32_t peer, const 
     return DORY_OK;
 }
 
+int dory_ghost_slots(const void *my_bin, size_t my_len, uint32_t my_id, const void *peer_bin, size_t peer_len,
+                     uint32_t dir, uint32_t *slots, uint32_t *n) {
+    dory_engine *e = nullptr;
+    if (!my_bin || !peer_bin || !n || dir > 1) return fail(e, DORY_EINVAL, "dory_ghost_slots: bad argument");
+    PartitionView mine, peer;
+    std::string msg = parse_partition(my_bin, my_len, mine);
+    if (msg.empty()) msg = parse_partition(peer_bin, peer_len, peer);
+    if (!msg.empty()) return fail(e, DORY_EFORMAT, "%s", msg.c_str());
+    if (mine.numNodes != peer.numNodes || my_id >= peer.numNodes)
+        return fail(e, DORY_EINVAL, "dory_ghost_slots: images are of %u and %u partitions, my_id %u", mine.numNodes, peer.numNodes, my_id);
+    const auto &list = dir == 0 ? peer.fwdSend[my_id] : peer.bwdSend[my_id];
+    *n = list.second;
+    if (!slots) return DORY_OK;
+    // my ghosts: (gvid, lvid) pairs; lvid = localVtxCnt + slot (graph/dataloader.cpp:311-322)
+    const uint8_t *pairs = dir == 0 ? mine.srcGhostPairs : mine.dstGhostPairs;
+    const uint32_t G = dir == 0 ? mine.srcGhostCnt : mine.dstGhostCnt;
+    std::vector<std::pair<uint32_t, uint32_t>> ghosts(G);
+    for (uint32_t k = 0; k < G; ++k) {
+        std::memcpy(&ghosts[k].first, pairs + 8 * (size_t)k, 4);
+        std::memcpy(&ghosts[k].second, pairs + 8 * (size_t)k + 4, 4);
+        if (ghosts[k].second < mine.localVtxCnt || ghosts[k].second - mine.localVtxCnt >= G)
+            return fail(e, DORY_EFORMAT, "dory_ghost_slots: ghost vertex id out of range");
+    }
+    std::sort(ghosts.begin(), ghosts.end());
+    for (uint32_t i = 0; i < list.second; ++i) {
+        uint32_t lvid, gvid;
+        std::memcpy(&lvid, list.first + 4 * (size_t)i, 4);
+        if (lvid >= peer.localVtxCnt) return fail(e, DORY_EFORMAT, "dory_ghost_slots: send list references vertex %u >= %u", lvid, peer.localVtxCnt);
+        std::memcpy(&gvid, peer.localToGlobal + 4 * (size_t)lvid, 4);
+        auto it = std::lower_bound(ghosts.begin(), ghosts.end(), std::make_pair(gvid, 0u));
+        if (it == ghosts.end() || it->first != gvid)
+            return fail(e, DORY_EINVAL, "dory_ghost_slots: peer sends vertex %u, which is not a ghost of this partition", gvid);
+        slots[i] = it->second - mine.localVtxCnt;
+    }
+    return DORY_OK;
+}
+
 int dory_comm_set_send_slots(dory_engine *e, uint32_t dir, uint32_t peer, const uint32_t *slots, uint32_t n) {
     int rc = check_loaded(e);
     if (rc) return rc;

@@ -121,6 +121,24 @@ def read_labels(labels_file: str, image, kinds: int) -> np.ndarray:
     return onehot
 
 
+def ghost_slots(my_image, my_id: int, peer_image, dir: int) -> np.ndarray:
+    """== dory_ghost_slots: ghost slots (in partition `my_id`'s fg / bg block) of the rows the peer
+    partition sends it in direction `dir`, in the peer's send order -- computed from the two
+    graph.<id>.bin images alone (host only)."""
+    lib = _lib.load()
+    _mk, mp, ml = _image_buffer(my_image)
+    _pk, pp, pl = _image_buffer(peer_image)
+    n = C.c_uint32(0)
+    rc = lib.dory_ghost_slots(mp, ml, my_id, pp, pl, dir, None, C.byref(n))
+    if rc != 0:
+        raise DoryError(rc, lib.dory_last_error(None).decode())
+    out = np.zeros(max(int(n.value), 1), np.uint32)
+    rc = lib.dory_ghost_slots(mp, ml, my_id, pp, pl, dir, out.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(n))
+    if rc != 0:
+        raise DoryError(rc, lib.dory_last_error(None).decode())
+    return out[:int(n.value)]
+
+
 def partition_edges(src: np.ndarray, dst: np.ndarray, num_vertices: int, num_parts: int, passes: int = 0):
     """== inputs/partitioner.cpp without METIS: owner per global vertex (int32) and the edge cut
     (records whose endpoints have different owners).  Host only."""

@@ -314,6 +314,16 @@ int dory_comm_init(dory_engine *e, const void *id128);
  * in the order the peer sends them.  dorylus_b200.dist.GhostPlan computes it. */
 int dory_comm_set_recv_slots(dory_engine *e, uint32_t dir, uint32_t peer, const uint32_t *slots,
                              uint32_t n);
+/* Host-only helper for callers without a side channel between ranks (host/dorylus_b200_run): the
+ * receive plan of one (direction, peer) computed from the two partition images alone -- on one box
+ * every rank can read its peers' graph.<id>.bin from the dataset directory.  For the rows partition
+ * `peer_bin` sends to partition `my_id` in direction `dir` (its forwardLocalVtxDsts[my_id] /
+ * backwardLocalVtxDsts[my_id] list, in order), writes the ghost slot each one occupies in `my_bin`'s
+ * fg / bg block: globalToGhostVtcs[gvid] - localVtxCnt, the lookup ghostReceiverGCN does per row
+ * (gcn_ops.cpp:310-318).  slots may be NULL to query *n.  The same call with the roles swapped gives
+ * dory_comm_set_send_slots its argument.  No GPU needed; errors through dory_last_error(NULL). */
+int dory_ghost_slots(const void *my_bin, size_t my_len, uint32_t my_id, const void *peer_bin, size_t peer_len,
+                     uint32_t dir, uint32_t *slots, uint32_t *n);
 /* Peer-memory exchange (optional, same-node ranks): instead of pack -> NCCL send/recv -> unpack,
  * dory_scatter runs ONE kernel that reads each boundary row once and stores it straight into the
  * owning peers' ghost blocks through NVLink-mapped pointers; NCCL is only used for the two barriers

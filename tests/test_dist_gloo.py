@@ -94,3 +94,25 @@ def test_recv_slots_rejects_foreign_vertex():
     assert recv_slots(ghosts, np.array([8, 3], np.uint32)).tolist() == [1, 0]
     with pytest.raises(ValueError):
         recv_slots(ghosts, np.array([9], np.uint32))
+
+
+def test_ghost_slots_from_images_equal_the_exchanged_plan():
+    """dory_ghost_slots (host only: the receive plan from two graph.<id>.bin images) equals what
+    GhostPlan derives from the id lists the ranks swap -- for every (direction, receiver, sender)."""
+    from dorylus_b200 import engine as dengine
+    from dorylus_b200.dist import BACKWARD, FORWARD, recv_slots
+    from helpers import random_dataset
+
+    ds = random_dataset(V=500, E_und=3000, dims=[8, 4, 3], P=4, seed=9)
+    for me, g in enumerate(ds.graphs):
+        for peer, gp in enumerate(ds.graphs):
+            if peer == me:
+                continue
+            for d, sends, ghosts in ((FORWARD, gp.fwd_send, g.src_ghost_gvid), (BACKWARD, gp.bwd_send, g.dst_ghost_gvid)):
+                want = recv_slots(ghosts, gp.local_to_global[sends[me]])
+                got = dengine.ghost_slots(ds.images[me], me, ds.images[peer], d)
+                assert np.array_equal(got, want), (me, peer, d)
+    # a partition image of a different cut is refused
+    other = random_dataset(V=500, E_und=3000, dims=[8, 4, 3], P=2, seed=9)
+    with pytest.raises(dengine.DoryError):
+        dengine.ghost_slots(ds.images[0], 0, other.images[1], FORWARD)

@@ -34,10 +34,10 @@ def test_pipeline_shell_unit_checks(tmp_path):
 
 def write_dataset(ds):
     root = tempfile.mkdtemp()
-    d = os.path.join(root, "parts_1") + "/"
+    d = os.path.join(root, "parts_%d" % ds.P) + "/"
     os.makedirs(d)
     formats.write_bsnap_edges(d + "graph.bsnap.edges", ds.V, ds.src, ds.dst)
-    formats.write_parts(d + "graph.bsnap.parts", np.zeros(ds.V, np.int32))
+    formats.write_parts(d + "graph.bsnap.parts", ds.parts.astype(np.int32))
     formats.write_features(os.path.join(root, "features.bsnap"), ds.feats)
     formats.write_labels(os.path.join(root, "labels.bsnap"), ds.labels, ds.dims[-1])
     formats.write_layer_config(os.path.join(root, "layers.config"), ds.dims)
@@ -64,6 +64,42 @@ def test_driver_dry_run_reads_the_dataset_directory():
     r = subprocess.run([c if c != cmd[4] else cmd[4] + ".gone" for c in cmd] + ["--dry-run", "1"],
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "dry run: V 300" in r.stdout, r.stderr
+
+
+def test_driver_dry_run_multi_partition_plan():
+    """--numnodes 3 --nodeid 1 --dry-run 1: the driver preprocesses its own partition (and, having no
+    peers in a dry run, theirs), reads its local AND ghost feature rows, and derives the receive / send
+    plan of every exchange from the partition images (dory_ghost_slots) -- compared with the plan the
+    Python mirror builds from the id lists the ranks swap."""
+    from dorylus_b200.dist import recv_slots
+
+    ds = random_dataset(V=400, E_und=2500, dims=[9, 6, 4], P=3, seed=83)
+    cmd = write_dataset(ds)
+    d, me = cmd[2], 1
+    r = subprocess.run(cmd + ["--dry-run", "1", "--numnodes", "3", "--nodeid", str(me)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    g = ds.graphs[me]
+    m = re.search(r"dry run: V (\d+) ghosts (\d+) F0 (\d+)", r.stdout)
+    assert m and (int(m.group(1)), int(m.group(2)), int(m.group(3))) == (g.local_vtx_cnt, g.src_ghost_cnt, 9), r.stdout
+    for p in range(3):
+        assert open(d + "graph.%d.bin" % p, "rb").read() == ds.images[p]
+    cache = np.fromfile(d + "feats9.%d.bin" % me, dtype=np.float32).reshape(-1, 9)
+    assert np.array_equal(cache, np.concatenate([ds.feats[g.local_to_global], ds.feats[g.src_ghost_gvid]]))
+
+    def checksum(slots):
+        return int(sum((int(s) + 1) * (i + 1) for i, s in enumerate(slots)))
+
+    plans = {(int(a), int(b)): tuple(int(x) for x in rest) for a, b, *rest in
+             re.findall(r"plan: dir (\d) peer (\d+) recv (\d+) (\d+) send (\d+) (\d+)", r.stdout)}
+    assert len(plans) == 4
+    for q in (0, 2):
+        gq = ds.graphs[q]
+        for dname, (mine_ghosts, their_ghosts, my_send, their_send) in enumerate((
+                (g.src_ghost_gvid, gq.src_ghost_gvid, g.fwd_send, gq.fwd_send),
+                (g.dst_ghost_gvid, gq.dst_ghost_gvid, g.bwd_send, gq.bwd_send))):
+            recv = recv_slots(mine_ghosts, gq.local_to_global[their_send[me]])
+            send = recv_slots(their_ghosts, g.local_to_global[my_send[q]])
+            assert plans[(dname, q)] == (recv.size, checksum(recv), send.size, checksum(send)), (dname, q)
 
 
 @pytest.mark.gpu

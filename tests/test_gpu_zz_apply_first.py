@@ -169,3 +169,35 @@ def test_gat_source_windows_match_oracle(oracle, nb):
             for name in ("z", "ah", "grad", "aTg"):
                 assert rel_err(e.get_tensor(l, name), t[l][name]) < TOL, (l, name)
             assert rel_err(e.get_weight_grad(l), orc.dW[0][l]) < TOL
+
+
+@pytest.mark.parametrize("extra", [[], ["--exchange", "nccl"], ["--apply-first", "1"]], ids=["p2p", "nccl", "apply-first"])
+def test_cpp_driver_two_partitions_match_oracle(oracle, extra):
+    """host/run_onnode.sh: one dorylus_b200_run process per GPU, the plan from the partition images,
+    NCCL id and IPC handles through the rendezvous directory -- per-partition accuracy / loss of every
+    epoch against the oracle's partitioned run (needs >= 2 GPUs)."""
+    import re
+    import subprocess
+
+    import torch
+
+    from test_gpu_host_driver import ROOT, write_dataset
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    ds = random_dataset(V=900, E_und=7000, dims=[50, 16, 6], P=2, seed=77)
+    cmd = write_dataset(ds)
+    r = subprocess.run([os.path.join(ROOT, "host", "run_onnode.sh"), "2"] + cmd[1:] + ["--numepochs", "3"] + extra,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = {(int(m.group(1)), int(m.group(2))): (float(m.group(3)), float(m.group(4)))
+           for m in re.finditer(r"\[ Node\s+(\d+) \]\s+Epoch (\d+), acc: ([0-9.]+), loss: ([0-9.]+)", r.stdout)}
+    assert len(got) == 6, r.stdout
+    orc = OracleGCN(oracle, ds.graphs, ds.dims)
+    orc.load_features(ds.feats, ds.onehot)
+    for ep in (1, 2, 3):
+        w = orc.epoch()
+        for p, g in enumerate(ds.graphs):
+            val = int(g.local_vtx_cnt * 0.1)
+            assert abs(got[(p, ep)][0] - w["acc"][p] / val) < 2e-3, (p, ep)
+            assert abs(got[(p, ep)][1] - w["loss"][p] / val) < 2e-3, (p, ep)
