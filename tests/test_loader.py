@@ -59,6 +59,39 @@ def test_live_against_compiled_reference(ref):
             assert np.array_equal(getattr(g, k), r[k]), k
 
 
+def test_randomized_differential_against_compiled_reference(ref):
+    """40 small random inputs with everything the format allows at once -- self loops, duplicate
+    records, partitions that own no vertex, empty edge lists, single-vertex graphs, both settings of
+    --undirected -- through the reference's own DataLoader::preprocess and through ours: every
+    graph.<id>.bin must be the same bytes."""
+    import shutil
+
+    cases = 0
+    for seed in range(40):
+        rng = np.random.default_rng(seed)
+        V, E, P = int(rng.integers(1, 60)), int(rng.integers(0, 300)), int(rng.integers(1, 6))
+        src = rng.integers(0, V, E).astype(np.uint32)
+        dst = rng.integers(0, V, E).astype(np.uint32)
+        if E > 10:
+            src[:3] = dst[:3]                              # self loops (dropped on read)
+            src[3:6], dst[3:6] = src[6:9], dst[6:9]        # duplicates (kept, count toward the degree)
+        owners = rng.choice(P, size=int(rng.integers(1, P + 1)), replace=False)  # the others own nothing
+        parts = owners[rng.integers(0, owners.size, V)].astype(np.int32)
+        d = tempfile.mkdtemp() + "/"
+        try:
+            formats.write_bsnap_edges(d + "graph.bsnap.edges", V, src, dst)
+            formats.write_parts(d + "graph.bsnap.parts", parts)
+            for p in range(P):
+                f = ref.preprocess(d, p, P, bool(seed & 1))
+                want = open(f, "rb").read()
+                os.remove(f)
+                assert dengine.preprocess_edges(src, dst, parts, V, p, P, bool(seed & 1)) == want, (seed, p)
+                cases += 1
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    assert cases > 100
+
+
 def test_edge_cases():
     # empty edge list, a partition without local edges, isolated vertices
     parts = np.array([0, 0, 1, 1], np.int32)
