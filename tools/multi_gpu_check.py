@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--parts", default="random")
     ap.add_argument("--epochs", type=int, default=2)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--apply-first", action="store_true", help="DORY_FLAG_APPLY_FIRST: check z / h / aTg / dW of the "
+                    "reordered schedule (exchanges of t and dL/dz) against the reference-order oracle")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -34,6 +36,7 @@ def main():
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 
     from helpers import random_dataset, rel_err
+    from dorylus_b200 import _lib as dlib
     from dorylus_b200 import dist as ddist
     from dorylus_b200.engine import GCN, Engine
     from oracle.driver import OracleGCN
@@ -47,7 +50,8 @@ def main():
     orc.load_features(ds.feats, ds.onehot)
 
     g = ds.graphs[rank]
-    e = Engine(dims, GCN, node_id=rank, num_nodes=world, device=local)
+    e = Engine(dims, GCN, node_id=rank, num_nodes=world, device=local,
+               flags=dlib.FLAG_APPLY_FIRST if args.apply_first else 0)
     e.load_partition(ds.images[rank])
     e.set_tensor(0, "x", ds.feats[g.local_to_global])
     e.set_tensor(1, "lab", ds.onehot[g.local_to_global])
@@ -56,9 +60,10 @@ def main():
     # layer-0 ghost rows are NOT uploaded: every rank ships the rows it owns (scatter of a layer-0
     # FORWARD chunk); ghost rows are copies, so they must equal the owner's rows to the bit
     from dorylus_b200.engine import FORWARD
-    e.scatter(e.whole_chunk(0, FORWARD))
     ok = True
-    if g.src_ghost_cnt:
+    if not args.apply_first:  # an apply-first layer 0 gathers t = x . W and needs no ghost rows of x
+        e.scatter(e.whole_chunk(0, FORWARD))
+    if g.src_ghost_cnt and not args.apply_first:
         ok = np.array_equal(e.get_tensor(0, "fg"), ds.feats[g.src_ghost_gvid])
         print("[rank %d] layer-0 input exchange %s (%d ghost rows)" % (rank, "OK" if ok else "FAIL", g.src_ghost_cnt), flush=True)
 
@@ -67,7 +72,16 @@ def main():
         want = orc.epoch()
         st = e.epoch()
         t = orc.saved[rank]
-        errs = {
+        if args.apply_first:  # ah / grad / bg are not formed; dW is the all-reduced sum over partitions
+            errs = {
+                "z0": rel_err(e.get_tensor(0, "z"), t[0]["z"]),
+                "h0": rel_err(e.get_tensor(0, "h"), t[0]["h"]),
+                "aTg0": rel_err(e.get_tensor(0, "aTg"), t[0]["aTg"]) / 2,  # 2e-5 bar (two roundings more)
+                "dW0": rel_err(e.get_weight_grad(0), sum(orc.dW[p][0] for p in range(world))) / 2,
+                "dW1": rel_err(e.get_weight_grad(1), sum(orc.dW[p][1] for p in range(world))) / 2,
+            }
+        else:
+          errs = {
             "ah0": rel_err(e.get_tensor(0, "ah"), t[0]["ah"]),
             "h0": rel_err(e.get_tensor(0, "h"), t[0]["h"]),
             "fg1": rel_err(e.get_tensor(1, "fg"), t[1]["fg"]) if g.src_ghost_cnt else 0.0,
@@ -75,7 +89,7 @@ def main():
             "grad1": rel_err(e.get_tensor(1, "grad"), t[1]["grad"]),
             "bg0": rel_err(e.get_tensor(0, "bg"), t[0]["bg"]) if g.dst_ghost_cnt else 0.0,
             "aTg0": rel_err(e.get_tensor(0, "aTg"), t[0]["aTg"]),
-        }
+          }
         # post-Adam weights: the looser bar of tests/test_gpu_parity.py (Adam's first steps are
         # sign-like, so entries whose gradient is rounding noise move by O(lr) either way), then
         # re-synced so that every epoch's tensors are checked from identical weights
@@ -93,8 +107,9 @@ def main():
     e.close()
     dist.destroy_process_group()
     if rank == 0:
-        print("MULTI_GPU_CHECK %s world=%d parts=%s exchange=%s worst_rel_err=%.2e"
-              % ("PASS" if flag.item() == 0 else "FAIL", world, args.parts, args.exchange, worst), flush=True)
+        print("MULTI_GPU_CHECK %s world=%d parts=%s exchange=%s%s worst_rel_err=%.2e"
+              % ("PASS" if flag.item() == 0 else "FAIL", world, args.parts, args.exchange,
+                 " apply-first" if args.apply_first else "", worst), flush=True)
     sys.exit(0 if flag.item() == 0 else 1)
 
 

@@ -23,3 +23,12 @@ for n in ("shape_reddit_gat", "shape_reddit_gat_windows"):
     except Exception as ex:
         print(n, "missing:", ex)
 PY
+# with >= 2 GPUs (gpurun --gpus 2): the apply-first exchanges (t forward, dL/dz backward) on both paths,
+# and the C++ driver's multi-partition mode
+if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
+    for ex in p2p nccl; do
+        timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 \
+            tools/multi_gpu_check.py --apply-first --exchange $ex 2>&1 | grep -E "rank|MULTI_GPU" | tee -a gpurun_out/multi_apply_first.log
+    done
+    DORY_TEST_UNVERIFIED=1 timeout 900 python -m pytest tests/test_gpu_zz_apply_first.py -q -m gpu -k cpp_driver 2>&1 | tail -20 | tee gpurun_out/cpp_multi.log
+fi
