@@ -31,8 +31,15 @@
  *                 miscs/numpy-gnn, IMPORTED and run by make_golden.py on a small symmetric graph
  *                 (numpy_gnn.npz), and against the dense statement (D^-1/2 A D^-1/2 + D^-1) X built
  *                 from the compiled reference loader's own arrays
- *   - still unpinned by the reference (nothing that states them runs here): the loss scale, the
- *                 float-wise maskout (Q6) and CPUComm's validation statistics.
+ *   - apply step a second time, against the reference's own C++: the Lambda functions' tensor ops
+ *                 (src/funcs/gcn/ops, src/funcs/gat/ops) compiled into oracle/_ref and sequenced as
+ *                 funcs/gcn/main.cpp / funcs/gat/main.cpp do (funcs_ops.npz + live): soft-max, the
+ *                 float-wise maskout (Q6), the scaled output gradient, tanh', weight gradients, the
+ *                 GAT edge scores and their backward
+ *   - still unpinned by the reference (nothing that states them runs here): CPUComm's validation
+ *                 statistics getTrainStat (the Lambda twin sendAccLoss sits in a ZeroMQ translation
+ *                 unit) and which of the two loss scales applies (float V*0.66 in CPUComm, its integer
+ *                 truncation in the Lambda payload; the oracle follows CPUComm).
  */
 #include <algorithm>
 #include <cmath>
