@@ -44,3 +44,29 @@ def golden():
 
     d = os.path.join(ROOT, "tests", "golden")
     return {n: np.load(os.path.join(d, n + ".npz")) for n in ("xavier", "masks", "reference_runs", "weight_dump", "numpy_gnn", "funcs_ops")}
+
+
+@pytest.fixture()
+def hostcheck():
+    """The product's engine object linked against a host-memory fake of the CUDA runtime and scalar CPU
+    statements of the kernel launchers (tests/hostcheck/): `Engine` then runs its HOST logic here, without
+    a GPU.  Test infrastructure: the product binding never loads this library by itself."""
+    import ctypes as C
+    import importlib.util
+
+    from dorylus_b200 import _lib
+
+    spec = importlib.util.spec_from_file_location("hostcheck_build", os.path.join(ROOT, "tests", "hostcheck", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = C.CDLL(mod.build())
+    for name, (res, args) in _lib.SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    saved = _lib._lib
+    _lib._lib = lib
+    try:
+        yield lib
+    finally:
+        _lib._lib = saved

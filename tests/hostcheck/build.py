@@ -1,0 +1,47 @@
+"""Links the PRODUCT's engine object (dorylus_b200/_obj/engine_cu.o, compiled by nvcc for sm_100a --
+not recompiled, not modified) and the host-only objects (loader, partition) against a host-memory fake
+of the CUDA runtime and scalar CPU statements of the kernel launchers:
+
+    tests/hostcheck/_build/libdorylus_hostcheck.so
+
+TEST INFRASTRUCTURE ONLY.  It exists so that the engine's host logic (tensor tables, operator order,
+the apply-first schedule, window passes, error paths) can be exercised by `pytest -m "not gpu"` in a
+container without a GPU.  The product binding (dorylus_b200/_lib.py) opens
+dorylus_b200/libdorylus_b200.so by absolute path and knows nothing about this library.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+OBJ = os.path.join(ROOT, "dorylus_b200", "_obj")
+OUT_DIR = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT_DIR, "libdorylus_hostcheck.so")
+CUDA_INC = os.environ.get("CUDA_INC", "/usr/local/cuda/include")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def build(force: bool = False) -> str:
+    from dorylus_b200 import build as product_build
+
+    product_build.build()  # makes sure engine_cu.o / loader_cpp.o / partition_cpp.o are current
+    objs = [os.path.join(OBJ, n) for n in ("engine_cu.o", "loader_cpp.o", "partition_cpp.o")]
+    srcs = [os.path.join(HERE, n) for n in ("fake_cudart.cpp", "cpu_kernels.cpp")]
+    hdrs = [os.path.join(ROOT, "dorylus_b200", "csrc", n) for n in ("common.cuh", "comm.h", "gat.cuh", "gemm_tc.cuh")]
+    deps = objs + srcs + hdrs + [os.path.abspath(__file__)]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+        return LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-I" + CUDA_INC, "-o", LIB] + srcs + objs + ["-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("hostcheck build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True))

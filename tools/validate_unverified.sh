@@ -5,7 +5,7 @@
 #   gpurun --timeout 900 -- 'bash tools/validate_unverified.sh'
 set -x
 mkdir -p gpurun_out
-DORY_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_zz_apply_first.py tests/test_gpu_zz_lambda_golden.py \
+DORY_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_zzz_apply_first.py tests/test_gpu_zz_lambda_golden.py \
     -q -m gpu 2>&1 | tail -40 > gpurun_out/unverified_tests.log
 cat gpurun_out/unverified_tests.log
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_reference_order.json 2> gpurun_out/bench_reference_order.log
@@ -30,5 +30,5 @@ if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
         timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 \
             tools/multi_gpu_check.py --apply-first --exchange $ex 2>&1 | grep -E "rank|MULTI_GPU" | tee -a gpurun_out/multi_apply_first.log
     done
-    DORY_TEST_UNVERIFIED=1 timeout 900 python -m pytest tests/test_gpu_zz_apply_first.py -q -m gpu -k cpp_driver 2>&1 | tail -20 | tee gpurun_out/cpp_multi.log
+    DORY_TEST_UNVERIFIED=1 timeout 900 python -m pytest tests/test_gpu_zzz_apply_first.py -q -m gpu -k cpp_driver 2>&1 | tail -20 | tee gpurun_out/cpp_multi.log
 fi
