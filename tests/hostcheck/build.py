@@ -36,7 +36,9 @@ def build(force: bool = False) -> str:
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-I" + CUDA_INC, "-o", LIB] + srcs + objs + ["-lpthread"]
+    # -Bsymbolic: the engine's calls to cudaMalloc & co. must bind to the fakes in THIS library even when
+    # a real libcudart is already in the process's global scope (torch loads its CUDA libraries RTLD_GLOBAL)
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-Wl,-Bsymbolic", "-I" + CUDA_INC, "-o", LIB] + srcs + objs + ["-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("hostcheck build failed:\n%s\n%s" % (r.stdout, r.stderr))
