@@ -210,16 +210,147 @@ int launch_gat_predict(const float *logits, uint32_t ldl, const float *lab, floa
     return up > low ? 1 : 0;
 }
 
-// ------------------------------------------------------------------ Comm: no NCCL in this build
-Comm::~Comm() {}
-std::string Comm::unique_id(void *) { return "hostcheck build: no NCCL"; }
-std::string Comm::init(const void *, int, int, int) { return "hostcheck build: no NCCL"; }
-std::string Comm::set_send_lists(int, const std::vector<std::vector<uint32_t>> &, uint32_t, cudaStream_t) { return "hostcheck build: no NCCL"; }
-std::string Comm::set_recv_slots(int, int, const uint32_t *, uint32_t, uint32_t, cudaStream_t) { return "hostcheck build: no NCCL"; }
-std::string Comm::exchange(int, const float *, float *, uint32_t, cudaStream_t, int &) { return "hostcheck build: no NCCL"; }
-std::string Comm::allreduce_sum(float *, size_t, cudaStream_t) { return "hostcheck build: no NCCL"; }
-std::string Comm::set_send_slots(int, int, const uint32_t *, uint32_t) { return "hostcheck build: no NCCL"; }
-std::string Comm::exchange_p2p(int, const float *, float *const *, uint32_t, cudaStream_t, int &, bool) { return "hostcheck build: no NCCL"; }
+// ------------------------------------------------------------------ Comm: ranks are THREADS of this process
+// Stand-in for comm.cu's NCCL communicator: every rank is an engine driven by its own host thread, a
+// collective is a rendezvous of those threads, and "the wire" is a memcpy between their buffers.  It
+// implements the pack -> all-to-all-v -> unpack path (Comm::exchange) and the dW all-reduce; the
+// peer-memory path needs CUDA IPC and reports itself unavailable, so the engine falls back to it.
+}  // namespace dory
+
+#include <condition_variable>
+#include <map>
+#include <mutex>
+
+namespace dory {
+namespace {
+struct World {
+    std::mutex m;
+    std::condition_variable cv;
+    int nranks = 0, arrived = 0;
+    uint64_t generation = 0;
+    std::vector<Comm *> members;
+    std::vector<const float *> local;  // what each rank currently offers (exchange) / reduces (all-reduce)
+    std::vector<float *> buf;
+    std::vector<uint32_t> ld;
+    void barrier() {
+        std::unique_lock<std::mutex> lk(m);
+        const uint64_t g = generation;
+        if (++arrived == nranks) {
+            arrived = 0;
+            ++generation;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return generation != g; });
+        }
+    }
+};
+std::mutex g_worlds_mutex;
+std::map<uint64_t, World> g_worlds;
+uint64_t g_next_world = 1;
+}  // namespace
+
+Comm::~Comm() {
+    for (auto &p : plan_) std::free(p.dSendIds);
+}
+
+std::string Comm::unique_id(void *id128) {
+    std::lock_guard<std::mutex> lk(g_worlds_mutex);
+    std::memset(id128, 0, 128);
+    const uint64_t id = g_next_world++;
+    std::memcpy(id128, &id, sizeof id);
+    return "";
+}
+
+std::string Comm::init(const void *id128, int rank, int nranks, int device) {
+    uint64_t id;
+    std::memcpy(&id, id128, sizeof id);
+    World *w;
+    {
+        std::lock_guard<std::mutex> lk(g_worlds_mutex);
+        w = &g_worlds[id];
+        std::lock_guard<std::mutex> lk2(w->m);
+        if (w->nranks == 0) {
+            w->nranks = nranks;
+            w->members.assign(nranks, nullptr);
+            w->local.assign(nranks, nullptr);
+            w->buf.assign(nranks, nullptr);
+            w->ld.assign(nranks, 0);
+        }
+        if (w->nranks != nranks || rank < 0 || rank >= nranks || w->members[rank]) return "hostcheck comm: inconsistent init";
+        w->members[rank] = this;
+    }
+    nccl_ = w;
+    rank_ = rank;
+    nranks_ = nranks;
+    device_ = device;
+    w->barrier();
+    return "";
+}
+
+std::string Comm::set_send_lists(int dir, const std::vector<std::vector<uint32_t>> &ids, uint32_t, cudaStream_t) {
+    Plan &p = plan_[dir];
+    p.sendCount.assign(nranks_, 0);
+    p.sendOff.assign(nranks_, 0);
+    p.recvSlots.assign(nranks_, {});
+    p.sendTotal = 0;
+    for (int q = 0; q < nranks_; ++q) {
+        p.sendOff[q] = p.sendTotal;
+        p.sendCount[q] = (uint32_t)ids[q].size();
+        p.sendTotal += p.sendCount[q];
+    }
+    std::free(p.dSendIds);
+    p.dSendIds = static_cast<uint32_t *>(std::malloc(4 * (size_t)std::max(1u, p.sendTotal)));
+    for (int q = 0; q < nranks_; ++q)
+        if (!ids[q].empty()) std::memcpy(p.dSendIds + p.sendOff[q], ids[q].data(), 4 * ids[q].size());
+    return "";
+}
+
+std::string Comm::set_recv_slots(int dir, int peer, const uint32_t *slots, uint32_t n, uint32_t, cudaStream_t) {
+    if (peer < 0 || peer >= nranks_) return "hostcheck comm: bad peer";
+    plan_[dir].recvSlots[peer].assign(slots, slots + n);
+    return "";
+}
+
+std::string Comm::exchange(int dir, const float *local, float *ghost, uint32_t ld, cudaStream_t, int &launches) {
+    World &w = *static_cast<World *>(nccl_);
+    w.local[rank_] = local;
+    w.ld[rank_] = ld;
+    w.barrier();  // every rank has published the tensor it ships
+    std::string err;
+    for (int q = 0; q < nranks_; ++q) {
+        if (q == rank_) continue;
+        const Plan &theirs = w.members[q]->plan_[dir];
+        const std::vector<uint32_t> &slots = plan_[dir].recvSlots[q];
+        if (theirs.sendCount[rank_] != slots.size() || w.ld[q] != ld) {
+            err = "hostcheck comm: send list and receive plan disagree";
+            continue;
+        }
+        const uint32_t *ids = theirs.dSendIds + theirs.sendOff[rank_];
+        for (size_t i = 0; i < slots.size(); ++i)
+            std::memcpy(ghost + (size_t)slots[i] * ld, w.local[q] + (size_t)ids[i] * ld, sizeof(float) * ld);
+    }
+    w.barrier();  // nobody overwrites its tensor while a peer still reads it
+    launches += 2;
+    return err;
+}
+
+std::string Comm::allreduce_sum(float *buf, size_t n, cudaStream_t) {
+    World &w = *static_cast<World *>(nccl_);
+    w.buf[rank_] = buf;
+    w.barrier();
+    std::vector<float> sum(n, 0.f);
+    for (int q = 0; q < nranks_; ++q)  // rank order on every rank: identical bits everywhere
+        for (size_t i = 0; i < n; ++i) sum[i] += w.buf[q][i];
+    w.barrier();
+    std::memcpy(buf, sum.data(), sizeof(float) * n);
+    w.barrier();
+    return "";
+}
+
+std::string Comm::set_send_slots(int, int, const uint32_t *, uint32_t) { return ""; }
+std::string Comm::exchange_p2p(int, const float *, float *const *, uint32_t, cudaStream_t, int &, bool) {
+    return "hostcheck comm: the peer-memory path needs CUDA IPC";
+}
 bool Comm::p2p_ready(int) const { return false; }
 
 }  // namespace dory

@@ -82,3 +82,99 @@ def test_remaining_host_paths(hostcheck, oracle):
     for F in (16, 100):
         for light in (1, 2):
             gp.test_light_row_kernels(oracle, F, light)
+
+
+def _run_ranks(P, body):
+    """One host thread per rank (ctypes releases the GIL inside the library, where the emulated
+    collectives rendezvous); re-raises the first failure."""
+    import threading
+
+    errs = [None] * P
+
+    def run(r):
+        try:
+            body(r)
+        except BaseException as ex:  # noqa: BLE001 -- reported to the main thread
+            errs[r] = ex
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(P)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    assert not any(t.is_alive() for t in th), "a rank hung in a collective"
+    for ex in errs:
+        if ex is not None:
+            raise ex
+
+
+@pytest.mark.parametrize("dims,P,mask", [([48, 16, 5], 3, "off"), ([48, 16, 5], 3, None), ([24, 16, 16, 4], 2, [True, False, True]),
+                                         ([24, 16, 16, 4], 4, [False, True, False]), ([12, 20, 6], 2, [True, False])],
+                         ids=["reference-order", "apply-first", "mixed-TFT", "mixed-FTF", "mixed-TF"])
+def test_partitions_with_emulated_collectives(hostcheck, oracle, dims, P, mask):
+    """P engines, one per partition, each on its own thread, with the ghost exchanges and the dW
+    all-reduce carried by the emulated communicator: the whole multi-partition epoch -- receive plan
+    from the partition images (dory_ghost_slots), forward and backward exchanges of whatever the
+    schedule ships (h / grad, or t / dL/dz for apply-first layers), summed weight gradients, Adam --
+    against the oracle's partitioned reference-order run."""
+    import threading
+
+    from helpers import random_dataset, rel_err
+    from dorylus_b200 import _lib
+    from dorylus_b200 import engine as dengine
+    from dorylus_b200.engine import GCN, Engine
+    from oracle.driver import OracleGCN
+
+    ds = random_dataset(V=500, E_und=4000, dims=dims, P=P, seed=23)
+    orc = OracleGCN(oracle, ds.graphs, dims)
+    orc.load_features(ds.feats, ds.onehot)
+    L = len(dims) - 1
+    uid = Engine.comm_unique_id()
+    gate = threading.Barrier(P)
+    want, checked = {}, []
+
+    def rank(r):
+        g = ds.graphs[r]
+        flags = _lib.FLAG_APPLY_FIRST if mask is None else 0
+        e = Engine(dims, GCN, node_id=r, num_nodes=P, flags=flags)
+        if mask not in (None, "off"):
+            e.set_option("apply_first_mask", sum(1 << l for l, m in enumerate(mask) if m))
+        e.load_partition(ds.images[r])
+        with e:
+            e.set_tensor(0, "x", ds.feats[g.local_to_global])
+            if g.src_ghost_cnt:
+                e.set_tensor(0, "fg", ds.feats[g.src_ghost_gvid])
+            e.set_tensor(L - 1, "lab", ds.onehot[g.local_to_global])
+            e.init_weights()
+            e.comm_init(uid)
+            for d in (0, 1):
+                for q in range(P):
+                    if q != r:
+                        e.comm_set_recv_slots(d, q, dengine.ghost_slots(ds.images[r], r, ds.images[q], d))
+            sched = [e.apply_first(l) for l in range(L)]
+            for ep in range(2):
+                if gate.wait() == 0:
+                    want[ep] = orc.epoch()
+                gate.wait()
+                st = e.epoch()
+                t = orc.saved[r]
+                assert st["acc_sum"] == want[ep]["acc"][r]
+                for l in range(L - 1):
+                    assert rel_err(e.get_tensor(l, "z"), t[l]["z"]) < 1e-5, (r, ep, l, "z")
+                    assert rel_err(e.get_tensor(l, "h"), t[l]["h"]) < 1e-5, (r, ep, l, "h")
+                    assert rel_err(e.get_tensor(l, "aTg"), t[l]["aTg"]) < 2e-5, (r, ep, l, "aTg")
+                for l in range(L):
+                    total = sum(orc.dW[p][l] for p in range(P))
+                    assert rel_err(e.get_weight_grad(l), total) < 2e-5, (r, ep, l, "dW")
+                    if not sched[l]:
+                        assert rel_err(e.get_tensor(l, "ah"), t[l]["ah"]) < 1e-5, (r, ep, l, "ah")
+                        if l > 0 and g.src_ghost_cnt:
+                            assert rel_err(e.get_tensor(l, "fg"), t[l]["fg"]) < 1e-5, (r, ep, l, "fg")
+                    assert rel_err(e.get_weights(l), orc.W[l]) < 5e-4, (r, ep, l, "W")
+                gate.wait()  # everybody has compared before anybody re-syncs
+                for l in range(L):
+                    e.set_weights(l, orc.W[l])
+                checked.append((r, ep))
+
+    _run_ranks(P, rank)
+    assert len(checked) == 2 * P
