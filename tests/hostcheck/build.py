@@ -45,5 +45,20 @@ def build(force: bool = False) -> str:
     return LIB
 
 
+def build_driver(force: bool = False) -> str:
+    """host/dorylus_b200_run.cpp linked against the hostcheck library instead of libdorylus_b200.so."""
+    lib = build(force)
+    src = os.path.join(ROOT, "host", "dorylus_b200_run.cpp")
+    out = os.path.join(OUT_DIR, "dorylus_b200_run_hostcheck")
+    deps = [src, lib, os.path.join(ROOT, "host", "saga_pipeline.hpp"), os.path.join(ROOT, "include", "dorylus_b200.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", src, "-o", out, lib, "-Wl,-rpath," + OUT_DIR],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("hostcheck driver build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True))

@@ -3,6 +3,9 @@ JSON line it prints against the contract the driver reads (one line on stdout, t
 `impl` / `cpu_baseline` / `e2e` shape of the reference arm)."""
 import json
 import os
+
+import numpy as np
+import pytest
 import subprocess
 import sys
 
@@ -110,7 +113,7 @@ class _FakeEngine:
         pass
 
 
-def _run_our_arm_with_fake_engine(monkeypatch, capfd, argv):
+def _run_our_arm_with_fake_engine(monkeypatch, capfd, argv, fake_engine=True):
     import importlib
 
     import torch
@@ -121,7 +124,8 @@ def _run_our_arm_with_fake_engine(monkeypatch, capfd, argv):
     monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
-    monkeypatch.setattr(dengine, "Engine", _FakeEngine)
+    if fake_engine:
+        monkeypatch.setattr(dengine, "Engine", _FakeEngine)
     monkeypatch.setattr(sys, "argv", ["bench.py"] + argv)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
@@ -167,3 +171,15 @@ def test_our_arm_apply_first_flag(monkeypatch, capfd):
     assert c["aggregated_row_widths"]["L0_fwd"] == 128 and c["aggregated_row_widths"]["L1_bwd"] == 41
     assert "apply-first on layers [0, 1]" in c["schedule"] and "F=128" in d["roofline"]["kernel"]
     assert d["roofline"]["traffic"] is None and "cpu_baseline" not in d
+
+
+@pytest.mark.parametrize("extra", [[], ["--apply-first"]], ids=["reference-order", "apply-first"])
+def test_our_arm_on_the_emulated_engine(hostcheck, monkeypatch, capfd, extra):
+    """bench.py's own arm against the REAL engine object on the emulated runtime (tests/hostcheck):
+    uploads, the input pipeline (prefetch / commit), stream-ordered statistics, per-aggregation timing
+    calls -- every ABI call the bench makes is executed, on the tiny Reddit-width workload."""
+    d = _run_our_arm_with_fake_engine(monkeypatch, capfd, ["--workload", "reddit-tiny", "--steps", "2", "--no-cpu-baseline"] + extra,
+                                      fake_engine=False)
+    assert d["gpu_launches"] > 0 and d["value"] > 0 and d["e2e"]["value"] > 0
+    assert np.isfinite(d["loss_sum"]) and d["loss_sum"] > 0
+    assert d["config"]["aggregations_launched_per_step"] == (4 if extra else 3)

@@ -178,3 +178,47 @@ def test_partitions_with_emulated_collectives(hostcheck, oracle, dims, P, mask):
 
     _run_ranks(P, rank)
     assert len(checked) == 2 * P
+
+
+def test_cpp_driver_host_logic(hostcheck, oracle, monkeypatch):
+    """host/dorylus_b200_run.cpp linked against the hostcheck library: the C++ driver's epoch loop, the
+    pipeline shell over the real engine (1 and 3 chunks per partition) and --apply-first, against the
+    oracle's accuracy / loss per epoch -- the bodies of tests/test_gpu_host_driver.py, plus one run of
+    the apply-first flag."""
+    import importlib.util
+    import os
+    import re
+    import subprocess
+
+    import test_gpu_host_driver as hd
+    from helpers import random_dataset
+    from oracle.driver import OracleGCN
+
+    spec = importlib.util.spec_from_file_location("hostcheck_build", os.path.join(hd.ROOT, "tests", "hostcheck", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr(hd, "BIN", mod.build_driver())
+    hd.test_driver_epochs_match_oracle(oracle)
+    for lambdas in (1, 3):
+        hd.test_pipeline_mode_matches_oracle(oracle, lambdas)
+    ds = random_dataset(V=900, E_und=7000, dims=[50, 16, 6], seed=77)
+    cmd = hd.write_dataset(ds)
+    r = subprocess.run(cmd + ["--numepochs", "3", "--apply-first", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = [(float(m.group(1)), float(m.group(2))) for m in re.finditer(r"Epoch \d+, acc: ([0-9.]+), loss: ([0-9.]+)", r.stdout)]
+    orc = OracleGCN(oracle, ds.graphs, ds.dims)
+    orc.load_features(ds.feats, ds.onehot)
+    val = int(ds.V * 0.1)
+    assert len(got) == 3
+    for acc, loss in got:
+        w = orc.epoch()
+        assert abs(acc - w["acc"][0] / val) < 2e-3 and abs(loss - w["loss"][0] / val) < 2e-3
+    r = subprocess.run(cmd + ["--apply-first", "1", "--pipeline", "1"], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "apply-first" in r.stderr
+
+
+def test_graft_entry_smoke_host_logic(hostcheck):
+    """__graft_entry__.smoke() (what the driver runs on the B200 before the bench), on the emulated runtime."""
+    import __graft_entry__ as ge
+
+    ge.smoke()
