@@ -490,6 +490,7 @@ int launch_spmm_rows(const SpmmArgs &a, cudaStream_t s) {
     const int occ = a.cfg_occ ? a.cfg_occ : 4;
     DORY_SPMM_CASE(4, 1);
     DORY_SPMM_CASE(4, 2);
+    DORY_SPMM_CASE(4, 4);  // 8 edges per gather instruction: candidate for 33..64-float rows (not a default yet)
     DORY_SPMM_CASE(8, 1);
     DORY_SPMM_CASE(8, 2);
     DORY_SPMM_CASE(8, 4);

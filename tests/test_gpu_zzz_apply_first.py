@@ -204,3 +204,20 @@ def test_cpp_driver_two_partitions_match_oracle(oracle, extra):
             val = int(g.local_vtx_cnt * 0.1)
             assert abs(got[(p, ep)][0] - w["acc"][p] / val) < 2e-3, (p, ep)
             assert abs(got[(p, ep)][1] - w["loss"][p] / val) < 2e-3, (p, ep)
+
+
+@pytest.mark.parametrize("F", [41, 64, 100])
+def test_aggregation_shape_4_lanes_by_4_float4(oracle, F):
+    """The (4 lanes x 4 float4) kernel shape -- 8 edges per gather instruction, a candidate for the
+    33..64-float rows of the apply-first schedule (tools/width_sweep.py) -- forced through the options,
+    on warp-per-row and CTA-per-row rows, one and two column slabs."""
+    from test_gpu_parity import HUB, gcn_engine
+
+    ds = random_dataset(V=1600, E_und=60000, dims=[F, 8, 3], seed=19, extra_edges=HUB)
+    g = ds.graphs[0]
+    with gcn_engine(ds) as e:
+        for k, v in (("spmm_lg", 4), ("spmm_vec", 4), ("spmm_light", 1)):
+            e.set_option(k, v)
+        e.aggregateGCN(e.whole_chunk(0, FORWARD))
+        want = oracle.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, ds.feats, None)
+        assert rel_err(e.get_tensor(0, "ah"), want) < TOL

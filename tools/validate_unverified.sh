@@ -32,3 +32,6 @@ if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
     done
     DORY_TEST_UNVERIFIED=1 timeout 900 python -m pytest tests/test_gpu_zzz_apply_first.py -q -m gpu -k cpp_driver 2>&1 | tail -20 | tee gpurun_out/cpp_multi.log
 fi
+# narrow-row kernel shapes for the apply-first widths (incl. the new 4 x 4 shape)
+timeout 900 python tools/width_sweep.py --widths 41,64 --out gpurun_out/width_sweep.json > gpurun_out/width_sweep.log 2>&1
+tail -30 gpurun_out/width_sweep.log
