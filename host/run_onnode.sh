@@ -5,10 +5,11 @@
 set -e
 N=$1; shift
 HERE=$(cd "$(dirname "$0")" && pwd)
+BIN=${DORY_RUN_BIN:-$HERE/dorylus_b200_run}
 RDV=$(mktemp -d /tmp/dory_rendezvous.XXXXXX)
 pids=()
 for ((i = 0; i < N; ++i)); do
-    "$HERE/dorylus_b200_run" "$@" --numnodes "$N" --nodeid "$i" --device "$i" --rendezvous "$RDV" &
+    "$BIN" "$@" --numnodes "$N" --nodeid "$i" --device "$i" --rendezvous "$RDV" &
     pids+=($!)
 done
 rc=0

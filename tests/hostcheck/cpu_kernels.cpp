@@ -210,81 +210,88 @@ int launch_gat_predict(const float *logits, uint32_t ldl, const float *lab, floa
     return up > low ? 1 : 0;
 }
 
-// ------------------------------------------------------------------ Comm: ranks are THREADS of this process
-// Stand-in for comm.cu's NCCL communicator: every rank is an engine driven by its own host thread, a
-// collective is a rendezvous of those threads, and "the wire" is a memcpy between their buffers.  It
+// ------------------------------------------------------------------ Comm: collectives through a directory
+// Stand-in for comm.cu's NCCL communicator.  Ranks may be threads of one process (the Python tests) or
+// separate processes (host/run_onnode.sh): the "unique id" is the path of a fresh directory, a barrier
+// is one marker file per rank and generation, and the wire is a file per (sender, receiver).  It
 // implements the pack -> all-to-all-v -> unpack path (Comm::exchange) and the dW all-reduce; the
 // peer-memory path needs CUDA IPC and reports itself unavailable, so the engine falls back to it.
 }  // namespace dory
 
-#include <condition_variable>
-#include <map>
-#include <mutex>
+#include <chrono>
+#include <cstdio>
+#include <fstream>
+#include <thread>
+
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace dory {
 namespace {
 struct World {
-    std::mutex m;
-    std::condition_variable cv;
-    int nranks = 0, arrived = 0;
-    uint64_t generation = 0;
-    std::vector<Comm *> members;
-    std::vector<const float *> local;  // what each rank currently offers (exchange) / reduces (all-reduce)
-    std::vector<float *> buf;
-    std::vector<uint32_t> ld;
-    void barrier() {
-        std::unique_lock<std::mutex> lk(m);
-        const uint64_t g = generation;
-        if (++arrived == nranks) {
-            arrived = 0;
-            ++generation;
-            cv.notify_all();
-        } else {
-            cv.wait(lk, [&] { return generation != g; });
+    std::string dir;
+    uint64_t gen = 0;
+    int rank = 0, nranks = 1;
+    std::string path(const char *kind, uint64_t g, int a, int b = -1) const {
+        return dir + "/" + kind + "." + std::to_string(g) + "." + std::to_string(a) + (b >= 0 ? "." + std::to_string(b) : "");
+    }
+    static void put(const std::string &p, const void *data, size_t n) {
+        const std::string tmp = p + ".tmp";
+        FILE *f = std::fopen(tmp.c_str(), "wb");
+        if (f) {
+            if (n) std::fwrite(data, 1, n, f);
+            std::fclose(f);
+            std::rename(tmp.c_str(), p.c_str());
         }
     }
+    static bool get(const std::string &p, std::vector<char> &out) {
+        std::ifstream f(p, std::ios::binary | std::ios::ate);
+        if (!f.good()) return false;
+        out.resize((size_t)f.tellg());
+        f.seekg(0);
+        if (!out.empty()) f.read(out.data(), (std::streamsize)out.size());
+        return true;
+    }
+    bool barrier() {  // false on timeout (a peer died)
+        const uint64_t g = ++gen;
+        put(path("b", g, rank), "", 0);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int q = 0; q < nranks; ++q) {
+            struct stat st;
+            while (::stat(path("b", g, q).c_str(), &st) != 0) {
+                if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0) return false;
+                std::this_thread::sleep_for(std::chrono::microseconds(200));
+            }
+        }
+        if (g > 2) ::unlink(path("b", g - 2, rank).c_str());  // everybody is past generation g-2 by now
+        return true;
+    }
 };
-std::mutex g_worlds_mutex;
-std::map<uint64_t, World> g_worlds;
-uint64_t g_next_world = 1;
 }  // namespace
 
 Comm::~Comm() {
     for (auto &p : plan_) std::free(p.dSendIds);
+    delete static_cast<World *>(nccl_);
 }
 
 std::string Comm::unique_id(void *id128) {
-    std::lock_guard<std::mutex> lk(g_worlds_mutex);
+    char tmpl[] = "/tmp/dory_hostcheck_XXXXXX";
+    if (!::mkdtemp(tmpl)) return "hostcheck comm: mkdtemp failed";
     std::memset(id128, 0, 128);
-    const uint64_t id = g_next_world++;
-    std::memcpy(id128, &id, sizeof id);
+    std::memcpy(id128, tmpl, sizeof tmpl);
     return "";
 }
 
 std::string Comm::init(const void *id128, int rank, int nranks, int device) {
-    uint64_t id;
-    std::memcpy(&id, id128, sizeof id);
-    World *w;
-    {
-        std::lock_guard<std::mutex> lk(g_worlds_mutex);
-        w = &g_worlds[id];
-        std::lock_guard<std::mutex> lk2(w->m);
-        if (w->nranks == 0) {
-            w->nranks = nranks;
-            w->members.assign(nranks, nullptr);
-            w->local.assign(nranks, nullptr);
-            w->buf.assign(nranks, nullptr);
-            w->ld.assign(nranks, 0);
-        }
-        if (w->nranks != nranks || rank < 0 || rank >= nranks || w->members[rank]) return "hostcheck comm: inconsistent init";
-        w->members[rank] = this;
-    }
+    World *w = new World();
+    w->dir = std::string(static_cast<const char *>(id128));
+    w->rank = rank;
+    w->nranks = nranks;
     nccl_ = w;
     rank_ = rank;
     nranks_ = nranks;
     device_ = device;
-    w->barrier();
-    return "";
+    return w->barrier() ? "" : "hostcheck comm: a rank did not show up";
 }
 
 std::string Comm::set_send_lists(int dir, const std::vector<std::vector<uint32_t>> &ids, uint32_t, cudaStream_t) {
@@ -313,37 +320,51 @@ std::string Comm::set_recv_slots(int dir, int peer, const uint32_t *slots, uint3
 
 std::string Comm::exchange(int dir, const float *local, float *ghost, uint32_t ld, cudaStream_t, int &launches) {
     World &w = *static_cast<World *>(nccl_);
-    w.local[rank_] = local;
-    w.ld[rank_] = ld;
-    w.barrier();  // every rank has published the tensor it ships
-    std::string err;
+    const Plan &p = plan_[dir];
+    const uint64_t g = w.gen + 1;  // the generation of the barrier that follows the writes
+    std::vector<float> pack;
     for (int q = 0; q < nranks_; ++q) {
         if (q == rank_) continue;
-        const Plan &theirs = w.members[q]->plan_[dir];
-        const std::vector<uint32_t> &slots = plan_[dir].recvSlots[q];
-        if (theirs.sendCount[rank_] != slots.size() || w.ld[q] != ld) {
+        pack.resize((size_t)p.sendCount[q] * ld);
+        for (uint32_t i = 0; i < p.sendCount[q]; ++i)
+            std::memcpy(pack.data() + (size_t)i * ld, local + (size_t)p.dSendIds[p.sendOff[q] + i] * ld, sizeof(float) * ld);
+        World::put(w.path("x", g, rank_, q), pack.data(), pack.size() * sizeof(float));
+    }
+    if (!w.barrier()) return "hostcheck comm: exchange timed out";
+    std::string err;
+    std::vector<char> in;
+    for (int q = 0; q < nranks_; ++q) {
+        if (q == rank_) continue;
+        const std::vector<uint32_t> &slots = p.recvSlots[q];
+        if (!World::get(w.path("x", g, q, rank_), in) || in.size() != slots.size() * ld * sizeof(float)) {
             err = "hostcheck comm: send list and receive plan disagree";
             continue;
         }
-        const uint32_t *ids = theirs.dSendIds + theirs.sendOff[rank_];
         for (size_t i = 0; i < slots.size(); ++i)
-            std::memcpy(ghost + (size_t)slots[i] * ld, w.local[q] + (size_t)ids[i] * ld, sizeof(float) * ld);
+            std::memcpy(ghost + (size_t)slots[i] * ld, in.data() + i * ld * sizeof(float), sizeof(float) * ld);
     }
-    w.barrier();  // nobody overwrites its tensor while a peer still reads it
+    if (!w.barrier()) return "hostcheck comm: exchange timed out";
+    for (int q = 0; q < nranks_; ++q)
+        if (q != rank_) ::unlink(w.path("x", g, rank_, q).c_str());
     launches += 2;
     return err;
 }
 
 std::string Comm::allreduce_sum(float *buf, size_t n, cudaStream_t) {
     World &w = *static_cast<World *>(nccl_);
-    w.buf[rank_] = buf;
-    w.barrier();
+    const uint64_t g = w.gen + 1;
+    World::put(w.path("r", g, rank_), buf, n * sizeof(float));
+    if (!w.barrier()) return "hostcheck comm: all-reduce timed out";
     std::vector<float> sum(n, 0.f);
-    for (int q = 0; q < nranks_; ++q)  // rank order on every rank: identical bits everywhere
-        for (size_t i = 0; i < n; ++i) sum[i] += w.buf[q][i];
-    w.barrier();
+    std::vector<char> in;
+    for (int q = 0; q < nranks_; ++q) {  // rank order on every rank: identical bits everywhere
+        if (!World::get(w.path("r", g, q), in) || in.size() != n * sizeof(float)) return "hostcheck comm: all-reduce size mismatch";
+        const float *v = reinterpret_cast<const float *>(in.data());
+        for (size_t i = 0; i < n; ++i) sum[i] += v[i];
+    }
+    if (!w.barrier()) return "hostcheck comm: all-reduce timed out";
+    ::unlink(w.path("r", g, rank_).c_str());
     std::memcpy(buf, sum.data(), sizeof(float) * n);
-    w.barrier();
     return "";
 }
 

@@ -53,7 +53,7 @@ cudaError_t cudaLaunchKernel(const void *, dim3, dim3, void **args, size_t, cuda
 
 // ---- device management
 cudaError_t cudaGetDeviceCount(int *n) {
-    *n = 1;
+    *n = 8;  // one emulated 8-GPU box (host/run_onnode.sh hands rank i device i)
     return cudaSuccess;
 }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {

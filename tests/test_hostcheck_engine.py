@@ -222,3 +222,42 @@ def test_graft_entry_smoke_host_logic(hostcheck):
     import __graft_entry__ as ge
 
     ge.smoke()
+
+
+@pytest.mark.parametrize("P,extra", [(2, []), (3, []), (2, ["--apply-first", "1"])], ids=["2-ranks", "3-ranks", "2-ranks-apply-first"])
+def test_cpp_driver_multi_process_host_logic(hostcheck, oracle, P, extra):
+    """host/run_onnode.sh with the hostcheck build of the driver: P PROCESSES, each preprocessing and
+    loading its partition, deriving the exchange plan from its peers' images, meeting through the
+    rendezvous directory (the communicator id), and running epochs with the emulated collectives --
+    per-partition accuracy / loss of every epoch against the oracle's partitioned run."""
+    import importlib.util
+    import os
+    import re
+    import subprocess
+
+    import test_gpu_host_driver as hd
+    from helpers import random_dataset
+    from oracle.driver import OracleGCN
+
+    spec = importlib.util.spec_from_file_location("hostcheck_build", os.path.join(hd.ROOT, "tests", "hostcheck", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ds = random_dataset(V=900, E_und=7000, dims=[50, 16, 6], P=P, seed=77)
+    cmd = hd.write_dataset(ds)
+    env = dict(os.environ, DORY_RUN_BIN=mod.build_driver())
+    r = subprocess.run([os.path.join(hd.ROOT, "host", "run_onnode.sh"), str(P)] + cmd[1:] +
+                       ["--numepochs", "3", "--exchange", "nccl"] + extra, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = {(int(m.group(1)), int(m.group(2))): (float(m.group(3)), float(m.group(4)))
+           for m in re.finditer(r"\[ Node\s+(\d+) \]\s+Epoch (\d+), acc: ([0-9.]+), loss: ([0-9.]+)", r.stdout)}
+    assert len(got) == 3 * P, r.stdout
+    orc = OracleGCN(oracle, ds.graphs, ds.dims)
+    orc.load_features(ds.feats, ds.onehot)
+    for ep in (1, 2, 3):
+        w = orc.epoch()
+        for p, g in enumerate(ds.graphs):
+            val = int(g.local_vtx_cnt * 0.1)
+            assert abs(got[(p, ep)][0] - w["acc"][p] / val) < 2e-3, (p, ep)
+            assert abs(got[(p, ep)][1] - w["loss"][p] / val) < 2e-3, (p, ep)
+    for p in range(P):  # every rank preprocessed its own partition: the reference's bytes
+        assert open(cmd[2] + "graph.%d.bin" % p, "rb").read() == ds.images[p]
