@@ -41,6 +41,7 @@ CONFIGS = {
     # BASELINE.json configs[3]: Amazon GCN 3-layer, synthetic 100-dim features (V, E are our choice)
     "amazon": GraphSpec("amazon", 9_430_088, 231_594_310, [100, 64, 64, 25], seed=41, sigma=0.9,
                         locality=0.9, communities=4096),
+    "amazon-tiny": GraphSpec("amazon-tiny", 900, 900 * 20, [100, 64, 64, 25], seed=43, sigma=0.9, locality=0.9, communities=16),
     # BASELINE.json configs[4]: Friendster GCN 2-layer (65M verts, 1.8B edges, 16-dim features)
     "friendster": GraphSpec("friendster", 65_608_366, 1_800_000_000, [16, 48, 51], seed=51, sigma=0.9,
                             locality=0.9, communities=32768),

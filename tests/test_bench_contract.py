@@ -173,6 +173,17 @@ def test_our_arm_apply_first_flag(monkeypatch, capfd):
     assert d["roofline"]["traffic"] is None and "cpu_baseline" not in d
 
 
+def test_our_arm_three_layers_on_the_emulated_engine(hostcheck, monkeypatch, capfd):
+    """The Amazon widths (3 layers; apply-first picks layers 0 and 2, layer 1 keeps the reference order)."""
+    d = _run_our_arm_with_fake_engine(monkeypatch, capfd, ["--workload", "amazon-tiny", "--steps", "2", "--no-cpu-baseline",
+                                                           "--apply-first"], fake_engine=False)
+    c = d["config"]
+    assert c["aggregations_per_step"] == 5 and c["aggregations_launched_per_step"] == 6
+    assert set(d["per_layer_ms"]) == {"L0_fwd", "L1_fwd", "L2_fwd", "L2_bwd", "L1_bwd", "L0_bwd"}
+    assert c["aggregated_row_widths"]["L0_fwd"] == 64 and c["aggregated_row_widths"]["L1_fwd"] == 64 and c["aggregated_row_widths"]["L2_bwd"] == 25
+    assert np.isfinite(d["loss_sum"]) and d["loss_sum"] > 0
+
+
 @pytest.mark.parametrize("extra", [[], ["--apply-first"]], ids=["reference-order", "apply-first"])
 def test_our_arm_on_the_emulated_engine(hostcheck, monkeypatch, capfd, extra):
     """bench.py's own arm against the REAL engine object on the emulated runtime (tests/hostcheck):
