@@ -10,7 +10,8 @@
 //                    [--numepochs 10] [--lr 0.01] [--gnn GCN|GAT] [--undirected 0]
 //                    [--pipeline 1 [--numlambdas N] [--targetacc A] [--switchthreshold T]] [--dry-run 1]
 //                    [--apply-first 1]
-//                    [--numnodes N --nodeid I [--device D] [--rendezvous DIR] [--exchange p2p|nccl]]
+//                    [--numnodes N --nodeid I [--device D] [--rendezvous DIR] [--exchange p2p|nccl]
+//                     [--rendezvous-timeout SECONDS]]
 //
 // --pipeline 1 drives the epochs through host/saga_pipeline.hpp -- the reference's chunk queues,
 // priority order, barriers, early-stop state machine and <EM> report (engine/ops/pipeline.cpp) --
@@ -76,7 +77,9 @@ void publish(const std::string &path, const void *data, size_t n) {
     }
 }
 
-void await(const std::string &path, std::vector<char> &out, size_t expect, double timeout_s = 300.0) {
+double g_rendezvous_timeout_s = 3600.0;  // --rendezvous-timeout: a peer may still be preprocessing a large partition
+
+void await(const std::string &path, std::vector<char> &out, size_t expect, double timeout_s = g_rendezvous_timeout_s) {
     const auto t0 = std::chrono::steady_clock::now();
     for (;;) {
         if (read_file(path, out) && out.size() == expect) return;
@@ -150,6 +153,7 @@ int main(int argc, char **argv) {
         else if (k == "--device") device = std::atoi(v.c_str());
         else if (k == "--rendezvous") rendezvous = v;
         else if (k == "--exchange") exchange = v;
+        else if (k == "--rendezvous-timeout") g_rendezvous_timeout_s = std::atof(v.c_str());
         else if (k == "--numlambdas") numLambdas = (unsigned)std::max(1, std::atoi(v.c_str()));
         else if (k == "--targetacc") targetAcc = (float)std::atof(v.c_str());
         else if (k == "--switchthreshold") switchThreshold = (float)std::atof(v.c_str());
