@@ -116,3 +116,86 @@ def test_ghost_slots_from_images_equal_the_exchanged_plan():
     other = random_dataset(V=500, E_und=3000, dims=[8, 4, 3], P=2, seed=9)
     with pytest.raises(dengine.DoryError):
         dengine.ghost_slots(ds.images[0], 0, other.images[1], FORWARD)
+
+
+def _engine_worker(rank, world, port, hostcheck_lib, apply_first, q):
+    """One rank of the bench-style start-up on the CPU: gloo for the host plumbing (dist.setup_engine_comm:
+    communicator id broadcast, id lists swapped, receive plan installed), the product's engine object on
+    the emulated CUDA runtime (tests/hostcheck) for the compute, epochs checked against the oracle."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ctypes as C
+
+    import torch.distributed as dist
+
+    from helpers import random_dataset, rel_err
+    from dorylus_b200 import _lib
+    from dorylus_b200 import dist as ddist
+    from dorylus_b200.engine import GCN, Engine
+    from oracle.driver import OracleGCN
+    from oracle.pyoracle import Oracle
+
+    lib = C.CDLL(hostcheck_lib)
+    for name, (res, args) in _lib.SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib._lib = lib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dims = [40, 12, 5]
+        ds = random_dataset(V=400, E_und=3000, dims=dims, P=world, seed=29)
+        o = Oracle(build=False)
+        o.set_threads(1)
+        orc = OracleGCN(o, ds.graphs, dims)
+        orc.load_features(ds.feats, ds.onehot)
+        g = ds.graphs[rank]
+        with Engine(dims, GCN, node_id=rank, num_nodes=world, device=rank,
+                    flags=_lib.FLAG_APPLY_FIRST if apply_first else 0) as e:
+            e.load_partition(ds.images[rank])
+            e.set_tensor(0, "x", ds.feats[g.local_to_global])
+            e.set_tensor(0, "fg", ds.feats[g.src_ghost_gvid])
+            e.set_tensor(1, "lab", ds.onehot[g.local_to_global])
+            e.init_weights()
+            ddist.setup_engine_comm(e, g, rank, world, peer_memory=False)
+            errs = {}
+            for ep in range(2):
+                want = orc.epoch()
+                st = e.epoch()
+                assert st["acc_sum"] == want["acc"][rank]
+                errs["h0.%d" % ep] = rel_err(e.get_tensor(0, "h"), orc.saved[rank][0]["h"])
+                errs["aTg0.%d" % ep] = rel_err(e.get_tensor(0, "aTg"), orc.saved[rank][0]["aTg"]) / 2
+                for l in range(2):
+                    errs["dW%d.%d" % (l, ep)] = rel_err(e.get_weight_grad(l), sum(orc.dW[p][l] for p in range(world))) / 2
+                    e.set_weights(l, orc.W[l])
+        q.put((rank, errs))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("apply_first", [False, True], ids=["reference-order", "apply-first"])
+def test_two_rank_gloo_engines_on_the_emulated_runtime(apply_first):
+    import importlib.util
+
+    import torch.multiprocessing as mp
+
+    from oracle.pyoracle import Oracle
+
+    Oracle()
+    spec = importlib.util.spec_from_file_location("hostcheck_build", os.path.join(ROOT, "tests", "hostcheck", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = mod.build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_engine_worker, args=(r, 2, port, lib, apply_first, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, errs in results:
+        assert max(errs.values()) < 1e-5, (rank, errs)
