@@ -35,3 +35,10 @@ fi
 # narrow-row kernel shapes for the apply-first widths (incl. the new 4 x 4 shape)
 timeout 900 python tools/width_sweep.py --widths 41,64 --out gpurun_out/width_sweep.json > gpurun_out/width_sweep.log 2>&1
 tail -30 gpurun_out/width_sweep.log
+# ncu evidence for the apply-first schedule: launch list of the bench command (kernel shares of the step)
+# and one full capture of its aggregation launches (F = 128 and F = 41 rows)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_apply_first.csv \
+    python bench.py --apply-first --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_apply_first.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:spmm -s 8 -c 8 -o gpurun_out/apply_first_spmm_full -f \
+    python bench.py --apply-first --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_apply_first.log 2>&1
+ls -la gpurun_out/
