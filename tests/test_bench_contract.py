@@ -113,7 +113,7 @@ class _FakeEngine:
         pass
 
 
-def _run_our_arm_with_fake_engine(monkeypatch, capfd, argv, fake_engine=True):
+def _run_our_arm_with_fake_engine(monkeypatch, capfd, argv, fake_engine=True, child_arm=False):
     import importlib
 
     import torch
@@ -126,7 +126,7 @@ def _run_our_arm_with_fake_engine(monkeypatch, capfd, argv, fake_engine=True):
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     if fake_engine:
         monkeypatch.setattr(dengine, "Engine", _FakeEngine)
-    monkeypatch.setattr(sys, "argv", ["bench.py"] + argv)
+    monkeypatch.setattr(sys, "argv", ["bench.py"] + ([] if child_arm else ["--no-apply-first-arm"]) + argv)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
     sys.path.insert(0, ROOT)
@@ -194,3 +194,13 @@ def test_our_arm_on_the_emulated_engine(hostcheck, monkeypatch, capfd, extra):
     assert d["gpu_launches"] > 0 and d["value"] > 0 and d["e2e"]["value"] > 0
     assert np.isfinite(d["loss_sum"]) and d["loss_sum"] > 0
     assert d["config"]["aggregations_launched_per_step"] == (4 if extra else 3)
+
+
+def test_apply_first_child_arm_cannot_cost_the_headline(monkeypatch, capfd):
+    """At N = 1 the bench measures the opt-in apply-first schedule in a CHILD process after the headline
+    measurement.  Here the child finds no GPU and fails: the headline line must come out regardless,
+    carrying the child's failure under 'apply_first_arm'."""
+    d = _run_our_arm_with_fake_engine(monkeypatch, capfd, ["--workload", "reddit-tiny", "--steps", "2", "--no-cpu-baseline"],
+                                      child_arm=True)
+    assert d["value"] > 0 and d["gpu_launches"] == 40 and "reference order" in d["config"]["schedule"]
+    assert "error" in d["apply_first_arm"] and "exit 2" in d["apply_first_arm"]["error"]

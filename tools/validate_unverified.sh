@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 DORY_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_zzz_apply_first.py tests/test_gpu_zz_lambda_golden.py \
     -q -m gpu 2>&1 | tail -40 > gpurun_out/unverified_tests.log
 cat gpurun_out/unverified_tests.log
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_reference_order.json 2> gpurun_out/bench_reference_order.log
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-apply-first-arm > gpurun_out/bench_reference_order.json 2> gpurun_out/bench_reference_order.log
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --apply-first > gpurun_out/bench_apply_first.json 2> gpurun_out/bench_apply_first.log
 cat gpurun_out/bench_reference_order.json gpurun_out/bench_apply_first.json
 # Reddit GAT (configs[2]) with and without source windows
