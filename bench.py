@@ -422,7 +422,7 @@ def main():
         try:
             child = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", str(args.steps), "--warmup",
                                     str(args.warmup), "--workload", args.workload, "--apply-first", "--no-cpu-baseline"],
-                                   capture_output=True, text=True, timeout=900)
+                                   capture_output=True, text=True, timeout=300)
             lines = [ln for ln in child.stdout.splitlines() if ln.startswith("{")]
             if child.returncode != 0 or len(lines) != 1:
                 af_arm = {"error": "exit %d: %s" % (child.returncode, child.stderr.strip()[-300:])}
