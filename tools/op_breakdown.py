@@ -32,7 +32,9 @@ def main():
                          "per-rank kernel shapes of a P-GPU run, e.g. under ncu")
     ap.add_argument("--sustain", type=int, default=150, help="epochs of the sustained (clock-sampled) run")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
+    ap.add_argument("--apply-first", action="store_true", help="DORY_FLAG_APPLY_FIRST (not with --emulate-parts)")
     args = ap.parse_args()
+    assert not (args.apply_first and args.emulate_parts), "--emulate-parts fills the reference order's ghost blocks only"
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
@@ -46,6 +48,7 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 
     import bench
+    from dorylus_b200 import _lib as dlib
     from dorylus_b200 import dist as ddist
     from dorylus_b200 import formats
     from dorylus_b200.engine import BACKWARD, FORWARD, GCN, Engine
@@ -54,7 +57,8 @@ def main():
     spec, image, graph, feats, labels, n_edges, cut = bench.build_workload(args.workload, emu or world, rank)
     dims = spec.dims
     L = len(dims) - 1
-    e = Engine(dims, GCN, node_id=rank, num_nodes=emu or world, device=local)
+    e = Engine(dims, GCN, node_id=rank, num_nodes=emu or world, device=local,
+               flags=dlib.FLAG_APPLY_FIRST if args.apply_first else 0)
     for kv in args.opt:
         k, v = kv.split("=", 1)
         e.set_option(k, v)
@@ -68,25 +72,35 @@ def main():
         e.set_tensor(0, "bg", rng.standard_normal((graph.dst_ghost_cnt, dims[1])).astype(np.float32))
     e.set_tensor(L - 1, "lab", formats.one_hot(labels[graph.local_to_global], dims[-1]))
     e.init_weights()
+    sched = [e.apply_first(l) for l in range(L)]
     if world > 1:
         ddist.setup_engine_comm(e, graph, rank, world, peer_memory=args.exchange == "p2p")
-        e.scatter(e.whole_chunk(0, FORWARD))
+        if not sched[0]:  # an apply-first layer 0 gathers t = x . W: no ghost rows of x
+            e.scatter(e.whole_chunk(0, FORWARD))
 
-    # the operator sequence of dory_epoch (csrc/engine.cu) for GCN
+    # the operator sequence of dory_epoch (csrc/engine.cu: dory_forward / dory_backward) for GCN
     ops = []
     for l in range(L):
         c = e.whole_chunk(l, FORWARD)
-        ops.append(("GA fwd L%d (F=%d)" % (l, dims[l]), e.aggregate, c))
-        ops.append(("AV fwd L%d" % l, e.applyVertex, c))
+        if sched[l]:  # AV -> SC -> GA (+ activation)
+            ops.append(("AV fwd L%d (t = in.W)" % l, e.applyVertex, c))
+            if not emu:
+                ops.append(("SC fwd L%d (t)" % l, e.scatter, c))
+            ops.append(("GA fwd L%d (F=%d) + act" % (l, dims[l + 1]), e.aggregate, c))
+        else:
+            ops.append(("GA fwd L%d (F=%d)" % (l, dims[l]), e.aggregate, c))
+            ops.append(("AV fwd L%d" % l, e.applyVertex, c))
         n = e.incLayer(c)
-        if not emu:
+        if not emu and not (n.dir == FORWARD and sched[n.layer]):
             ops.append(("SC %s L%d" % ("fwd" if n.dir == FORWARD else "bwd", n.layer), e.scatter, n))
-    for l in range(L - 1, 0, -1):
+    for l in list(range(L - 1, 0, -1)) + ([0] if sched[0] else []):
         c = e.whole_chunk(l, BACKWARD)
-        ops.append(("GA bwd L%d (F=%d)" % (l, dims[l]), e.aggregate, c))
-        ops.append(("AV bwd L%d" % (l - 1), e.applyVertex, c))
+        ops.append(("GA bwd L%d (F=%d)" % (l, dims[l + 1] if sched[l] else dims[l]), e.aggregate, c))
+        ops.append(("AV bwd L%d" % (l if sched[l] else l - 1), e.applyVertex, c))
+        if l == 0:
+            continue
         n = e.incLayer(c)
-        if n.layer != 0 and not emu:
+        if (n.layer != 0 or sched[0]) and not emu:
             ops.append(("SC bwd L%d" % n.layer, e.scatter, n))
     for l in range(L - 1, -1, -1):
         ops.append(("update W%d" % l, lambda layer, _l=l: e.apply_update(_l), l))
