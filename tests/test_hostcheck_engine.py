@@ -261,3 +261,44 @@ def test_cpp_driver_multi_process_host_logic(hostcheck, oracle, P, extra):
             assert abs(got[(p, ep)][1] - w["loss"][p] / val) < 2e-3, (p, ep)
     for p in range(P):  # every rank preprocessed its own partition: the reference's bytes
         assert open(cmd[2] + "graph.%d.bin" % p, "rb").read() == ds.images[p]
+
+
+def test_random_models_and_schedules(hostcheck, oracle):
+    """16 random models -- 2 to 4 layers, widths from 3 to 130 (every pitch class), any per-layer mix of
+    the two schedules, with and without source windows -- two epochs each against the reference-order
+    oracle: h, dL/dh and the weight gradients of every layer, and the validation accuracy."""
+    from helpers import random_dataset, rel_err
+    from dorylus_b200.engine import GCN, Engine
+    from oracle.driver import OracleGCN
+
+    rng = np.random.default_rng(0)
+    for it in range(16):
+        L = int(rng.integers(2, 5))
+        dims = [int(rng.choice([3, 7, 16, 17, 33, 48, 64, 100, 130])) for _ in range(L)] + [int(rng.integers(2, 12))]
+        mask = [bool(rng.integers(0, 2)) for _ in range(L)]
+        V = int(rng.integers(40, 300))
+        E = int(rng.integers(V, 8 * V))
+        nb = int(rng.choice([0, 0, 2, 3]))
+        ds = random_dataset(V=V, E_und=E, dims=dims, seed=100 + it)
+        orc = OracleGCN(oracle, ds.graphs, dims)
+        orc.load_features(ds.feats, ds.onehot)
+        e = Engine(dims, GCN)
+        e.set_option("apply_first_mask", sum(1 << l for l, m in enumerate(mask) if m))
+        if nb:
+            e.set_option("src_blocks", nb)
+        e.load_partition(ds.images[0])
+        with e:
+            e.set_tensor(0, "x", ds.feats)
+            e.set_tensor(L - 1, "lab", ds.onehot)
+            e.init_weights()
+            for ep in range(2):
+                want = orc.epoch()
+                st = e.epoch()
+                case = (it, dims, mask, nb, ep)
+                assert st["acc_sum"] == want["acc"][0], case
+                for l in range(L - 1):
+                    assert rel_err(e.get_tensor(l, "h"), orc.saved[0][l]["h"]) < 1e-5, case
+                    assert rel_err(e.get_tensor(l, "aTg"), orc.saved[0][l]["aTg"]) < 2e-5, case
+                for l in range(L):
+                    assert rel_err(e.get_weight_grad(l), orc.dW[0][l]) < 2e-5, case
+                    e.set_weights(l, orc.W[l])
