@@ -106,8 +106,9 @@ def read_layer_config(path: str) -> List[int]:
 def convert_graph_text(snap_path: str, out_path: str, undirected: bool = False, with_header: bool = True):
     """== inputs/graphToBinary.cpp: a text edge list ("src dst" per line, lines starting with '#' or
     '%' skipped, reading stops at the first line that does not parse) -> graph.bsnap.  Self loops
-    are dropped; with `undirected` every record is followed by its reverse.  Like the reference the
-    header counts the non-loop LINES (graphToBinary.cpp:36-53), not the doubled records.
+    are dropped; with `undirected` every record is followed by its reverse and the header's edge
+    count is doubled too (graphToBinary.cpp:36-53 counts the non-loop lines, main() :151 doubles).
+    Byte-identical to the reference tool's output (tests/test_formats.py runs it).
     Returns (numVertices, numEdges as written in the header)."""
     src, dst = [], []
     with open(snap_path) as f:
@@ -128,7 +129,7 @@ def convert_graph_text(snap_path: str, out_path: str, undirected: bool = False, 
     s = np.asarray(src, dtype=np.uint32)
     d = np.asarray(dst, dtype=np.uint32)
     nv = int(max(s.max(initial=0), d.max(initial=0))) + 1
-    ne = int(s.size)
+    ne = int(s.size) * (2 if undirected else 1)
     rec = np.empty((s.size, 4 if undirected else 2), dtype=np.uint32)
     rec[:, 0], rec[:, 1] = s, d
     if undirected:

@@ -103,6 +103,32 @@ def build_ref(force: bool = False) -> str | None:
     return out
 
 
+# The reference's dataset tools that build from one file each (inputs/Makefile; labelsToBinary.cpp and
+# featuresToBinary.cpp need Boost and do not).
+REF_TOOLS = {
+    "graphToBinary": "inputs/graphToBinary.cpp",      # text edge list -> graph.bsnap
+    "generateFeatues": "inputs/generateFeatues.cpp",  # random features.bsnap writer ("<name>.feats")
+    "generateLabels": "inputs/generateLabels.cpp",    # random labels.bsnap writer ("<name>.labels")
+}
+
+
+def build_ref_tools(force: bool = False) -> dict:
+    """Compile the reference's own input tools in place into oracle/_ref/<tool>.  Returns
+    {name: path} for the tools that exist (prebuilt ones included when /root/reference is absent)."""
+    out = {}
+    for name, rel in REF_TOOLS.items():
+        exe = os.path.join(REF_DIR, name)
+        src = os.path.join(REF_ROOT, rel)
+        if os.path.exists(src):
+            os.makedirs(REF_DIR, exist_ok=True)
+            if force or _newer(exe, [src, __file__]):
+                _run(["g++", "-std=c++11", "-O2", "-w", "-pthread", src, "-o", exe])
+        if os.path.exists(exe):
+            out[name] = exe
+    return out
+
+
 if __name__ == "__main__":
     print(build_oracle(force="--force" in sys.argv))
     print(build_ref(force="--force" in sys.argv))
+    print(build_ref_tools(force="--force" in sys.argv))

@@ -234,7 +234,36 @@ def funcs_fixture():
     np.savez_compressed(os.path.join(HERE, "funcs_ops.npz"), **out)
 
 
+def input_tools_fixture():
+    """inputs/graphToBinary.cpp, generateFeatues.cpp and generateLabels.cpp compiled as they are
+    (oracle/build.py: build_ref_tools) and run on small inputs: the .bsnap bytes of four text edge lists
+    (both --undirected settings) and the generators' output files."""
+    import subprocess
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import build as ob
+    from test_formats import GRAPH_TEXTS
+
+    tools = ob.build_ref_tools()
+    out = {}
+    d = tempfile.mkdtemp()
+    for name, text in GRAPH_TEXTS.items():
+        for und in (0, 1):
+            t = os.path.join(d, "%s_%d.txt" % (name, und))
+            open(t, "w").write(text)
+            subprocess.run([tools["graphToBinary"], "--snapfile=%s" % t, "--undirected=%d" % und, "--header=1"],
+                           check=True, capture_output=True)
+            out["bsnap_%s_%d" % (name, und)] = np.frombuffer(open(t + ".bsnap", "rb").read(), dtype=np.uint8)
+    base = os.path.join(d, "ds")
+    subprocess.run([tools["generateFeatues"], "37", "24", base], check=True, capture_output=True)
+    subprocess.run([tools["generateLabels"], "37", "4", base], check=True, capture_output=True)
+    out["gen_feats"] = np.frombuffer(open(base + ".feats", "rb").read(), dtype=np.uint8)
+    out["gen_labels"] = np.frombuffer(open(base + ".labels", "rb").read(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "input_tools.npz"), **out)
+
+
 if __name__ == "__main__":
+    input_tools_fixture()
     funcs_fixture()
     xavier_fixture()
     weight_dump_fixture()
