@@ -241,6 +241,18 @@ void ref_funcs_gat_edge_backward(const float *grad, const float *az, const float
     take(av, nullptr);
 }
 
+/* Chunk::operator< (common/utils.hpp:76-89) -- the priority of the reference's chunk queues -- and
+ * Chunk::isFirstLayer / isLastLayer, on chunks given as 8 unsigned fields
+ * {localId, globalId, lowBound, upBound, layer, dir, epoch, vertex}. */
+static Chunk to_chunk(const unsigned *f) {
+    return Chunk{f[0], f[1], f[2], f[3], f[4], f[5] ? PROP_TYPE::BACKWARD : PROP_TYPE::FORWARD, f[6], f[7] != 0};
+}
+int ref_chunk_less(const unsigned *a, const unsigned *b) { return to_chunk(a) < to_chunk(b) ? 1 : 0; }
+int ref_chunk_flags(const unsigned *a) {
+    Chunk c = to_chunk(a);
+    return (c.isFirstLayer() ? 1 : 0) | (c.isLastLayer() ? 2 : 0);
+}
+
 /* expandDot, funcs/gat/ops/backward_ops.cpp (same body as CPU_comm.cpp:299-319). */
 void ref_funcs_gat_expand_dot(const float *m, const float *v, const unsigned long long *edgePtrs, unsigned V,
                               unsigned F, unsigned nEdges, float *out) {

@@ -316,3 +316,42 @@ def test_epoch_partitioned_equals_single_partition(oracle):
         r3.apply_vertex_backward(p, 0)
         tot = r3.dW[p][0] if tot is None else tot + r3.dW[p][0]
     assert rel_err(tot, r1.dW[0][0]) < 1e-5
+
+
+def test_chunk_priority_equals_reference_operator_less(ref, tmp_path):
+    """The chunk queues of host/saga_pipeline.hpp are ordered by a restatement of Chunk::operator<
+    (common/utils.hpp:76-89); here both are called on 20,000 random chunk pairs drawn from small field
+    ranges (so that ties on every prefix of the comparison chain occur), and the Python mirror's
+    isFirstLayer / isLastLayer are compared with the reference's."""
+    import ctypes as C
+    import os
+    import subprocess
+
+    from dorylus_b200.engine import Chunk
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "libsaga_bindings.so")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", os.path.join(root, "tests", "saga_bindings.cpp"), "-o", so],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    saga = C.CDLL(so)
+    rng = np.random.default_rng(5)
+    u32p = C.POINTER(C.c_uint)
+    n_true = 0
+    for _ in range(20000):
+        a = rng.integers(0, 3, 8).astype(np.uint32)
+        b = rng.integers(0, 3, 8).astype(np.uint32)
+        for f in (a, b):
+            f[5] %= 2
+            f[7] %= 2
+        if rng.random() < 0.3:
+            k = int(rng.integers(1, 8))
+            b[:k] = a[:k]  # force ties on a prefix of the fields
+        want = ref.lib.ref_chunk_less(a.ctypes.data_as(u32p), b.ctypes.data_as(u32p))
+        got = saga.saga_chunk_less(a.ctypes.data_as(u32p), b.ctypes.data_as(u32p))
+        assert want == got, (a, b)
+        n_true += want
+        flags = ref.lib.ref_chunk_flags(a.ctypes.data_as(u32p))
+        c = Chunk(*(int(x) for x in a[:7]), vertex=bool(a[7]))
+        assert (1 if c.isFirstLayer() else 0) | (2 if c.isLastLayer() else 0) == flags
+    assert 2000 < n_true < 18000
