@@ -56,3 +56,16 @@ def test_product_path_never_touches_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text and "libdoryref" not in text, f
+
+
+def test_product_path_never_touches_the_host_check_library():
+    """tests/hostcheck/ (the engine object on an emulated CUDA runtime) is test infrastructure: no
+    shipped file -- package, host driver, header, bench.py, __graft_entry__.py -- may name it."""
+    files = [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    for top in ("dorylus_b200", "host", "include", "tools"):
+        for dirpath, _, names in os.walk(os.path.join(ROOT, top)):
+            if "_obj" in dirpath or "__pycache__" in dirpath:
+                continue
+            files += [os.path.join(dirpath, n) for n in names if n.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".sh"))]
+    for f in files:
+        assert "hostcheck" not in open(f).read(), f
