@@ -32,6 +32,7 @@ REF_SOURCES = [
     "src/graph-server/graph/dataloader.cpp",
     "src/graph-server/utils/utils.cpp",
     "src/weight-server/AdamOptimizer.cpp",
+    "src/weight-server/weighttensor.cpp",
 ]
 # #included (inside namespaces) by ref_driver.cpp: the Lambda functions' tensor ops
 REF_INCLUDED = [

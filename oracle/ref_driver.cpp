@@ -9,6 +9,8 @@
  *   Graph::init              src/graph-server/graph/graph.cpp:7-115
  *   Matrix::dot              src/common/matrix.cpp:263-315   (-> cblas_sgemm)
  *   AdamOptimizer            src/weight-server/AdamOptimizer.cpp:3-51
+ *   WeightTensor             src/weight-server/weighttensor.cpp (the synchronous update: local and
+ *                            ghost gradient sums, then Adam -- tryApplyUpdate :246-284)
  *   the Lambda functions' tensor ops (the reference's SECOND statement of the apply step):
  *     src/funcs/gcn/ops/forward_ops.cpp, backward_ops.cpp   softmax, tanh, tanhDerivative, maskout,
  *                                                            checkAccuracy, checkLoss
@@ -29,8 +31,10 @@
 #include "graph-server/graph/graph.hpp"
 #include "common/matrix.hpp"
 #include "weight-server/AdamOptimizer.hpp"
+#include "weight-server/weighttensor.hpp"
 
 #include <algorithm>
+#include <mutex>
 #include <cassert>
 #include <cmath>
 
@@ -239,6 +243,44 @@ void ref_funcs_gat_edge_backward(const float *grad, const float *az, const float
     take(G, nullptr);
     take(AZ, nullptr);
     take(av, nullptr);
+}
+
+/* WeightTensor in sync mode (weighttensor.cpp): what one weight server does with the gradients of
+ * a layer -- those it receives from graph servers ("local") and those relayed by the other weight
+ * servers ("ghost") -- before and when it steps Adam. */
+struct RefWeightTensor {
+    std::mutex wmtx, umtx;
+    WeightTensor *wt = nullptr;
+};
+void *ref_wt_create(const float *w, unsigned rows, unsigned cols, unsigned localTot, unsigned ghostTot) {
+    RefWeightTensor *h = new RefWeightTensor();
+    Matrix m = own_copy(w, rows, cols);
+    h->wt = new WeightTensor(m, &h->wmtx, &h->umtx, true);
+    h->wt->setLocalUpdTot(localTot);
+    h->wt->setGhostUpdTot(ghostTot);
+    return h;
+}
+unsigned ref_wt_local_update(void *h, const float *upd, unsigned n) {
+    std::vector<float> u(upd, upd + n);
+    return static_cast<RefWeightTensor *>(h)->wt->localUpdate(u.data());
+}
+unsigned ref_wt_ghost_update(void *h, const float *upd, unsigned n) {
+    std::vector<float> u(upd, upd + n);
+    return static_cast<RefWeightTensor *>(h)->wt->ghostUpdate(u.data());
+}
+/* Returns 1 when the update was applied (both counters had reached their totals), 0 otherwise. */
+int ref_wt_try_apply(void *h, void *adam, unsigned layer, float *w_out) {
+    WeightTensor *wt = static_cast<RefWeightTensor *>(h)->wt;
+    const std::string info = wt->tryApplyUpdate(static_cast<AdamOptimizer *>(adam), layer);
+    Matrix &m = wt->currMat();
+    std::memcpy(w_out, m.getData(), m.getDataSize());
+    return info.empty() ? 0 : 1;
+}
+void ref_wt_destroy(void *h) {
+    RefWeightTensor *r = static_cast<RefWeightTensor *>(h);
+    r->wt->free();
+    delete r->wt;
+    delete r;
 }
 
 /* Chunk::operator< (common/utils.hpp:76-89) -- the priority of the reference's chunk queues -- and

@@ -355,3 +355,55 @@ def test_chunk_priority_equals_reference_operator_less(ref, tmp_path):
         c = Chunk(*(int(x) for x in a[:7]), vertex=bool(a[7]))
         assert (1 if c.isFirstLayer() else 0) | (2 if c.isLastLayer() else 0) == flags
     assert 2000 < n_true < 18000
+
+
+def test_sync_weight_update_matches_reference_weight_tensor(oracle, ref):
+    """The weight server's synchronous update, run through the reference's own WeightTensor +
+    AdamOptimizer (weighttensor.cpp compiled in oracle/_ref): gradients of 4 partitions arrive as
+    "local" updates (one weight server) or as 2 local updates + 1 relayed "ghost" sum (two weight
+    servers); nothing is applied until every expected update is in; then the summed gradient steps Adam.
+    The oracle's apply_updates (sum over partitions in order, then Adam) must give the same weights."""
+    import ctypes as C
+
+    L = ref.lib
+    L.ref_wt_create.restype = C.c_void_p
+    L.ref_adam_create.restype = C.c_void_p
+    f32p = C.POINTER(C.c_float)
+    rng = np.random.default_rng(8)
+    dims = [6, 5, 3]
+    for local_tot, ghost_tot in ((4, 0), (2, 1)):
+        W = [rng.standard_normal((dims[i], dims[i + 1])).astype(np.float32) for i in range(2)]
+        mine = [w.copy() for w in W]
+        d = np.asarray(dims, np.uint32)
+        radam = C.c_void_p(L.ref_adam_create(C.c_float(0.01), d.ctypes.data_as(C.POINTER(C.c_uint32)), 3))
+        oadam = oracle.adam(0.01, dims)
+        wts = [C.c_void_p(L.ref_wt_create(W[l].ctypes.data_as(f32p), dims[l], dims[l + 1], local_tot, ghost_tot)) for l in range(2)]
+        for ep in range(3):
+            for l in (1, 0):  # the order the updates reach the weight server
+                grads = [rng.standard_normal(W[l].shape).astype(np.float32) for _ in range(4)]
+                out = np.empty_like(W[l])
+                n = grads[0].size
+                for k in range(local_tot):
+                    # not ready yet: nothing is applied, the weights stay
+                    assert L.ref_wt_try_apply(wts[l], radam, l, out.ctypes.data_as(f32p)) == 0
+                    assert np.array_equal(out, mine[l])
+                    L.ref_wt_local_update(wts[l], grads[k].ctypes.data_as(f32p), n)
+                if ghost_tot:
+                    relayed = grads[2] + grads[3]  # what the other weight server summed and sent over
+                    assert L.ref_wt_try_apply(wts[l], radam, l, out.ctypes.data_as(f32p)) == 0
+                    L.ref_wt_ghost_update(wts[l], relayed.ctypes.data_as(f32p), n)
+                assert L.ref_wt_try_apply(wts[l], radam, l, out.ctypes.data_as(f32p)) == 1
+                # the oracle's statement (oracle/driver.py: apply_updates)
+                total = grads[0].copy()
+                if ghost_tot:
+                    total += grads[1]
+                    total += grads[2] + grads[3]
+                else:
+                    for k in range(1, 4):
+                        total += grads[k]
+                oadam.update(l, mine[l], total)
+                assert np.array_equal(out, mine[l]), (local_tot, ghost_tot, ep, l)
+        for h in wts:
+            L.ref_wt_destroy(h)
+        L.ref_adam_destroy(radam)
+        oadam.close()
