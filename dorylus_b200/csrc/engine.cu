@@ -1001,6 +1001,7 @@ int scatter_gat(dory_engine *e, const dory_chunk *c) {  // gat_ops.cpp:277-333
 
 int predict_gat(dory_engine *e, const dory_chunk *c) {  // gat_ops.cpp:247-265
     if (c->layer == 0 || c->layer > e->L()) return fail(e, DORY_EINVAL, "predictGAT: layer %u out of range", c->layer);
+    if (c->upBound > e->V || c->lowBound > c->upBound) return fail(e, DORY_EINVAL, "chunk bounds out of range");
     const uint32_t fl = c->layer - 1;
     const DevMat *lab = find_tensor(e, fl, "lab");
     if (!lab) return fail(e, DORY_EINVAL, "predictGAT: no labels at layer %u", fl);

@@ -59,7 +59,8 @@ def hostcheck():
     spec = importlib.util.spec_from_file_location("hostcheck_build", os.path.join(ROOT, "tests", "hostcheck", "build.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    lib = C.CDLL(mod.build())
+    # DORY_HOSTCHECK_LIB: an alternative build of the same library (e.g. with -fsanitize=address)
+    lib = C.CDLL(os.environ.get("DORY_HOSTCHECK_LIB") or mod.build())
     for name, (res, args) in _lib.SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -302,3 +302,56 @@ def test_random_models_and_schedules(hostcheck, oracle):
                 for l in range(L):
                     assert rel_err(e.get_weight_grad(l), orc.dW[0][l]) < 2e-5, case
                     e.set_weights(l, orc.W[l])
+
+
+def test_abi_survives_arbitrary_call_sequences(hostcheck):
+    """Every entry point answers a bad call with an error code, never with a crash or a stray write
+    ("nothing calls exit()/abort()", include/dorylus_b200.h): operators before a partition is loaded,
+    chunks with layers / bounds out of range or reversed, every flag combination, unknown tensor names,
+    in random order on GCN and GAT engines.  (Run under AddressSanitizer with DORY_HOSTCHECK_LIB; that
+    is how the missing bounds check of dory_predict was found.)"""
+    from helpers import random_dataset
+    from dorylus_b200.engine import GAT, GCN, Chunk, DoryError, Engine
+
+    rng = np.random.default_rng(1)
+    errs = ok = 0
+    for trial in range(30):
+        gnn = GCN if trial % 3 else GAT
+        dims = [int(rng.integers(2, 40)) for _ in range(int(rng.integers(3, 5)))]
+        ds = random_dataset(V=int(rng.integers(5, 80)), E_und=int(rng.integers(1, 300)), dims=dims, seed=trial)
+        try:
+            e = Engine(dims, gnn, flags=int(rng.integers(0, 16)))
+        except DoryError:
+            errs += 1
+            continue
+        with e:
+            if rng.random() < 0.3 and gnn == GCN:
+                try:
+                    e.set_option("apply_first_mask", int(rng.integers(0, 20)))
+                except DoryError:
+                    errs += 1
+            for fn in (e.aggregate, e.applyVertex, e.scatter, e.applyEdge):  # nothing loaded yet
+                with pytest.raises(DoryError):
+                    fn(Chunk(0, 0, 0, 1, 0, 0, 0, True))
+            e.load_partition(ds.images[0])
+            e.set_tensor(0, "x" if gnn == GCN else "h", ds.feats)
+            e.set_tensor(len(dims) - 2, "lab", ds.onehot)
+            e.init_weights()
+            names = ["ah", "z", "h", "grad", "aTg", "t", "g", "u", "fg", "bg", "nope"]
+            calls = [lambda: e.forward(int(rng.integers(0, 6))), lambda: e.backward(int(rng.integers(0, 6))), e.epoch,
+                     lambda: e.get_tensor(int(rng.integers(0, 5)), names[int(rng.integers(0, len(names)))]),
+                     lambda: e.apply_update(int(rng.integers(0, 6)))]
+            for _ in range(80):
+                if rng.random() < 0.75:
+                    c = Chunk(0, 0, int(rng.integers(0, ds.V + 3)), int(rng.integers(0, ds.V + 3)),
+                              int(rng.integers(0, len(dims) + 2)), int(rng.integers(0, 2)), 1, bool(rng.integers(0, 2)))
+                    call = lambda c=c, fn=[e.aggregate, e.applyVertex, e.scatter, e.applyEdge, e.predictGAT,
+                                           e.incLayer][int(rng.integers(0, 6))]: fn(c)
+                else:
+                    call = calls[int(rng.integers(0, len(calls)))]
+                try:
+                    call()
+                    ok += 1
+                except DoryError:
+                    errs += 1
+    assert ok > 500 and errs > 500
