@@ -355,3 +355,10 @@ def test_abi_survives_arbitrary_call_sequences(hostcheck):
                 except DoryError:
                     errs += 1
     assert ok > 500 and errs > 500
+
+
+def test_kernel_shape_option_plumbing(hostcheck, oracle):
+    """The body of the (4 lanes x 4 float4) shape test: here only its option plumbing and expectations
+    are exercised (the scalar statements ignore the kernel shape)."""
+    for F in (41, 100):
+        af.test_aggregation_shape_4_lanes_by_4_float4(oracle, F)
