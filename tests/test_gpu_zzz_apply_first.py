@@ -7,8 +7,10 @@ Status: written in a session whose GPU budget was spent.  The engine's host logi
 been run end to end on the CPU (tests/test_hostcheck_engine.py: the product's engine object against
 scalar statements of the kernels, same oracle comparisons); on the GPU they compose kernels the
 verified suites already exercise, plus one element-wise tanh.  The file sorts last so that a surprise
-here cannot mask those suites under -x.  Only the 2-GPU C++ driver test (NCCL id / IPC handles through
-files: nothing of it could be emulated) stays behind DORY_TEST_UNVERIFIED=1."""
+here cannot mask those suites under -x.  Only the 2-GPU C++ driver test stays behind
+DORY_TEST_UNVERIFIED=1: its host logic has run as separate processes on the emulated runtime too, but
+NCCL itself and the CUDA-IPC handles of the peer-memory exchange cannot be emulated, and a hang between
+two ranks is the one failure a test run does not survive."""
 import os
 
 import numpy as np
