@@ -7,6 +7,10 @@ One "step" = one synchronous GCN epoch of the hot path over the whole graph: 3 a
 (layer-0 forward at F=602, layer-1 forward and layer-1 backward at F=128), the 5 dense products,
 2 ghost exchanges (N > 1) and the Adam update -- every kernel of the path, nothing skipped.
 Prints ONE JSON line (rank 0).  Contract: see the task statement / DESIGN.md §7.
+
+The headline numbers are of the reference's operator order (aggregate, then apply).  At N = 1 the
+opt-in apply-first schedule (--apply-first) is measured as well, afterwards and in a
+child process, and reported under the extra key "apply_first_arm" (--no-apply-first-arm skips it).
 """
 from __future__ import annotations
 
