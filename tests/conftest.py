@@ -71,3 +71,37 @@ def hostcheck():
         yield lib
     finally:
         _lib._lib = saved
+
+
+@pytest.fixture()
+def launchcheck():
+    """Like `hostcheck`, but with the product's own kernel launchers (spmm.cu / dense.cu / gat.cu host
+    side) linked in: every launch is checked against the hardware's launch limits, nothing is executed.
+    Yields a function returning (launches, violations, first offender) since the last call."""
+    import ctypes as C
+    import importlib.util
+
+    from dorylus_b200 import _lib
+
+    spec = importlib.util.spec_from_file_location("hostcheck_build", os.path.join(ROOT, "tests", "hostcheck", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = C.CDLL(mod.build_launchcheck())
+    for name, (res, args) in _lib.SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+
+    def log():
+        n, v = C.c_ulonglong(), C.c_ulonglong()
+        buf = C.create_string_buffer(512)
+        lib.hostcheck_launch_log(C.byref(n), C.byref(v), buf, 512)
+        return int(n.value), int(v.value), buf.value.decode()
+
+    saved = _lib._lib
+    _lib._lib = lib
+    try:
+        log()
+        yield log
+    finally:
+        _lib._lib = saved

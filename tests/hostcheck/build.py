@@ -45,6 +45,29 @@ def build(force: bool = False) -> str:
     return LIB
 
 
+def build_launchcheck(force: bool = False) -> str:
+    """The launch-check variant: the product's engine AND its kernel translation units' host side
+    (spmm.cu, dense.cu, gat.cu objects: launchers, kernel selection, grid arithmetic) on the fake runtime,
+    which checks every launch against the hardware's launch limits and executes nothing.  The tcgen05
+    launchers (driver-API tensor maps) and the communicator stay stubbed."""
+    from dorylus_b200 import build as product_build
+
+    product_build.build()
+    out = os.path.join(OUT_DIR, "libdorylus_launchcheck.so")
+    objs = [os.path.join(OBJ, n) for n in ("engine_cu.o", "spmm_cu.o", "dense_cu.o", "gat_cu.o", "loader_cpp.o", "partition_cpp.o")]
+    srcs = [os.path.join(HERE, n) for n in ("fake_cudart.cpp", "cpu_kernels.cpp")]
+    deps = objs + srcs + [os.path.abspath(__file__)]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-DDORY_LAUNCHCHECK", "-Wl,-Bsymbolic", "-I" + CUDA_INC,
+           "-o", out] + srcs + objs + ["-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("launch-check build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return out
+
+
 def build_driver(force: bool = False) -> str:
     """host/dorylus_b200_run.cpp linked against the hostcheck library instead of libdorylus_b200.so."""
     lib = build(force)

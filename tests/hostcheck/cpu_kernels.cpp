@@ -18,6 +18,7 @@
 
 namespace dory {
 
+#ifndef DORY_LAUNCHCHECK  // the launch-check build links the product's own spmm.cu / dense.cu / gat.cu objects
 // ------------------------------------------------------------------ aggregation (spmm.cu)
 static void spmm_row(const SpmmArgs &a, uint32_t row) {
     const uint64_t pbase = (uint64_t)row * a.ptr_stride + a.ptr_off;
@@ -144,6 +145,8 @@ int launch_gather_rows(const float *src, const uint32_t *ids, uint32_t n, float 
     return 1;
 }
 
+#endif  // !DORY_LAUNCHCHECK
+
 // ------------------------------------------------------------------ tcgen05 paths: "shape not supported"
 int launch_gemm_tc(const float *, uint32_t, uint64_t, const float *, uint32_t, uint32_t, float *, float *, uint32_t, int,
                    cudaStream_t) {
@@ -154,6 +157,7 @@ int launch_gemm_tn_tc(const float *, uint32_t, uint32_t, const float *, uint32_t
     return 0;
 }
 
+#ifndef DORY_LAUNCHCHECK
 // ------------------------------------------------------------------ GAT edge operators (gat.cu)
 constexpr uint32_t kALd = 4;  // a_i is an F x 1 weight with row pitch 4
 constexpr float kAlpha = 0.01f;
@@ -209,6 +213,8 @@ int launch_gat_predict(const float *logits, uint32_t ldl, const float *lab, floa
     }
     return up > low ? 1 : 0;
 }
+
+#endif  // !DORY_LAUNCHCHECK
 
 // ------------------------------------------------------------------ Comm: collectives through a directory
 // Stand-in for comm.cu's NCCL communicator.  Ranks may be threads of one process (the Python tests) or

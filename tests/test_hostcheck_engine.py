@@ -362,3 +362,46 @@ def test_kernel_shape_option_plumbing(hostcheck, oracle):
     are exercised (the scalar statements ignore the kernel shape)."""
     for F in (41, 100):
         af.test_aggregation_shape_4_lanes_by_4_float4(oracle, F)
+
+
+def test_every_launch_is_within_the_hardware_limits(launchcheck):
+    """The product's own launchers (kernel selection, grid arithmetic, cluster attributes of spmm.cu;
+    dense.cu; gat.cu) driven by the engine over a sweep of shapes, schedules and options, on a runtime
+    that checks every launch against the sm_100 launch limits and executes nothing: one vertex to
+    20,000, widths 3 to 1433, hub rows on clusters, every light-row kernel, source windows, GAT."""
+    from helpers import random_dataset
+    from dorylus_b200 import _lib
+    from dorylus_b200.engine import GAT, GCN, Engine
+    from test_gpu_parity import HUB
+
+    total = 0
+    cases = [
+        (GCN, [602, 128, 41], 600, 7200, {}, None), (GCN, [602, 128, 41], 600, 7200, {}, "af"),
+        (GCN, [1433, 16, 7], 2708, 5278, {}, "af"), (GCN, [100, 64, 64, 25], 2000, 9000, {"src_blocks": 3}, "af"),
+        (GCN, [16, 48, 51], 1800, 6000, {"hub_degree": 64, "heavy_degree": 32}, None),
+        (GCN, [3, 5, 2], 1, 1, {}, None), (GCN, [3, 5, 2], 2, 1, {}, "af"),
+        (GCN, [130, 17, 9], 20000, 60000, {"spmm_light": 2, "row_order": 2, "locality_block": 100}, None),
+        (GCN, [64, 33, 4], 20000, 400000, {"spmm_light": 1, "src_blocks": 5, "hub_degree": 100}, "af"),
+        (GCN, [41, 8, 3], 1600, 60000, {"spmm_lg": 4, "spmm_vec": 4, "spmm_light": 1}, None),
+        (GCN, [200, 8, 3], 1600, 60000, {"spmm_lg": 32, "spmm_vec": 2, "spmm_unroll": 2, "spmm_occ": 8}, None),
+        (GAT, [24, 12, 5], 300, 1500, {}, None), (GAT, [602, 128, 41], 600, 7200, {"gat_windows": 1, "src_blocks": 2}, None),
+    ]
+    for gnn, dims, V, E, opts, sched in cases:
+        ds = random_dataset(V=V, E_und=E, dims=dims, seed=7, extra_edges=HUB if V >= 1500 else None)
+        flags = (_lib.FLAG_APPLY_FIRST if sched == "af" else 0) | (_lib.FLAG_GAT_PREDICT_AH if gnn == GAT else 0)
+        e = Engine(dims, gnn, flags=flags)
+        for k, v in opts.items():
+            e.set_option(k, v)
+        e.load_partition(ds.images[0])
+        with e:
+            e.set_tensor(0, "x" if gnn == GCN else "h", ds.feats)
+            e.set_tensor(len(dims) - 2, "lab", ds.onehot)
+            e.init_weights()
+            e.epoch()
+            e.epoch_async()
+            e.stats_enqueue(0)
+            e.stats_collect(0)
+        n, bad, first = launchcheck()
+        assert n > 0 and bad == 0, (dims, V, opts, sched, first)
+        total += n
+    assert total > 300
