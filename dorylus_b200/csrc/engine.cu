@@ -1408,7 +1408,10 @@ int dory_load_partition(dory_engine *e, const void *graph_bin, size_t len) {
     CU(cudaMemsetAsync(e->scratchB.p, 0, scr, e->stream));
     size_t wmax = 0;
     for (auto &w : e->W) wmax = std::max(wmax, w.floats());
-    CU(e->gemm_ws.alloc(std::max<size_t>(wmax * 64, (size_t)maxld * maxld * 64) * sizeof(float)));
+    size_t ws_floats = std::max<size_t>(wmax * 64, (size_t)maxld * maxld * 64);
+    if (e->cfg.gnn_type == DORY_GAT)  // launch_gat_edge_backward: one partial row per 512 vertices + z^T z + its split-K
+        ws_floats = std::max<size_t>(ws_floats, ((size_t)e->V / 512 + 1) * maxld + (size_t)maxld * maxld * 65);
+    CU(e->gemm_ws.alloc(ws_floats * sizeof(float)));
     CU(e->rowstat.alloc(2 * (size_t)e->V * sizeof(float)));
     CU(e->stats_dev.alloc(2 * sizeof(float)));
     CU(cudaMemsetAsync(e->stats_dev.p, 0, 2 * sizeof(float), e->stream));

@@ -385,6 +385,9 @@ def test_every_launch_is_within_the_hardware_limits(launchcheck):
         (GCN, [41, 8, 3], 1600, 60000, {"spmm_lg": 4, "spmm_vec": 4, "spmm_light": 1}, None),
         (GCN, [200, 8, 3], 1600, 60000, {"spmm_lg": 32, "spmm_vec": 2, "spmm_unroll": 2, "spmm_occ": 8}, None),
         (GAT, [24, 12, 5], 300, 1500, {}, None), (GAT, [602, 128, 41], 600, 7200, {"gat_windows": 1, "src_blocks": 2}, None),
+        # many vertices, tiny widths: the GAT edge-backward workspace has to grow with V (it did not: the
+        # launch failed at the Friendster / 8 size, found by running this check at that size)
+        (GAT, [8, 4, 3], 600000, 300000, {}, None),
     ]
     for gnn, dims, V, E, opts, sched in cases:
         ds = random_dataset(V=V, E_und=E, dims=dims, seed=7, extra_edges=HUB if V >= 1500 else None)
