@@ -109,8 +109,9 @@ def _run_ranks(P, body):
 
 
 @pytest.mark.parametrize("dims,P,mask", [([48, 16, 5], 3, "off"), ([48, 16, 5], 3, None), ([24, 16, 16, 4], 2, [True, False, True]),
-                                         ([24, 16, 16, 4], 4, [False, True, False]), ([12, 20, 6], 2, [True, False])],
-                         ids=["reference-order", "apply-first", "mixed-TFT", "mixed-FTF", "mixed-TF"])
+                                         ([24, 16, 16, 4], 4, [False, True, False]), ([12, 20, 6], 2, [True, False]),
+                                         ([48, 16, 5], 8, None)],
+                         ids=["reference-order", "apply-first", "mixed-TFT", "mixed-FTF", "mixed-TF", "apply-first-8-ranks"])
 def test_partitions_with_emulated_collectives(hostcheck, oracle, dims, P, mask):
     """P engines, one per partition, each on its own thread, with the ghost exchanges and the dW
     all-reduce carried by the emulated communicator: the whole multi-partition epoch -- receive plan
