@@ -105,3 +105,29 @@ def launchcheck():
         yield log
     finally:
         _lib._lib = saved
+
+
+@pytest.fixture()
+def commcheck():
+    """Like `hostcheck`, with the product's REAL communicator object (comm.cu) linked in over an NCCL
+    whose ranks are threads of this process, pointer-carrying CUDA IPC handles and scalar statements of
+    comm.cu's kernels (tests/hostcheck/fake_nccl.cpp)."""
+    import ctypes as C
+    import importlib.util
+
+    from dorylus_b200 import _lib
+
+    spec = importlib.util.spec_from_file_location("hostcheck_build", os.path.join(ROOT, "tests", "hostcheck", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = C.CDLL(mod.build_commcheck())
+    for name, (res, args) in _lib.SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    saved = _lib._lib
+    _lib._lib = lib
+    try:
+        yield lib
+    finally:
+        _lib._lib = saved

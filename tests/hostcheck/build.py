@@ -68,6 +68,29 @@ def build_launchcheck(force: bool = False) -> str:
     return out
 
 
+def build_commcheck(force: bool = False) -> str:
+    """The comm-check variant: the product's REAL communicator object (comm.cu: plans, staging, grouped
+    all-to-all-v, the peer-memory store plan) over an NCCL whose ranks are threads of this process,
+    pointer-carrying IPC handles and scalar statements of comm.cu's kernels (fake_nccl.cpp); compute as
+    in the plain hostcheck build."""
+    from dorylus_b200 import build as product_build
+
+    product_build.build()
+    out = os.path.join(OUT_DIR, "libdorylus_commcheck.so")
+    objs = [os.path.join(OBJ, n) for n in ("engine_cu.o", "comm_cu.o", "loader_cpp.o", "partition_cpp.o")]
+    srcs = [os.path.join(HERE, n) for n in ("fake_cudart.cpp", "cpu_kernels.cpp", "fake_nccl.cpp")]
+    deps = objs + srcs + [os.path.abspath(__file__)]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-DDORY_COMMCHECK", "-Wl,-Bsymbolic", "-I" + CUDA_INC,
+           "-o", out] + srcs + objs + ["-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("comm-check build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return out
+
+
 def build_driver(force: bool = False) -> str:
     """host/dorylus_b200_run.cpp linked against the hostcheck library instead of libdorylus_b200.so."""
     lib = build(force)

@@ -216,6 +216,7 @@ int launch_gat_predict(const float *logits, uint32_t ldl, const float *lab, floa
 
 #endif  // !DORY_LAUNCHCHECK
 
+#ifndef DORY_COMMCHECK  // the comm-check build links the product's own comm.cu object (fake_nccl.cpp)
 // ------------------------------------------------------------------ Comm: collectives through a directory
 // Stand-in for comm.cu's NCCL communicator.  Ranks may be threads of one process (the Python tests) or
 // separate processes (host/run_onnode.sh): the "unique id" is the path of a fresh directory, a barrier
@@ -381,3 +382,6 @@ std::string Comm::exchange_p2p(int, const float *, float *const *, uint32_t, cud
 bool Comm::p2p_ready(int) const { return false; }
 
 }  // namespace dory
+#else
+}  // namespace dory
+#endif  // !DORY_COMMCHECK

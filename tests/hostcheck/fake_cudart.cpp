@@ -66,6 +66,10 @@ extern "C" void hostcheck_launch_log(unsigned long long *launches, unsigned long
     g_first_violation.clear();
 }
 
+#ifdef DORY_COMMCHECK
+bool hostcheck_comm_kernel(const std::string &name, void **args);  // fake_nccl.cpp
+#endif
+
 extern "C" {
 
 // ---- what nvcc's host stubs need
@@ -100,11 +104,16 @@ cudaError_t __cudaPopCallConfiguration(dim3 *grid, dim3 *block, size_t *shmem, v
 cudaError_t cudaLaunchKernel(const void *func, dim3 grid, dim3 block, void **args, size_t shmem, cudaStream_t) {
     check_launch(func, grid, block, shmem, 1, 1, 1);
     bool publish;
+    std::string name;
     {
         std::lock_guard<std::mutex> lk(g_log_mutex);
         auto it = g_kernel_names.find(func);
-        publish = it != g_kernel_names.end() && it->second.find("publish_stats") != std::string::npos;
+        if (it != g_kernel_names.end()) name = it->second;
+        publish = name.find("publish_stats") != std::string::npos;
     }
+#ifdef DORY_COMMCHECK
+    if (!publish && hostcheck_comm_kernel(name, args)) return cudaSuccess;
+#endif
     if (publish) {
         const float *dev = *static_cast<const float **>(args[0]);
         float *host = *static_cast<float **>(args[1]);
@@ -208,9 +217,22 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) {
     return cudaSuccess;
 }
 
-// ---- peer memory: not emulated
+// ---- peer memory
+#ifdef DORY_COMMCHECK
+// ranks are threads of one process: the handle carries the pointer itself
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
+    std::memset(h, 0, sizeof *h);
+    std::memcpy(h, &p, sizeof p);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
+    std::memcpy(p, &h, sizeof *p);
+    return cudaSuccess;
+}
+#else
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
 cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+#endif
 cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 
 }  // extern "C"

@@ -409,3 +409,82 @@ def test_every_launch_is_within_the_hardware_limits(launchcheck):
         assert n > 0 and bad == 0, (dims, V, opts, sched, first)
         total += n
     assert total > 300
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+@pytest.mark.parametrize("dims,P,parts,mask", [([48, 16, 5], 3, "random", "off"), ([48, 16, 5], 3, "random", None),
+                                               ([48, 16, 5], 4, "contiguous", None), ([24, 16, 16, 4], 2, "random", [True, False, True]),
+                                               ([40, 12, 5], 8, "contiguous", "off")],
+                         ids=["reference-order", "apply-first", "apply-first-contiguous", "mixed", "reference-order-8-ranks"])
+def test_real_communicator_on_emulated_nccl(commcheck, oracle, dims, P, parts, mask, exchange):
+    """The product's own communicator (comm.cu host logic: send / receive plans, staging buffers, the
+    grouped all-to-all-v with its receive-in-place shortcut for contiguous partitions, and the
+    peer-memory path -- send slots, per-peer pointers from the IPC import, the interleaved issue order)
+    between P engines on P threads: whole epochs of both schedules against the partitioned oracle,
+    the plan computed as the bench does it (send slots = the peer's receive slots for me) and the
+    ghost blocks registered through dory_comm_ipc_export / import as dist.setup_peer_memory does."""
+    import threading
+
+    from helpers import random_dataset, rel_err
+    from dorylus_b200 import _lib
+    from dorylus_b200 import engine as dengine
+    from dorylus_b200.engine import GCN, Engine
+    from oracle.driver import OracleGCN
+
+    ds = random_dataset(V=500, E_und=4000, dims=dims, P=P, seed=23, parts=parts)
+    orc = OracleGCN(oracle, ds.graphs, dims)
+    orc.load_features(ds.feats, ds.onehot)
+    L = len(dims) - 1
+    uid = Engine.comm_unique_id()
+    gate = threading.Barrier(P)
+    want, blobs, checked = {}, [None] * P, []
+
+    def rank(r):
+        g = ds.graphs[r]
+        e = Engine(dims, GCN, node_id=r, num_nodes=P, flags=_lib.FLAG_APPLY_FIRST if mask is None else 0)
+        if mask not in (None, "off"):
+            e.set_option("apply_first_mask", sum(1 << l for l, m in enumerate(mask) if m))
+        e.load_partition(ds.images[r])
+        with e:
+            e.set_tensor(0, "x", ds.feats[g.local_to_global])
+            if g.src_ghost_cnt:
+                e.set_tensor(0, "fg", ds.feats[g.src_ghost_gvid])
+            e.set_tensor(L - 1, "lab", ds.onehot[g.local_to_global])
+            e.init_weights()
+            e.comm_init(uid)
+            for d in (0, 1):
+                for q in range(P):
+                    if q != r:
+                        e.comm_set_recv_slots(d, q, dengine.ghost_slots(ds.images[r], r, ds.images[q], d))
+                        if exchange == "p2p":  # where MY rows land on q == q's receive slots for me
+                            e.comm_set_send_slots(d, q, dengine.ghost_slots(ds.images[q], q, ds.images[r], d))
+            if exchange == "p2p":
+                blobs[r] = {key: e.comm_ipc_export(*key) for key in e.ghost_tensors()}
+                gate.wait()
+                for q in range(P):
+                    if q != r:
+                        for (layer, name), blob in blobs[q].items():
+                            e.comm_ipc_import(layer, name, q, blob)
+            sched = [e.apply_first(l) for l in range(L)]
+            for ep in range(2):
+                if gate.wait() == 0:
+                    want[ep] = orc.epoch()
+                gate.wait()
+                st = e.epoch()
+                t = orc.saved[r]
+                assert st["acc_sum"] == want[ep]["acc"][r]
+                for l in range(L - 1):
+                    assert rel_err(e.get_tensor(l, "h"), t[l]["h"]) < 1e-5, (r, ep, l, "h")
+                    assert rel_err(e.get_tensor(l, "aTg"), t[l]["aTg"]) < 2e-5, (r, ep, l, "aTg")
+                for l in range(L):
+                    assert rel_err(e.get_weight_grad(l), sum(orc.dW[p][l] for p in range(P))) < 2e-5, (r, ep, l, "dW")
+                    if not sched[l] and l > 0 and g.src_ghost_cnt:
+                        assert rel_err(e.get_tensor(l, "fg"), t[l]["fg"]) < 1e-5, (r, ep, l, "fg")
+                gate.wait()
+                for l in range(L):
+                    e.set_weights(l, orc.W[l])
+                checked.append((r, ep))
+            gate.wait()  # nobody frees memory a peer may still store into
+
+    _run_ranks(P, rank)
+    assert len(checked) == 2 * P
