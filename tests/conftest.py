@@ -120,7 +120,7 @@ def commcheck():
     spec = importlib.util.spec_from_file_location("hostcheck_build", os.path.join(ROOT, "tests", "hostcheck", "build.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    lib = C.CDLL(mod.build_commcheck())
+    lib = C.CDLL(os.environ.get("DORY_COMMCHECK_LIB") or mod.build_commcheck())
     for name, (res, args) in _lib.SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype = res
