@@ -488,3 +488,72 @@ def test_real_communicator_on_emulated_nccl(commcheck, oracle, dims, P, parts, m
 
     _run_ranks(P, rank)
     assert len(checked) == 2 * P
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+@pytest.mark.parametrize("windows", [0, 1], ids=["no-windows", "source-windows"])
+def test_gat_partitions_on_the_real_communicator(commcheck, oracle, exchange, windows):
+    """GAT on several partitions (z forward, grad backward through fg_z / bg_d) -- a combination no GPU
+    suite covers yet -- on the real communicator over the emulated NCCL / IPC, against OracleGAT's
+    partitioned epoch."""
+    import threading
+
+    from helpers import random_dataset, rel_err
+    from dorylus_b200 import _lib
+    from dorylus_b200 import engine as dengine
+    from dorylus_b200.engine import GAT, Engine
+    from oracle.driver import OracleGAT
+
+    dims, P = [24, 12, 5], 3
+    ds = random_dataset(V=400, E_und=2500, dims=dims, P=P, seed=71)
+    orc = OracleGAT(oracle, ds.graphs, dims, predict_from="ah")
+    orc.load_features(ds.feats, ds.onehot)
+    orc.epoch()
+    uid = Engine.comm_unique_id()
+    gate = threading.Barrier(P)
+    blobs, done = [None] * P, []
+
+    def rank(r):
+        g = ds.graphs[r]
+        e = Engine(dims, GAT, node_id=r, num_nodes=P, flags=_lib.FLAG_GAT_PREDICT_AH)
+        if windows:
+            e.set_option("gat_windows", 1)
+            e.set_option("src_blocks", 3)
+        e.load_partition(ds.images[r])
+        with e:
+            e.set_tensor(0, "h", ds.feats[g.local_to_global])
+            e.set_tensor(1, "lab", ds.onehot[g.local_to_global])
+            e.init_weights()
+            for l in range(2):
+                e.set_weights(l, orc.a[l], "a_i")
+            e.comm_init(uid)
+            for d in (0, 1):
+                for q in range(P):
+                    if q != r:
+                        e.comm_set_recv_slots(d, q, dengine.ghost_slots(ds.images[r], r, ds.images[q], d))
+                        if exchange == "p2p":
+                            e.comm_set_send_slots(d, q, dengine.ghost_slots(ds.images[q], q, ds.images[r], d))
+            if exchange == "p2p":
+                blobs[r] = {key: e.comm_ipc_export(*key) for key in e.ghost_tensors()}
+                gate.wait()
+                for q in range(P):
+                    if q != r:
+                        for (layer, name), blob in blobs[q].items():
+                            e.comm_ipc_import(layer, name, q, blob)
+            gate.wait()
+            e.epoch()
+            t = orc.saved[r]
+            for l in range(2):
+                for name in ("z", "ah", "grad", "aTg"):
+                    assert rel_err(e.get_tensor(l, name), t[l][name]) < 1e-5, (r, l, name)
+                if g.src_ghost_cnt:
+                    assert rel_err(e.get_tensor(l, "fg_z"), t[l]["fg_z"]) < 1e-5, (r, l, "fg_z")
+                if g.dst_ghost_cnt:
+                    assert rel_err(e.get_tensor(l, "bg_d"), t[l]["bg_d"]) < 1e-5, (r, l, "bg_d")
+                # the weight gradient every rank holds after the epoch is the all-reduced sum
+                assert rel_err(e.get_weight_grad(l), sum(orc.dW[p][l] for p in range(P))) < 1e-5, (r, l, "dW")
+            done.append(r)
+            gate.wait()
+
+    _run_ranks(P, rank)
+    assert len(done) == P
