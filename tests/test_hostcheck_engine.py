@@ -466,6 +466,17 @@ def test_real_communicator_on_emulated_nccl(commcheck, oracle, dims, P, parts, m
                         for (layer, name), blob in blobs[q].items():
                             e.comm_ipc_import(layer, name, q, blob)
             sched = [e.apply_first(l) for l in range(L)]
+            if not sched[0] and g.src_ghost_cnt:
+                # the layer-0 input exchange bench.py uses (no reference counterpart): overwrite the ghost
+                # features with noise, ship the owned rows of x, and find the owners' rows there, to the bit
+                e.set_tensor(0, "fg", np.full((g.src_ghost_cnt, dims[0]), 7.0, np.float32))
+            gate.wait()
+            if not sched[0]:
+                from dorylus_b200.engine import FORWARD
+
+                e.scatter(e.whole_chunk(0, FORWARD))
+                if g.src_ghost_cnt:
+                    assert np.array_equal(e.get_tensor(0, "fg"), ds.feats[g.src_ghost_gvid])
             for ep in range(2):
                 if gate.wait() == 0:
                     want[ep] = orc.epoch()
