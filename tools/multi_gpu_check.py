@@ -19,11 +19,51 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def check_gat(args, ds, dims, o, rank, world, local, dist, torch):
+    from helpers import rel_err
+    from dorylus_b200 import _lib as dlib
+    from dorylus_b200 import dist as ddist
+    from dorylus_b200.engine import GAT, Engine
+    from oracle.driver import OracleGAT
+
+    orc = OracleGAT(o, ds.graphs, dims, predict_from="ah")
+    orc.load_features(ds.feats, ds.onehot)
+    orc.epoch()
+    g = ds.graphs[rank]
+    e = Engine(dims, GAT, node_id=rank, num_nodes=world, device=local, flags=dlib.FLAG_GAT_PREDICT_AH)
+    e.load_partition(ds.images[rank])
+    e.set_tensor(0, "h", ds.feats[g.local_to_global])
+    e.set_tensor(1, "lab", ds.onehot[g.local_to_global])
+    e.init_weights()
+    for l in range(2):
+        e.set_weights(l, orc.a[l], "a_i")
+    ddist.setup_engine_comm(e, g, rank, world, peer_memory=args.exchange == "p2p")
+    e.epoch()
+    t = orc.saved[rank]
+    errs = {}
+    for l in range(2):
+        for name in ("z", "ah", "grad", "aTg"):
+            errs["%s%d" % (name, l)] = rel_err(e.get_tensor(l, name), t[l][name])
+        errs["dW%d" % l] = rel_err(e.get_weight_grad(l), sum(orc.dW[p][l] for p in range(world)))
+    ok = max(errs.values()) < 1e-5
+    print("[rank %d] GAT epoch %s errs %s" % (rank, "OK" if ok else "FAIL", {k: float("%.1e" % v) for k, v in errs.items()}), flush=True)
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    e.close()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_GPU_CHECK %s world=%d parts=%s exchange=%s GAT worst_rel_err=%.2e"
+              % ("PASS" if flag.item() == 0 else "FAIL", world, args.parts, args.exchange, max(errs.values())), flush=True)
+    sys.exit(0 if flag.item() == 0 else 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--parts", default="random")
     ap.add_argument("--epochs", type=int, default=2)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--gnn", default="GCN", choices=["GCN", "GAT"], help="GAT: one epoch with fixed weights (quirk Q10) "
+                    "against OracleGAT's partitioned run (z / ah / grad / aTg / all-reduced dW)")
     ap.add_argument("--apply-first", action="store_true", help="DORY_FLAG_APPLY_FIRST: check z / h / aTg / dW of the "
                     "reordered schedule (exchanges of t and dL/dz) against the reference-order oracle")
     args = ap.parse_args()
@@ -46,6 +86,8 @@ def main():
     ds = random_dataset(V=6000, E_und=90000, dims=dims, P=world, seed=17, parts=args.parts)
     o = Oracle()
     o.set_threads(max(1, (os.cpu_count() or 8) // world))
+    if args.gnn == "GAT":
+        return check_gat(args, ds, dims, o, rank, world, local, dist, torch)
     orc = OracleGCN(o, ds.graphs, dims)
     orc.load_features(ds.feats, ds.onehot)
 

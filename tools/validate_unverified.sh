@@ -30,6 +30,10 @@ if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
         timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 \
             tools/multi_gpu_check.py --apply-first --exchange $ex 2>&1 | grep -E "rank|MULTI_GPU" | tee -a gpurun_out/multi_apply_first.log
     done
+    for ex in p2p nccl; do  # GAT on several GPUs: never run on hardware either
+        timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29532 \
+            tools/multi_gpu_check.py --gnn GAT --exchange $ex 2>&1 | grep -E "rank|MULTI_GPU" | tee -a gpurun_out/multi_gat.log
+    done
     DORY_TEST_UNVERIFIED=1 timeout 900 python -m pytest tests/test_gpu_zzz_apply_first.py -q -m gpu -k cpp_driver 2>&1 | tail -20 | tee gpurun_out/cpp_multi.log
 fi
 # narrow-row kernel shapes for the apply-first widths (incl. the new 4 x 4 shape)
