@@ -97,15 +97,15 @@ def _run_ranks(P, body):
         except BaseException as ex:  # noqa: BLE001 -- reported to the main thread
             errs[r] = ex
 
-    th = [threading.Thread(target=run, args=(r,)) for r in range(P)]
-    for t in th:
+    th = [threading.Thread(target=run, args=(r,), daemon=True) for r in range(P)]  # daemon: a hung rank must not
+    for t in th:                                                                     # keep the test process alive
         t.start()
     for t in th:
-        t.join(timeout=300)
-    assert not any(t.is_alive() for t in th), "a rank hung in a collective"
-    for ex in errs:
+        t.join(timeout=180)
+    for ex in errs:  # a rank that failed is the cause; the ranks waiting for it are the symptom
         if ex is not None:
             raise ex
+    assert not any(t.is_alive() for t in th), "a rank hung in a collective"
 
 
 @pytest.mark.parametrize("dims,P,mask", [([48, 16, 5], 3, "off"), ([48, 16, 5], 3, None), ([24, 16, 16, 4], 2, [True, False, True]),
