@@ -60,6 +60,8 @@ SYMBOLS = {
     "dory_preprocess_edges": (C.c_int, [_u32p, _u32p, _u64, C.POINTER(C.c_int32), _u32, _u32, _u32, C.c_int,
                                         C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "dory_preprocess_dir": (C.c_int, [C.c_char_p, _u32, _u32, C.c_int]),
+    "dory_preprocess_incident_edges": (C.c_int, [_u32p, _u32p, _u64, C.POINTER(C.c_int32), _u32, _u32, _u32, _u32p, _u64,
+                                                 C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "dory_free": (None, [_P]),
     "dory_read_features": (C.c_int, [C.c_char_p, C.c_char_p, _P, C.c_size_t, _u32, _u32, _f32p, _f32p]),
     "dory_read_labels": (C.c_int, [C.c_char_p, _P, C.c_size_t, _u32, _f32p]),

@@ -1237,14 +1237,26 @@ int dory_preprocess_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_e
     if (!parts || !image || !image_len || (n_edges && (!src || !dst))) return fail(e, DORY_EINVAL, "null argument");
     EdgeList el;
     el.src = src; el.dst = dst; el.stride = 1; el.n = n_edges;
-    std::vector<uint8_t> img;
+    HostImage img;
     std::string msg = preprocess_partition(el, parts, n_vertices, part, n_parts, undirected != 0, img);
     if (!msg.empty()) return fail(e, DORY_EINVAL, "%s", msg.c_str());
-    void *p = std::malloc(img.size());
-    if (!p) return fail(e, DORY_ENOMEM, "out of host memory for a %zu-byte image", img.size());
-    std::memcpy(p, img.data(), img.size());
-    *image = p;
     *image_len = img.size();
+    *image = img.release();
+    return DORY_OK;
+}
+
+int dory_preprocess_incident_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_edges, const int32_t *parts,
+                                   uint32_t n_vertices, uint32_t part, uint32_t n_parts, const uint32_t *in_degree,
+                                   uint64_t global_edges, void **image, size_t *image_len) {
+    dory_engine *e = nullptr;
+    if (!parts || !image || !image_len || !in_degree || (n_edges && (!src || !dst))) return fail(e, DORY_EINVAL, "null argument");
+    EdgeList el;
+    el.src = src; el.dst = dst; el.stride = 1; el.n = n_edges;
+    HostImage img;
+    std::string msg = preprocess_partition(el, parts, n_vertices, part, n_parts, false, img, in_degree, global_edges);
+    if (!msg.empty()) return fail(e, DORY_EINVAL, "%s", msg.c_str());
+    *image_len = img.size();
+    *image = img.release();
     return DORY_OK;
 }
 
@@ -1287,7 +1299,7 @@ int dory_preprocess_dir(const char *dir, uint32_t part, uint32_t n_parts, int un
     }
     EdgeList el;
     el.src = pairs.data(); el.dst = pairs.data() + 1; el.stride = 2; el.n = pairs.size() / 2;
-    std::vector<uint8_t> img;
+    HostImage img;
     std::string msg = preprocess_partition(el, parts.data(), (uint32_t)parts.size(), part, n_parts, undirected != 0, img);
     if (!msg.empty()) return fail(e, DORY_EINVAL, "%s", msg.c_str());
     char name[64];

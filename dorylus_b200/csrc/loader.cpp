@@ -19,10 +19,24 @@
 #include <cstring>
 #include <functional>
 #include <limits>
+#include <chrono>
+#include <cstdio>
 #include <thread>
 
 namespace dory {
 namespace {
+
+// DORY_LOADER_VERBOSE=1: phase timings of preprocess_partition on stderr
+struct PhaseTimer {
+    bool on = std::getenv("DORY_LOADER_VERBOSE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void mark(const char *what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[loader] %-28s %.2f s\n", what, std::chrono::duration<double>(n - t).count());
+        t = n;
+    }
+};
 
 constexpr uint32_t kNone = std::numeric_limits<uint32_t>::max();
 
@@ -143,8 +157,11 @@ std::string parse_partition(const void *image, size_t len, PartitionView &g) {
 }
 
 std::string preprocess_partition(const EdgeList &el, const int32_t *parts, uint32_t nV, uint32_t me,
-                                 uint32_t nParts, bool undirected, std::vector<uint8_t> &image) {
+                                 uint32_t nParts, bool undirected, HostImage &image,
+                                 const uint32_t *inDegree, uint64_t globalEdgesGiven) {
     if (me >= nParts) return "part id out of range";
+    if (inDegree && undirected) return "incident-edge lists carry both directions explicitly (undirected = 0)";
+    PhaseTimer pt_;
     // ---- local ids: order of appearance in the parts file (dataloader.cpp:66-83)
     std::vector<uint32_t> g2l(nV, kNone), l2g;
     for (uint32_t g = 0; g < nV; ++g) {
@@ -155,10 +172,14 @@ std::string preprocess_partition(const EdgeList &el, const int32_t *parts, uint3
         }
     }
     const uint32_t V = (uint32_t)l2g.size();
+    pt_.mark("local ids");
 
     // ---- pass 1: degrees, ghost discovery, boundary flags
     std::vector<uint64_t> inPtr(V + 1, 0), outPtr(V + 1, 0);
-    std::vector<uint32_t> rawInDeg(nV, 0);  // findGhostDegrees: raw records only, keyed by dst
+    // findGhostDegrees: raw records only, keyed by dst (or the caller's whole-graph degrees)
+    std::vector<uint32_t> rawInDegOwn(inDegree ? 0 : nV, 0);
+    uint32_t *rawInDegW = inDegree ? nullptr : rawInDegOwn.data();
+    const uint32_t *rawInDeg = inDegree ? inDegree : rawInDegOwn.data();
     std::vector<uint32_t> srcGhostSlot(nV, kNone), dstGhostSlot(nV, kNone);
     std::vector<std::vector<uint8_t>> fwdFlag(nParts), bwdFlag(nParts);
     for (uint32_t p = 0; p < nParts; ++p)
@@ -176,6 +197,7 @@ std::string preprocess_partition(const EdgeList &el, const int32_t *parts, uint3
         const uint32_t lo = (uint32_t)((uint64_t)nV * t / nThreads), hi = (uint32_t)((uint64_t)nV * (t + 1) / nThreads);
         auto own = [&](uint32_t g) { return g >= lo && g < hi; };
         auto visit = [&](uint32_t from, uint32_t to) {  // processEdge, dataloader.cpp:94-146 (counting)
+            if (!own(from) && !own(to)) return;  // before the two random reads of parts[]: most edges are not this thread's
             const uint32_t pf = (uint32_t)parts[from], pt = (uint32_t)parts[to];
             if (pf == me) {
                 if (own(from)) {
@@ -202,7 +224,7 @@ std::string preprocess_partition(const EdgeList &el, const int32_t *parts, uint3
                 return;
             }
             if (s == d) continue;  // dataloader.cpp:268-269
-            if (own(d)) ++rawInDeg[d];
+            if (rawInDegW && own(d)) ++rawInDegW[d];
             visit(s, d);
             if (undirected) visit(d, s);
             ++cnt;
@@ -210,7 +232,8 @@ std::string preprocess_partition(const EdgeList &el, const int32_t *parts, uint3
         edgeCount[t] = cnt;
     });
     if (bad) return "edge endpoint out of range";
-    const uint64_t globalEdges = edgeCount[0];
+    pt_.mark("pass 1 (count, discover)");
+    const uint64_t globalEdges = globalEdgesGiven ? globalEdgesGiven : edgeCount[0];
     for (uint32_t v = 0; v < V; ++v) {
         inPtr[v + 1] += inPtr[v];
         outPtr[v + 1] += outPtr[v];
@@ -230,10 +253,15 @@ std::string preprocess_partition(const EdgeList &el, const int32_t *parts, uint3
         }
     }
 
+    pt_.mark("ghost slots");
     // ---- per-vertex (in-degree + 1)^-1/2.  Local: edges held (incl. undirected expansion);
     // ghost: raw-file in-degree (quirk Q3).
     std::vector<float> locNorm(V);
     for (uint32_t v = 0; v < V; ++v) locNorm[v] = inv_sqrt_deg((uint32_t)(inPtr[v + 1] - inPtr[v]) + 1);
+    if (inDegree)  // the caller's degrees must agree with the in-edges it handed over for the local rows
+        for (uint32_t v = 0; v < V; ++v)
+            if (inDegree[l2g[v]] != inPtr[v + 1] - inPtr[v])
+                return "inDegree[" + std::to_string(l2g[v]) + "] disagrees with the in-edges of that local vertex";
 
     // ---- image layout
     size_t bytes = 4 * 4 + 3 * 8 + 4 * (size_t)V * 2 + 8 * (srcGhosts.size() + dstGhosts.size()) + 4;
@@ -250,7 +278,9 @@ std::string preprocess_partition(const EdgeList &el, const int32_t *parts, uint3
     bytes += 4 + 8 + 4 * nIn + 8 * ((size_t)V + 1) + 4 * nIn;
     const size_t csrOff = bytes;
     bytes += 4 + 8 + 4 * nOut + 8 * ((size_t)V + 1) + 4 * nOut;
-    image.assign(bytes, 0);
+    pt_.mark("norms, send lists");
+    if (!image.alloc(bytes)) return "out of host memory for a " + std::to_string(bytes) + "-byte image";
+    pt_.mark("image alloc");
 
     Writer w{image.data()};
     w.put(V);
@@ -297,12 +327,14 @@ std::string preprocess_partition(const EdgeList &el, const int32_t *parts, uint3
         std::memcpy(csrPtrs, outPtr.data(), 8 * ((size_t)V + 1));
     }
 
+    pt_.mark("image header");
     // ---- pass 2: place every in-/out-edge at its slot (insertion order == edge-file order, Q4)
     std::vector<uint64_t> inCur(inPtr.begin(), inPtr.end() - 1), outCur(outPtr.begin(), outPtr.end() - 1);
     run_threads(nThreads, [&](unsigned t) {
         const uint32_t lo = (uint32_t)((uint64_t)nV * t / nThreads), hi = (uint32_t)((uint64_t)nV * (t + 1) / nThreads);
         auto own = [&](uint32_t g) { return g >= lo && g < hi; };
         auto place = [&](uint32_t from, uint32_t to) {
+            if (!own(from) && !own(to)) return;
             const uint32_t pf = (uint32_t)parts[from], pt = (uint32_t)parts[to];
             if (pf == me && own(from)) {
                 const uint32_t lf = g2l[from];
@@ -344,6 +376,7 @@ std::string preprocess_partition(const EdgeList &el, const int32_t *parts, uint3
             if (undirected) place(d, s);
         }
     });
+    pt_.mark("pass 2 (place)");
     return "";
 }
 

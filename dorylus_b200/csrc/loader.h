@@ -3,6 +3,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -35,10 +36,42 @@ struct EdgeList {
     uint64_t n = 0;
 };
 
+// A malloc'ed, UNINITIALISED byte image (a multi-GB image is written exactly once by the preprocessor;
+// zero-filling it first and copying it out afterwards cost 12 s of a 45 s Friendster/8 partition).
+struct HostImage {
+    uint8_t *p = nullptr;
+    size_t n = 0;
+    HostImage() = default;
+    HostImage(const HostImage &) = delete;
+    HostImage &operator=(const HostImage &) = delete;
+    ~HostImage() { std::free(p); }
+    bool alloc(size_t bytes) {
+        std::free(p);
+        p = static_cast<uint8_t *>(std::malloc(bytes ? bytes : 1));
+        n = p ? bytes : 0;
+        return p != nullptr;
+    }
+    uint8_t *data() { return p; }
+    size_t size() const { return n; }
+    uint8_t *release() {  // the caller frees with free() (dory_free)
+        uint8_t *r = p;
+        p = nullptr;
+        n = 0;
+        return r;
+    }
+};
+
 // == DataLoader::preprocess + RawGraph::dump.  Returns "" on success.
+// `inDegree` / `globalEdges` (optional): for callers that hold only the edge records INCIDENT to the
+// partition (either endpoint owned by `part`) instead of the whole edge file -- every in- and out-edge
+// of a local vertex is among those, but the raw in-degree of a ghost vertex (findGhostDegrees re-reads
+// the whole file for it, graph/dataloader.cpp:192-218) and the global edge count are not.  inDegree[g]
+// = in-degree of global vertex g in the whole graph (self loops excluded), globalEdges = records in
+// the whole graph.  With both null / 0 the list is taken to be the whole edge file.
 std::string preprocess_partition(const EdgeList &edges, const int32_t *parts, uint32_t nVertices,
                                  uint32_t part, uint32_t nParts, bool undirected,
-                                 std::vector<uint8_t> &image);
+                                 HostImage &image, const uint32_t *inDegree = nullptr,
+                                 uint64_t globalEdges = 0);
 
 // == Engine::readFeaturesFile incl. the feats<F0>.<id>.bin cache / Engine::readLabelsFile
 // (engine/utils.cpp:486-596) for one partition.  local: [V x F], ghost: [Gs x F], onehot: [V x kinds].

@@ -62,14 +62,68 @@ def preprocess_edges(src: np.ndarray, dst: np.ndarray, parts: np.ndarray, num_ve
                                    num_parts, int(undirected), C.byref(img), C.byref(n))
     if rc != 0:
         raise DoryError(rc, lib.dory_last_error(None).decode())
-    try:
-        if n.value < (1 << 31):
-            return C.string_at(img, n.value)
-        # images beyond 2 GiB (e.g. one eighth of the Friendster shape) do not fit a bytes object built
-        # through ctypes: hand back a uint8 array (load_partition and parse_graph_bin accept both)
-        return np.ctypeslib.as_array((C.c_ubyte * n.value).from_address(img.value)).copy()
-    finally:
-        lib.dory_free(img)
+    return _take_image(lib, img, n.value)
+
+
+def preprocess_incident_edges(src: np.ndarray, dst: np.ndarray, parts: np.ndarray, num_vertices: int, part: int,
+                              num_parts: int, in_degree: np.ndarray, global_edges: int):
+    """== dory_preprocess_incident_edges: the graph.<part>.bin image from the edge records incident to
+    `part` alone, the whole graph's in-degrees and its record count."""
+    lib = _lib.load()
+    src = np.ascontiguousarray(src, dtype=np.uint32)
+    dst = np.ascontiguousarray(dst, dtype=np.uint32)
+    parts = np.ascontiguousarray(parts, dtype=np.int32)
+    in_degree = np.ascontiguousarray(in_degree, dtype=np.uint32)
+    if parts.size != num_vertices or in_degree.size != num_vertices:
+        raise ValueError("parts and in_degree must have one entry per global vertex")
+    img, n = C.c_void_p(), C.c_size_t()
+    u32p = C.POINTER(C.c_uint32)
+    rc = lib.dory_preprocess_incident_edges(src.ctypes.data_as(u32p), dst.ctypes.data_as(u32p), src.size,
+                                            parts.ctypes.data_as(C.POINTER(C.c_int32)), num_vertices, part, num_parts,
+                                            in_degree.ctypes.data_as(u32p), int(global_edges), C.byref(img), C.byref(n))
+    if rc != 0:
+        raise DoryError(rc, lib.dory_last_error(None).decode())
+    return _take_image(lib, img, n.value)
+
+
+_BYTES_LIMIT = 1 << 31  # larger images are handed out as arrays (tests lower it)
+
+
+class _OwnedImage:
+    """Keeps a dory_free()-able allocation alive for the numpy view that wraps it."""
+
+    def __init__(self, lib, ptr):
+        self.lib, self.ptr = lib, ptr
+
+    def __del__(self):
+        if self.ptr:
+            self.lib.dory_free(self.ptr)
+            self.ptr = None
+
+
+def _take_image(lib, img, n: int):
+    """bytes for small images; beyond 2 GiB (one eighth of the Friendster shape is 4.1 GB) a uint8 array
+    that wraps the library's allocation without copying it (load_partition / parse_graph_bin take both)."""
+    if n < _BYTES_LIMIT:
+        try:
+            return C.string_at(img, n)
+        finally:
+            lib.dory_free(img)
+    arr = np.ctypeslib.as_array((C.c_ubyte * n).from_address(img.value))
+    owner = _OwnedImage(lib, C.c_void_p(img.value))
+    view = arr.view()
+    view.flags.writeable = False
+    return _ImageArray(view, owner)
+
+
+class _ImageArray(np.ndarray):
+    def __new__(cls, arr, owner):
+        obj = np.asarray(arr).view(cls)
+        obj._owner = owner
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
 
 
 def preprocess_dir(dataset_dir: str, part: int, num_parts: int, undirected: bool = False) -> str:

@@ -128,6 +128,115 @@ def _configuration_model(rng, V: int, n_und: int, sigma: float):
     return src, dst
 
 
+# ---------------------------------------------------------------------------- per-rank (streamed) generation
+# The Amazon / Friendster shapes (BASELINE.json configs[3], [4]) are run on 8 GPUs with one process per
+# GPU; a 1.8 G-record edge list (14 GB) must never exist in one process.  The generator below is a
+# pure function of (spec, chunk): every rank walks the same chunk sequence and keeps the records
+# incident to its own vertex range, so the union over ranks is one consistent graph and a rank's list
+# equals the whole list filtered by incidence, in the same order (tests/test_synth_streamed.py).
+#
+# Degrees: inside a community block of B vertices, position i has weight
+#   w(i) = mass of N(sigma, 1) on the i-th 1/B-quantile cell of N(0, 1)
+# i.e. the size-biased (edge-endpoint) distribution of log-normal(sigma) weights assigned by rank, so an
+# endpoint is drawn without any table: z ~ N(sigma, 1), i = floor(Phi(z) * B).  A fixed affine map
+# scatters the ranks over the block's ids.  Every block receives the same number of first endpoints;
+# the second endpoint stays in the block with probability `locality`, else it falls into a uniformly
+# drawn block.
+_CHUNK_EDGES = 2_000_000  # undirected edges per generation chunk (target)
+_PERM_MUL = 1_000_003     # affine scatter of degree ranks inside a block (prime; coprime to any block size here)
+
+
+class StreamedLayout:
+    """Chunking of a community-structured GraphSpec: blocks of `blk` vertices, chunks of `bpc` blocks."""
+
+    def __init__(self, spec: GraphSpec):
+        V = spec.num_vertices
+        self.V, self.n_und = V, spec.num_edges // 2
+        self.blk = (V + spec.communities - 1) // max(spec.communities, 1)
+        self.nblocks = (V + self.blk - 1) // self.blk
+        target = max(1, self.n_und // _CHUNK_EDGES)
+        self.bpc = (self.nblocks + target - 1) // target  # blocks per chunk
+        self.nchunks = (self.nblocks + self.bpc - 1) // self.bpc
+        # undirected edges whose first endpoint lies in chunk c: proportional to its block count
+        cum = (np.minimum(np.arange(self.nchunks + 1, dtype=np.int64) * self.bpc, self.nblocks) * self.n_und) // self.nblocks
+        self.quota = np.diff(cum)
+        self.n_local = (self.quota * spec.locality).astype(np.int64)  # stay inside the block
+        self.n_remote = self.quota - self.n_local
+
+    def chunk_vertex_range(self, c: int):
+        return c * self.bpc * self.blk, min((c + 1) * self.bpc * self.blk, self.V)
+
+
+def _draw_in_blocks(rng, blocks: np.ndarray, lay: StreamedLayout, sigma: float) -> np.ndarray:
+    from scipy.special import ndtr
+
+    base = blocks * lay.blk
+    size = np.minimum(base + lay.blk, lay.V) - base
+    q = ndtr(rng.standard_normal(blocks.size) + sigma)
+    i = np.minimum((q * size).astype(np.int64), size - 1)
+    return base + (i * _PERM_MUL + 7) % size
+
+
+def _chunk_edges(spec: GraphSpec, lay: StreamedLayout, c: int, part: int):
+    """Undirected edges (u, v) of chunk c: part 0 = both endpoints in one block, part 1 = second endpoint
+    in a uniformly drawn block.  Deterministic in (spec.seed, c, part)."""
+    n = int(lay.n_local[c] if part == 0 else lay.n_remote[c])
+    if n == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    rng = np.random.default_rng([spec.seed, c, part])
+    b0, b1 = c * lay.bpc, min((c + 1) * lay.bpc, lay.nblocks)
+    ub = rng.integers(b0, b1, size=n, dtype=np.int64)
+    u = _draw_in_blocks(rng, ub, lay, spec.sigma)
+    vb = ub if part == 0 else rng.integers(0, lay.nblocks, size=n, dtype=np.int64)
+    v = _draw_in_blocks(rng, vb, lay, spec.sigma)
+    # no self loops: move the second endpoint to the next vertex of its block (a block has >= 2 vertices)
+    base = vb * lay.blk
+    size = np.minimum(base + lay.blk, lay.V) - base
+    v = np.where(u == v, base + (v - base + 1) % size, v)
+    return u, v
+
+
+def generate_incident_edges(spec: GraphSpec, rank: int, world: int, threads: int = 1):
+    """Edge records (both directions of every undirected edge) incident to the vertex range of `rank`
+    under contiguous_parts(V, world), in the order of the whole graph's record list; world = 1 gives the
+    whole list.  Returns (src, dst, in_degree_of_own_vertices, (lo, hi))."""
+    import concurrent.futures as cf
+
+    lay = StreamedLayout(spec)
+    V = lay.V
+    pblk = (V + world - 1) // world
+    lo, hi = min(rank * pblk, V), min((rank + 1) * pblk, V)
+
+    def work(c: int):
+        out = []
+        c_lo, c_hi = lay.chunk_vertex_range(c)
+        for part in (0, 1):
+            if part == 0 and (c_hi <= lo or c_lo >= hi):
+                continue  # both endpoints inside the chunk: nothing incident to this rank
+            u, v = _chunk_edges(spec, lay, c, part)
+            if world > 1:
+                keep = ((u >= lo) & (u < hi)) | ((v >= lo) & (v < hi))
+                u, v = u[keep], v[keep]
+            s = np.empty(2 * u.size, np.uint32)
+            d = np.empty(2 * u.size, np.uint32)
+            s[0::2], d[0::2] = u, v
+            s[1::2], d[1::2] = v, u
+            out.append((s, d))
+        return out
+
+    if threads > 1:
+        with cf.ThreadPoolExecutor(max_workers=threads) as ex:
+            pieces = list(ex.map(work, range(lay.nchunks)))
+    else:
+        pieces = [work(c) for c in range(lay.nchunks)]
+    flat = [p for ps in pieces for p in ps]
+    src = np.concatenate([p[0] for p in flat]) if flat else np.zeros(0, np.uint32)
+    dst = np.concatenate([p[1] for p in flat]) if flat else np.zeros(0, np.uint32)
+    own = (dst >= lo) & (dst < hi)
+    deg = np.bincount(dst[own].astype(np.int64) - lo, minlength=hi - lo).astype(np.uint32)
+    return src, dst, deg, (lo, hi)
+
+
 def generate_features(num_vertices: int, dim: int, seed: int, dense: bool = True) -> np.ndarray:
     rng = np.random.default_rng(seed)
     x = rng.random((num_vertices, dim), dtype=np.float32) * 2.0 - 1.0
@@ -141,6 +250,30 @@ def generate_features(num_vertices: int, dim: int, seed: int, dense: bool = True
 
 def generate_labels(num_vertices: int, kinds: int, seed: int) -> np.ndarray:
     return np.random.default_rng(seed).integers(0, kinds, size=num_vertices, dtype=np.uint32)
+
+
+def generate_feature_rows(lo: int, hi: int, dim: int, seed: int, rows_per_chunk: int = 1 << 16) -> np.ndarray:
+    """Dense U(-1, 1) feature rows of the global vertices [lo, hi), identical whatever range is asked
+    for: rows are drawn in fixed chunks of `rows_per_chunk` vertices, each from its own stream."""
+    out = np.empty((hi - lo, dim), np.float32)
+    for c in range(lo // rows_per_chunk, (max(hi, lo + 1) - 1) // rows_per_chunk + 1):
+        a, b = c * rows_per_chunk, (c + 1) * rows_per_chunk
+        rows = np.random.default_rng([seed, c]).random((rows_per_chunk, dim), dtype=np.float32) * 2.0 - 1.0
+        s, e = max(a, lo), min(b, hi)
+        if s < e:
+            out[s - lo:e - lo] = rows[s - a:e - a]
+    return out
+
+
+def generate_label_rows(lo: int, hi: int, kinds: int, seed: int, rows_per_chunk: int = 1 << 20) -> np.ndarray:
+    out = np.empty(hi - lo, np.uint32)
+    for c in range(lo // rows_per_chunk, (max(hi, lo + 1) - 1) // rows_per_chunk + 1):
+        a, b = c * rows_per_chunk, (c + 1) * rows_per_chunk
+        lab = np.random.default_rng([seed, c]).integers(0, kinds, size=rows_per_chunk, dtype=np.uint32)
+        s, e = max(a, lo), min(b, hi)
+        if s < e:
+            out[s - lo:e - lo] = lab[s - a:e - a]
+    return out
 
 
 def contiguous_parts(num_vertices: int, num_parts: int) -> np.ndarray:

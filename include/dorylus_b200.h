@@ -159,6 +159,18 @@ int dory_preprocess_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_e
                           const int32_t *parts, uint32_t n_vertices, uint32_t part,
                           uint32_t n_parts, int undirected, void **image, size_t *image_len);
 int dory_preprocess_dir(const char *dir, uint32_t part, uint32_t n_parts, int undirected);
+/* dory_preprocess_incident_edges == dory_preprocess_edges for a caller that holds only the edge records
+ * INCIDENT to partition `part` (either endpoint owned by it), in edge-file order -- a pre-split edge
+ * file, or a generator that runs per rank so that no process ever holds a 1.8 G-edge list.  The
+ * reference reads the whole graph.bsnap.edges on every node (dataloader.cpp:241-275) and re-reads it
+ * once more for the raw in-degrees of its ghost vertices (findGhostDegrees, :192-218); here those come
+ * in as `in_degree[g]` (in-degree of global vertex g over the WHOLE graph, self loops excluded) and
+ * `global_edges` (records in the whole graph).  The image equals the one dory_preprocess_edges builds
+ * from the whole list (tests/test_loader.py). */
+int dory_preprocess_incident_edges(const uint32_t *src, const uint32_t *dst, uint64_t n_edges,
+                                   const int32_t *parts, uint32_t n_vertices, uint32_t part, uint32_t n_parts,
+                                   const uint32_t *in_degree, uint64_t global_edges, void **image,
+                                   size_t *image_len);
 void dory_free(void *p);
 
 /* ---- dataset inputs (host only) ----------------------------------------------------------------
