@@ -28,6 +28,7 @@ class OracleGCN:
         self.o, self.graphs, self.dims, self.L = oracle, graphs, list(dims), len(dims) - 1
         self.P = len(graphs)
         self.saved: List[Dict[int, Dict[str, np.ndarray]]] = []
+        self._tables = {}
         for g in graphs:
             V, Gs, Gd = g.local_vtx_cnt, g.src_ghost_cnt, g.dst_ghost_cnt
             t: Dict[int, Dict[str, np.ndarray]] = {l: {} for l in range(self.L)}
@@ -60,15 +61,25 @@ class OracleGCN:
             self.saved[p][self.L - 1]["lab"][:] = labels_onehot[g.local_to_global]
 
     # ------------------------------------------------------------------ operators
+    def _table(self, p: int, layer: int, dir: int, ptrs, idxs, local, ghost):
+        """savedEdgeTensors[layer]["fedge" | "bedge"]: the reference builds every pointer table ONCE, in
+        preallocateGCN (gcn_ops.cpp:38,66,86); the tensors they point into never move (updated in place)."""
+        key = (p, layer, dir)
+        if key not in self._tables:
+            self._tables[key] = self.o.edge_table(ptrs, idxs, local, ghost)
+        return self._tables[key]
+
     def aggregate(self, p: int, layer: int, dir: int, low: int = 0, up=None):
         g, t = self.graphs[p], self.saved[p]
         if dir == FORWARD:  # gcn_ops.cpp:139-147
             local = t[0]["x"] if layer == 0 else t[layer - 1]["h"]
+            tab = self._table(p, layer, dir, g.col_ptrs, g.row_idxs, local, t[layer]["fg"])
             self.o.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, local, t[layer]["fg"],
-                                 low, up, out=t[layer]["ah"])
+                                 low, up, out=t[layer]["ah"], table=tab)
         else:  # :148-154
+            tab = self._table(p, layer, dir, g.row_ptrs, g.col_idxs, t[layer]["grad"], t[layer - 1]["bg"])
             self.o.aggregate_gcn(g.row_ptrs, g.col_idxs, g.bwd_vals, g.norms, t[layer]["grad"], t[layer - 1]["bg"],
-                                 low, up, out=t[layer - 1]["aTg"])
+                                 low, up, out=t[layer - 1]["aTg"], table=tab)
 
     def apply_vertex_forward(self, p: int, layer: int):
         g, t = self.graphs[p], self.saved[p]

@@ -126,7 +126,9 @@ def _run_our_arm_with_fake_engine(monkeypatch, capfd, argv, fake_engine=True, ch
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     if fake_engine:
         monkeypatch.setattr(dengine, "Engine", _FakeEngine)
-    monkeypatch.setattr(sys, "argv", ["bench.py"] + ([] if child_arm else ["--no-apply-first-arm"]) + argv)
+    monkeypatch.setattr(sys, "argv", ["bench.py"] + ([] if child_arm else ["--no-arms"]) + (["--no-invariants"] if fake_engine else []) + argv)
+    if child_arm:
+        monkeypatch.setenv("DORY_BENCH_ARMS", "reddit_gcn_apply_first")
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
     sys.path.insert(0, ROOT)
@@ -145,7 +147,7 @@ def _run_our_arm_with_fake_engine(monkeypatch, capfd, argv, fake_engine=True, ch
 
 def test_our_arm_control_flow_and_contract_keys(monkeypatch, capfd):
     d = _run_our_arm_with_fake_engine(monkeypatch, capfd, ["--workload", "reddit-tiny", "--steps", "3", "--warmup", "3",
-                                                           "--cpu-seconds", "0.5"])
+                                                           "--cpu-steps", "1"])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in d, k
@@ -159,14 +161,15 @@ def test_our_arm_control_flow_and_contract_keys(monkeypatch, capfd):
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 600 * 602 * 4 + 600 * 41 * 4 and e["d2h_bytes_per_step"] == 8 and e["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
-    assert d["config"]["aggregations_per_step"] == 3 and "reference order" in d["config"]["schedule"]
+    assert d["details"]["aggregations_per_step"] == 3 and "reference order" in d["details"]["schedule"]
+    assert set(d["config"]) == {"workload", "V", "E", "dims", "parallelism", "l2_policy"}
 
 
 def test_our_arm_apply_first_flag(monkeypatch, capfd):
     d = _run_our_arm_with_fake_engine(monkeypatch, capfd, ["--workload", "reddit-tiny", "--steps", "2", "--apply-first",
                                                            "--no-cpu-baseline"])
     assert set(d["per_layer_ms"]) == {"L0_fwd", "L1_fwd", "L1_bwd", "L0_bwd"}
-    c = d["config"]
+    c = d["details"]
     assert c["aggregations_per_step"] == 3 and c["aggregations_launched_per_step"] == 4  # value stays on the reference's job
     assert c["aggregated_row_widths"]["L0_fwd"] == 128 and c["aggregated_row_widths"]["L1_bwd"] == 41
     assert "apply-first on layers [0, 1]" in c["schedule"] and "F=128" in d["roofline"]["kernel"]
@@ -177,7 +180,7 @@ def test_our_arm_three_layers_on_the_emulated_engine(hostcheck, monkeypatch, cap
     """The Amazon widths (3 layers; apply-first picks layers 0 and 2, layer 1 keeps the reference order)."""
     d = _run_our_arm_with_fake_engine(monkeypatch, capfd, ["--workload", "amazon-tiny", "--steps", "2", "--no-cpu-baseline",
                                                            "--apply-first"], fake_engine=False)
-    c = d["config"]
+    c = d["details"]
     assert c["aggregations_per_step"] == 5 and c["aggregations_launched_per_step"] == 6
     assert set(d["per_layer_ms"]) == {"L0_fwd", "L1_fwd", "L2_fwd", "L2_bwd", "L1_bwd", "L0_bwd"}
     assert c["aggregated_row_widths"]["L0_fwd"] == 64 and c["aggregated_row_widths"]["L1_fwd"] == 64 and c["aggregated_row_widths"]["L2_bwd"] == 25
@@ -193,14 +196,17 @@ def test_our_arm_on_the_emulated_engine(hostcheck, monkeypatch, capfd, extra):
                                       fake_engine=False)
     assert d["gpu_launches"] > 0 and d["value"] > 0 and d["e2e"]["value"] > 0
     assert np.isfinite(d["loss_sum"]) and d["loss_sum"] > 0
-    assert d["config"]["aggregations_launched_per_step"] == (4 if extra else 3)
+    assert d["details"]["aggregations_launched_per_step"] == (4 if extra else 3)
+    inv = d["invariants"]  # checksums of the first epoch, computed for real on the emulated engine
+    assert inv["fwd_checksum_rel_err"] < 1e-5 and inv["bwd_checksum_rel_err"] < 1e-5
 
 
 def test_apply_first_child_arm_cannot_cost_the_headline(monkeypatch, capfd):
     """At N = 1 the bench measures the opt-in apply-first schedule in a CHILD process after the headline
     measurement.  Here the child finds no GPU and fails: the headline line must come out regardless,
-    carrying the child's failure under 'apply_first_arm'."""
+    carrying the child's failure under configs.reddit_gcn_apply_first."""
     d = _run_our_arm_with_fake_engine(monkeypatch, capfd, ["--workload", "reddit-tiny", "--steps", "2", "--no-cpu-baseline"],
                                       child_arm=True)
-    assert d["value"] > 0 and d["gpu_launches"] == 40 and "reference order" in d["config"]["schedule"]
-    assert "error" in d["apply_first_arm"] and "exit 2" in d["apply_first_arm"]["error"]
+    assert d["value"] > 0 and d["gpu_launches"] == 40 and "reference order" in d["details"]["schedule"]
+    arm = d["configs"]["reddit_gcn_apply_first"]
+    assert "error" in arm and "exit 2" in arm["error"]

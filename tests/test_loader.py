@@ -164,3 +164,30 @@ def test_read_features_and_labels_like_the_reference(tmp_path):
     formats.write_labels(d + "bad.bsnap", bad, 5)
     with pytest.raises(DoryError):
         read_labels(d + "bad.bsnap", ds.images[0], 5)
+
+
+def test_numpy_single_partition_loader_equals_the_preprocessor():
+    """oracle/np_loader.py (what `bench.py --impl reference` builds its workload with, so that the
+    reference arm never loads the product library) against dory_preprocess_edges -- which the tests
+    above hold byte-identical to the compiled reference loader: every array of the partition."""
+    import dataclasses
+
+    from dorylus_b200 import synth
+    from oracle.np_loader import single_partition_graph
+
+    for name in ("reddit-tiny", "cora", "amazon-tiny"):
+        spec = synth.CONFIGS[name]
+        src, dst = synth.generate_edges(spec)
+        src = np.concatenate([src, [1, 2, 3, 3]]).astype(np.uint32)  # self loops (dropped) and a duplicate edge (kept)
+        dst = np.concatenate([dst, [1, 2, 4, 4]]).astype(np.uint32)
+        V = spec.num_vertices
+        got = single_partition_graph(src, dst, V)
+        want = formats.parse_graph_bin(dengine.preprocess_edges(src, dst, np.zeros(V, np.int32), V, 0, 1))
+        for f in dataclasses.fields(got):
+            a, b = getattr(got, f.name), getattr(want, f.name)
+            if isinstance(a, np.ndarray):
+                assert a.dtype == b.dtype and np.array_equal(a, b), (name, f.name)
+            elif isinstance(a, list):
+                assert all(np.array_equal(x, y) for x, y in zip(a, b)), (name, f.name)
+            else:
+                assert a == b, (name, f.name)

@@ -54,7 +54,9 @@ def main():
     from dorylus_b200.engine import BACKWARD, FORWARD, GCN, Engine
 
     emu = args.emulate_parts if world == 1 else 0
-    spec, image, graph, feats, labels, n_edges, cut = bench.build_workload(args.workload, emu or world, rank)
+    streamed = bench.ARMS.get(args.workload + "_gcn", {}).get("streamed", False)
+    wl = bench.build_workload(args.workload, emu or world, rank, streamed=streamed, dist=dist)
+    spec, image, graph, n_edges, cut = wl.spec, wl.image, wl.graph, wl.n_edges, wl.cut
     dims = spec.dims
     L = len(dims) - 1
     e = Engine(dims, GCN, node_id=rank, num_nodes=emu or world, device=local,
@@ -63,14 +65,13 @@ def main():
         k, v = kv.split("=", 1)
         e.set_option(k, v)
     e.load_partition(image)
-    x_loc, x_gh = formats.partition_rows(graph, feats)
-    e.set_tensor(0, "x", np.ascontiguousarray(x_loc))
+    e.set_tensor(0, "x", wl.x_loc)
     if emu:
-        e.set_tensor(0, "fg", np.ascontiguousarray(x_gh))
         rng = np.random.default_rng(1)
+        e.set_tensor(0, "fg", rng.standard_normal((graph.src_ghost_cnt, dims[0])).astype(np.float32))
         e.set_tensor(1, "fg", rng.standard_normal((graph.src_ghost_cnt, dims[1])).astype(np.float32))
         e.set_tensor(0, "bg", rng.standard_normal((graph.dst_ghost_cnt, dims[1])).astype(np.float32))
-    e.set_tensor(L - 1, "lab", formats.one_hot(labels[graph.local_to_global], dims[-1]))
+    e.set_tensor(L - 1, "lab", wl.onehot)
     e.init_weights()
     sched = [e.apply_first(l) for l in range(L)]
     if world > 1:
