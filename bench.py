@@ -647,6 +647,8 @@ def parity_n(ctx: Ctx, exchange_default: str) -> dict:
     e.set_tensor(1, "grad", tg[1]["grad"])
     e.backward(2)
     e.backward(1)
+    for l in (1, 0):  # all-reduces dW over the partitions; GAT weights themselves are never stepped (quirk Q10)
+        e.apply_update(l)
     for l in range(2):
         for n in ("grad", "aTg"):
             errs["%s%d" % (n, l)] = rel_err(e.get_tensor(l, n), tg[l][n])

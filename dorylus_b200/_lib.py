@@ -68,6 +68,7 @@ SYMBOLS = {
     "dory_partition_edges": (C.c_int, [_u32p, _u32p, _u64, _u32, _u32, _u32, C.POINTER(C.c_int32), _u64p]),
     "dory_partition_file": (C.c_int, [C.c_char_p, _u32, C.c_char_p]),
     "dory_load_partition": (C.c_int, [_P, _P, C.c_size_t]),
+    "dory_tile_info": (C.c_int, [_P, _u32, C.POINTER(C.c_double), _u32p, _u32p, _u32p]),
     "dory_graph_counts": (C.c_int, [_P, _u64p]),
     "dory_set_tensor": (C.c_int, [_P, _u32, C.c_char_p, _f32p, _u64, _u32]),
     "dory_get_tensor": (C.c_int, [_P, _u32, C.c_char_p, _f32p, _u64, _u32]),

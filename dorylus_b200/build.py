@@ -20,8 +20,9 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libdorylus_b200.so")
 
-SOURCES = ["engine.cu", "spmm.cu", "dense.cu", "gat.cu", "gemm_tc.cu", "comm.cu", "loader.cpp", "partition.cpp"]
-HEADERS = ["common.cuh", "gat.cuh", "gemm_tc.cuh", "comm.h", "loader.h", "partition.h", "../../include/dorylus_b200.h"]
+SOURCES = ["engine.cu", "spmm.cu", "spmm_tile.cu", "dense.cu", "gat.cu", "gemm_tc.cu", "comm.cu", "loader.cpp", "partition.cpp",
+           "tile_plan.cpp"]
+HEADERS = ["common.cuh", "gat.cuh", "gemm_tc.cuh", "comm.h", "loader.h", "partition.h", "tile_plan.h", "../../include/dorylus_b200.h"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -67,6 +67,28 @@ struct SpmmArgs {
 
 // Launches the aggregation; returns the number of kernels launched, or -1 on a launch error.
 int launch_spmm(const SpmmArgs &a, cudaStream_t s);
+// Heavy / light rows through the warp- and CTA-per-row kernels only (no lane-group selection).
+int launch_spmm_rows(const SpmmArgs &a, cudaStream_t s);
+
+// ---- shared-memory-staged aggregation (spmm_tile.cu, plan: tile_plan.h) ----------------------------
+struct TilePlanDev {
+    const uint64_t *ptrs;        // [2V + 1] row v: in-window edges [ptrs[2v], ptrs[2v+1]), the rest [ptrs[2v+1], ptrs[2v+2])
+    const uint32_t *idx;         // [E] regrouped source rows
+    const float *vals;           // [E]
+    const uint32_t *rows;        // rows grouped by tile (team rows first, degree-descending)
+    const uint32_t *tile_ptr;    // [n_tiles + 1]
+    const uint32_t *tile_team;   // [n_tiles] leading rows walked by the whole CTA
+    const uint32_t *tile_wlo;    // [n_tiles] first source row of the staged window
+    const uint32_t *tile_wrows;  // [n_tiles] rows of the window (0: nothing staged)
+    uint32_t n_tiles;
+    uint32_t max_wrows;
+    int low_degree;              // 1: lane group per row (rows fit one slab), 0: warp / CTA per row
+    int slab_floats;             // high-degree mode: column slab width (32, 64, 96 or 128 floats)
+};
+// Returns kernels launched, 0 when the shape has no tile kernel (caller falls back), -1 on a launch error.
+int launch_spmm_tile(const SpmmArgs &a, const TilePlanDev &t, cudaStream_t s);
+// Dynamic shared memory one CTA of the tile kernel needs for rows of pitch ld / nvec float4 of data.
+size_t tile_smem_bytes(uint32_t ld, uint32_t nvec, uint32_t windowRows, bool lowDegree, int slabFloats);
 
 // ---- dense apply (dense.cu) ----------------------------------------------------------------
 enum GemmEpilogue : int { EPI_NONE = 0, EPI_TANH = 1 };

@@ -27,6 +27,7 @@
 #include "gemm_tc.cuh"
 #include "loader.h"
 #include "partition.h"
+#include "tile_plan.h"
 
 using namespace dory;
 
@@ -69,7 +70,17 @@ struct DevBuf {
     T *as() const { return static_cast<T *>(p); }
 };
 
+// Device copy of a tile plan (tile_plan.h) for the shared-memory-staged aggregation (spmm_tile.cu).
+struct TilePlanBuf {
+    DevBuf ptrs, idx, vals, rows, tptr, tteam, twlo, twrows;
+    uint32_t n_tiles = 0, max_wrows = 0, tile_rows = 0, window_rows = 0;
+    double coverage = 0.0;
+    bool low_degree = false;
+    int slab_floats = 0;
+};
+
 struct Adjacency {
+    std::unique_ptr<TilePlanBuf> tile;  // null: no plan (option off, or the graph has no locality to stage)
     DevBuf ptrs, idx, vals, heavy, light;
     uint64_t nnz = 0;
     uint32_t n_heavy = 0, n_light = 0;
@@ -132,6 +143,9 @@ struct dory_engine {
     uint32_t heavy_degree = kHeavyDegree;
     uint32_t hub_degree = 0;  // rows with more edges get a cluster of 8 CTAs (0 = from the partition's size)
     uint32_t locality_block = 0;  // rows per block of the locality-preserving row order (0 = from L2)
+    // shared-memory-staged aggregation (options "tile*", include/dorylus_b200.h)
+    int tile_mode = 2;            // 0 off, 1 on whenever a plan can be built, 2 on when the plan covers enough edges
+    uint32_t tile_rows = 0, tile_window = 0, tile_smem_kb = 100, tile_slab = 0, tile_min_coverage = 50, tile_team = 512;
     // apply-first schedule (DORY_FLAG_APPLY_FIRST, include/dorylus_b200.h): af[l] != 0 -> layer l runs
     // A_hat . (in . W); decided in dory_load_partition from the flag / the "apply_first_mask" option
     std::vector<uint8_t> af;
@@ -339,6 +353,65 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
     if (!light.empty())
         CU(cudaMemcpyAsync(adj.light.p, light.data(), 4 * light.size(), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));  // host staging vectors die at scope exit
+
+    // ---- tile plan for the shared-memory-staged kernel (spmm_tile.cu): only kept when the vertex numbering
+    // has enough locality for a window of source rows to serve a good share of a tile's edges
+    adj.tile.reset();
+    if (e->tile_mode && nnz && V >= 64) {
+        const uint64_t avgDeg = nnz / V;
+        const bool lowDeg = avgDeg < 96;
+        // bytes per staged window row, widest layer this model aggregates
+        uint32_t rowBytes = 0;
+        int slabFloats = 0;
+        const uint32_t lo = e->cfg.gnn_type == DORY_GCN ? 0 : 1, hi = e->cfg.gnn_type == DORY_GCN ? e->cfg.n_layers : e->cfg.n_layers + 1;
+        if (lowDeg) {
+            for (uint32_t l = lo; l < hi; ++l) {
+                const uint32_t w = e->apply_first(l) ? e->cfg.dims[l + 1] : e->cfg.dims[l];
+                const uint32_t nvec = (w + 3) / 4;
+                if (nvec > 32) continue;  // that layer keeps the gather kernels
+                rowBytes = std::max<uint32_t>(rowBytes, (uint32_t)tile_smem_bytes(padded_ld(w), nvec, 1, true, 0));
+            }
+        } else {
+            slabFloats = e->tile_slab ? (int)e->tile_slab : 64;
+            rowBytes = (uint32_t)slabFloats * 4;
+        }
+        if (rowBytes) {
+            TilePlanParams prm;
+            prm.tileRows = e->tile_rows;
+            prm.windowRows = e->tile_window;
+            prm.maxWindowRows = std::max<uint32_t>(32, (e->tile_smem_kb * 1024u) / rowBytes);
+            if (prm.windowRows > prm.maxWindowRows) prm.windowRows = prm.maxWindowRows;
+            prm.teamDegree = lowDeg ? 0xffffffffu : e->tile_team;
+            prm.excludeDegree = lowDeg ? e->heavy_degree : 0;
+            TilePlanHost hp_;
+            build_tile_plan(ptrs, idx, vals, V, nSrcRows, prm, hp_);
+            if (e->tile_mode == 1 || hp_.coverage() * 100.0 >= (double)e->tile_min_coverage) {
+                auto tb = std::make_unique<TilePlanBuf>();
+                auto up = [&](DevBuf &b, const void *src, size_t bytes) -> cudaError_t {
+                    cudaError_t c = b.alloc(bytes);
+                    if (c == cudaSuccess && bytes) c = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, e->stream);
+                    return c;
+                };
+                CU(up(tb->ptrs, hp_.ptrs.data(), 8 * hp_.ptrs.size()));
+                CU(up(tb->idx, hp_.idx.data(), 4 * hp_.idx.size()));
+                CU(up(tb->vals, hp_.vals.data(), 4 * hp_.vals.size()));
+                CU(up(tb->rows, hp_.rows.data(), 4 * hp_.rows.size()));
+                CU(up(tb->tptr, hp_.tilePtr.data(), 4 * hp_.tilePtr.size()));
+                CU(up(tb->tteam, hp_.tileTeam.data(), 4 * hp_.tileTeam.size()));
+                CU(up(tb->twlo, hp_.tileWlo.data(), 4 * hp_.tileWlo.size()));
+                CU(up(tb->twrows, hp_.tileWrows.data(), 4 * hp_.tileWrows.size()));
+                CU(cudaStreamSynchronize(e->stream));
+                tb->n_tiles = (uint32_t)hp_.tileTeam.size();
+                tb->max_wrows = hp_.maxWrows;
+                tb->tile_rows = hp_.tileRows;
+                tb->window_rows = hp_.windowRows;
+                tb->coverage = hp_.coverage();
+                tb->low_degree = lowDeg;
+                tb->slab_floats = slabFloats;
+                adj.tile = std::move(tb);
+            }
+        }
+    }
 
     // ---- source-blocked copy.  A 128-float slab of the [V+G] x F block is (V+G) * 512 B; it only
     // stays L2-resident when that is well below the 126 MB L2 (the two L2 halves mirror lines that
@@ -648,6 +721,35 @@ int run_spmm(dory_engine *e, const Adjacency *adj, const float *selfw, int mode,
              uint32_t low, uint32_t up, const float *vals = nullptr) {
     SpmmArgs a = spmm_args(e, *adj, selfw, mode, *src, *out, low, up, e->V);
     if (vals) a.vals = vals;
+    if (adj->tile && !vals && low == 0 && up == e->V) {
+        // shared-memory-staged kernel (spmm_tile.cu) when this layer's rows fit its launch limits
+        const TilePlanBuf &tb = *adj->tile;
+        const bool shapeOk = tb.low_degree ? a.nvec <= 32 : true;
+        const size_t smem = tile_smem_bytes(a.ld, a.nvec, tb.max_wrows, tb.low_degree, tb.slab_floats);
+        if (shapeOk && smem <= 200u * 1024u) {
+            TilePlanDev t{};
+            t.ptrs = tb.ptrs.as<uint64_t>();
+            t.idx = tb.idx.as<uint32_t>();
+            t.vals = tb.vals.as<float>();
+            t.rows = tb.rows.as<uint32_t>();
+            t.tile_ptr = tb.tptr.as<uint32_t>();
+            t.tile_team = tb.tteam.as<uint32_t>();
+            t.tile_wlo = tb.twlo.as<uint32_t>();
+            t.tile_wrows = tb.twrows.as<uint32_t>();
+            t.n_tiles = tb.n_tiles;
+            t.max_wrows = tb.max_wrows;
+            t.low_degree = tb.low_degree;
+            t.slab_floats = tb.slab_floats;
+            if (tb.low_degree && adj->n_heavy) {  // rows the plan leaves out: CTA-per-row kernel of spmm.cu
+                SpmmArgs h = a;
+                h.n_light = 0;
+                LAUNCHED(launch_spmm_rows(h, e->stream));
+            }
+            LAUNCHED(launch_spmm_tile(a, t, e->stream));
+            e->stats.edges_aggregated += adj->nnz;
+            return DORY_OK;
+        }
+    }
     if (adj->nb > 1) {
         // one pass per group of source windows; passes are separate launches (stream order) because
         // they accumulate into the same output rows.  A group holds as many windows as keep
@@ -1221,6 +1323,29 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
         if (e->cfg.gnn_type != DORY_GCN) return fail(e, DORY_EINVAL, "apply_first_mask is a GCN option");
         if (v >= (1L << e->cfg.n_layers)) return fail(e, DORY_EINVAL, "apply_first_mask has bits beyond layer %u", e->cfg.n_layers - 1);
         e->af_mask = v;
+    } else if (std::strncmp(key, "tile", 4) == 0) {
+        if (e->loaded) return fail(e, DORY_ESTATE, "%s must be set before dory_load_partition", key);
+        if (std::strcmp(key, "tile") == 0) {
+            if (v > 2) return fail(e, DORY_EINVAL, "tile must be 0 (off), 1 (on) or 2 (on when the plan covers enough edges)");
+            e->tile_mode = (int)v;
+        } else if (std::strcmp(key, "tile_rows") == 0) {
+            e->tile_rows = (uint32_t)v;
+        } else if (std::strcmp(key, "tile_window") == 0) {
+            e->tile_window = (uint32_t)v;
+        } else if (std::strcmp(key, "tile_smem_kb") == 0) {
+            if (v < 8 || v > 200) return fail(e, DORY_EINVAL, "tile_smem_kb must be 8..200");
+            e->tile_smem_kb = (uint32_t)v;
+        } else if (std::strcmp(key, "tile_slab") == 0) {
+            if (v != 0 && v != 32 && v != 64 && v != 96 && v != 128) return fail(e, DORY_EINVAL, "tile_slab must be 0, 32, 64, 96 or 128");
+            e->tile_slab = (uint32_t)v;
+        } else if (std::strcmp(key, "tile_min_coverage") == 0) {
+            if (v > 100) return fail(e, DORY_EINVAL, "tile_min_coverage is a percentage");
+            e->tile_min_coverage = (uint32_t)v;
+        } else if (std::strcmp(key, "tile_team") == 0) {
+            e->tile_team = (uint32_t)std::max<long>(v, 1);
+        } else {
+            return fail(e, DORY_EINVAL, "unknown option '%s'", key);
+        }
     } else if (std::strcmp(key, "heavy_degree") == 0) {
         if (e->loaded) return fail(e, DORY_ESTATE, "heavy_degree must be set before dory_load_partition");
         e->heavy_degree = (uint32_t)std::max<long>(v, 1);
@@ -1892,6 +2017,18 @@ int dory_comm_send_gvids(const dory_engine *e, uint32_t dir, uint32_t peer, uint
     *n = (uint32_t)l.size();
     if (ids)
         for (size_t i = 0; i < l.size(); ++i) ids[i] = e->l2g[l[i]];
+    return DORY_OK;
+}
+
+int dory_tile_info(const dory_engine *e, uint32_t dir, double *coverage, uint32_t *window_rows, uint32_t *tile_rows,
+                   uint32_t *n_tiles) {
+    if (!e || !e->loaded || dir > 1) return DORY_EINVAL;
+    const Adjacency &adj = dir == 0 ? e->fwd : e->bwd;
+    const TilePlanBuf *t = adj.tile.get();
+    if (coverage) *coverage = t ? t->coverage : 0.0;
+    if (window_rows) *window_rows = t ? t->window_rows : 0;
+    if (tile_rows) *tile_rows = t ? t->tile_rows : 0;
+    if (n_tiles) *n_tiles = t ? t->n_tiles : 0;
     return DORY_OK;
 }
 

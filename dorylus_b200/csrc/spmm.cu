@@ -456,8 +456,6 @@ int launch_unroll(const SpmmArgs &a, int unroll, int occ, cudaStream_t s) {
 #define DORY_SPMM_CASE(LG_, VEC_) \
     if (lg == LG_ && vec == VEC_) return launch_unroll<LG_, VEC_>(a, unroll, occ, s)
 
-int launch_spmm_rows(const SpmmArgs &a, cudaStream_t s);
-
 int launch_spmm(const SpmmArgs &a, cudaStream_t s) {
     // low-degree light rows that fit one slab: a lane group per row (cfg_light: 0 auto, 1 warp, 2 group)
     const bool fits = a.nvec <= 32;

@@ -461,6 +461,12 @@ class Engine:
         self._check(self._lib.dory_comm_set_send_slots(self._h, dir, peer, slots.ctypes.data_as(C.POINTER(C.c_uint32)),
                                                        slots.size))
 
+    def tile_info(self, dir: int = FORWARD) -> dict:
+        """== dory_tile_info: the shared-memory-staged aggregation's plan for one adjacency."""
+        cov, w, r, n = C.c_double(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._check(self._lib.dory_tile_info(self._h, dir, C.byref(cov), C.byref(w), C.byref(r), C.byref(n)))
+        return dict(coverage=float(cov.value), window_rows=int(w.value), tile_rows=int(r.value), n_tiles=int(n.value))
+
     def apply_first(self, layer: int) -> bool:
         """True when `layer` runs the apply-first schedule (DORY_FLAG_APPLY_FIRST, dory_layer_schedule)."""
         v = C.c_int(0)

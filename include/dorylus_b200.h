@@ -144,6 +144,17 @@ int dory_sync(dory_engine *e);
  *                           the widest gathered slab; set before load).
  *   "tensor_cores"          1: run H.W on tcgen05 (3xTF32, fp32-level accuracy) when the shape
  *                           qualifies; 0: always the fp32 CUDA-core GEMM.
+ *   "tile"                  shared-memory-staged aggregation (spmm_tile.cu) for graphs whose vertex numbering
+ *                           has locality: destination rows are cut into tiles, each tile's best window of
+ *                           consecutive source rows is staged in shared memory by bulk TMA copies and the
+ *                           edges into it never touch L2.  0 off, 1 on whenever a plan can be built, 2
+ *                           (default) on when the plan serves at least "tile_min_coverage" % of the edges
+ *                           from shared memory.  GCN aggregations of whole-partition chunks; set before load.
+ *   "tile_rows" / "tile_window"   destination rows per tile / source rows per window (0 = choose: the smallest
+ *                           power-of-two window that keeps 92 % of the best coverage, tiles of half a window).
+ *   "tile_smem_kb"          shared memory a CTA may spend on its window (default 100: two CTAs per SM).
+ *   "tile_slab"             high-degree graphs: column slab in floats (32, 64, 96, 128; 0 = 64).
+ *   "tile_team"             high-degree graphs: rows with at least this many edges are walked by the whole CTA.
  *   "apply_first_mask"      bit l = 1: layer l runs apply-first (overrides the width rule of
  *                           DORY_FLAG_APPLY_FIRST; GCN only; set before dory_load_partition). */
 int dory_set_option(dory_engine *e, const char *key, const char *value);
@@ -354,6 +365,12 @@ int dory_comm_ipc_import(dory_engine *e, uint32_t layer, const char *ghost_name,
  * returns the count through *n; ids may be NULL to query the count. */
 int dory_comm_send_gvids(const dory_engine *e, uint32_t dir, uint32_t peer, uint32_t *ids,
                          uint32_t *n);
+
+/* What the tile plan of direction `dir` (DORY_FORWARD: CSC, DORY_BACKWARD: CSR) looks like: share of the
+ * edges served from shared memory, window / tile sizes in rows, number of tiles; all zero when the
+ * staged kernel is not in use for that adjacency.  Any output pointer may be NULL. */
+int dory_tile_info(const dory_engine *e, uint32_t dir, double *coverage, uint32_t *window_rows, uint32_t *tile_rows,
+                   uint32_t *n_tiles);
 
 /* ---- timing on the engine's own stream (bench.py's roofline leg) ------------------------------
  * CUDA events recorded on the stream the kernels are launched on; slots 0..63. */
