@@ -48,6 +48,7 @@ struct SpmmArgs {
     const float *vals;      // [E]
     const float *selfw;     // [V]   vtxDataVec (SELF_NORM only)
     const float *src;       // [(V+G) x ld] local rows then ghost rows
+    uint32_t src_rows;      // rows of the block `src` points at (local + ghost): bounds of its TMA tensor map
     float *out;             // [V x ld]
     uint32_t ld;            // common row pitch of src and out, in floats
     uint32_t nvec;          // row width in float4 units to process (data columns only, <= ld / 4)
@@ -80,8 +81,13 @@ struct TilePlanDev {
     const uint32_t *tile_team;   // [n_tiles] leading rows walked by the whole CTA
     const uint32_t *tile_wlo;    // [n_tiles] first source row of the staged window
     const uint32_t *tile_wrows;  // [n_tiles] rows of the window (0: nothing staged)
+    const uint64_t *tile_e0;     // [n_tiles] edge run [e0, e1) of the tile's rows in idx / vals (low-degree mode:
+    const uint64_t *tile_e1;     //           the rows are consecutive, so the run is contiguous)
     uint32_t n_tiles;
     uint32_t max_wrows;
+    uint32_t max_tile_rows;
+    uint64_t max_tile_edges;
+    uint32_t smem_ptr_off, smem_idx_off, smem_val_off;  // filled by the launcher (low-degree mode)
     int low_degree;              // 1: lane group per row (rows fit one slab), 0: warp / CTA per row
     int slab_floats;             // high-degree mode: column slab width (32, 64, 96 or 128 floats)
 };
@@ -89,6 +95,8 @@ struct TilePlanDev {
 int launch_spmm_tile(const SpmmArgs &a, const TilePlanDev &t, cudaStream_t s);
 // Dynamic shared memory one CTA of the tile kernel needs for rows of pitch ld / nvec float4 of data.
 size_t tile_smem_bytes(uint32_t ld, uint32_t nvec, uint32_t windowRows, bool lowDegree, int slabFloats);
+// ... plus, in low-degree mode, what the tile's staged offsets / ids / weights take.
+size_t tile_edge_smem_bytes(uint64_t maxTileEdges, uint32_t maxTileRows);
 
 // ---- dense apply (dense.cu) ----------------------------------------------------------------
 enum GemmEpilogue : int { EPI_NONE = 0, EPI_TANH = 1 };

@@ -72,8 +72,9 @@ struct DevBuf {
 
 // Device copy of a tile plan (tile_plan.h) for the shared-memory-staged aggregation (spmm_tile.cu).
 struct TilePlanBuf {
-    DevBuf ptrs, idx, vals, rows, tptr, tteam, twlo, twrows;
-    uint32_t n_tiles = 0, max_wrows = 0, tile_rows = 0, window_rows = 0;
+    DevBuf ptrs, idx, vals, rows, tptr, tteam, twlo, twrows, te0, te1;
+    uint32_t n_tiles = 0, max_wrows = 0, tile_rows = 0, window_rows = 0, max_tile_rows = 0;
+    uint64_t max_tile_edges = 0;
     double coverage = 0.0;
     bool low_degree = false;
     int slab_floats = 0;
@@ -84,6 +85,7 @@ struct Adjacency {
     DevBuf ptrs, idx, vals, heavy, light;
     uint64_t nnz = 0;
     uint32_t n_heavy = 0, n_light = 0;
+    uint32_t n_src_rows = 0;  // rows of the block the indices address (local + ghost)
     uint32_t n_vheavy = 0;  // leading entries of `heavy` with degree >= hub_degree (a CTA cluster each)
     uint32_t light_avg_degree = 0;
     // Source-blocked copy (GCN): every row's edge list regrouped by source-row block so that one
@@ -146,6 +148,7 @@ struct dory_engine {
     // shared-memory-staged aggregation (options "tile*", include/dorylus_b200.h)
     int tile_mode = 2;            // 0 off, 1 on whenever a plan can be built, 2 on when the plan covers enough edges
     uint32_t tile_rows = 0, tile_window = 0, tile_smem_kb = 100, tile_slab = 0, tile_min_coverage = 50, tile_team = 512;
+    uint32_t tile_edges = 4096;   // low-degree mode: edges per tile (their ids / weights are staged too)
     // apply-first schedule (DORY_FLAG_APPLY_FIRST, include/dorylus_b200.h): af[l] != 0 -> layer l runs
     // A_hat . (in . W); decided in dory_load_partition from the flag / the "apply_first_mask" option
     std::vector<uint8_t> af;
@@ -290,6 +293,7 @@ void build_row_lists(const std::vector<uint64_t> &ptrs, uint32_t heavyDegree, bo
 int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const uint8_t *idx,
                      const uint8_t *vals, uint64_t nnz, uint32_t V, uint32_t nSrcRows) {
     adj.nnz = nnz;
+    adj.n_src_rows = nSrcRows;
     std::vector<uint64_t> hp(V + 1);
     std::memcpy(hp.data(), ptrs, 8 * ((size_t)V + 1));
     for (uint32_t v = 0; v < V; ++v)
@@ -369,7 +373,7 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
                 const uint32_t w = e->apply_first(l) ? e->cfg.dims[l + 1] : e->cfg.dims[l];
                 const uint32_t nvec = (w + 3) / 4;
                 if (nvec > 32) continue;  // that layer keeps the gather kernels
-                rowBytes = std::max<uint32_t>(rowBytes, (uint32_t)tile_smem_bytes(padded_ld(w), nvec, 1, true, 0));
+                rowBytes = std::max<uint32_t>(rowBytes, (uint32_t)(tile_smem_bytes(padded_ld(w), nvec, 64, true, 0) / 64));
             }
         } else {
             slabFloats = e->tile_slab ? (int)e->tile_slab : 64;
@@ -382,13 +386,18 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
             prm.maxWindowRows = std::max<uint32_t>(32, (e->tile_smem_kb * 1024u) / rowBytes);
             if (prm.windowRows > prm.maxWindowRows) prm.windowRows = prm.maxWindowRows;
             prm.teamDegree = lowDeg ? 0xffffffffu : e->tile_team;
+            // rows the heavy (CTA-per-row) launch owns stay out of the tiles; a tile must be able to hold any other row
             prm.excludeDegree = lowDeg ? e->heavy_degree : 0;
+            prm.edgeCap = lowDeg ? std::max(e->tile_edges, e->heavy_degree) : 0;
+            prm.keepRowOrder = lowDeg;
             TilePlanHost hp_;
             build_tile_plan(ptrs, idx, vals, V, nSrcRows, prm, hp_);
             if (e->tile_mode == 1 || hp_.coverage() * 100.0 >= (double)e->tile_min_coverage) {
                 auto tb = std::make_unique<TilePlanBuf>();
+                // 64 spare bytes behind every array: the low-degree kernel's bulk copies round their runs up to 16 B
                 auto up = [&](DevBuf &b, const void *src, size_t bytes) -> cudaError_t {
-                    cudaError_t c = b.alloc(bytes);
+                    cudaError_t c = b.alloc(bytes + 64);
+                    if (c == cudaSuccess) c = cudaMemsetAsync(static_cast<uint8_t *>(b.p) + bytes, 0, 64, e->stream);
                     if (c == cudaSuccess && bytes) c = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, e->stream);
                     return c;
                 };
@@ -400,6 +409,10 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
                 CU(up(tb->tteam, hp_.tileTeam.data(), 4 * hp_.tileTeam.size()));
                 CU(up(tb->twlo, hp_.tileWlo.data(), 4 * hp_.tileWlo.size()));
                 CU(up(tb->twrows, hp_.tileWrows.data(), 4 * hp_.tileWrows.size()));
+                CU(up(tb->te0, hp_.tileE0.data(), 8 * hp_.tileE0.size()));
+                CU(up(tb->te1, hp_.tileE1.data(), 8 * hp_.tileE1.size()));
+                tb->max_tile_rows = hp_.maxTileRows;
+                tb->max_tile_edges = hp_.maxTileEdges;
                 CU(cudaStreamSynchronize(e->stream));
                 tb->n_tiles = (uint32_t)hp_.tileTeam.size();
                 tb->max_wrows = hp_.maxWrows;
@@ -684,6 +697,7 @@ SpmmArgs spmm_args(const dory_engine *e, const Adjacency &adj, const float *self
     a.vals = adj.vals.as<float>();
     a.selfw = selfw;
     a.src = src.p;
+    a.src_rows = adj.n_src_rows;
     a.out = out.p;
     a.ld = src.ld;
     // float4 columns that carry data: the padding columns of a row (zero on both sides, never written)
@@ -725,7 +739,8 @@ int run_spmm(dory_engine *e, const Adjacency *adj, const float *selfw, int mode,
         // shared-memory-staged kernel (spmm_tile.cu) when this layer's rows fit its launch limits
         const TilePlanBuf &tb = *adj->tile;
         const bool shapeOk = tb.low_degree ? a.nvec <= 32 : true;
-        const size_t smem = tile_smem_bytes(a.ld, a.nvec, tb.max_wrows, tb.low_degree, tb.slab_floats);
+        const size_t smem = tile_smem_bytes(a.ld, a.nvec, tb.max_wrows, tb.low_degree, tb.slab_floats) +
+                            (tb.low_degree ? tile_edge_smem_bytes(tb.max_tile_edges, tb.max_tile_rows) : 0);
         if (shapeOk && smem <= 200u * 1024u) {
             TilePlanDev t{};
             t.ptrs = tb.ptrs.as<uint64_t>();
@@ -736,6 +751,10 @@ int run_spmm(dory_engine *e, const Adjacency *adj, const float *selfw, int mode,
             t.tile_team = tb.tteam.as<uint32_t>();
             t.tile_wlo = tb.twlo.as<uint32_t>();
             t.tile_wrows = tb.twrows.as<uint32_t>();
+            t.tile_e0 = tb.te0.as<uint64_t>();
+            t.tile_e1 = tb.te1.as<uint64_t>();
+            t.max_tile_rows = tb.max_tile_rows;
+            t.max_tile_edges = tb.max_tile_edges;
             t.n_tiles = tb.n_tiles;
             t.max_wrows = tb.max_wrows;
             t.low_degree = tb.low_degree;
@@ -1341,6 +1360,9 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
         } else if (std::strcmp(key, "tile_min_coverage") == 0) {
             if (v > 100) return fail(e, DORY_EINVAL, "tile_min_coverage is a percentage");
             e->tile_min_coverage = (uint32_t)v;
+        } else if (std::strcmp(key, "tile_edges") == 0) {
+            if (v < 256 || v > 16384) return fail(e, DORY_EINVAL, "tile_edges must be 256..16384");
+            e->tile_edges = (uint32_t)v;
         } else if (std::strcmp(key, "tile_team") == 0) {
             e->tile_team = (uint32_t)std::max<long>(v, 1);
         } else {

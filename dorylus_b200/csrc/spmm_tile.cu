@@ -18,6 +18,9 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "common.cuh"
 
@@ -98,22 +101,40 @@ __device__ __forceinline__ void add4(float4 &a, const float4 &b) {
     a.w += b.w;
 }
 
-// Stage the window: `wrows` rows of `slab4` float4 each, source rows wlo.. at pitch ld4, column col0.
-// Every thread issues a share of the copies; thread 0 posts the byte count first.
-__device__ __forceinline__ void stage_window(float4 *win, const float4 *src4, uint32_t ld4, uint32_t col0, uint32_t slab4,
-                                             uint32_t wlo, uint32_t wrows, uint32_t bar) {
-    if (threadIdx.x == 0) mbar_expect_tx(bar, wrows * slab4 * 16u);
-    __syncthreads();
-    if (slab4 == ld4) {  // whole rows: the window is one contiguous run, copied in 4 KB pieces
+// 2-D tiled TMA load (cp.async.bulk.tensor): box {boxCols floats, kBoxRows rows} at (col, row) of the source block
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int col, int row, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(col), "r"(row)
+        : "memory");
+}
+
+constexpr uint32_t kBoxRows = 64;  // rows per TMA box of a column-slab window
+
+// Bytes the staged window occupies in shared memory: whole rows are one contiguous run; a column slab is
+// fetched in boxes of kBoxRows rows (the last one may overhang the window; the buffer has room for it).
+__host__ __device__ __forceinline__ uint32_t window_rows_padded(uint32_t wrows, bool contiguous) {
+    return contiguous ? wrows : (wrows + kBoxRows - 1) / kBoxRows * kBoxRows;
+}
+
+// Posts the copies of the window (`wrows` rows of `slab4` float4, source rows wlo.. at pitch ld4, column
+// col0) on `bar`; returns the bytes they will deliver.  Whole rows: 4 KB bulk copies issued by all threads.
+// Column slab: one tiled TMA load per kBoxRows rows through the tensor map of (source block, slab width).
+__device__ __forceinline__ uint32_t window_bytes(uint32_t ld4, uint32_t slab4, uint32_t wrows) {
+    return window_rows_padded(wrows, slab4 == ld4) * slab4 * 16u;
+}
+__device__ __forceinline__ void issue_window(float4 *win, const float4 *src4, const CUtensorMap *map, uint32_t ld4, uint32_t col0,
+                                             uint32_t slab4, uint32_t wlo, uint32_t wrows, uint32_t bar) {
+    if (slab4 == ld4) {
         const uint32_t total4 = wrows * ld4;
         const float4 *base = src4 + (size_t)wlo * ld4;
         for (uint32_t c = threadIdx.x * 256u; c < total4; c += blockDim.x * 256u)
             bulk_g2s(smem_u32(win + c), base + c, min(256u, total4 - c) * 16u, bar);
     } else {
-        for (uint32_t r = threadIdx.x; r < wrows; r += blockDim.x)
-            bulk_g2s(smem_u32(win + (size_t)r * slab4), src4 + (size_t)(wlo + r) * ld4 + col0, slab4 * 16u, bar);
+        const uint32_t nbox = (wrows + kBoxRows - 1) / kBoxRows;
+        for (uint32_t b = threadIdx.x; b < nbox; b += blockDim.x)
+            tma_load_2d(smem_u32(win + (size_t)b * kBoxRows * slab4), map, (int)(col0 * 4), (int)(wlo + b * kBoxRows), bar);
     }
-    mbar_wait(bar, 0);
 }
 
 // One part of a row's edge list walked by `warps` warps (this one is number `rank`): 32 edges per warp
@@ -196,7 +217,7 @@ __device__ __forceinline__ float4 self_term(const SpmmArgs &a, uint32_t row, siz
 // ---------------------------------------------------------------------------- high-degree tiles
 template <int LG, int VEC, int OCC>
 __global__ void __launch_bounds__(32 * kTileWarps, OCC)
-spmm_tile_kernel(const SpmmArgs a, const TilePlanDev t) {
+spmm_tile_kernel(const SpmmArgs a, const TilePlanDev t, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) float4 win[];
     __shared__ __align__(8) uint64_t bar_mem;
     __shared__ uint32_t next_row;
@@ -207,7 +228,9 @@ spmm_tile_kernel(const SpmmArgs a, const TilePlanDev t) {
     const uint32_t tile = blockIdx.x;
     const uint32_t col0 = blockIdx.y * SLAB;  // slab start, float4 units
     const uint32_t ld4 = a.ld >> 2;
-    const uint32_t slab4 = min((uint32_t)SLAB, ld4 - col0);
+    // window row pitch: the whole row when it fits one slab, else a full slab for EVERY slab -- the last one
+    // overhangs the row pitch and its TMA box is zero-filled there (the box shape is fixed per launch)
+    const uint32_t slab4 = min((uint32_t)SLAB, ld4);
     const uint32_t wlo = t.tile_wlo[tile], wrows = t.tile_wrows[tile];
     const uint32_t r_begin = t.tile_ptr[tile], r_end = t.tile_ptr[tile + 1];
     const uint32_t n_team = min(t.tile_team[tile], r_end - r_begin);
@@ -218,8 +241,12 @@ spmm_tile_kernel(const SpmmArgs a, const TilePlanDev t) {
         fence_barrier_init();
         next_row = r_begin + n_team;
     }
+    if (wrows && threadIdx.x == 0) mbar_expect_tx(bar, window_bytes(ld4, slab4, wrows));
     __syncthreads();
-    if (wrows) stage_window(win, src4, ld4, col0, slab4, wlo, wrows, bar);
+    if (wrows) {
+        issue_window(win, src4, &tmap, ld4, col0, slab4, wlo, wrows, bar);
+        mbar_wait(bar, 0);
+    }
     const uint64_t pol_stream = policy_evict_first();
     const uint64_t pol_keep = policy_evict_last();
     bool act[VEC];
@@ -291,12 +318,16 @@ spmm_tile_kernel(const SpmmArgs a, const TilePlanDev t) {
 
 // ---------------------------------------------------------------------------- low-degree tiles
 // A lane group of LG lanes per row, G = 32 / LG rows per warp (spmm_group_kernel's mapping): self term
-// first, then the in-window edges from shared memory, then the rest from L2 -- per group in the row's own
-// edge order within each part.  The row fits one slab (nvec <= LG * VEC).
+// first, then the in-window edges, then the rest -- per group in the row's own edge order within each part.
+// The row fits one slab (nvec <= LG * VEC).  Besides the window, the tile's offsets, edge ids and edge
+// weights are staged too: a tile's rows are consecutive, so each of the three is ONE contiguous run of the
+// plan's arrays and one bulk copy.  The walk then reads nothing but shared memory, except the rows of the
+// out-of-window edges (L2) -- no dependent chain of global loads per row (offsets -> ids -> rows), which is
+// what bounds the gather kernel at this degree.
 template <int LG, int VEC, int WARPS, int OCC>
 __global__ void __launch_bounds__(32 * WARPS, OCC)
-spmm_tile_group_kernel(const SpmmArgs a, const TilePlanDev t) {
-    extern __shared__ __align__(128) float4 win[];
+spmm_tile_group_kernel(const SpmmArgs a, const TilePlanDev t, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_mem;
     constexpr int G = 32 / LG;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -305,27 +336,47 @@ spmm_tile_group_kernel(const SpmmArgs a, const TilePlanDev t) {
     const uint32_t ld4 = a.ld >> 2;
     const uint32_t slab4 = min((uint32_t)(LG * VEC), ld4);
     const uint32_t wlo = t.tile_wlo[tile], wrows = t.tile_wrows[tile];
-    const uint32_t r_begin = t.tile_ptr[tile], r_end = t.tile_ptr[tile + 1];
+    const uint32_t r_begin = t.tile_ptr[tile], nrows = t.tile_ptr[tile + 1] - r_begin;
+    const uint64_t e0 = t.tile_e0[tile], e1 = t.tile_e1[tile];
+    const uint32_t row0 = t.rows[r_begin];  // rows of a tile are consecutive: row0 .. row0 + nrows - 1
     const float4 *__restrict__ src4 = reinterpret_cast<const float4 *>(a.src);
+    // shared-memory layout: window | offsets | ids | weights
+    float4 *win = reinterpret_cast<float4 *>(smem);
+    uint64_t *sptr = reinterpret_cast<uint64_t *>(smem + t.smem_ptr_off);
+    uint32_t *sidx = reinterpret_cast<uint32_t *>(smem + t.smem_idx_off);
+    float *sval = reinterpret_cast<float *>(smem + t.smem_val_off);
+    const uint64_t ea = e0 & ~(uint64_t)3;                       // 16-byte aligned start of the edge run
+    const uint32_t ebytes = (uint32_t)(((e1 + 3) & ~(uint64_t)3) - ea) * 4u;
+    const uint32_t pbytes = (2u * nrows + 2u) * 8u;              // offsets 2*row0 .. 2*(row0+nrows), padded to 16 B
     const uint32_t bar = smem_u32(&bar_mem);
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         fence_barrier_init();
+        mbar_expect_tx(bar, (wrows ? window_bytes(ld4, slab4, wrows) : 0u) + pbytes + 2u * ebytes);
     }
     __syncthreads();
-    if (wrows) stage_window(win, src4, ld4, 0u, slab4, wlo, wrows, bar);
+    if (wrows) issue_window(win, src4, &tmap, ld4, 0u, slab4, wlo, wrows, bar);
+    if (warp == WARPS - 1) {  // the last warp posts the three edge-data runs (32 KB pieces)
+        if (lane == 0) bulk_g2s(smem_u32(sptr), t.ptrs + 2 * (size_t)row0, pbytes, bar);
+        for (uint32_t c = lane * 32768u; c < ebytes; c += 32u * 32768u) {
+            const uint32_t n = min(32768u, ebytes - c);
+            bulk_g2s(smem_u32(sidx) + c, reinterpret_cast<const uint8_t *>(t.idx + ea) + c, n, bar);
+            bulk_g2s(smem_u32(sval) + c, reinterpret_cast<const uint8_t *>(t.vals + ea) + c, n, bar);
+        }
+    }
+    mbar_wait(bar, 0);
     const uint64_t pol_keep = policy_evict_last();
     const uint32_t win_base = smem_u32(win);
 
-    for (uint32_t i0 = r_begin + (uint32_t)warp * G; i0 < r_end; i0 += WARPS * G) {
+    for (uint32_t i0 = (uint32_t)warp * G; i0 < nrows; i0 += WARPS * G) {
         const uint32_t i = i0 + g;
-        const bool live = i < r_end;
-        const uint32_t row = live ? t.rows[i] : 0;
-        uint64_t e = 0, e_mid = 0, e_end = 0;
+        const bool live = i < nrows;
+        const uint32_t row = row0 + (live ? i : 0u);
+        uint32_t e = 0, e_mid = 0, e_end = 0;  // positions inside the staged run
         if (live) {
-            e = t.ptrs[2 * (size_t)row];
-            e_mid = t.ptrs[2 * (size_t)row + 1];
-            e_end = t.ptrs[2 * (size_t)row + 2];
+            e = (uint32_t)(sptr[2 * i] - ea);
+            e_mid = (uint32_t)(sptr[2 * i + 1] - ea);
+            e_end = (uint32_t)(sptr[2 * i + 2] - ea);
         }
         bool act[VEC];
         float4 acc[VEC];
@@ -347,22 +398,14 @@ spmm_tile_group_kernel(const SpmmArgs a, const TilePlanDev t) {
         // two parts: [e, e_mid) from the window, [e_mid, e_end) from L2
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
-            uint64_t pe = part == 0 ? e : e_mid;
-            const uint64_t pend = part == 0 ? e_mid : e_end;
-            uint32_t s_n = 0;
-            float w_n = 0.f;
-            if (pe + l < pend) {
-                s_n = __ldg(t.idx + pe + l);
-                w_n = __ldg(t.vals + pe + l);
-            }
+            uint32_t pe = part == 0 ? e : e_mid;
+            const uint32_t pend = part == 0 ? e_mid : e_end;
             while (__any_sync(kFull, pe < pend)) {
-                const uint32_t s_c = s_n;
-                const float w_c = w_n;
-                s_n = 0;
-                w_n = 0.f;
-                if (pe + LG + l < pend) {
-                    s_n = __ldg(t.idx + pe + LG + l);
-                    w_n = __ldg(t.vals + pe + LG + l);
+                uint32_t s_c = 0;
+                float w_c = 0.f;
+                if (pe + l < pend) {
+                    s_c = sidx[pe + l];
+                    w_c = sval[pe + l];
                 }
                 constexpr int U = VEC >= 3 ? 2 : 4;  // gathers in flight per group before their FMAs
 #pragma unroll
@@ -397,6 +440,53 @@ spmm_tile_group_kernel(const SpmmArgs a, const TilePlanDev t) {
     }
 }
 
+// ---------------------------------------------------------------------------- host side
+using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn encode_fn() {
+    static EncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeFn>(p);
+    }
+    return fn;
+}
+
+// Tensor map of the source block [rows x ld floats] with a box of {boxCols floats, kBoxRows rows}, no swizzle:
+// the box lands in shared memory row-major with a pitch of boxCols floats, which is the window's layout.
+// Cached per (block, pitch, rows, box width).
+bool window_map(const float *src, uint32_t ld, uint64_t rows, uint32_t boxCols, CUtensorMap &out) {
+    static std::mutex mu;
+    static std::map<std::tuple<const float *, uint32_t, uint64_t, uint32_t>, CUtensorMap> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_tuple(src, ld, rows, boxCols);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        EncodeFn fn = encode_fn();
+        if (!fn) return false;
+        CUtensorMap m;
+        const cuuint64_t dims[2] = {ld, rows};
+        const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+        const cuuint32_t box[2] = {boxCols, kBoxRows};
+        const cuuint32_t estr[2] = {1, 1};
+        if (fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(src), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+        if (cache.size() > 256) cache.clear();  // tensors of engines long gone
+        it = cache.emplace(key, m).first;
+    }
+    out = it->second;
+    return true;
+}
+
 // Opt-in dynamic shared memory; remembered per kernel instantiation (and device) so that the attribute
 // call is off the launch path after the first use.
 template <class K>
@@ -420,23 +510,39 @@ bool set_smem(K kernel, size_t bytes, size_t (&granted)[16]) {
 
 template <int LG, int VEC, int OCC>
 int launch_tile(const SpmmArgs &a, const TilePlanDev &t, cudaStream_t s) {
-    const uint32_t slab = LG * VEC;
+    const uint32_t slab = LG * VEC, ld4 = a.ld / 4;
     const uint32_t nslab = (a.nvec + slab - 1) / slab;
-    const size_t smem = (size_t)t.max_wrows * std::min<uint32_t>(slab, a.ld / 4) * 16;
+    const uint32_t slab4 = std::min<uint32_t>(slab, ld4);
+    const bool contiguous = slab4 == ld4;
+    const size_t smem = (size_t)window_rows_padded(t.max_wrows, contiguous) * slab4 * 16;
+    CUtensorMap map{};
+    if (!contiguous && !window_map(a.src, a.ld, a.src_rows, slab4 * 4, map)) return -1;
     static thread_local size_t granted[16] = {};  // per kernel instantiation
     if (!set_smem(spmm_tile_kernel<LG, VEC, OCC>, smem, granted)) return -1;
-    spmm_tile_kernel<LG, VEC, OCC><<<dim3(t.n_tiles, nslab), 32 * kTileWarps, smem, s>>>(a, t);
+    spmm_tile_kernel<LG, VEC, OCC><<<dim3(t.n_tiles, nslab), 32 * kTileWarps, smem, s>>>(a, t, map);
     const cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) fprintf(stderr, "[dorylus_b200] tile kernel <%d,%d> launch (%u tiles x %u slabs, %zu B smem): %s\n", LG, VEC, t.n_tiles, nslab, smem, cudaGetErrorString(ce));
     return ce == cudaSuccess ? 1 : -1;
 }
 
 template <int LG, int VEC, int WARPS, int OCC>
-int launch_tile_group(const SpmmArgs &a, const TilePlanDev &t, cudaStream_t s) {
-    const size_t smem = (size_t)t.max_wrows * std::min<uint32_t>(LG * VEC, a.ld / 4) * 16;
+int launch_tile_group(const SpmmArgs &a, TilePlanDev t, cudaStream_t s) {
+    const uint32_t ld4 = a.ld / 4;
+    const uint32_t slab4 = std::min<uint32_t>(LG * VEC, ld4);
+    const bool contiguous = slab4 == ld4;
+    auto up = [](size_t x) { return (x + 127) & ~(size_t)127; };
+    const size_t winBytes = up((size_t)window_rows_padded(t.max_wrows, contiguous) * slab4 * 16);
+    const size_t ptrBytes = up(((size_t)2 * t.max_tile_rows + 2) * 8);
+    const size_t edgeBytes = up(((size_t)t.max_tile_edges + 8) * 4);
+    t.smem_ptr_off = (uint32_t)winBytes;
+    t.smem_idx_off = (uint32_t)(winBytes + ptrBytes);
+    t.smem_val_off = (uint32_t)(winBytes + ptrBytes + edgeBytes);
+    const size_t smem = winBytes + ptrBytes + 2 * edgeBytes;
+    CUtensorMap map{};
+    if (!contiguous && !window_map(a.src, a.ld, a.src_rows, slab4 * 4, map)) return -1;
     static thread_local size_t granted[16] = {};  // per kernel instantiation
     if (!set_smem(spmm_tile_group_kernel<LG, VEC, WARPS, OCC>, smem, granted)) return -1;
-    spmm_tile_group_kernel<LG, VEC, WARPS, OCC><<<t.n_tiles, 32 * WARPS, smem, s>>>(a, t);
+    spmm_tile_group_kernel<LG, VEC, WARPS, OCC><<<t.n_tiles, 32 * WARPS, smem, s>>>(a, t, map);
     const cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) fprintf(stderr, "[dorylus_b200] tile group kernel <%d,%d> launch (%u tiles, %zu B smem): %s\n", LG, VEC, t.n_tiles, smem, cudaGetErrorString(ce));
     return ce == cudaSuccess ? 1 : -1;
@@ -447,9 +553,14 @@ int launch_tile_group(const SpmmArgs &a, const TilePlanDev &t, cudaStream_t s) {
 size_t tile_smem_bytes(uint32_t ld, uint32_t nvec, uint32_t windowRows, bool lowDegree, int slabFloats) {
     const uint32_t ld4 = ld / 4;
     uint32_t slab4;
-    if (lowDegree) slab4 = std::min(ld4, nvec <= 4 ? 4u : nvec <= 8 ? 8u : nvec <= 16 ? 16u : 32u);
+    if (lowDegree) slab4 = std::min(ld4, nvec <= 4 ? 4u : nvec <= 8 ? 8u : nvec <= 12 ? 12u : nvec <= 16 ? 16u : 32u);
     else slab4 = std::min<uint32_t>(ld4, (uint32_t)slabFloats / 4);
-    return (size_t)windowRows * slab4 * 16;
+    return (size_t)window_rows_padded(windowRows, slab4 == ld4) * slab4 * 16;
+}
+
+size_t tile_edge_smem_bytes(uint64_t maxTileEdges, uint32_t maxTileRows) {
+    auto up = [](size_t x) { return (x + 127) & ~(size_t)127; };
+    return up(((size_t)2 * maxTileRows + 2) * 8) + 2 * up(((size_t)maxTileEdges + 8) * 4);
 }
 
 // Returns the number of kernels launched, 0 when this shape has no tile kernel, -1 on a launch error.

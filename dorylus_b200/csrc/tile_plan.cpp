@@ -115,19 +115,61 @@ void build_tile_plan(const uint8_t *ptrs, const uint8_t *idx, const uint8_t *val
     }
     W = std::max(1u, std::min(W, std::max(nSrcRows, 1u)));
     const uint32_t R = std::max(1u, prm.tileRows ? prm.tileRows : std::max(16u, W / 2));
-    const uint32_t nTiles = (V + R - 1) / R;
+    auto degree = [&](uint32_t v) { return rd64(ptrs, (size_t)v + 1) - rd64(ptrs, v); };
+    // ---- tile boundaries: runs of consecutive rows, at most R rows and (edgeCap > 0) edgeCap edges each; a
+    // row of excludeDegree edges or more belongs to no tile and ends the run it falls into
+    std::vector<std::pair<uint32_t, uint32_t>> ranges;
+    {
+        uint32_t r0 = 0;
+        uint64_t edges = 0;
+        auto close = [&](uint32_t r1) {
+            if (r1 > r0) ranges.emplace_back(r0, r1);
+        };
+        for (uint32_t v = 0; v < V; ++v) {
+            const uint64_t d = degree(v);
+            if (prm.excludeDegree && d >= prm.excludeDegree) {
+                close(v);
+                r0 = v + 1;
+                edges = 0;
+                continue;
+            }
+            if (v - r0 >= R || (prm.edgeCap && v > r0 && edges + d > prm.edgeCap)) {
+                close(v);
+                r0 = v;
+                edges = 0;
+            }
+            edges += d;
+        }
+        close(V);
+    }
+    const uint32_t nTiles = (uint32_t)ranges.size();
     out.tileRows = R;
     out.windowRows = W;
     out.ptrs.assign(2 * (size_t)V + 1, 0);
     out.idx.resize(E);
     out.vals.resize(E);
-    out.rows.resize(V);
+    std::vector<uint32_t> natural(V);  // rows of a tile at [r0, r0 + count) in issue order
     std::vector<uint32_t> wlo(nTiles, 0), wrows(nTiles, 0), team(nTiles, 0);
     std::vector<uint64_t> tileEdges(nTiles, 0);
-    std::vector<uint32_t> tileCount(nTiles, 0);  // rows listed per tile (all of them unless excludeDegree drops some)
     std::atomic<uint64_t> inWin{0};
+    // rows outside every tile keep their whole edge list in the "rest" part (nobody walks it through the plan)
+    {
+        std::vector<uint8_t> covered(V, 0);
+        for (auto &rg : ranges)
+            for (uint32_t v = rg.first; v < rg.second; ++v) covered[v] = 1;
+        for (uint32_t v = 0; v < V; ++v)
+            if (!covered[v]) {
+                const uint64_t b = rd64(ptrs, v), e = rd64(ptrs, (size_t)v + 1);
+                out.ptrs[2 * (size_t)v] = b;
+                out.ptrs[2 * (size_t)v + 1] = b;
+                for (uint64_t k = b; k < e; ++k) {
+                    out.idx[k] = rd32(idx, k);
+                    std::memcpy(&out.vals[k], vals + 4 * k, 4);
+                }
+            }
+    }
     parallel_tiles(nTiles, [&](uint32_t t, std::vector<uint32_t> &scratch) {
-        const uint32_t r0 = t * R, r1 = (uint32_t)std::min<uint64_t>((uint64_t)r0 + R, V);
+        const uint32_t r0 = ranges[t].first, r1 = ranges[t].second;
         const uint64_t e0 = rd64(ptrs, r0), e1 = rd64(ptrs, r1);
         tileEdges[t] = e1 - e0;
         uint32_t lo = 0, n = 0;
@@ -168,19 +210,16 @@ void build_tile_plan(const uint8_t *ptrs, const uint8_t *idx, const uint8_t *val
             mine += cin;
         }
         inWin += mine;
-        // rows of the tile, degree-descending (stable): the long rows start first, and the rows the whole
-        // CTA walks together are a prefix
-        uint32_t *rows = out.rows.data() + r0;
-        uint32_t cnt = 0;
-        for (uint32_t v = r0; v < r1; ++v)
-            if (!prm.excludeDegree || rd64(ptrs, (size_t)v + 1) - rd64(ptrs, v) < prm.excludeDegree) rows[cnt++] = v;
-        std::stable_sort(rows, rows + cnt, [&](uint32_t a, uint32_t b) {
-            return rd64(ptrs, (size_t)a + 1) - rd64(ptrs, a) > rd64(ptrs, (size_t)b + 1) - rd64(ptrs, b);
-        });
+        uint32_t *rows = natural.data() + r0;
+        std::iota(rows, rows + (r1 - r0), r0);
         uint32_t nt = 0;
-        while (nt < cnt && rd64(ptrs, (size_t)rows[nt] + 1) - rd64(ptrs, rows[nt]) >= prm.teamDegree) ++nt;
+        if (!prm.keepRowOrder) {
+            // degree-descending (stable): the long rows start first, and the rows the whole CTA walks together
+            // are a prefix
+            std::stable_sort(rows, rows + (r1 - r0), [&](uint32_t a, uint32_t b) { return degree(a) > degree(b); });
+            while (nt < r1 - r0 && degree(rows[nt]) >= prm.teamDegree) ++nt;
+        }
         team[t] = nt;
-        tileCount[t] = cnt;
     });
     out.ptrs[2 * (size_t)V] = E;
     out.inWindowEdges = inWin.load();
@@ -192,26 +231,28 @@ void build_tile_plan(const uint8_t *ptrs, const uint8_t *idx, const uint8_t *val
     out.tileTeam.resize(nTiles);
     out.tileWlo.resize(nTiles);
     out.tileWrows.resize(nTiles);
-    // `rows` is laid out in natural tile order; tilePtr therefore holds (begin) per ordered tile and the end
-    // is begin + count: store begin / end pairs compactly as begin in tilePtr[i] and count via tileRows
-    // arithmetic -- simpler: re-pack rows in the issue order
-    std::vector<uint32_t> packed(V);
-    uint32_t off = 0;
+    out.tileE0.resize(nTiles);
+    out.tileE1.resize(nTiles);
+    out.rows.clear();
+    out.rows.reserve(V);
     out.maxWrows = 0;
+    out.maxTileEdges = 0;
+    out.maxTileRows = 0;
     for (uint32_t i = 0; i < nTiles; ++i) {
         const uint32_t t = order[i];
-        const uint32_t r0 = t * R;
-        out.tilePtr[i] = off;
-        std::memcpy(packed.data() + off, out.rows.data() + r0, 4 * (size_t)tileCount[t]);
-        off += tileCount[t];
+        const uint32_t r0 = ranges[t].first, r1 = ranges[t].second;
+        out.tilePtr[i] = (uint32_t)out.rows.size();
+        out.rows.insert(out.rows.end(), natural.begin() + r0, natural.begin() + r1);
         out.tileTeam[i] = team[t];
         out.tileWlo[i] = wlo[t];
         out.tileWrows[i] = wrows[t];
+        out.tileE0[i] = rd64(ptrs, r0);
+        out.tileE1[i] = rd64(ptrs, r1);
         out.maxWrows = std::max(out.maxWrows, wrows[t]);
+        out.maxTileEdges = std::max<uint64_t>(out.maxTileEdges, tileEdges[t]);
+        out.maxTileRows = std::max(out.maxTileRows, r1 - r0);
     }
-    out.tilePtr[nTiles] = off;
-    packed.resize(off);
-    out.rows.swap(packed);
+    out.tilePtr[nTiles] = (uint32_t)out.rows.size();
 }
 
 }  // namespace dory

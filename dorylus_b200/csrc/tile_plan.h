@@ -24,8 +24,11 @@ struct TilePlanHost {
     std::vector<uint32_t> tileTeam;         // [nTiles] leading rows of the tile that the whole CTA walks together
     std::vector<uint32_t> tileWlo;          // [nTiles] first source row of the window
     std::vector<uint32_t> tileWrows;        // [nTiles] rows in the window (0 = none worth staging)
+    std::vector<uint64_t> tileE0, tileE1;   // [nTiles] edge range [e0, e1) of the tile's rows (consecutive rows: one run)
     uint64_t inWindowEdges = 0;             // edges served from shared memory
     uint32_t maxWrows = 0;
+    uint64_t maxTileEdges = 0;
+    uint32_t maxTileRows = 0;
     double coverage() const { return idx.empty() ? 0.0 : (double)inWindowEdges / (double)idx.size(); }
 };
 
@@ -37,6 +40,10 @@ struct TilePlanParams {
     uint32_t teamDegree = 512; // rows with at least this many edges are walked by the whole CTA
     uint32_t excludeDegree = 0; // rows with at least this many edges are left out of the tiles (0 = none): the
                                 // low-degree kernel hands them to the CTA-per-row kernel of spmm.cu
+    uint32_t edgeCap = 0;       // > 0: a tile holds at most this many edges (the low-degree kernel stages a tile's
+                                // ids / weights in shared memory as well)
+    bool keepRowOrder = false;  // true: rows of a tile stay in vertex order (the low-degree kernel addresses them as
+                                // row0 + i); false: degree-descending with the team rows first
     double minTileCoverage = 0.25;  // a tile whose best window holds less than this share of its edges stages nothing
 };
 

@@ -154,6 +154,8 @@ int dory_sync(dory_engine *e);
  *                           power-of-two window that keeps 92 % of the best coverage, tiles of half a window).
  *   "tile_smem_kb"          shared memory a CTA may spend on its window (default 100: two CTAs per SM).
  *   "tile_slab"             high-degree graphs: column slab in floats (32, 64, 96, 128; 0 = 64).
+ *   "tile_edges"            low-degree graphs: edges per tile (default 4096); a tile's offsets, ids and weights are
+ *                           staged in shared memory beside its window.
  *   "tile_team"             high-degree graphs: rows with at least this many edges are walked by the whole CTA.
  *   "apply_first_mask"      bit l = 1: layer l runs apply-first (overrides the width rule of
  *                           DORY_FLAG_APPLY_FIRST; GCN only; set before dory_load_partition). */
