@@ -88,6 +88,8 @@ struct TilePlanDev {
     uint32_t max_tile_rows;
     uint64_t max_tile_edges;
     uint32_t smem_ptr_off, smem_idx_off, smem_val_off;  // filled by the launcher (low-degree mode)
+    uint32_t smem_win_off, stage_bytes;                 // pipelined kernel: layout of one stage
+    int pipeline;                // low-degree mode: 1 = persistent CTAs with a two-stage TMA pipeline
     int low_degree;              // 1: lane group per row (rows fit one slab), 0: warp / CTA per row
     int slab_floats;             // high-degree mode: column slab width (32, 64, 96 or 128 floats)
 };

@@ -146,9 +146,12 @@ struct dory_engine {
     uint32_t hub_degree = 0;  // rows with more edges get a cluster of 8 CTAs (0 = from the partition's size)
     uint32_t locality_block = 0;  // rows per block of the locality-preserving row order (0 = from L2)
     // shared-memory-staged aggregation (options "tile*", include/dorylus_b200.h)
-    int tile_mode = 2;            // 0 off, 1 on whenever a plan can be built, 2 on when the plan covers enough edges
+    // 0 off (default: on every shape measured in round 2 the gather kernels of spmm.cu are faster, see
+    // profiles/round2_tile_kernel.md), 1 on whenever a plan can be built, 2 on when the plan covers enough edges
+    int tile_mode = 0;
     uint32_t tile_rows = 0, tile_window = 0, tile_smem_kb = 100, tile_slab = 0, tile_min_coverage = 50, tile_team = 512;
     uint32_t tile_edges = 4096;   // low-degree mode: edges per tile (their ids / weights are staged too)
+    int tile_pipe = 1;            // low-degree mode: persistent CTAs with a two-stage TMA pipeline
     // apply-first schedule (DORY_FLAG_APPLY_FIRST, include/dorylus_b200.h): af[l] != 0 -> layer l runs
     // A_hat . (in . W); decided in dory_load_partition from the flag / the "apply_first_mask" option
     std::vector<uint8_t> af;
@@ -739,8 +742,9 @@ int run_spmm(dory_engine *e, const Adjacency *adj, const float *selfw, int mode,
         // shared-memory-staged kernel (spmm_tile.cu) when this layer's rows fit its launch limits
         const TilePlanBuf &tb = *adj->tile;
         const bool shapeOk = tb.low_degree ? a.nvec <= 32 : true;
-        const size_t smem = tile_smem_bytes(a.ld, a.nvec, tb.max_wrows, tb.low_degree, tb.slab_floats) +
-                            (tb.low_degree ? tile_edge_smem_bytes(tb.max_tile_edges, tb.max_tile_rows) : 0);
+        size_t smem = tile_smem_bytes(a.ld, a.nvec, tb.max_wrows, tb.low_degree, tb.slab_floats) +
+                      (tb.low_degree ? tile_edge_smem_bytes(tb.max_tile_edges, tb.max_tile_rows) : 0);
+        if (tb.low_degree && e->tile_pipe) smem = 2 * (smem + 256);  // two stages
         if (shapeOk && smem <= 200u * 1024u) {
             TilePlanDev t{};
             t.ptrs = tb.ptrs.as<uint64_t>();
@@ -758,6 +762,7 @@ int run_spmm(dory_engine *e, const Adjacency *adj, const float *selfw, int mode,
             t.n_tiles = tb.n_tiles;
             t.max_wrows = tb.max_wrows;
             t.low_degree = tb.low_degree;
+            t.pipeline = e->tile_pipe;
             t.slab_floats = tb.slab_floats;
             if (tb.low_degree && adj->n_heavy) {  // rows the plan leaves out: CTA-per-row kernel of spmm.cu
                 SpmmArgs h = a;
@@ -1343,7 +1348,7 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
         if (v >= (1L << e->cfg.n_layers)) return fail(e, DORY_EINVAL, "apply_first_mask has bits beyond layer %u", e->cfg.n_layers - 1);
         e->af_mask = v;
     } else if (std::strncmp(key, "tile", 4) == 0) {
-        if (e->loaded) return fail(e, DORY_ESTATE, "%s must be set before dory_load_partition", key);
+        if (e->loaded && std::strcmp(key, "tile_pipe") != 0) return fail(e, DORY_ESTATE, "%s must be set before dory_load_partition", key);
         if (std::strcmp(key, "tile") == 0) {
             if (v > 2) return fail(e, DORY_EINVAL, "tile must be 0 (off), 1 (on) or 2 (on when the plan covers enough edges)");
             e->tile_mode = (int)v;
@@ -1363,6 +1368,8 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
         } else if (std::strcmp(key, "tile_edges") == 0) {
             if (v < 256 || v > 16384) return fail(e, DORY_EINVAL, "tile_edges must be 256..16384");
             e->tile_edges = (uint32_t)v;
+        } else if (std::strcmp(key, "tile_pipe") == 0) {
+            e->tile_pipe = v != 0;
         } else if (std::strcmp(key, "tile_team") == 0) {
             e->tile_team = (uint32_t)std::max<long>(v, 1);
         } else {

@@ -37,6 +37,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {
@@ -440,6 +443,176 @@ spmm_tile_group_kernel(const SpmmArgs a, const TilePlanDev t, const __grid_const
     }
 }
 
+// ---------------------------------------------------------------------------- low-degree tiles, pipelined
+// The same walk as spmm_tile_group_kernel, as a PERSISTENT CTA with a two-stage TMA pipeline: one producer
+// warp stages tile k+1 (window, offsets, ids, weights; completion on full[stage]) while the CW consumer
+// warps walk tile k out of the other stage, and hands a stage back to the producer through empty[stage].
+// A CTA that stages, waits and then computes keeps its shared memory idle for the whole load latency, and
+// the window leaves room for only two or three such CTAs per SM; here the load of the next tile is always
+// in flight behind the current one.  Tiles are dealt round-robin (tile = blockIdx.x + k * gridDim.x) from
+// the plan's heaviest-first order.
+struct StageHeader {
+    uint32_t row0, nrows, wlo, wrows;
+    uint64_t ea;  // first edge of the staged (16 B-aligned) run
+    uint32_t pad[2];
+};
+
+template <int LG, int VEC, int CW, int OCC>
+__global__ void __launch_bounds__(32 * (CW + 1), OCC)
+spmm_tile_pipe_kernel(const SpmmArgs a, const TilePlanDev t, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_mem[2], empty_mem[2];
+    constexpr int G = 32 / LG;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane / LG, l = lane % LG;
+    const uint32_t ld4 = a.ld >> 2;
+    const uint32_t slab4 = min((uint32_t)(LG * VEC), ld4);
+    const float4 *__restrict__ src4 = reinterpret_cast<const float4 *>(a.src);
+    const uint32_t full0 = smem_u32(&full_mem[0]), empty0 = smem_u32(&empty_mem[0]);
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < 2; ++st) {
+            mbar_init(full0 + 8 * st, 1);
+            mbar_init(empty0 + 8 * st, CW);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const uint32_t n_my = t.n_tiles > blockIdx.x ? (t.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == CW) {
+        // ------------------------------------------------------------------ producer warp
+        for (uint32_t k = 0; k < n_my; ++k) {
+            const uint32_t st = k & 1;
+            uint8_t *base = smem + (size_t)st * t.stage_bytes;
+            if (k >= 2) mbar_wait(empty0 + 8 * st, ((k >> 1) - 1) & 1);
+            const uint32_t tile = blockIdx.x + k * gridDim.x;
+            const uint32_t wlo = t.tile_wlo[tile], wrows = t.tile_wrows[tile];
+            const uint32_t r_begin = t.tile_ptr[tile], nrows = t.tile_ptr[tile + 1] - r_begin;
+            const uint64_t e0 = t.tile_e0[tile], e1 = t.tile_e1[tile];
+            const uint32_t row0 = t.rows[r_begin];
+            const uint64_t ea = e0 & ~(uint64_t)3;
+            const uint32_t ebytes = (uint32_t)(((e1 + 3) & ~(uint64_t)3) - ea) * 4u;
+            const uint32_t pbytes = (2u * nrows + 2u) * 8u;
+            const uint32_t bar = full0 + 8 * st;
+            if (lane == 0) {
+                StageHeader *h = reinterpret_cast<StageHeader *>(base);
+                h->row0 = row0;
+                h->nrows = nrows;
+                h->wlo = wlo;
+                h->wrows = wrows;
+                h->ea = ea;
+                mbar_expect_tx(bar, (wrows ? window_bytes(ld4, slab4, wrows) : 0u) + pbytes + 2u * ebytes);
+            }
+            __syncwarp();
+            float4 *win = reinterpret_cast<float4 *>(base + t.smem_win_off);
+            if (wrows) {
+                if (slab4 == ld4) {
+                    const uint32_t total4 = wrows * ld4;
+                    const float4 *wb = src4 + (size_t)wlo * ld4;
+                    for (uint32_t c = lane * 256u; c < total4; c += 32u * 256u)
+                        bulk_g2s(smem_u32(win + c), wb + c, min(256u, total4 - c) * 16u, bar);
+                } else {
+                    const uint32_t nbox = (wrows + kBoxRows - 1) / kBoxRows;
+                    for (uint32_t b = lane; b < nbox; b += 32)
+                        tma_load_2d(smem_u32(win + (size_t)b * kBoxRows * slab4), &tmap, 0, (int)(wlo + b * kBoxRows), bar);
+                }
+            }
+            if (lane == 31) bulk_g2s(smem_u32(base + t.smem_ptr_off), t.ptrs + 2 * (size_t)row0, pbytes, bar);
+            for (uint32_t c = lane * 8192u; c < ebytes; c += 32u * 8192u) {
+                const uint32_t n = min(8192u, ebytes - c);
+                bulk_g2s(smem_u32(base + t.smem_idx_off) + c, reinterpret_cast<const uint8_t *>(t.idx + ea) + c, n, bar);
+                bulk_g2s(smem_u32(base + t.smem_val_off) + c, reinterpret_cast<const uint8_t *>(t.vals + ea) + c, n, bar);
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumer warps
+    const uint64_t pol_keep = policy_evict_last();
+    for (uint32_t k = 0; k < n_my; ++k) {
+        const uint32_t st = k & 1;
+        uint8_t *base = smem + (size_t)st * t.stage_bytes;
+        mbar_wait(full0 + 8 * st, (k >> 1) & 1);
+        const StageHeader h = *reinterpret_cast<const StageHeader *>(base);
+        const uint64_t *sptr = reinterpret_cast<const uint64_t *>(base + t.smem_ptr_off);
+        const uint32_t *sidx = reinterpret_cast<const uint32_t *>(base + t.smem_idx_off);
+        const float *sval = reinterpret_cast<const float *>(base + t.smem_val_off);
+        const uint32_t win_base = smem_u32(base + t.smem_win_off);
+        const uint32_t wlo = h.wlo;
+        for (uint32_t i0 = (uint32_t)warp * G; i0 < h.nrows; i0 += CW * G) {
+            const uint32_t i = i0 + g;
+            const bool live = i < h.nrows;
+            const uint32_t row = h.row0 + (live ? i : 0u);
+            uint32_t e = 0, e_mid = 0, e_end = 0;  // positions inside the staged run
+            if (live) {
+                e = (uint32_t)(sptr[2 * i] - h.ea);
+                e_mid = (uint32_t)(sptr[2 * i + 1] - h.ea);
+                e_end = (uint32_t)(sptr[2 * i + 2] - h.ea);
+            }
+            bool act[VEC];
+            float4 acc[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                act[j] = live && (uint32_t)(l + j * LG) < a.nvec;
+                acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (a.self_mode != SELF_ZERO) {  // self term first, like the reference (gcn_ops.cpp:166-171)
+                const float sw = a.self_mode == SELF_NORM ? a.selfw[row] : 1.f;
+                const float4 *sbase = a.self_mode == SELF_ACCUM ? reinterpret_cast<const float4 *>(a.out) : src4;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                    if (act[j]) {
+                        const float4 x = sbase[(size_t)row * ld4 + l + j * LG];
+                        acc[j] = make_float4(x.x * sw, x.y * sw, x.z * sw, x.w * sw);
+                    }
+            }
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                uint32_t pe = part == 0 ? e : e_mid;
+                const uint32_t pend = part == 0 ? e_mid : e_end;
+                while (__any_sync(kFull, pe < pend)) {
+                    uint32_t s_c = 0;
+                    float w_c = 0.f;
+                    if (pe + l < pend) {
+                        s_c = sidx[pe + l];
+                        w_c = sval[pe + l];
+                    }
+                    constexpr int U = VEC >= 3 ? 2 : 4;
+#pragma unroll
+                    for (int k0 = 0; k0 < LG; k0 += U) {
+                        float4 x[U][VEC];
+                        float w[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int from = g * LG + k0 + u;
+                            const uint32_t s = __shfl_sync(kFull, s_c, from);
+                            w[u] = __shfl_sync(kFull, w_c, from);
+                            const bool ev = pe + (k0 + u) < pend;  // a padding edge never touches memory
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) {
+                                x[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (act[j] && ev)
+                                    x[u][j] = part == 0 ? lds_f4(win_base + ((s - wlo) * slab4 + l + j * LG) * 16u)
+                                                        : ld_row_f4(src4 + (size_t)s * ld4 + l + j * LG, pol_keep);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) fma4(acc[j], x[u][j], w[u]);
+                    }
+                    pe += LG;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                if (act[j]) reinterpret_cast<float4 *>(a.out)[(size_t)row * ld4 + l + j * LG] = acc[j];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * st);  // this warp is done with the stage
+    }
+}
+
 // ---------------------------------------------------------------------------- host side
 using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -548,6 +721,40 @@ int launch_tile_group(const SpmmArgs &a, TilePlanDev t, cudaStream_t s) {
     return ce == cudaSuccess ? 1 : -1;
 }
 
+template <int LG, int VEC, int CW, int OCC>
+int launch_tile_pipe(const SpmmArgs &a, TilePlanDev t, cudaStream_t s) {
+    const uint32_t ld4 = a.ld / 4;
+    const uint32_t slab4 = std::min<uint32_t>(LG * VEC, ld4);
+    const bool contiguous = slab4 == ld4;
+    auto up = [](size_t x) { return (x + 127) & ~(size_t)127; };
+    const size_t winBytes = up((size_t)window_rows_padded(t.max_wrows, contiguous) * slab4 * 16);
+    const size_t ptrBytes = up(((size_t)2 * t.max_tile_rows + 2) * 8);
+    const size_t edgeBytes = up(((size_t)t.max_tile_edges + 8) * 4);
+    t.smem_win_off = 128;  // after the stage header
+    t.smem_ptr_off = (uint32_t)(128 + winBytes);
+    t.smem_idx_off = (uint32_t)(128 + winBytes + ptrBytes);
+    t.smem_val_off = (uint32_t)(128 + winBytes + ptrBytes + edgeBytes);
+    t.stage_bytes = (uint32_t)(128 + winBytes + ptrBytes + 2 * edgeBytes);
+    const size_t smem = 2 * (size_t)t.stage_bytes;
+    CUtensorMap map{};
+    if (!contiguous && !window_map(a.src, a.ld, a.src_rows, slab4 * 4, map)) return -1;
+    static thread_local size_t granted[16] = {};  // per kernel instantiation
+    if (!set_smem(spmm_tile_pipe_kernel<LG, VEC, CW, OCC>, smem, granted)) return -1;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const uint32_t perSm = (uint32_t)std::max<size_t>(1, std::min<size_t>(OCC, (227u * 1024u) / (smem + 1024)));
+    const uint32_t grid = std::min<uint32_t>(t.n_tiles, (uint32_t)sms * perSm);
+    spmm_tile_pipe_kernel<LG, VEC, CW, OCC><<<grid, 32 * (CW + 1), smem, s>>>(a, t, map);
+    const cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) fprintf(stderr, "[dorylus_b200] tile pipe kernel <%d,%d> launch (%u CTAs, %zu B smem): %s\n", LG, VEC, grid, smem, cudaGetErrorString(ce));
+    return ce == cudaSuccess ? 1 : -1;
+}
+
 }  // namespace
 
 size_t tile_smem_bytes(uint32_t ld, uint32_t nvec, uint32_t windowRows, bool lowDegree, int slabFloats) {
@@ -566,6 +773,15 @@ size_t tile_edge_smem_bytes(uint64_t maxTileEdges, uint32_t maxTileRows) {
 // Returns the number of kernels launched, 0 when this shape has no tile kernel, -1 on a launch error.
 int launch_spmm_tile(const SpmmArgs &a, const TilePlanDev &t, cudaStream_t s) {
     if (t.n_tiles == 0) return 0;
+    if (t.low_degree && t.pipeline) {
+        const uint32_t n = a.nvec;
+        if (n <= 4) return launch_tile_pipe<4, 1, 8, 3>(a, t, s);
+        if (n <= 8) return launch_tile_pipe<4, 2, 8, 3>(a, t, s);
+        if (n <= 12) return launch_tile_pipe<4, 3, 8, 2>(a, t, s);
+        if (n <= 16) return launch_tile_pipe<4, 4, 8, 2>(a, t, s);
+        if (n <= 32) return launch_tile_pipe<8, 4, 8, 2>(a, t, s);
+        return 0;
+    }
     if (t.low_degree) {
         const uint32_t n = a.nvec;
         if (n <= 4) return launch_tile_group<4, 1, 8, 4>(a, t, s);

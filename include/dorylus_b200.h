@@ -147,15 +147,19 @@ int dory_sync(dory_engine *e);
  *   "tile"                  shared-memory-staged aggregation (spmm_tile.cu) for graphs whose vertex numbering
  *                           has locality: destination rows are cut into tiles, each tile's best window of
  *                           consecutive source rows is staged in shared memory by bulk TMA copies and the
- *                           edges into it never touch L2.  0 off, 1 on whenever a plan can be built, 2
- *                           (default) on when the plan serves at least "tile_min_coverage" % of the edges
- *                           from shared memory.  GCN aggregations of whole-partition chunks; set before load.
+ *                           edges into it never touch L2.  0 (default) off, 1 on whenever a plan can be built,
+ *                           2 on when the plan serves at least "tile_min_coverage" % of the edges from shared
+ *                           memory.  GCN aggregations of whole-partition chunks; set before load.  Off by default
+ *                           because it lost to the gather kernels on every shape measured so far
+ *                           (profiles/round2_tile_kernel.md); kept selectable, parity-tested.
  *   "tile_rows" / "tile_window"   destination rows per tile / source rows per window (0 = choose: the smallest
  *                           power-of-two window that keeps 92 % of the best coverage, tiles of half a window).
  *   "tile_smem_kb"          shared memory a CTA may spend on its window (default 100: two CTAs per SM).
  *   "tile_slab"             high-degree graphs: column slab in floats (32, 64, 96, 128; 0 = 64).
  *   "tile_edges"            low-degree graphs: edges per tile (default 4096); a tile's offsets, ids and weights are
  *                           staged in shared memory beside its window.
+ *   "tile_pipe"             low-degree graphs: 1 (default) persistent CTAs whose producer warp stages tile k+1 while
+ *                           the other warps walk tile k (two-stage TMA pipeline); 0: one tile per CTA.
  *   "tile_team"             high-degree graphs: rows with at least this many edges are walked by the whole CTA.
  *   "apply_first_mask"      bit l = 1: layer l runs apply-first (overrides the width rule of
  *                           DORY_FLAG_APPLY_FIRST; GCN only; set before dory_load_partition). */

@@ -63,7 +63,8 @@ LOW = {
 
 
 @pytest.mark.parametrize("opts", [{}, {"tile_window": 128, "tile_rows": 50}, {"tile_window": 1024, "tile_rows": 333},
-                                  {"tile_smem_kb": 8}], ids=["auto", "small-window", "large-window", "8KB"])
+                                  {"tile_smem_kb": 8}, {"tile_pipe": 0}, {"tile_pipe": 0, "tile_window": 128, "tile_edges": 1024}],
+                         ids=["auto", "small-window", "large-window", "8KB", "one-tile-per-cta", "one-tile-per-cta-small"])
 @pytest.mark.parametrize("name", list(LOW))
 def test_low_degree_tiles(oracle, name, opts):
     ds = Community(**LOW[name])
@@ -124,5 +125,9 @@ def test_tile_results_are_bit_reproducible_and_auto_mode_declines_without_locali
     src, dst = synth.generate_edges(spec)
     image = dengine.preprocess_edges(src, dst, np.zeros(spec.num_vertices, np.int32), spec.num_vertices, 0, 1)
     with Engine(spec.dims, GCN) as e:
+        e.set_option("tile", 2)
         e.load_partition(image)
+        assert e.tile_info(FORWARD)["n_tiles"] == 0
+    with Engine(spec.dims, GCN) as e:  # and the default is off altogether
+        e.load_partition(ds.image) if ds.dims == spec.dims else e.load_partition(image)
         assert e.tile_info(FORWARD)["n_tiles"] == 0
