@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 
@@ -291,6 +292,14 @@ std::string Comm::set_send_slots(int dir, int peer, const uint32_t *slots, uint3
     p.sendSlots[peer].assign(slots, slots + n);
     p.sendSlotsDirty = true;
     return "";
+}
+
+uint32_t Comm::send_slot_bound(int dir, int peer) const {
+    const Plan &p = plan_[dir];
+    if (p.sendSlots.size() != (size_t)nranks_) return 0;
+    uint32_t b = 0;
+    for (uint32_t sl : p.sendSlots[peer]) b = std::max(b, sl + 1);
+    return b;
 }
 
 bool Comm::p2p_ready(int dir) const {

@@ -45,6 +45,8 @@ public:
     // 0: 4 rows per warp (default), 1 / 2: that many rows per warp, 9: one row + system fence per warp
     void set_p2p_variant(int v) { p2p_variant_ = v; }
     bool p2p_ready(int dir) const;
+    // Largest ghost slot any row shipped to `peer` lands in (+1); 0 when nothing is shipped there.
+    uint32_t send_slot_bound(int dir, int peer) const;
     int rank() const { return rank_; }
     int nranks() const { return nranks_; }
 

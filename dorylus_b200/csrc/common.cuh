@@ -68,6 +68,8 @@ struct SpmmArgs {
 
 // Launches the aggregation; returns the number of kernels launched, or -1 on a launch error.
 int launch_spmm(const SpmmArgs &a, cudaStream_t s);
+// True for the (lanes per row, float4 per lane) shapes the row kernels are instantiated for (0, 0 = derive).
+bool spmm_shape_supported(int lg, int vec);
 // Heavy / light rows through the warp- and CTA-per-row kernels only (no lane-group selection).
 int launch_spmm_rows(const SpmmArgs &a, cudaStream_t s);
 

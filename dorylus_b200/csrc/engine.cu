@@ -174,6 +174,10 @@ struct dory_engine {
     // peer-memory exchange: local ghost tensor -> per-peer pointer to THEIR ghost tensor of the same
     // (layer, name), mapped with cudaIpcOpenMemHandle; ipc_bases are the mappings to close
     std::map<const float *, std::vector<float *>> peer_ghost;
+    // what every peer said about ITS block when it exported it (rows of the ghost block), and which
+    // (ghost tensor, direction) plans have been checked against that since the plan last changed
+    std::map<const float *, std::vector<uint64_t>> peer_ghost_rows;
+    std::set<std::pair<const float *, uint32_t>> p2p_validated;
     std::vector<void *> ipc_bases;
     int p2p = 1;
     int p2p_variant = 0;        // option "p2p_rows": rows per warp of the store kernel (comm.cu)
@@ -738,6 +742,9 @@ int run_spmm(dory_engine *e, const Adjacency *adj, const float *selfw, int mode,
              uint32_t low, uint32_t up, const float *vals = nullptr) {
     SpmmArgs a = spmm_args(e, *adj, selfw, mode, *src, *out, low, up, e->V);
     if (vals) a.vals = vals;
+    if (!spmm_shape_supported(a.cfg_lg, a.cfg_vec))
+        return fail(e, DORY_EINVAL, "options spmm_lg = %d, spmm_vec = %d: no aggregation kernel of that shape (lanes x float4 "
+                    "per lane: 4 x {1,2,4}, 8 x {1,2,4}, 16 x {1,2}, 32 x {1,2,4}; set both or neither)", a.cfg_lg, a.cfg_vec);
     if (adj->tile && !vals && low == 0 && up == e->V) {
         // shared-memory-staged kernel (spmm_tile.cu) when this layer's rows fit its launch limits
         const TilePlanBuf &tb = *adj->tile;
@@ -764,14 +771,17 @@ int run_spmm(dory_engine *e, const Adjacency *adj, const float *selfw, int mode,
             t.low_degree = tb.low_degree;
             t.pipeline = e->tile_pipe;
             t.slab_floats = tb.slab_floats;
-            if (tb.low_degree && adj->n_heavy) {  // rows the plan leaves out: CTA-per-row kernel of spmm.cu
-                SpmmArgs h = a;
-                h.n_light = 0;
-                LAUNCHED(launch_spmm_rows(h, e->stream));
+            const int n = launch_spmm_tile(a, t, e->stream);
+            LAUNCHED(n);
+            if (n > 0) {  // 0: no tile kernel for this shape -> the gather kernels below
+                if (tb.low_degree && adj->n_heavy) {  // rows the plan leaves out: CTA-per-row kernel of spmm.cu
+                    SpmmArgs h = a;
+                    h.n_light = 0;
+                    LAUNCHED(launch_spmm_rows(h, e->stream));
+                }
+                e->stats.edges_aggregated += adj->nnz;
+                return DORY_OK;
             }
-            LAUNCHED(launch_spmm_tile(a, t, e->stream));
-            e->stats.edges_aggregated += adj->nnz;
-            return DORY_OK;
         }
     }
     if (adj->nb > 1) {
@@ -990,6 +1000,21 @@ int exchange(dory_engine *e, uint32_t dir, const DevMat &local, const DevMat &gh
     if (p2p)
         for (uint32_t q = 0; q < e->cfg.num_nodes; ++q)
             if (q != e->cfg.node_id && !pit->second[q]) p2p = false;
+    if (p2p && !e->p2p_validated.count({ghost.p, dir})) {
+        // the store kernel writes peerGhost[q] + slot * ld over NVLink: a slot beyond the block the peer
+        // exported (images of another partitioning, a peer whose schedule differs) would land in memory
+        // that is not ours to write.  Checked once per (tensor, direction) plan.
+        const auto &rows = e->peer_ghost_rows[ghost.p];
+        for (uint32_t q = 0; q < e->cfg.num_nodes; ++q) {
+            if (q == e->cfg.node_id) continue;
+            const uint32_t bound = e->comm->send_slot_bound((int)dir, (int)q);
+            if (bound > rows[q])
+                return fail(e, DORY_EINVAL, "peer-memory exchange: rows shipped to partition %u land in ghost slots up to %u, "
+                            "but its block has %llu rows (send plan and peer image disagree)", q, bound - 1,
+                            (unsigned long long)rows[q]);
+        }
+        e->p2p_validated.insert({ghost.p, dir});
+    }
     if (p2p) {
         const bool pre = !e->elide_pre_barrier || e->ghost_reads_pending.count(ghost.p) != 0;
         e->comm->set_p2p_variant(e->p2p_variant);
@@ -998,7 +1023,10 @@ int exchange(dory_engine *e, uint32_t dir, const DevMat &local, const DevMat &gh
         msg = e->comm->exchange((int)dir, local.p, ghost.p, local.ld, e->stream, launches);
     }
     if (!msg.empty()) return fail(e, DORY_ECOMM, "%s", msg.c_str());
-    e->ghost_reads_pending.clear();  // both paths end in a collective
+    // Only the peer-memory path ends in a true all-rank collective (the "writers done" all-reduce); a grouped
+    // ncclSend/ncclRecv synchronises the pairs that exchange rows in that direction and nobody else, so after
+    // it a later peer-memory exchange still needs its "readers done" barrier.
+    if (p2p) e->ghost_reads_pending.clear();
     e->stats.kernel_launches += launches;
     return DORY_OK;
 }
@@ -1113,6 +1141,9 @@ int edge_backward_gat(dory_engine *e, uint32_t layer) {  // CPU_comm.cpp:205-242
     a.scratch_floats = e->scratchA.bytes / 4;
     a.ws = e->gemm_ws.as<float>();
     a.ws_floats = e->gemm_ws.bytes / 4;
+    if (a.scratch_floats < (size_t)a.V + 2 * a.ld)
+        return fail(e, DORY_EINVAL, "apply_edge backward: partition of %u vertices is too small for the edge-gradient workspace "
+                    "(needs V * pitch >= V + 2 * pitch floats)", a.V);
     LAUNCHED(launch_gat_edge_backward(a, e->stream));
     return DORY_OK;
 }
@@ -1308,7 +1339,7 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
         if (v != 0 && v != 4 && v != 8 && v != 16 && v != 32) return fail(e, DORY_EINVAL, "spmm_lg must be 0, 4, 8, 16 or 32");
         e->spmm_lg = (int)v;
     } else if (std::strcmp(key, "spmm_vec") == 0) {
-        if (v > 4) return fail(e, DORY_EINVAL, "spmm_vec must be 0..4");
+        if (v > 4 || v == 3) return fail(e, DORY_EINVAL, "spmm_vec must be 0, 1, 2 or 4");
         e->spmm_vec = (int)v;
     } else if (std::strcmp(key, "p2p") == 0) {
         e->p2p = v != 0;
@@ -1988,6 +2019,7 @@ int dory_comm_set_send_slots(dory_engine *e, uint32_t dir, uint32_t peer, const 
     if (dir > 1 || peer >= e->cfg.num_nodes || peer == e->cfg.node_id || (n && !slots)) return fail(e, DORY_EINVAL, "bad argument");
     std::string msg = e->comm->set_send_slots((int)dir, (int)peer, slots, n);
     if (!msg.empty()) return fail(e, DORY_EINVAL, "%s", msg.c_str());
+    e->p2p_validated.clear();  // checked against the peers' exported blocks before the next peer-memory exchange
     return DORY_OK;
 }
 
@@ -1995,7 +2027,8 @@ namespace {
 struct IpcBlob {
     cudaIpcMemHandle_t handle;
     uint64_t ghost_offset_bytes;
-    uint64_t ghost_rows;
+    uint32_t ghost_rows;
+    uint32_t ld;  // row pitch of the exporter's block, floats
 };
 static_assert(sizeof(IpcBlob) <= DORY_IPC_BLOB_BYTES, "IPC blob does not fit DORY_IPC_BLOB_BYTES");
 
@@ -2014,7 +2047,8 @@ int dory_comm_ipc_export(dory_engine *e, uint32_t layer, const char *ghost_name,
     // ghost rows follow the V local rows inside one allocation
     IpcBlob b{};
     b.ghost_offset_bytes = (uint64_t)e->V * m->ld * 4;
-    b.ghost_rows = m->rows;
+    b.ghost_rows = (uint32_t)m->rows;
+    b.ld = m->ld;
     void *base = reinterpret_cast<uint8_t *>(m->p) - b.ghost_offset_bytes;
     CU(cudaIpcGetMemHandle(&b.handle, base));
     std::memset(blob80, 0, DORY_IPC_BLOB_BYTES);
@@ -2031,12 +2065,19 @@ int dory_comm_ipc_import(dory_engine *e, uint32_t layer, const char *ghost_name,
     if (!m) return fail(e, DORY_EINVAL, "no tensor '%s' at layer %u", ghost_name, layer);
     IpcBlob b;
     std::memcpy(&b, blob80, sizeof b);
+    if (b.ld != m->ld)
+        return fail(e, DORY_EINVAL, "peer %u exports '%s'[%u] with a row pitch of %u floats, ours is %u: the two engines were "
+                    "configured with different layer widths or schedules", peer, ghost_name, layer, b.ld, m->ld);
     void *base = nullptr;
     CU(cudaIpcOpenMemHandle(&base, b.handle, cudaIpcMemLazyEnablePeerAccess));
     e->ipc_bases.push_back(base);
     auto &v = e->peer_ghost[m->p];
     if (v.size() != e->cfg.num_nodes) v.assign(e->cfg.num_nodes, nullptr);
     v[peer] = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(base) + b.ghost_offset_bytes);
+    auto &rows = e->peer_ghost_rows[m->p];
+    if (rows.size() != e->cfg.num_nodes) rows.assign(e->cfg.num_nodes, 0);
+    rows[peer] = b.ghost_rows;
+    e->p2p_validated.clear();
     return DORY_OK;
 }
 

@@ -453,6 +453,18 @@ int launch_unroll(const SpmmArgs &a, int unroll, int occ, cudaStream_t s) {
 
 }  // namespace
 
+// (lanes per row, float4 per lane) pairs that have a kernel instantiation below
+bool spmm_shape_supported(int lg, int vec) {
+    if (lg == 0 || vec == 0) return lg == 0 && vec == 0;  // both derived from the row width, or both given
+    switch (lg) {
+    case 4: return vec == 1 || vec == 2 || vec == 4;
+    case 8: return vec == 1 || vec == 2 || vec == 4;
+    case 16: return vec == 1 || vec == 2;
+    case 32: return vec == 1 || vec == 2 || vec == 4;
+    default: return false;
+    }
+}
+
 #define DORY_SPMM_CASE(LG_, VEC_) \
     if (lg == LG_ && vec == VEC_) return launch_unroll<LG_, VEC_>(a, unroll, occ, s)
 
@@ -486,6 +498,7 @@ int launch_spmm_rows(const SpmmArgs &a, cudaStream_t s) {
     }
     if (unroll == 0) unroll = 1;
     const int occ = a.cfg_occ ? a.cfg_occ : 4;
+    if (!spmm_shape_supported(lg, vec)) return -2;  // dory_set_option refuses these; defensive
     DORY_SPMM_CASE(4, 1);
     DORY_SPMM_CASE(4, 2);
     DORY_SPMM_CASE(4, 4);  // 8 edges per gather instruction: candidate for 33..64-float rows (not a default yet)

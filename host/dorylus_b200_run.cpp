@@ -10,7 +10,7 @@
 //                    [--numepochs 10] [--lr 0.01] [--gnn GCN|GAT] [--undirected 0]
 //                    [--pipeline 1 [--numlambdas N] [--targetacc A] [--switchthreshold T]] [--dry-run 1]
 //                    [--apply-first 1]
-//                    [--numnodes N --nodeid I [--device D] [--rendezvous DIR] [--exchange p2p|nccl]
+//                    [--numnodes N --nodeid I [--device D] [--rendezvous DIR | --run-id ID] [--exchange p2p|nccl]
 //                     [--rendezvous-timeout SECONDS]]
 //
 // --pipeline 1 drives the epochs through host/saga_pipeline.hpp -- the reference's chunk queues,
@@ -130,7 +130,7 @@ std::vector<uint32_t> plan_slots(const std::vector<char> &recvImage, uint32_t re
 }  // namespace
 
 int main(int argc, char **argv) {
-    std::string dir, featuresFile, labelsFile, layerFile, gnn = "GCN", rendezvous, exchange = "p2p";
+    std::string dir, featuresFile, labelsFile, layerFile, gnn = "GCN", rendezvous, runId, exchange = "p2p";
     unsigned epochs = 10, undirected = 0, pipeline = 0, numLambdas = 1, dryRun = 0, applyFirst = 0;
     unsigned numNodes = 1, nodeId = 0;
     int device = -1;
@@ -152,6 +152,7 @@ int main(int argc, char **argv) {
         else if (k == "--nodeid") nodeId = (unsigned)std::atoi(v.c_str());
         else if (k == "--device") device = std::atoi(v.c_str());
         else if (k == "--rendezvous") rendezvous = v;
+        else if (k == "--run-id") runId = v;
         else if (k == "--exchange") exchange = v;
         else if (k == "--rendezvous-timeout") g_rendezvous_timeout_s = std::atof(v.c_str());
         else if (k == "--numlambdas") numLambdas = (unsigned)std::max(1, std::atoi(v.c_str()));
@@ -176,8 +177,18 @@ int main(int argc, char **argv) {
         std::fprintf(stderr, "--pipeline 1 drives one partition (the shell's barriers are per process)\n");
         return EXIT_FAILURE;
     }
+    // The ranks of a run meet through files.  Files of an EARLIER run in the same directory (its NCCL id, its
+    // CUDA IPC handles, its image.<q>.ready markers) would be accepted as this run's, so several partitions
+    // need either a directory of their own (--rendezvous, what host/run_onnode.sh passes: mktemp -d) or a
+    // --run-id that every rank of the run shares and that becomes part of every file name.
+    if (numNodes > 1 && rendezvous.empty() && runId.empty() && !dryRun) {
+        std::fprintf(stderr, "--numnodes %u needs --rendezvous <fresh directory> or --run-id <unique per run>: the default "
+                             "directory may hold the files of a previous run\n", numNodes);
+        return EXIT_FAILURE;
+    }
     if (rendezvous.empty()) rendezvous = dir.substr(0, dir.size() - 1) + ".rendezvous";
     if (rendezvous.back() != '/') rendezvous += '/';
+    const std::string rdvTag = runId.empty() ? "" : "." + runId;
 
     // readLayerConfigFile, engine/utils.cpp:460-479
     dory_config cfg{};
@@ -239,7 +250,7 @@ int main(int argc, char **argv) {
     if (numNodes > 1) {
         if (!dryRun) {
             ::mkdir(rendezvous.c_str(), 0777);
-            publish(rendezvous + "image." + std::to_string(nodeId) + ".ready", "1", 1);
+            publish(rendezvous + "image." + std::to_string(nodeId) + ".ready" + rdvTag, "1", 1);
         }
         for (int d = 0; d < 2; ++d) {
             recvSlots[d].resize(numNodes);
@@ -249,7 +260,7 @@ int main(int argc, char **argv) {
             if (q == nodeId) continue;
             const std::string peerName = dir + "graph." + std::to_string(q) + ".bin";
             std::vector<char> peerImage, marker;
-            if (!dryRun) await(rendezvous + "image." + std::to_string(q) + ".ready", marker, 1);
+            if (!dryRun) await(rendezvous + "image." + std::to_string(q) + ".ready" + rdvTag, marker, 1);
             if (!read_file(peerName, peerImage)) {
                 if (!dryRun) die(nullptr, "peer partition image missing");
                 if (dory_preprocess_dir(dir.c_str(), q, numNodes, (int)undirected) != DORY_OK) die(nullptr, "dory_preprocess_dir(peer)");
@@ -297,9 +308,9 @@ int main(int argc, char **argv) {
         std::vector<char> id(DORY_UNIQUE_ID_BYTES);
         if (nodeId == 0) {
             if (dory_comm_unique_id(id.data()) != DORY_OK) die(nullptr, "dory_comm_unique_id");
-            publish(rendezvous + "nccl_id", id.data(), id.size());
+            publish(rendezvous + "nccl_id" + rdvTag, id.data(), id.size());
         } else {
-            await(rendezvous + "nccl_id", id, DORY_UNIQUE_ID_BYTES);
+            await(rendezvous + "nccl_id" + rdvTag, id, DORY_UNIQUE_ID_BYTES);
         }
         if (dory_comm_init(e, id.data()) != DORY_OK) die(e, "dory_comm_init");
         for (uint32_t d = 0; d < 2; ++d)
@@ -317,11 +328,11 @@ int main(int argc, char **argv) {
             for (size_t i = 0; i < ghosts.size(); ++i)
                 if (dory_comm_ipc_export(e, ghosts[i].first, ghosts[i].second.c_str(), blobs.data() + i * DORY_IPC_BLOB_BYTES) != DORY_OK)
                     die(e, "dory_comm_ipc_export");
-            publish(rendezvous + "ipc." + std::to_string(nodeId), blobs.data(), blobs.size());
+            publish(rendezvous + "ipc." + std::to_string(nodeId) + rdvTag, blobs.data(), blobs.size());
             for (unsigned q = 0; q < numNodes; ++q) {
                 if (q == nodeId) continue;
                 std::vector<char> theirs;
-                await(rendezvous + "ipc." + std::to_string(q), theirs, blobs.size());
+                await(rendezvous + "ipc." + std::to_string(q) + rdvTag, theirs, blobs.size());
                 for (size_t i = 0; i < ghosts.size(); ++i)
                     if (dory_comm_ipc_import(e, ghosts[i].first, ghosts[i].second.c_str(), q, theirs.data() + i * DORY_IPC_BLOB_BYTES) != DORY_OK)
                         die(e, "dory_comm_ipc_import");

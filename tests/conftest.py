@@ -22,6 +22,31 @@ def pytest_configure(config):
         raise pytest.UsageError("libdorylus_b200.so is missing and nvcc is not available to build it")
 
 
+def _cuda_device_visible() -> bool:
+    """True when dory_create can find an sm_100 device (asked of the library itself: no torch needed)."""
+    try:
+        from dorylus_b200 import _lib
+        from dorylus_b200.engine import DoryError, Engine
+
+        try:
+            Engine([4, 4, 2]).close()
+            return True
+        except DoryError as ex:
+            return ex.code != _lib.ENODEV
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a box without a GPU: the gpu-marked tests are skipped instead of erroring in their
+    fixtures with DORY_ENODEV (the product has no CPU fallback to run them on)."""
+    gpu_items = [it for it in items if it.get_closest_marker("gpu")]
+    if gpu_items and not _cuda_device_visible():
+        skip = pytest.mark.skip(reason="no CUDA device visible (dory_create: DORY_ENODEV)")
+        for it in gpu_items:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle.pyoracle import Oracle

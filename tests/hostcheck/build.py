@@ -29,7 +29,7 @@ def build(force: bool = False) -> str:
     from dorylus_b200 import build as product_build
 
     product_build.build()  # makes sure engine_cu.o / loader_cpp.o / partition_cpp.o are current
-    objs = [os.path.join(OBJ, n) for n in ("engine_cu.o", "loader_cpp.o", "partition_cpp.o")]
+    objs = [os.path.join(OBJ, n) for n in ("engine_cu.o", "loader_cpp.o", "partition_cpp.o", "tile_plan_cpp.o")]
     srcs = [os.path.join(HERE, n) for n in ("fake_cudart.cpp", "cpu_kernels.cpp")]
     hdrs = [os.path.join(ROOT, "dorylus_b200", "csrc", n) for n in ("common.cuh", "comm.h", "gat.cuh", "gemm_tc.cuh")]
     deps = objs + srcs + hdrs + [os.path.abspath(__file__)]
@@ -54,7 +54,7 @@ def build_launchcheck(force: bool = False) -> str:
 
     product_build.build()
     out = os.path.join(OUT_DIR, "libdorylus_launchcheck.so")
-    objs = [os.path.join(OBJ, n) for n in ("engine_cu.o", "spmm_cu.o", "dense_cu.o", "gat_cu.o", "loader_cpp.o", "partition_cpp.o")]
+    objs = [os.path.join(OBJ, n) for n in ("engine_cu.o", "spmm_cu.o", "dense_cu.o", "gat_cu.o", "loader_cpp.o", "partition_cpp.o", "tile_plan_cpp.o")]
     srcs = [os.path.join(HERE, n) for n in ("fake_cudart.cpp", "cpu_kernels.cpp")]
     deps = objs + srcs + [os.path.abspath(__file__)]
     if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
@@ -77,7 +77,7 @@ def build_commcheck(force: bool = False) -> str:
 
     product_build.build()
     out = os.path.join(OUT_DIR, "libdorylus_commcheck.so")
-    objs = [os.path.join(OBJ, n) for n in ("engine_cu.o", "comm_cu.o", "loader_cpp.o", "partition_cpp.o")]
+    objs = [os.path.join(OBJ, n) for n in ("engine_cu.o", "comm_cu.o", "loader_cpp.o", "partition_cpp.o", "tile_plan_cpp.o")]
     srcs = [os.path.join(HERE, n) for n in ("fake_cudart.cpp", "cpu_kernels.cpp", "fake_nccl.cpp")]
     deps = objs + srcs + [os.path.abspath(__file__)]
     if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):

@@ -41,6 +41,11 @@ static void spmm_row(const SpmmArgs &a, uint32_t row) {
     }
 }
 
+// entry points spmm.cu gained in round 2 (engine.cu references them): same scalar statement / always-true
+int launch_spmm(const SpmmArgs &a, cudaStream_t);
+int launch_spmm_rows(const SpmmArgs &a, cudaStream_t s) { return launch_spmm(a, s); }
+bool spmm_shape_supported(int, int) { return true; }
+
 int launch_spmm(const SpmmArgs &a, cudaStream_t) {
     if (a.nvec > a.ld / 4 || a.ptr_span == 0 || a.ptr_off + a.ptr_span > a.ptr_stride) return -1;
     int launches = 0;
@@ -146,6 +151,13 @@ int launch_gather_rows(const float *src, const uint32_t *ids, uint32_t n, float 
 }
 
 #endif  // !DORY_LAUNCHCHECK
+
+// The shared-memory-staged kernel (spmm_tile.cu; product option "tile", off by default) is not emulated:
+// "no kernel for this shape" sends the engine back to the gather path.
+int launch_spmm_tile(const SpmmArgs &, const TilePlanDev &, cudaStream_t) { return 0; }
+size_t tile_smem_bytes(uint32_t, uint32_t, uint32_t, bool, int) { return 0; }
+size_t tile_edge_smem_bytes(uint64_t, uint32_t) { return 0; }
+
 
 // ------------------------------------------------------------------ tcgen05 paths: "shape not supported"
 int launch_gemm_tc(const float *, uint32_t, uint64_t, const float *, uint32_t, uint32_t, float *, float *, uint32_t, int,
@@ -380,6 +392,7 @@ std::string Comm::exchange_p2p(int, const float *, float *const *, uint32_t, cud
     return "hostcheck comm: the peer-memory path needs CUDA IPC";
 }
 bool Comm::p2p_ready(int) const { return false; }
+uint32_t Comm::send_slot_bound(int, int) const { return 0; }
 
 }  // namespace dory
 #else
