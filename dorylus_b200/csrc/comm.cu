@@ -7,6 +7,8 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -26,6 +28,7 @@ struct NcclApi {
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclCommSplit) CommSplit = nullptr;  // optional (NCCL >= 2.18)
     std::string error;
 };
 
@@ -57,6 +60,7 @@ NcclApi &api() {
         DORY_SYM(AllReduce, ncclAllReduce)
         DORY_SYM(GetErrorString, ncclGetErrorString)
 #undef DORY_SYM
+        a.CommSplit = reinterpret_cast<decltype(a.CommSplit)>(dlsym(a.handle, "ncclCommSplit"));
     });
     return a;
 }
@@ -96,6 +100,7 @@ Comm::~Comm() {
         if (p.dSendOrder) cudaFree(p.dSendOrder);
     }
     if (barrier_buf_) cudaFree(barrier_buf_);
+    if (nccl2_ && api().CommDestroy) api().CommDestroy(static_cast<ncclComm_t>(nccl2_));
     if (nccl_ && api().CommDestroy) api().CommDestroy(static_cast<ncclComm_t>(nccl_));
 }
 
@@ -120,6 +125,15 @@ std::string Comm::init(const void *id128, int rank, int nranks, int device) {
     ncclComm_t c;
     NC(a.CommInitRank(&c, nranks, id, rank));
     nccl_ = c;
+    if (a.CommSplit && !std::getenv("DORY_NO_AUX_COMM")) {  // second communicator over the same ranks (collective call)
+        ncclComm_t c2 = nullptr;
+        const ncclResult_t r = a.CommSplit(c, 0, rank, &c2, nullptr);
+        if (r == ncclSuccess && c2) nccl2_ = c2;
+        else if (rank == 0) fprintf(stderr, "[dorylus_b200] ncclCommSplit: %s -- exchanges stay on the compute stream\n", a.GetErrorString(r));
+    } else if (rank == 0 && !a.CommSplit) {
+        fprintf(stderr, "[dorylus_b200] this NCCL has no ncclCommSplit -- exchanges stay on the compute stream\n");
+    }
+    if (rank == 0 && std::getenv("DORY_VERBOSE")) fprintf(stderr, "[dorylus_b200] second communicator: %s\n", nccl2_ ? "yes" : "no");
     for (Plan &p : plan_) {
         p.sendCount.assign(nranks, 0);
         p.sendOff.assign(nranks, 0);
@@ -218,11 +232,13 @@ std::string Comm::exchange(int dir, const float *local, float *ghost, uint32_t l
     return "";
 }
 
-std::string Comm::allreduce_sum(float *buf, size_t n, cudaStream_t s) {
+std::string Comm::allreduce_on(void *comm, float *buf, size_t n, cudaStream_t s) {
     NcclApi &a = api();
-    NC(a.AllReduce(buf, buf, n, ncclFloat, ncclSum, static_cast<ncclComm_t>(nccl_), s));
+    NC(a.AllReduce(buf, buf, n, ncclFloat, ncclSum, static_cast<ncclComm_t>(comm), s));
     return "";
 }
+
+std::string Comm::allreduce_sum(float *buf, size_t n, cudaStream_t s) { return allreduce_on(nccl_, buf, n, s); }
 
 // ------------------------------------------------------------------ peer-memory exchange
 namespace {
@@ -242,7 +258,7 @@ template <int RPW>
 __global__ void __launch_bounds__(256)
 p2p_scatter_kernel(const float4 *__restrict__ local, const uint32_t *__restrict__ ids,
                    const uint32_t *__restrict__ slots, const uint8_t *__restrict__ peer,
-                   const uint32_t *__restrict__ order, uint32_t n, PeerPtrs pp, uint32_t ld4) {
+                   const uint32_t *__restrict__ order, uint32_t n, PeerPtrs pp, uint32_t ld4, uint32_t n4) {
     const uint32_t v0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW;
     const uint32_t lane = threadIdx.x & 31;
     const float4 *s[RPW];
@@ -257,7 +273,7 @@ p2p_scatter_kernel(const float4 *__restrict__ local, const uint32_t *__restrict_
             d[k] = pp.p[peer[r]] + (size_t)slots[r] * ld4;
         }
     }
-    for (uint32_t c = lane; c < ld4; c += 32) {
+    for (uint32_t c = lane; c < n4; c += 32) {  // data columns only: the padding of a row stays zero on both sides
         float4 x[RPW];
 #pragma unroll
         for (int k = 0; k < RPW; ++k)
@@ -311,9 +327,11 @@ bool Comm::p2p_ready(int dir) const {
 }
 
 std::string Comm::exchange_p2p(int dir, const float *local, float *const *peerGhost, uint32_t ld, cudaStream_t s,
-                               int &launches, bool pre_barrier) {
+                               int &launches, bool pre_barrier, uint32_t cols, bool aux) {
     Plan &p = plan_[dir];
     launches = 0;
+    void *bcomm = aux && nccl2_ ? nccl2_ : nccl_;
+    float *bbuf_off = nullptr;  // set below: the two communicators use different words of barrier_buf_
     if (!p2p_ready(dir)) return "peer-memory exchange: send slots not installed";
     if (p.sendSlotsDirty) {
         std::vector<uint32_t> slots(p.sendTotal), order;
@@ -347,14 +365,15 @@ std::string Comm::exchange_p2p(int dir, const float *local, float *const *peerGh
         p.sendSlotsDirty = false;
     }
     if (!barrier_buf_) {
-        CUS(cudaMalloc(&barrier_buf_, 16));
-        CUS(cudaMemsetAsync(barrier_buf_, 0, 16, s));
+        CUS(cudaMalloc(&barrier_buf_, 32));
+        CUS(cudaMemsetAsync(barrier_buf_, 0, 32, s));
     }
+    bbuf_off = barrier_buf_ + (bcomm == nccl_ ? 0 : 4);
     // barrier 1: every peer has finished reading the ghost block we are about to overwrite.  The
     // caller elides it when a collective already separates those reads from this call (every rank
     // runs the same operator sequence, so a collective that follows MY reads follows the peers' too).
     if (pre_barrier) {
-        std::string m = allreduce_sum(barrier_buf_, 1, s);
+        std::string m = allreduce_on(bcomm, bbuf_off, 1, s);
         if (!m.empty()) return m;
     }
     if (p.sendTotal) {
@@ -362,18 +381,19 @@ std::string Comm::exchange_p2p(int dir, const float *local, float *const *peerGh
         for (int q = 0; q < nranks_; ++q) pp.p[q] = q == rank_ ? nullptr : reinterpret_cast<float4 *>(peerGhost[q]);
         const float4 *l4 = reinterpret_cast<const float4 *>(local);
         const uint32_t n = p.sendTotal;
+        const uint32_t n4 = cols ? std::min(ld / 4, (cols + 3) / 4) : ld / 4;  // float4 per row that carry data
         auto grid = [n](uint32_t rpw) { return (n + 8 * rpw - 1) / (8 * rpw); };
         switch (p2p_variant_) {
-        case 1: p2p_scatter_kernel<1><<<grid(1), 256, 0, s>>>(l4, p.dSendIds, p.dSendSlots, p.dSendPeer, p.dSendOrder, n, pp, ld / 4); break;
-        case 2: p2p_scatter_kernel<2><<<grid(2), 256, 0, s>>>(l4, p.dSendIds, p.dSendSlots, p.dSendPeer, p.dSendOrder, n, pp, ld / 4); break;
+        case 1: p2p_scatter_kernel<1><<<grid(1), 256, 0, s>>>(l4, p.dSendIds, p.dSendSlots, p.dSendPeer, p.dSendOrder, n, pp, ld / 4, n4); break;
+        case 2: p2p_scatter_kernel<2><<<grid(2), 256, 0, s>>>(l4, p.dSendIds, p.dSendSlots, p.dSendPeer, p.dSendOrder, n, pp, ld / 4, n4); break;
         case 9: p2p_scatter_fenced_kernel<<<grid(1), 256, 0, s>>>(l4, p.dSendIds, p.dSendSlots, p.dSendPeer, p.dSendOrder, n, pp, ld / 4); break;
-        default: p2p_scatter_kernel<4><<<grid(4), 256, 0, s>>>(l4, p.dSendIds, p.dSendSlots, p.dSendPeer, p.dSendOrder, n, pp, ld / 4); break;
+        default: p2p_scatter_kernel<4><<<grid(4), 256, 0, s>>>(l4, p.dSendIds, p.dSendSlots, p.dSendPeer, p.dSendOrder, n, pp, ld / 4, n4); break;
         }
         if (cudaGetLastError() != cudaSuccess) return "peer-memory scatter kernel launch failed";
         ++launches;
     }
     // barrier 2: every peer's stores into OUR ghost block are complete (their kernels have finished)
-    return allreduce_sum(barrier_buf_ + 1, 1, s);
+    return allreduce_on(bcomm, bbuf_off + 1, 1, s);
 }
 
 }  // namespace dory

@@ -40,8 +40,12 @@ public:
     // peerGhost[q]: device pointer (mapped with cudaIpcOpenMemHandle) to peer q's ghost block for
     // this exchange; entries for q == rank are ignored.
     // pre_barrier = false skips the barrier in front of the stores (see exchange_p2p).
+    // cols: data columns of a row (0 = the whole pitch): only those cross NVLink, the padding stays zero.
+    // aux: the barriers go to the second communicator (has_aux()), for an exchange issued on its own stream
+    // while collectives of the first one (dW all-reduce) are issued on the compute stream.
     std::string exchange_p2p(int dir, const float *local, float *const *peerGhost, uint32_t ld, cudaStream_t s,
-                             int &launches, bool pre_barrier = true);
+                             int &launches, bool pre_barrier = true, uint32_t cols = 0, bool aux = false);
+    bool has_aux() const { return nccl2_ != nullptr; }
     // 0: 4 rows per warp (default), 1 / 2: that many rows per warp, 9: one row + system fence per warp
     void set_p2p_variant(int v) { p2p_variant_ = v; }
     bool p2p_ready(int dir) const;
@@ -73,7 +77,9 @@ private:
     int p2p_variant_ = 0;
     std::string finalize_recv(Plan &p, uint32_t maxld, cudaStream_t s);
 
-    void *nccl_ = nullptr;  // ncclComm_t
+    void *nccl_ = nullptr;   // ncclComm_t
+    void *nccl2_ = nullptr;  // ncclCommSplit of it (same ranks): the exchange stream's barriers
+    std::string allreduce_on(void *comm, float *buf, size_t n, cudaStream_t s);
     int rank_ = 0, nranks_ = 1, device_ = 0;
     Plan plan_[2];
 };

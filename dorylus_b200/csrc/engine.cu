@@ -92,6 +92,9 @@ struct Adjacency {
     // launch only gathers from a (V+G)/nb-row window of the feature block (an L2-sized working set).
     DevBuf bptrs, bidx, bvals;  // [V*nb + 1], [E], [E]
     uint32_t nb = 1;
+    // > 0: the first nb_local windows hold the partition's OWN rows, the others its ghost rows -- an
+    // aggregation can then walk the local part while the ghost exchange is still in flight
+    uint32_t nb_local = 0;
 };
 
 struct WeightSet {
@@ -180,6 +183,14 @@ struct dory_engine {
     std::set<std::pair<const float *, uint32_t>> p2p_validated;
     std::vector<void *> ipc_bases;
     int p2p = 1;
+    // exchange / compute overlap (option "overlap"): a peer-memory exchange runs on its own high-priority
+    // stream with its own communicator; the aggregation that consumes the ghost block walks the edges from
+    // local rows first and only then waits for it (interior first, boundary after the receive)
+    int overlap = 1;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
+    bool comm_pending = false;                 // work on comm_stream the compute stream has not waited for yet
+    const float *comm_pending_ghost = nullptr; // the ghost block the pending exchange fills
     int p2p_variant = 0;        // option "p2p_rows": rows per warp of the store kernel (comm.cu)
     int elide_pre_barrier = 1;  // option "p2p_elide_barrier"
     // ghost blocks an aggregation has read since this engine last took part in a collective: only
@@ -441,19 +452,36 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
     // narrower rows walk `span` consecutive windows per launch (aggregate_gcn), which works because a
     // row's windows are stored back to back.
     uint32_t nb = e->src_blocks;
+    const uint64_t avgDeg = V ? nnz / V : 0;
     if (nb == 0) {
         nb = (uint32_t)(((uint64_t)nSrcRows * e->max_slab_bytes() + kWindowBytes - 1) / kWindowBytes);
         // every window costs one more pass over the rows (offsets, read-modify-write of `out`, a
         // partly filled 32-edge batch): only worth it while a (row, window) still holds ~64 edges.
         // Reddit (degree 492): 2 windows; Amazon / Friendster shapes (degree ~25): none
         // (tools/shape_bench.py: 10 windows made the Amazon-shape aggregation 4x slower).
-        const uint64_t avgDeg = V ? nnz / V : 0;
         nb = (uint32_t)std::min<uint64_t>(nb, std::max<uint64_t>(1, avgDeg / 64));
     }
     nb = std::max(1u, std::min(nb, 64u));
+    // Several partitions (GCN, option "overlap"): the window boundaries are laid so that one of them falls
+    // between the partition's own rows [0, V) and its ghost rows [V, V + G).  nbL windows of local rows,
+    // nbG of ghost rows, each sized like the plain windows (and at least one of either).
+    uint32_t nbL = 0, nbG = 0;
+    const uint32_t G = nSrcRows - V;
+    if (e->cfg.num_nodes > 1 && e->overlap && e->cfg.gnn_type == DORY_GCN && G > 0 && nnz && e->src_blocks == 0) {
+        const uint64_t cap = std::max<uint64_t>(1, avgDeg / 64);
+        nbL = (uint32_t)std::min<uint64_t>(cap, std::max<uint64_t>(1, ((uint64_t)V * e->max_slab_bytes() + kWindowBytes - 1) / kWindowBytes));
+        nbG = (uint32_t)std::min<uint64_t>(cap, std::max<uint64_t>(1, ((uint64_t)G * e->max_slab_bytes() + kWindowBytes - 1) / kWindowBytes));
+        nb = nbL + nbG;
+    }
     adj.nb = 1;
+    adj.nb_local = 0;
     if (nb > 1 && nnz && (e->cfg.gnn_type == DORY_GCN || e->gat_windows)) {
         const uint32_t rowsPerBlock = (nSrcRows + nb - 1) / nb;
+        const uint32_t rowsPerL = nbL ? (V + nbL - 1) / nbL : 1, rowsPerG = nbG ? (G + nbG - 1) / nbG : 1;
+        auto block_of = [&](uint32_t src) -> uint32_t {
+            if (!nbL) return src / rowsPerBlock;
+            return src < V ? src / rowsPerL : nbL + (src - V) / rowsPerG;
+        };
         std::vector<uint64_t> bp((size_t)V * nb + 1);
         std::vector<uint32_t> bi(nnz);
         std::vector<float> bv(nnz);
@@ -467,7 +495,7 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
                 for (uint64_t k = hp[v]; k < hp[v + 1]; ++k) {
                     uint32_t s;
                     std::memcpy(&s, idx + 4 * k, 4);
-                    ++cnt[s / rowsPerBlock];
+                    ++cnt[block_of(s)];
                 }
                 uint64_t off = hp[v];
                 for (uint32_t b = 0; b < nb; ++b) {
@@ -481,7 +509,7 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
                     float w;
                     std::memcpy(&s, idx + 4 * k, 4);
                     std::memcpy(&w, vals + 4 * k, 4);
-                    const uint64_t pos = cnt[s / rowsPerBlock]++;
+                    const uint64_t pos = cnt[block_of(s)]++;
                     bi[pos] = s;
                     bv[pos] = w;
                 }
@@ -499,6 +527,7 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
         CU(cudaMemcpyAsync(adj.bvals.p, bv.data(), 4 * nnz, cudaMemcpyHostToDevice, e->stream));
         CU(cudaStreamSynchronize(e->stream));
         adj.nb = nb;
+        adj.nb_local = nbL;
     }
     return DORY_OK;
 }
@@ -681,10 +710,14 @@ void adam_next_iteration(dory_engine *e) {
     e->lr_t = (float)((double)e->cfg.learning_rate * std::sqrt((double)(1 - b2p)) / (double)(1 - b1p));
 }
 
-int check_loaded(dory_engine *e) {
+int join_comm(dory_engine *e);
+
+// join: every operator but Gather and Scatter first waits for an exchange still in flight on the exchange
+// stream (those two order themselves against it)
+int check_loaded(dory_engine *e, bool join = true) {
     if (!e) return DORY_EINVAL;
     if (!e->loaded) return fail(e, DORY_ESTATE, "no partition loaded (call dory_load_partition first)");
-    return DORY_OK;
+    return join ? join_comm(e) : DORY_OK;
 }
 
 SpmmArgs spmm_args(const dory_engine *e, const Adjacency &adj, const float *selfw, int mode, const DevMat &src,
@@ -738,14 +771,16 @@ uint64_t edges_in_range(dory_engine *e, const Adjacency &adj, uint32_t low, uint
 // the adjacency when it has them.  `vals` overrides the adjacency's edge values; with windows that is
 // only valid for values that are constant along a destination row (the regrouped copy permutes a row's
 // edges inside the row's own range) -- true of the GAT attention values and their gradients (quirk Q8).
+// phase: 0 = the whole aggregation; 1 = self term + edges from the partition's own rows (the windows below
+// nb_local); 2 = edges from ghost rows, accumulated onto phase 1's output.  Phases 1 and 2 need nb_local > 0.
 int run_spmm(dory_engine *e, const Adjacency *adj, const float *selfw, int mode, const DevMat *src, const DevMat *out,
-             uint32_t low, uint32_t up, const float *vals = nullptr) {
+             uint32_t low, uint32_t up, const float *vals = nullptr, int phase = 0) {
     SpmmArgs a = spmm_args(e, *adj, selfw, mode, *src, *out, low, up, e->V);
     if (vals) a.vals = vals;
     if (!spmm_shape_supported(a.cfg_lg, a.cfg_vec))
         return fail(e, DORY_EINVAL, "options spmm_lg = %d, spmm_vec = %d: no aggregation kernel of that shape (lanes x float4 "
                     "per lane: 4 x {1,2,4}, 8 x {1,2,4}, 16 x {1,2}, 32 x {1,2,4}; set both or neither)", a.cfg_lg, a.cfg_vec);
-    if (adj->tile && !vals && low == 0 && up == e->V) {
+    if (adj->tile && !vals && low == 0 && up == e->V && phase == 0) {
         // shared-memory-staged kernel (spmm_tile.cu) when this layer's rows fit its launch limits
         const TilePlanBuf &tb = *adj->tile;
         const bool shapeOk = tb.low_degree ? a.nvec <= 32 : true;
@@ -794,21 +829,45 @@ int run_spmm(dory_engine *e, const Adjacency *adj, const float *selfw, int mode,
         a.idx = adj->bidx.as<uint32_t>();
         a.vals = vals ? vals : adj->bvals.as<float>();
         a.ptr_stride = adj->nb;
-        for (uint32_t b = 0; b < adj->nb; b += span) {
+        const uint32_t b_begin = phase == 2 ? adj->nb_local : 0, b_end = phase == 1 ? adj->nb_local : adj->nb;
+        for (uint32_t b = b_begin; b < b_end;) {
+            // a launch never spans the local / ghost boundary (the two sides may run at different times)
+            const uint32_t limit = (adj->nb_local && b < adj->nb_local) ? adj->nb_local : b_end;
             a.ptr_off = b;
-            a.ptr_span = std::min(span, adj->nb - b);
+            a.ptr_span = std::min(span, limit - b);
             a.self_mode = b == 0 ? mode : SELF_ACCUM;
             LAUNCHED(launch_spmm(a, e->stream));
+            b += a.ptr_span;
         }
     } else {
         LAUNCHED(launch_spmm(a, e->stream));
     }
-    e->stats.edges_aggregated += edges_in_range(e, *adj, low, up);
+    if (phase != 2) e->stats.edges_aggregated += edges_in_range(e, *adj, low, up);
     return DORY_OK;
 }
 
-int run_gcn_spmm(dory_engine *e, const Adjacency *adj, const DevMat *src, const DevMat *out, uint32_t low, uint32_t up) {
-    return run_spmm(e, adj, e->norms.as<float>(), SELF_NORM, src, out, low, up);
+// Makes the compute stream wait for whatever the exchange stream still has in flight.
+int join_comm(dory_engine *e) {
+    if (!e->comm_pending) return DORY_OK;
+    CU(cudaStreamWaitEvent(e->stream, e->ev_comm, 0));
+    e->comm_pending = false;
+    e->comm_pending_ghost = nullptr;
+    return DORY_OK;
+}
+
+int run_gcn_spmm(dory_engine *e, const Adjacency *adj, const DevMat *src, const DevMat *out, const DevMat *ghost, uint32_t low,
+                 uint32_t up) {
+    const float *nw = e->norms.as<float>();
+    // the exchange that fills this aggregation's ghost block is still in flight: local rows first
+    if (e->comm_pending && ghost && e->comm_pending_ghost == ghost->p && adj->nb_local > 0 && low == 0 && up == e->V) {
+        int rc = run_spmm(e, adj, nw, SELF_NORM, src, out, low, up, nullptr, 1);
+        if (rc) return rc;
+        if ((rc = join_comm(e))) return rc;
+        return run_spmm(e, adj, nw, SELF_NORM, src, out, low, up, nullptr, 2);
+    }
+    int rc = join_comm(e);
+    if (rc) return rc;
+    return run_spmm(e, adj, nw, SELF_NORM, src, out, low, up);
 }
 
 int softmax_ce_gcn(dory_engine *e, const float *logits, const DevMat &lab, float *d);
@@ -847,7 +906,7 @@ int aggregate_gcn(dory_engine *e, const dory_chunk *c) {
         adj = &e->bwd;
     }
     if (ghost) e->ghost_reads_pending.insert(ghost->p);
-    int rc = run_gcn_spmm(e, adj, src, out, c->lowBound, c->upBound);
+    int rc = run_gcn_spmm(e, adj, src, out, ghost, c->lowBound, c->upBound);
     if (rc || !af || c->dir != DORY_FORWARD) return rc;
     if (c->layer + 1 < L) {  // h = tanh(z), activate(): CPU_comm.cpp:265-274
         const DevMat &h = *find_tensor(e, c->layer, "h");
@@ -1015,18 +1074,47 @@ int exchange(dory_engine *e, uint32_t dir, const DevMat &local, const DevMat &gh
         }
         e->p2p_validated.insert({ghost.p, dir});
     }
+    // Overlap: the peer-memory exchange goes to the exchange stream (its collectives to the second
+    // communicator), ordered behind everything the compute stream has been given so far; whoever needs its
+    // result waits for ev_comm (join_comm / run_gcn_spmm).
+    const bool async = p2p && e->overlap && e->cfg.gnn_type == DORY_GCN && e->comm->has_aux();
+    cudaStream_t xs = e->stream;
+    if (async) {
+        if (!e->comm_stream) {
+            int lo = 0, hi = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CU(cudaStreamCreateWithPriority(&e->comm_stream, cudaStreamNonBlocking, hi));
+            CU(cudaEventCreateWithFlags(&e->ev_compute, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&e->ev_comm, cudaEventDisableTiming));
+        }
+        CU(cudaEventRecord(e->ev_compute, e->stream));
+        CU(cudaStreamWaitEvent(e->comm_stream, e->ev_compute, 0));
+        xs = e->comm_stream;
+    } else {
+        int rc = join_comm(e);
+        if (rc) return rc;
+    }
     if (p2p) {
         const bool pre = !e->elide_pre_barrier || e->ghost_reads_pending.count(ghost.p) != 0;
         e->comm->set_p2p_variant(e->p2p_variant);
-        msg = e->comm->exchange_p2p((int)dir, local.p, pit->second.data(), local.ld, e->stream, launches, pre);
+        msg = e->comm->exchange_p2p((int)dir, local.p, pit->second.data(), local.ld, xs, launches, pre, local.cols, async);
+        if (pre) e->ghost_reads_pending.erase(ghost.p);  // that barrier followed every rank's reads of this block
     } else {
-        msg = e->comm->exchange((int)dir, local.p, ghost.p, local.ld, e->stream, launches);
+        msg = e->comm->exchange((int)dir, local.p, ghost.p, local.ld, xs, launches);
     }
     if (!msg.empty()) return fail(e, DORY_ECOMM, "%s", msg.c_str());
-    // Only the peer-memory path ends in a true all-rank collective (the "writers done" all-reduce); a grouped
-    // ncclSend/ncclRecv synchronises the pairs that exchange rows in that direction and nobody else, so after
-    // it a later peer-memory exchange still needs its "readers done" barrier.
-    if (p2p) e->ghost_reads_pending.clear();
+    if (async) {
+        CU(cudaEventRecord(e->ev_comm, e->comm_stream));
+        e->comm_pending = true;
+        e->comm_pending_ghost = ghost.p;
+    } else if (p2p) {
+        // Only the peer-memory path on the COMPUTE stream ends in a collective that every rank's earlier reads
+        // precede (the "writers done" all-reduce); a grouped ncclSend/ncclRecv synchronises the pairs that
+        // exchange rows and nobody else, and a collective on the exchange stream does not order the peers'
+        // compute streams -- after either, a later peer-memory exchange still needs its "readers done" barrier
+        // for blocks read since (the dW all-reduce at the end of the epoch clears them).
+        e->ghost_reads_pending.clear();
+    }
     e->stats.kernel_launches += launches;
     return DORY_OK;
 }
@@ -1183,6 +1271,8 @@ int predict_gat(dory_engine *e, const dory_chunk *c) {  // gat_ops.cpp:247-265
 
 int apply_update_impl(dory_engine *e, uint32_t layer) {
     WeightSet &W = e->W[layer];
+    int jrc = join_comm(e);  // no collective of the first communicator while the exchange stream is busy
+    if (jrc) return jrc;
     if (e->comm && e->cfg.num_nodes > 1) {  // weighttensor.cpp:263-267: local + ghost updates summed
         std::string msg = e->comm->allreduce_sum(W.dw.as<float>(), W.floats(), e->stream);
         if (!msg.empty()) return fail(e, DORY_ECOMM, "%s", msg.c_str());
@@ -1256,6 +1346,7 @@ void dory_destroy(dory_engine *e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+    if (e->comm_stream) cudaStreamSynchronize(e->comm_stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
     e->comm.reset();
     for (void *b : e->ipc_bases) cudaIpcCloseMemHandle(b);
@@ -1269,6 +1360,9 @@ void dory_destroy(dory_engine *e) {
         if (ev) cudaEventDestroy(ev);
     if (e->stats_host) cudaFreeHost(e->stats_host);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->comm_stream) cudaStreamDestroy(e->comm_stream);
+    if (e->ev_compute) cudaEventDestroy(e->ev_compute);
+    if (e->ev_comm) cudaEventDestroy(e->ev_comm);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -1323,6 +1417,10 @@ int dory_commit_prefetch(dory_engine *e) {
 
 int dory_sync(dory_engine *e) {
     if (!e) return DORY_EINVAL;
+    if (e->comm_pending) {
+        int rc = join_comm(e);
+        if (rc) return rc;
+    }
     CU(cudaStreamSynchronize(e->stream));
     return DORY_OK;
 }
@@ -1343,6 +1441,9 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
         e->spmm_vec = (int)v;
     } else if (std::strcmp(key, "p2p") == 0) {
         e->p2p = v != 0;
+    } else if (std::strcmp(key, "overlap") == 0) {
+        if (e->loaded) return fail(e, DORY_ESTATE, "overlap must be set before dory_load_partition");
+        e->overlap = v != 0;
     } else if (std::strcmp(key, "p2p_rows") == 0) {
         e->p2p_variant = (int)v;
     } else if (std::strcmp(key, "p2p_elide_barrier") == 0) {
@@ -1763,7 +1864,7 @@ int dory_inc_layer(const dory_engine *e, dory_chunk *c) {
 }
 
 int dory_aggregate(dory_engine *e, const dory_chunk *c) {
-    int rc = check_loaded(e);
+    int rc = check_loaded(e, e && e->cfg.gnn_type != DORY_GCN);  // GCN: run_gcn_spmm joins where it has to
     if (rc) return rc;
     if (!c) return fail(e, DORY_EINVAL, "null chunk");
     return e->cfg.gnn_type == DORY_GCN ? aggregate_gcn(e, c) : aggregate_gat(e, c);
@@ -1792,7 +1893,7 @@ int dory_apply_vertex(dory_engine *e, const dory_chunk *c) {
 }
 
 int dory_scatter(dory_engine *e, const dory_chunk *c) {
-    int rc = check_loaded(e);
+    int rc = check_loaded(e, false);  // exchange() orders itself against the exchange stream
     if (rc) return rc;
     if (!c) return fail(e, DORY_EINVAL, "null chunk");
     return e->cfg.gnn_type == DORY_GCN ? scatter_gcn(e, c) : scatter_gat(e, c);
@@ -2104,6 +2205,10 @@ int dory_tile_info(const dory_engine *e, uint32_t dir, double *coverage, uint32_
 
 int dory_event_record(dory_engine *e, uint32_t slot) {
     if (!e || slot >= kNumEvents) return DORY_EINVAL;
+    if (e->comm_pending) {  // a timing mark covers the exchange that was started before it
+        int rc = join_comm(e);
+        if (rc) return rc;
+    }
     CU(cudaEventRecord(e->events[slot], e->stream));
     return DORY_OK;
 }

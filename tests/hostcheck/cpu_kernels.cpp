@@ -388,7 +388,7 @@ std::string Comm::allreduce_sum(float *buf, size_t n, cudaStream_t) {
 }
 
 std::string Comm::set_send_slots(int, int, const uint32_t *, uint32_t) { return ""; }
-std::string Comm::exchange_p2p(int, const float *, float *const *, uint32_t, cudaStream_t, int &, bool) {
+std::string Comm::exchange_p2p(int, const float *, float *const *, uint32_t, cudaStream_t, int &, bool, uint32_t, bool) {
     return "hostcheck comm: the peer-memory path needs CUDA IPC";
 }
 bool Comm::p2p_ready(int) const { return false; }

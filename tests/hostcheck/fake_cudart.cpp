@@ -201,6 +201,17 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
     *s = reinterpret_cast<cudaStream_t>(&g_dummy_handles);
     return cudaSuccess;
 }
+// (round 2: the exchange stream of the overlap path; never reached on the emulated runtime, present so that
+// the engine object links)
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) {
+    *s = reinterpret_cast<cudaStream_t>(&g_dummy_handles);
+    return cudaSuccess;
+}
+cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) {
+    *lo = 0;
+    *hi = 0;
+    return cudaSuccess;
+}
 cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
