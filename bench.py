@@ -95,7 +95,13 @@ def build_workload(name: str, world: int, rank: int, streamed: bool = False, dis
         threads = max(1, (os.cpu_count() or 8) // max(world, 1))
         src, dst, deg, (lo, hi) = synth.generate_incident_edges(spec, rank, world, threads=threads)
         t1 = time.time()
-        if world > 1:
+        if world > 1 and dist is None:
+            # one partition of `world` examined on its own (tools/op_breakdown.py --emulate-parts): the ghost
+            # vertices' degrees are unknown without the other ranks; 1 stands in (edge weights of ghost edges
+            # differ from the real graph's, shapes and timings do not)
+            in_degree = np.ones(V, np.uint32)
+            in_degree[lo:hi] = deg
+        elif world > 1:
             import torch
 
             pblk = (V + world - 1) // world
@@ -115,7 +121,7 @@ def build_workload(name: str, world: int, rank: int, streamed: bool = False, dis
         labels = synth.generate_label_rows(lo, hi, spec.dims[-1], spec.seed + 2)
         onehot = formats.one_hot(labels, spec.dims[-1])
         cut_local = np.array([np.count_nonzero(graph.row_idxs >= graph.local_vtx_cnt), graph.local_in_edge_cnt], np.float64)
-        if world > 1:
+        if world > 1 and dist is not None:
             import torch
 
             t = torch.from_numpy(cut_local).cuda()

@@ -259,28 +259,32 @@ __global__ void __launch_bounds__(256)
 p2p_scatter_kernel(const float4 *__restrict__ local, const uint32_t *__restrict__ ids,
                    const uint32_t *__restrict__ slots, const uint8_t *__restrict__ peer,
                    const uint32_t *__restrict__ order, uint32_t n, PeerPtrs pp, uint32_t ld4, uint32_t n4) {
-    const uint32_t v0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW;
     const uint32_t lane = threadIdx.x & 31;
-    const float4 *s[RPW];
-    float4 *d[RPW];
+    // grid-stride over the shipped rows: a launch that shares the chip with an aggregation (overlap mode) is
+    // sized to a CTA per SM -- the NVLink stores are posted, a few hundred warps keep the links busy -- instead
+    // of filling every SM slot with CTAs that mostly wait for the fabric
+    for (uint32_t v0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW; v0 < n; v0 += gridDim.x * 8 * RPW) {
+        const float4 *s[RPW];
+        float4 *d[RPW];
 #pragma unroll
-    for (int k = 0; k < RPW; ++k) {
-        s[k] = nullptr;
-        d[k] = nullptr;
-        if (v0 + k < n) {
-            const uint32_t r = order[v0 + k];
-            s[k] = local + (size_t)ids[r] * ld4;
-            d[k] = pp.p[peer[r]] + (size_t)slots[r] * ld4;
+        for (int k = 0; k < RPW; ++k) {
+            s[k] = nullptr;
+            d[k] = nullptr;
+            if (v0 + k < n) {
+                const uint32_t r = order[v0 + k];
+                s[k] = local + (size_t)ids[r] * ld4;
+                d[k] = pp.p[peer[r]] + (size_t)slots[r] * ld4;
+            }
         }
-    }
-    for (uint32_t c = lane; c < n4; c += 32) {  // data columns only: the padding of a row stays zero on both sides
-        float4 x[RPW];
+        for (uint32_t c = lane; c < n4; c += 32) {  // data columns only: the padding of a row stays zero on both sides
+            float4 x[RPW];
 #pragma unroll
-        for (int k = 0; k < RPW; ++k)
-            if (s[k]) x[k] = __ldg(s[k] + c);
+            for (int k = 0; k < RPW; ++k)
+                if (s[k]) x[k] = __ldg(s[k] + c);
 #pragma unroll
-        for (int k = 0; k < RPW; ++k)
-            if (s[k]) d[k][c] = x[k];
+            for (int k = 0; k < RPW; ++k)
+                if (s[k]) d[k][c] = x[k];
+        }
     }
 }
 
@@ -382,7 +386,13 @@ std::string Comm::exchange_p2p(int dir, const float *local, float *const *peerGh
         const float4 *l4 = reinterpret_cast<const float4 *>(local);
         const uint32_t n = p.sendTotal;
         const uint32_t n4 = cols ? std::min(ld / 4, (cols + 3) / 4) : ld / 4;  // float4 per row that carry data
-        auto grid = [n](uint32_t rpw) { return (n + 8 * rpw - 1) / (8 * rpw); };
+        static int sms = 0;
+        if (!sms) {
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_);
+            if (sms <= 0) sms = 148;
+        }
+        const uint32_t cap = aux ? (uint32_t)sms * (uint32_t)std::max(1, p2p_ctas_per_sm_) : 0xffffffffu;
+        auto grid = [n, cap](uint32_t rpw) { return std::min(cap, (n + 8 * rpw - 1) / (8 * rpw)); };
         switch (p2p_variant_) {
         case 1: p2p_scatter_kernel<1><<<grid(1), 256, 0, s>>>(l4, p.dSendIds, p.dSendSlots, p.dSendPeer, p.dSendOrder, n, pp, ld / 4, n4); break;
         case 2: p2p_scatter_kernel<2><<<grid(2), 256, 0, s>>>(l4, p.dSendIds, p.dSendSlots, p.dSendPeer, p.dSendOrder, n, pp, ld / 4, n4); break;

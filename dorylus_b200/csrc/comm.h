@@ -48,6 +48,8 @@ public:
     bool has_aux() const { return nccl2_ != nullptr; }
     // 0: 4 rows per warp (default), 1 / 2: that many rows per warp, 9: one row + system fence per warp
     void set_p2p_variant(int v) { p2p_variant_ = v; }
+    // CTAs per SM of the store kernel when it runs beside an aggregation (aux = true)
+    void set_p2p_ctas_per_sm(int v) { p2p_ctas_per_sm_ = v; }
     bool p2p_ready(int dir) const;
     // Largest ghost slot any row shipped to `peer` lands in (+1); 0 when nothing is shipped there.
     uint32_t send_slot_bound(int dir, int peer) const;
@@ -75,6 +77,7 @@ private:
     };
     float *barrier_buf_ = nullptr;
     int p2p_variant_ = 0;
+    int p2p_ctas_per_sm_ = 1;
     std::string finalize_recv(Plan &p, uint32_t maxld, cudaStream_t s);
 
     void *nccl_ = nullptr;   // ncclComm_t

@@ -186,12 +186,15 @@ struct dory_engine {
     // exchange / compute overlap (option "overlap"): a peer-memory exchange runs on its own high-priority
     // stream with its own communicator; the aggregation that consumes the ghost block walks the edges from
     // local rows first and only then waits for it (interior first, boundary after the receive)
-    int overlap = 1;
+    // Default 0: measured on the Amazon shape at 2 GPUs (profiles/round2_overlap_n2.md) the two passes over the
+    // rows cost more than the hidden exchange returns.
+    int overlap = 0;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
     bool comm_pending = false;                 // work on comm_stream the compute stream has not waited for yet
     const float *comm_pending_ghost = nullptr; // the ghost block the pending exchange fills
     int p2p_variant = 0;        // option "p2p_rows": rows per warp of the store kernel (comm.cu)
+    int p2p_ctas = 1;           // option "p2p_ctas": CTAs per SM of the store kernel in overlap mode
     int elide_pre_barrier = 1;  // option "p2p_elide_barrier"
     // ghost blocks an aggregation has read since this engine last took part in a collective: only
     // those need the barrier in front of a peer-memory exchange that overwrites them
@@ -819,7 +822,9 @@ int run_spmm(dory_engine *e, const Adjacency *adj, const float *selfw, int mode,
             }
         }
     }
-    if (adj->nb > 1) {
+    if (adj->nb > 1 && !(phase == 0 && adj->nb_local == 1 && adj->nb == 2 && !vals)) {
+        // (the [own rows | ghost rows] pair alone is only walked in two passes when an exchange is in flight:
+        // with nothing to wait for, the unsplit edge list below is one pass over the rows instead of two)
         // one pass per group of source windows; passes are separate launches (stream order) because
         // they accumulate into the same output rows.  A group holds as many windows as keep
         // rows x slab bytes within the L2 budget for THIS layer's row width.
@@ -1097,6 +1102,7 @@ int exchange(dory_engine *e, uint32_t dir, const DevMat &local, const DevMat &gh
     if (p2p) {
         const bool pre = !e->elide_pre_barrier || e->ghost_reads_pending.count(ghost.p) != 0;
         e->comm->set_p2p_variant(e->p2p_variant);
+        e->comm->set_p2p_ctas_per_sm(e->p2p_ctas);
         msg = e->comm->exchange_p2p((int)dir, local.p, pit->second.data(), local.ld, xs, launches, pre, local.cols, async);
         if (pre) e->ghost_reads_pending.erase(ghost.p);  // that barrier followed every rank's reads of this block
     } else {
@@ -1444,6 +1450,8 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
     } else if (std::strcmp(key, "overlap") == 0) {
         if (e->loaded) return fail(e, DORY_ESTATE, "overlap must be set before dory_load_partition");
         e->overlap = v != 0;
+    } else if (std::strcmp(key, "p2p_ctas") == 0) {
+        e->p2p_ctas = (int)std::max<long>(1, std::min<long>(v, 8));
     } else if (std::strcmp(key, "p2p_rows") == 0) {
         e->p2p_variant = (int)v;
     } else if (std::strcmp(key, "p2p_elide_barrier") == 0) {

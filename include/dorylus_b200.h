@@ -131,11 +131,13 @@ int dory_sync(dory_engine *e);
  *   "hub_degree"            rows with at least this many edges get a thread-block cluster of 8 CTAs
  *                           (partials combined through distributed shared memory); 0 = E_p / 2048,
  *                           at least 2048 (set before dory_load_partition).
- *   "overlap"               1 (default): with several partitions a GCN peer-memory exchange runs on its own
+ *   "overlap"               1: with several partitions a GCN peer-memory exchange runs on its own
  *                           stream and the aggregation that consumes its ghost block walks the edges from the
  *                           partition's own rows first, waiting for the exchange only before the edges from
  *                           ghost rows (the adjacency is regrouped into [own rows | ghost rows] windows at
- *                           load time).  0: the exchange stays on the compute stream.  Set before load.
+ *                           load time).  0 (default; the split's second pass over the rows cost more than the
+ *                           hidden exchange returned where it was measured, profiles/round2_overlap_n2.md): the
+ *                           exchange stays on the compute stream.  Set before load.
  *   "p2p_rows"              rows per warp of the peer-memory store kernel (0 = default 4, 1, 2;
  *                           9 = one row per warp with a system fence, the first version).
  *   "p2p_elide_barrier"     1 (default): skip the barrier in front of a peer-memory exchange when a

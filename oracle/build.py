@@ -104,6 +104,45 @@ def build_ref(force: bool = False) -> str | None:
     return out
 
 
+# The reference's hot path itself: Engine::aggregateGCN / preallocateGCN (engine/ops/gcn_ops.cpp) and CPUComm
+# (commmanager/CPU_comm.cpp: vtxNNForwardGCN / vtxNNBackwardGCN and their helpers), compiled in place against
+# the stub <zmq.hpp> / Boost headers of oracle/shim/ and linked with oracle/ref_engine.cpp (an in-process
+# stand-in for the ZeroMQ weight-server client; see its header).  Flags of the reference's CPU backend:
+# -O3 -march=native -fopenmp -D_CPU_ENABLED_ (CMakeLists.txt:7,23).
+REF_ENGINE_SOURCES = [
+    "src/graph-server/engine/ops/gcn_ops.cpp",
+    "src/graph-server/commmanager/CPU_comm.cpp",
+    "src/common/matrix.cpp",
+    "src/common/utils.cpp",
+    "src/graph-server/graph/graph.cpp",
+    "src/graph-server/graph/vertex.cpp",
+    "src/graph-server/graph/edge.cpp",
+    "src/graph-server/utils/utils.cpp",
+]
+
+
+def build_ref_engine(force: bool = False) -> str | None:
+    out = os.path.join(REF_DIR, "librefengine.so")
+    if not os.path.isdir(REF_ROOT):
+        return out if os.path.exists(out) else None
+    os.makedirs(REF_DIR, exist_ok=True)
+    srcs = [os.path.join(REF_ROOT, s) for s in REF_ENGINE_SOURCES]
+    drv = os.path.join(HERE, "ref_engine.cpp")
+    shim = os.path.join(HERE, "shim")
+    deps = srcs + [drv, __file__] + glob.glob(os.path.join(shim, "**", "*.h*"), recursive=True)
+    if force or _newer(out, deps):
+        blas = openblas_path()
+        objs = []
+        for i, s in enumerate(srcs + [drv]):
+            o = os.path.join(REF_DIR, "eng%d_%s.o" % (i, os.path.basename(s).replace(".cpp", "")))
+            _run(["g++", "-std=c++11", "-O3", "-march=native", "-fopenmp", "-fPIC", "-w", "-D_CPU_ENABLED_",
+                  "-I" + shim, "-I" + os.path.join(REF_ROOT, "src"), "-c", s, "-o", o])
+            objs.append(o)
+        _run(["g++", "-shared", "-fopenmp", "-o", out] + objs + [blas, "-Wl,-rpath," + os.path.dirname(blas), "-lpthread",
+                                                                   "-Wl,--no-undefined"])
+    return out
+
+
 # The reference's dataset tools that build from one file each (inputs/Makefile; labelsToBinary.cpp and
 # featuresToBinary.cpp need Boost and do not).
 REF_TOOLS = {
@@ -133,3 +172,4 @@ if __name__ == "__main__":
     print(build_oracle(force="--force" in sys.argv))
     print(build_ref(force="--force" in sys.argv))
     print(build_ref_tools(force="--force" in sys.argv))
+    print(build_ref_engine(force="--force" in sys.argv))
