@@ -19,6 +19,78 @@ namespace {
 constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4;
 constexpr int kGemmThreads = (BM / TM) * (BN / TN);  // 256
 
+// dW = A^T . G for a NARROW A (M = the layer's input width <= 64: Friendster's 16, the 48 / 64-wide hidden
+// layers): the 128-row tile below spends 128 x 64 FMAs per vertex whatever M is -- 4.2 ms for the 16 x 48
+// gradient of 8.2 M vertices, eight times the FMAs it needs.  Same structure with an M tile of BMs rows
+// (TMs = BMs / 16 outputs per thread along M); A is [K x M] (vector loads along m), B is [K x N].
+template <int BMs>
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_tn_small_kernel(const float *__restrict__ A, uint32_t lda, const float *__restrict__ B, uint32_t ldb,
+                     float *__restrict__ C, uint32_t ldc, uint64_t M, uint32_t N, uint64_t K, uint64_t kchunk,
+                     size_t split_stride) {
+    constexpr int TMs = BMs / 16;
+    constexpr int BKs = 32;  // deeper k tile: the tile is small, the barrier cost per k step is not
+    __shared__ __align__(16) float As[BKs][BMs + 4];
+    __shared__ __align__(16) float Bs[BKs][BN + 4];
+    const int tid = threadIdx.x;
+    const uint64_t m0 = (uint64_t)blockIdx.x * BMs;
+    const uint32_t n0 = blockIdx.y * BN;
+    const uint64_t kbeg = (uint64_t)blockIdx.z * kchunk;
+    const uint64_t kend = min(K, kbeg + kchunk);
+    const int ty = tid / (BN / TN), tx = tid % (BN / TN);
+    float acc[TMs][TN];
+#pragma unroll
+    for (int i = 0; i < TMs; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    constexpr int AV4 = BMs / 4;             // float4 per k row of the A tile
+    constexpr int ARows = kGemmThreads / AV4;  // k rows one pass of the CTA loads
+    for (uint64_t k0 = kbeg; k0 < kend; k0 += BKs) {
+#pragma unroll
+        for (int kk0 = 0; kk0 < BKs; kk0 += ARows) {
+            const int kk = kk0 + tid / AV4, m4 = (tid % AV4) * 4;
+            if (kk < BKs) {
+                const uint64_t k = k0 + kk, m = m0 + m4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < kend && m < M) v = *reinterpret_cast<const float4 *>(A + k * lda + m);
+                *reinterpret_cast<float4 *>(&As[kk][m4]) = v;
+            }
+        }
+#pragma unroll
+        for (int kk0 = 0; kk0 < BKs; kk0 += 16) {
+            const int kk = kk0 + tid / 16, n4 = (tid % 16) * 4;
+            const uint64_t k = k0 + kk;
+            const uint32_t n = n0 + n4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < kend && n < N) v = *reinterpret_cast<const float4 *>(B + k * ldb + n);
+            *reinterpret_cast<float4 *>(&Bs[kk][n4]) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BKs; ++kk) {
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][tx * TN]);
+            const float bv[TN] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < TMs; ++i) {
+                const float a = As[kk][ty * TMs + i];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a, bv[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+    float *Cz = C + (size_t)blockIdx.z * split_stride;
+    const uint32_t n = n0 + tx * TN;
+    if (n < N) {
+#pragma unroll
+        for (int i = 0; i < TMs; ++i) {
+            const uint64_t m = m0 + ty * TMs + i;
+            if (m >= M) continue;
+            *reinterpret_cast<float4 *>(Cz + m * ldc + n) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+    }
+}
+
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_simt_kernel(const float *__restrict__ A, uint32_t lda, const float *__restrict__ B, uint32_t ldb,
@@ -114,6 +186,152 @@ gemm_simt_kernel(const float *__restrict__ A, uint32_t lda, const float *__restr
                 *reinterpret_cast<float4 *>(C2 + m * ldc + n) = t;
             }
         }
+    }
+}
+
+// Last-layer apply, fused: logits = A . W for a row tile and -- all classes of a row sit in ONE tile (C <= 64)
+// -- the soft-max, the validation statistics, the maskout (quirk Q6) and d = (P - Y) / scale of
+// softmax_ce_kernel in the epilogue (CPU_comm.cpp:98-121, 276-297, 448-471).  The logits never go to HBM: on the
+// Friendster shape (8.2 M rows per GPU) the separate GEMM + soft-max pair moved 10.4 GB for what is 6.3 GB
+// here.  Thread layout of gemm_simt_kernel: thread (ty, tx) holds rows ty*8 .. +7, classes tx*4 .. +3, the 16
+// threads of a row are one half-warp.
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_softmax_ce_kernel(const float *__restrict__ A, uint32_t lda, const float *__restrict__ B, uint32_t ldb, uint64_t K,
+                       const SoftmaxCEArgs a) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const uint64_t M = a.V;
+    const uint64_t m0 = (uint64_t)blockIdx.x * BM;
+    const int ty = tid / (BN / TN), tx = tid % (BN / TN);
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    float4 pa[2], pb;  // next step's tiles, fetched while this step is multiplied (see gemm_simt_kernel)
+    auto fetch = [&](uint64_t k0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = tid / 4 + 64 * i, k4 = (tid % 4) * 4;
+            const uint64_t m = m0 + r, k = k0 + k4;
+            pa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M && k < K) pa[i] = *reinterpret_cast<const float4 *>(A + m * lda + k);
+        }
+        const int kk = tid / 16, n4 = (tid % 16) * 4;
+        const uint64_t k = k0 + kk;
+        pb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K && (uint32_t)n4 < a.ld) pb = *reinterpret_cast<const float4 *>(B + k * ldb + n4);
+    };
+    if (K) fetch(0);
+    for (uint64_t k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = tid / 4 + 64 * i, k4 = (tid % 4) * 4;
+            As[k4 + 0][r] = pa[i].x;
+            As[k4 + 1][r] = pa[i].y;
+            As[k4 + 2][r] = pa[i].z;
+            As[k4 + 3][r] = pa[i].w;
+        }
+        *reinterpret_cast<float4 *>(&Bs[tid / 16][(tid % 16) * 4]) = pb;
+        __syncthreads();
+        if (k0 + BK < K) fetch(k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[kk][ty * TM]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[kk][ty * TM + 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][tx * TN]);
+            const float av[TM] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[TN] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    // ---- epilogue: one row = the 16 lanes of a half-warp (xor offsets 8, 4, 2, 1 stay inside it)
+    const uint32_t c0 = tx * TN;
+    const uint64_t maskBeg = (uint64_t)a.trainEnd * a.C;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const uint64_t row = m0 + ty * TM + i;
+        const bool live = row < M;  // rows beyond the partition take part in the shuffles with neutral values
+        float lb[TN] = {0.f, 0.f, 0.f, 0.f};
+        if (live && c0 < a.ld) {
+            const float4 l4 = *reinterpret_cast<const float4 *>(a.lab + row * a.ld + c0);
+            lb[0] = l4.x; lb[1] = l4.y; lb[2] = l4.z; lb[3] = l4.w;
+        }
+        float v[TN];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            v[j] = (c0 + j) < a.C ? acc[i][j] : -INFINITY;
+            mx = fmaxf(mx, v[j]);
+        }
+#pragma unroll
+        for (int o = 8; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            v[j] = (c0 + j) < a.C ? expf(v[j] - mx) : 0.f;
+            sum += v[j];
+        }
+#pragma unroll
+        for (int o = 8; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float denom = 1e-20f + sum;  // CPU_comm.cpp:285-290
+        float pbest = -INFINITY, lbest = -INFINITY;
+        uint32_t pidx = 0, lidx = 0;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            v[j] = v[j] / denom;
+            if ((c0 + j) < a.C) {
+                if (v[j] > pbest) pbest = v[j], pidx = c0 + j;
+                if (lb[j] > lbest) lbest = lb[j], lidx = c0 + j;
+            }
+        }
+#pragma unroll
+        for (int o = 8; o; o >>= 1) {  // first maximum wins, like the reference's argmax helper
+            const float pb = __shfl_xor_sync(0xffffffffu, pbest, o);
+            const uint32_t pi = __shfl_xor_sync(0xffffffffu, pidx, o);
+            if (pb > pbest || (pb == pbest && pi < pidx)) pbest = pb, pidx = pi;
+            const float lbv = __shfl_xor_sync(0xffffffffu, lbest, o);
+            const uint32_t li = __shfl_xor_sync(0xffffffffu, lidx, o);
+            if (lbv > lbest || (lbv == lbest && li < lidx)) lbest = lbv, lidx = li;
+        }
+        // getTrainStat over the validation slice (CPU_comm.cpp:448-462)
+        const bool val = live && row >= a.trainEnd && row < a.valEnd;
+        float accv = 0.f, lossv = 0.f;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            if (c0 + j == pidx) accv = lb[j];
+            if (c0 + j == lidx) lossv = -logf(v[j]);
+        }
+#pragma unroll
+        for (int o = 8; o; o >>= 1) {
+            accv += __shfl_xor_sync(0xffffffffu, accv, o);
+            lossv += __shfl_xor_sync(0xffffffffu, lossv, o);
+        }
+        if (val && tx == 0) {
+            a.rowstat[row - a.trainEnd] = accv;
+            a.rowstat[(size_t)a.V + (row - a.trainEnd)] = lossv;
+        }
+        if (!live || c0 >= a.ld) continue;
+        // maskout + hadamardSub + scale (CPU_comm.cpp:118-121, 464-471); padding columns stay zero
+        float d[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const uint32_t c = c0 + j;
+            d[j] = 0.f;
+            if (c >= a.C) continue;
+            float p = v[j];
+            const uint64_t flat = row * a.C + c;  // index in the reference's dense V x C array
+            const bool masked = a.strictMask ? (row >= a.trainEnd) : (flat >= maskBeg && flat < maskBeg + a.maskFloats);
+            if (masked) p = lb[j];
+            d[j] = (p - lb[j]) / a.denom;
+        }
+        *reinterpret_cast<float4 *>(a.d + row * a.ld + c0) = make_float4(d[0], d[1], d[2], d[3]);
+        if (a.pred) *reinterpret_cast<float4 *>(a.pred + row * a.ld + c0) = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -328,7 +546,29 @@ __global__ void gather_rows_kernel(const float4 *__restrict__ src, const uint32_
 int launch_gemm(const GemmArgs &g, cudaStream_t s) {
     dim3 grid((unsigned)((g.M + BM - 1) / BM), (g.N + BN - 1) / BN, 1);
     int launches = 0;
-    if (g.transA) {
+    if (g.transA && !g.transB && g.M <= 64 && g.ws) {
+        // narrow input width: M tile of 16 / 32 / 64 rows (gemm_tn_small_kernel)
+        const unsigned bms = g.M <= 16 ? 16u : g.M <= 32 ? 32u : 64u;
+        grid.x = (unsigned)((g.M + bms - 1) / bms);
+        const size_t cfloats = (size_t)g.M * g.ldc;
+        // chunks of >= 8 K vertices, at most 4 CTAs per SM: the fixed-order reduce walks every partial
+        int nsplit = (int)std::min<uint64_t>((g.K + 8191) / 8192, 592 / std::max(1u, grid.x * grid.y));
+        nsplit = std::max(1, std::min<int>(nsplit, (int)(g.ws_floats / std::max<size_t>(cfloats, 1))));
+        uint64_t kchunk = (g.K + nsplit - 1) / nsplit;
+        kchunk = (kchunk + 31) / 32 * 32;
+        nsplit = (int)((g.K + kchunk - 1) / kchunk);
+        grid.z = nsplit;
+        float *out = nsplit > 1 ? g.ws : g.C;
+        if (bms == 16) gemm_tn_small_kernel<16><<<grid, kGemmThreads, 0, s>>>(g.A, g.lda, g.B, g.ldb, out, g.ldc, g.M, g.N, g.K, kchunk, cfloats);
+        else if (bms == 32) gemm_tn_small_kernel<32><<<grid, kGemmThreads, 0, s>>>(g.A, g.lda, g.B, g.ldb, out, g.ldc, g.M, g.N, g.K, kchunk, cfloats);
+        else gemm_tn_small_kernel<64><<<grid, kGemmThreads, 0, s>>>(g.A, g.lda, g.B, g.ldb, out, g.ldc, g.M, g.N, g.K, kchunk, cfloats);
+        ++launches;
+        if (nsplit > 1) {
+            const size_t n4 = cfloats / 4;
+            splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(g.ws, g.C, n4, n4, nsplit);
+            ++launches;
+        }
+    } else if (g.transA) {
         // split the vertex dimension so that ~4 CTAs per SM are in flight (chunks of >= 256 vertices:
         // one eighth of the Reddit shape got 15 CTAs for its 128 x 41 product with 2048-vertex chunks,
         // 185 us for 29 K rows); partials reduced in ascending order
@@ -390,6 +630,17 @@ int launch_softmax_ce(const SoftmaxCEArgs &a, cudaStream_t s) {
     else if (a.C <= 64) softmax_ce_kernel<2><<<grid, 256, 0, s>>>(a);
     else if (a.C <= 128) softmax_ce_kernel<4><<<grid, 256, 0, s>>>(a);
     else softmax_ce_kernel<kMaxPerLane><<<grid, 256, 0, s>>>(a);
+    stat_reduce_kernel<<<1, 1024, 0, s>>>(a.rowstat, a.V, a.valEnd - a.trainEnd, a.stats);
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
+
+// Fused last-layer logits + soft-max / statistics / maskout / scale; returns 0 when the shape does not qualify
+// (more than 64 classes: a row's classes must sit in one 64-wide tile).
+int launch_gemm_softmax_ce(const float *A, uint32_t lda, const float *W, uint32_t ldw, uint64_t K, const SoftmaxCEArgs &a,
+                           cudaStream_t s) {
+    if (a.ld > 64 || a.ld % 4 != 0 || a.C > a.ld || a.V == 0) return 0;
+    const unsigned grid = (unsigned)(((uint64_t)a.V + BM - 1) / BM);
+    gemm_softmax_ce_kernel<<<grid, kGemmThreads, 0, s>>>(A, lda, W, ldw, K, a);
     stat_reduce_kernel<<<1, 1024, 0, s>>>(a.rowstat, a.V, a.valEnd - a.trainEnd, a.stats);
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }

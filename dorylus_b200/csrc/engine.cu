@@ -155,6 +155,8 @@ struct dory_engine {
     uint32_t tile_rows = 0, tile_window = 0, tile_smem_kb = 100, tile_slab = 0, tile_min_coverage = 50, tile_team = 512;
     uint32_t tile_edges = 4096;   // low-degree mode: edges per tile (their ids / weights are staged too)
     int tile_pipe = 1;            // low-degree mode: persistent CTAs with a two-stage TMA pipeline
+    int tn_small = 1;             // option "tn_small": narrow-M fp32 kernel for dW of layers with input width <= 64
+    int fuse_softmax = 1;         // option "fuse_softmax": last-layer logits + soft-max / maskout in one kernel (C <= 64)
     // apply-first schedule (DORY_FLAG_APPLY_FIRST, include/dorylus_b200.h): af[l] != 0 -> layer l runs
     // A_hat . (in . W); decided in dory_load_partition from the flag / the "apply_first_mask" option
     std::vector<uint8_t> af;
@@ -956,7 +958,11 @@ int gemm_nt(dory_engine *e, const float *G, uint32_t ldg, uint64_t rows, const W
 
 // dW = A^T . G   (A: V x Fin, G: V x Fout -> dW: Fin x Fout), deterministic split over vertices
 int gemm_tn(dory_engine *e, const DevMat &A, const float *G, uint32_t ldg, WeightSet &W, float *out) {
-    if (use_tensor_cores(e)) {
+    // input width <= 64: the narrow fp32 kernel (dense.cu: gemm_tn_small_kernel); the tcgen05 kernel's 128-row M
+    // tile and TMA pipeline are sized for wide layers (Friendster's 64 x 64 gradient over 8.2 M vertices: 2.7 ms)
+    // (measured, profiles/round2_dense_skinny.md: 64-wide at 1.2 M vertices the tcgen05 kernel is the faster one)
+    const bool narrow = e->tn_small && (W.prows <= 32 || (W.prows <= 64 && A.rows > (4u << 20)));
+    if (use_tensor_cores(e) && !narrow) {
         int n = launch_gemm_tn_tc(A.p, A.ld, W.prows, G, ldg, A.rows, out, W.ld, e->gemm_ws.as<float>(),
                                   e->gemm_ws.bytes / 4, e->stream);
         if (n > 0) {
@@ -976,7 +982,16 @@ int gemm_tn(dory_engine *e, const DevMat &A, const float *G, uint32_t ldg, Weigh
 
 // Last-layer soft-max, validation statistics, maskout and gradient scale (CPU_comm.cpp:108-121):
 // d = (maskout(softmax(logits)) - lab) / (V_global * 0.66).
+SoftmaxCEArgs softmax_args(dory_engine *e, const float *logits, const DevMat &lab, float *d);
+
 int softmax_ce_gcn(dory_engine *e, const float *logits, const DevMat &lab, float *d) {
+    SoftmaxCEArgs s = softmax_args(e, logits, lab, d);
+    LAUNCHED(launch_softmax_ce(s, e->stream));
+    e->stats.val_rows = s.valEnd - s.trainEnd;
+    return DORY_OK;
+}
+
+SoftmaxCEArgs softmax_args(dory_engine *e, const float *logits, const DevMat &lab, float *d) {
     SoftmaxCEArgs s{};
     s.z = logits; s.lab = lab.p; s.d = d; s.pred = nullptr;
     s.ld = lab.ld; s.C = lab.cols; s.V = e->V;
@@ -987,9 +1002,7 @@ int softmax_ce_gcn(dory_engine *e, const float *logits, const DevMat &lab, float
     s.denom = (float)(e->gV * kTrainPortion);  // CPU_comm.cpp:121
     s.rowstat = e->rowstat.as<float>();
     s.stats = e->stats_dev.as<float>();
-    LAUNCHED(launch_softmax_ce(s, e->stream));
-    e->stats.val_rows = s.valEnd - s.trainEnd;
-    return DORY_OK;
+    return s;
 }
 
 // The rows a layer's dense product reads: "x" (layer 0) or the previous layer's "h", local rows.
@@ -1014,9 +1027,22 @@ int vtx_forward_gcn(dory_engine *e, uint32_t layer) {
     logits.p = e->scratchA.as<float>();
     DevMat d = lab;
     d.p = e->scratchB.as<float>();
-    int rc = gemm_nn(e, ah, W, logits, nullptr);
-    if (rc) return rc;
-    if ((rc = softmax_ce_gcn(e, logits.p, lab, d.p))) return rc;
+    int rc = DORY_OK;
+    bool fused = false;
+    if (e->fuse_softmax) {  // logits + soft-max in one kernel when a row's classes fit one tile (C <= 64)
+        SoftmaxCEArgs sa = softmax_args(e, nullptr, lab, d.p);
+        const int n = launch_gemm_softmax_ce(ah.p, ah.ld, W.w.as<float>(), W.ld, ah.ld, sa, e->stream);
+        LAUNCHED(n);
+        if (n > 0) {
+            fused = true;
+            e->stats.val_rows = sa.valEnd - sa.trainEnd;
+        }
+    }
+    if (!fused) {
+        rc = gemm_nn(e, ah, W, logits, nullptr);
+        if (rc) return rc;
+        if ((rc = softmax_ce_gcn(e, logits.p, lab, d.p))) return rc;
+    }
     if (layer > 0) {
         rc = gemm_nt(e, d.p, d.ld, e->V, W, *find_tensor(e, layer, "grad"));
         if (rc) return rc;
@@ -1477,6 +1503,10 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
         e->spmm_light = (int)v;
     } else if (std::strcmp(key, "spmm_occ") == 0) {
         e->spmm_occ = (int)v;
+    } else if (std::strcmp(key, "tn_small") == 0) {
+        e->tn_small = v != 0;
+    } else if (std::strcmp(key, "fuse_softmax") == 0) {
+        e->fuse_softmax = v != 0;
     } else if (std::strcmp(key, "tensor_cores") == 0) {
         e->tensor_cores = v != 0;
     } else if (std::strcmp(key, "spmm_unroll") == 0) {
@@ -1715,6 +1745,8 @@ int dory_load_partition(dory_engine *e, const void *graph_bin, size_t len) {
     size_t wmax = 0;
     for (auto &w : e->W) wmax = std::max(wmax, w.floats());
     size_t ws_floats = std::max<size_t>(wmax * 64, (size_t)maxld * maxld * 64);
+    // narrow layers (input width <= 64): gemm_tn_small_kernel splits the vertices 1184 ways (8 CTAs per SM)
+    ws_floats = std::max<size_t>(ws_floats, (size_t)1184 * 64 * std::min<uint32_t>(maxld, 128));
     if (e->cfg.gnn_type == DORY_GAT)  // launch_gat_edge_backward: one partial row per 512 vertices + z^T z + its split-K
         ws_floats = std::max<size_t>(ws_floats, ((size_t)e->V / 512 + 1) * maxld + (size_t)maxld * maxld * 65);
     CU(e->gemm_ws.alloc(ws_floats * sizeof(float)));

@@ -168,6 +168,9 @@ int dory_sync(dory_engine *e);
  *   "tile_pipe"             low-degree graphs: 1 (default) persistent CTAs whose producer warp stages tile k+1 while
  *                           the other warps walk tile k (two-stage TMA pipeline); 0: one tile per CTA.
  *   "tile_team"             high-degree graphs: rows with at least this many edges are walked by the whole CTA.
+ *   "fuse_softmax"          1 (default): the last layer's logits product and its soft-max / statistics / maskout /
+ *                           gradient scale run as one kernel when the classes fit one 64-wide tile (the logits
+ *                           never go to HBM); 0: GEMM, then softmax_ce_kernel.
  *   "apply_first_mask"      bit l = 1: layer l runs apply-first (overrides the width rule of
  *                           DORY_FLAG_APPLY_FIRST; GCN only; set before dory_load_partition). */
 int dory_set_option(dory_engine *e, const char *key, const char *value);

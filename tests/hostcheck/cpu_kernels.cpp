@@ -89,6 +89,9 @@ int launch_tanh_forward(const float *z, float *h, uint64_t n, cudaStream_t) {
     return n >= 4 ? 1 : 0;
 }
 
+// round 2: the fused logits + soft-max kernel is not emulated ("shape does not qualify" -> GEMM, then the statement below)
+int launch_gemm_softmax_ce(const float *, uint32_t, const float *, uint32_t, uint64_t, const SoftmaxCEArgs &, cudaStream_t) { return 0; }
+
 int launch_softmax_ce(const SoftmaxCEArgs &a, cudaStream_t) {
     float acc = 0.f, loss = 0.f;
     std::vector<float> p(a.C);
