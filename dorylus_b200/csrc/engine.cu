@@ -144,15 +144,19 @@ struct dory_engine {
     int row_order = 0;  // light-row issue order: 0 = decide from the graph, 1 = degree-descending, 2 = degree classes
     int tensor_cores = 1;  // tcgen05 path for H.W (option "tensor_cores")
     uint32_t src_blocks = 0;  // source windows per aggregation (0 = size from L2, 1 = off)
-    int gat_windows = 0;      // option "gat_windows": source windows for the GAT aggregations too
+    // option "gat_windows": source windows for the GAT aggregations too (default on since round 2: Reddit GAT
+    // epoch 18.0 -> 16.8 ms, profiles/round2_shape_reddit_gat*.json; parity at 602/128/41 in test_gpu_reddit_widths)
+    int gat_windows = 1;
     uint32_t heavy_degree = kHeavyDegree;
     uint32_t hub_degree = 0;  // rows with more edges get a cluster of 8 CTAs (0 = from the partition's size)
     uint32_t locality_block = 0;  // rows per block of the locality-preserving row order (0 = from L2)
     // shared-memory-staged aggregation (options "tile*", include/dorylus_b200.h)
-    // 0 off (default: on every shape measured in round 2 the gather kernels of spmm.cu are faster, see
-    // profiles/round2_tile_kernel.md), 1 on whenever a plan can be built, 2 on when the plan covers enough edges
-    int tile_mode = 0;
-    uint32_t tile_rows = 0, tile_window = 0, tile_smem_kb = 100, tile_slab = 0, tile_min_coverage = 50, tile_team = 512;
+    // 0 off; 1 on whenever a plan can be built; 2 (default) on for HIGH-degree graphs whose plan serves enough
+    // edges from shared memory -- measured (profiles/round2_tile_kernel.md): on the community-structured Reddit
+    // shape the staged kernel is 14-17 % faster than the gather kernels, on the low-degree shapes it is slower
+    // (there it needs an explicit tile=1), on a graph without locality no plan is kept at all.
+    int tile_mode = 2;
+    uint32_t tile_rows = 0, tile_window = 0, tile_smem_kb = 100, tile_slab = 0, tile_min_coverage = 50, tile_team = 4096;
     uint32_t tile_edges = 4096;   // low-degree mode: edges per tile (their ids / weights are staged too)
     int tile_pipe = 1;            // low-degree mode: persistent CTAs with a two-stage TMA pipeline
     int tn_small = 1;             // option "tn_small": narrow-M fp32 kernel for dW of layers with input width <= 64
@@ -384,7 +388,8 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
     // ---- tile plan for the shared-memory-staged kernel (spmm_tile.cu): only kept when the vertex numbering
     // has enough locality for a window of source rows to serve a good share of a tile's edges
     adj.tile.reset();
-    if (e->tile_mode && nnz && V >= 64) {
+    const bool tileLowDeg = V && nnz / V < 96;
+    if (e->tile_mode && nnz && V >= 64 && !(e->tile_mode == 2 && tileLowDeg)) {
         const uint64_t avgDeg = nnz / V;
         const bool lowDeg = avgDeg < 96;
         // bytes per staged window row, widest layer this model aggregates
@@ -399,8 +404,10 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
                 rowBytes = std::max<uint32_t>(rowBytes, (uint32_t)(tile_smem_bytes(padded_ld(w), nvec, 64, true, 0) / 64));
             }
         } else {
-            slabFloats = e->tile_slab ? (int)e->tile_slab : 64;
-            rowBytes = (uint32_t)slabFloats * 4;
+            // 0 = per launch: 64-float slabs for rows up to 128 floats, 96-float slabs for wider ones (fewer
+            // passes over the ids: 7 instead of 10 at F = 602); the window is sized for the wider of the two
+            slabFloats = (int)e->tile_slab;
+            rowBytes = (uint32_t)(slabFloats ? slabFloats : 96) * 4;
         }
         if (rowBytes) {
             TilePlanParams prm;
@@ -413,9 +420,18 @@ int upload_adjacency(dory_engine *e, Adjacency &adj, const uint8_t *ptrs, const 
             prm.excludeDegree = lowDeg ? e->heavy_degree : 0;
             prm.edgeCap = lowDeg ? std::max(e->tile_edges, e->heavy_degree) : 0;
             prm.keepRowOrder = lowDeg;
+            // mode 2: a cheap look first (every 16th tile, largest window the budget allows) -- a graph without
+            // locality does not pay for the regrouped copy of its adjacency
+            bool worth = true;
+            if (e->tile_mode == 2) {
+                uint32_t wmax = 32;
+                while (wmax * 2 <= prm.maxWindowRows) wmax *= 2;
+                const uint32_t w = prm.windowRows ? prm.windowRows : wmax;
+                worth = estimate_tile_coverage(ptrs, idx, V, nSrcRows, std::max(16u, w / 2), w, 16) * 100.0 >= (double)e->tile_min_coverage;
+            }
             TilePlanHost hp_;
-            build_tile_plan(ptrs, idx, vals, V, nSrcRows, prm, hp_);
-            if (e->tile_mode == 1 || hp_.coverage() * 100.0 >= (double)e->tile_min_coverage) {
+            if (worth) build_tile_plan(ptrs, idx, vals, V, nSrcRows, prm, hp_);
+            if (worth && (e->tile_mode == 1 || hp_.coverage() * 100.0 >= (double)e->tile_min_coverage)) {
                 auto tb = std::make_unique<TilePlanBuf>();
                 // 64 spare bytes behind every array: the low-degree kernel's bulk copies round their runs up to 16 B
                 auto up = [&](DevBuf &b, const void *src, size_t bytes) -> cudaError_t {
@@ -789,7 +805,7 @@ int run_spmm(dory_engine *e, const Adjacency *adj, const float *selfw, int mode,
         // shared-memory-staged kernel (spmm_tile.cu) when this layer's rows fit its launch limits
         const TilePlanBuf &tb = *adj->tile;
         const bool shapeOk = tb.low_degree ? a.nvec <= 32 : true;
-        size_t smem = tile_smem_bytes(a.ld, a.nvec, tb.max_wrows, tb.low_degree, tb.slab_floats) +
+        size_t smem = tile_smem_bytes(a.ld, a.nvec, tb.max_wrows, tb.low_degree, tb.slab_floats ? tb.slab_floats : (a.nvec <= 32 ? 64 : 96)) +
                       (tb.low_degree ? tile_edge_smem_bytes(tb.max_tile_edges, tb.max_tile_rows) : 0);
         if (tb.low_degree && e->tile_pipe) smem = 2 * (smem + 256);  // two stages
         if (shapeOk && smem <= 200u * 1024u) {
@@ -810,7 +826,7 @@ int run_spmm(dory_engine *e, const Adjacency *adj, const float *selfw, int mode,
             t.max_wrows = tb.max_wrows;
             t.low_degree = tb.low_degree;
             t.pipeline = e->tile_pipe;
-            t.slab_floats = tb.slab_floats;
+            t.slab_floats = tb.slab_floats ? tb.slab_floats : (a.nvec <= 32 ? 64 : 96);
             const int n = launch_spmm_tile(a, t, e->stream);
             LAUNCHED(n);
             if (n > 0) {  // 0: no tile kernel for this shape -> the gather kernels below

@@ -124,7 +124,7 @@ int dory_sync(dory_engine *e);
  *                           "A" and their gradients "dA" are constant along a destination row -- quirk
  *                           Q8, one-sided score -- so the regrouped edge ids can be used with value
  *                           arrays kept in the original edge order; a caller that overwrites "A" / "dA"
- *                           with values that vary inside a row must leave this off).  Default 0; set
+ *                           with values that vary inside a row must turn this off).  Default 1; set
  *                           before dory_load_partition.
  *   "heavy_degree"          rows with at least this many edges get a whole CTA (set before
  *                           dory_load_partition).
@@ -154,15 +154,17 @@ int dory_sync(dory_engine *e);
  *   "tile"                  shared-memory-staged aggregation (spmm_tile.cu) for graphs whose vertex numbering
  *                           has locality: destination rows are cut into tiles, each tile's best window of
  *                           consecutive source rows is staged in shared memory by bulk TMA copies and the
- *                           edges into it never touch L2.  0 (default) off, 1 on whenever a plan can be built,
- *                           2 on when the plan serves at least "tile_min_coverage" % of the edges from shared
- *                           memory.  GCN aggregations of whole-partition chunks; set before load.  Off by default
- *                           because it lost to the gather kernels on every shape measured so far
- *                           (profiles/round2_tile_kernel.md); kept selectable, parity-tested.
+ *                           edges into it never touch L2.  0 off, 1 on whenever a plan can be built, 2 (default) on
+ *                           for graphs of average degree >= 96 whose plan serves at least "tile_min_coverage" % of
+ *                           the edges from shared memory (measured 14-17 % faster than the gather kernels on the
+ *                           community-structured Reddit shape, slower on the low-degree shapes, which therefore
+ *                           need an explicit 1; profiles/round2_tile_kernel.md).  GCN aggregations of
+ *                           whole-partition chunks; set before load.
  *   "tile_rows" / "tile_window"   destination rows per tile / source rows per window (0 = choose: the smallest
  *                           power-of-two window that keeps 92 % of the best coverage, tiles of half a window).
  *   "tile_smem_kb"          shared memory a CTA may spend on its window (default 100: two CTAs per SM).
- *   "tile_slab"             high-degree graphs: column slab in floats (32, 64, 96, 128; 0 = 64).
+ *   "tile_slab"             high-degree graphs: column slab in floats (32, 64, 96, 128; 0 = per launch: 64 for rows
+ *                           up to 128 floats, 96 for wider ones).
  *   "tile_edges"            low-degree graphs: edges per tile (default 4096); a tile's offsets, ids and weights are
  *                           staged in shared memory beside its window.
  *   "tile_pipe"             low-degree graphs: 1 (default) persistent CTAs whose producer warp stages tile k+1 while

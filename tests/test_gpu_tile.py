@@ -124,10 +124,27 @@ def test_tile_results_are_bit_reproducible_and_auto_mode_declines_without_locali
     spec = synth.CONFIGS["reddit-small"]  # Chung-Lu, no communities: the default mode keeps the gather kernels
     src, dst = synth.generate_edges(spec)
     image = dengine.preprocess_edges(src, dst, np.zeros(spec.num_vertices, np.int32), spec.num_vertices, 0, 1)
-    with Engine(spec.dims, GCN) as e:
-        e.set_option("tile", 2)
+    with Engine(spec.dims, GCN) as e:  # default mode (2): no locality, no plan
         e.load_partition(image)
         assert e.tile_info(FORWARD)["n_tiles"] == 0
-    with Engine(spec.dims, GCN) as e:  # and the default is off altogether
-        e.load_partition(ds.image) if ds.dims == spec.dims else e.load_partition(image)
+    with Engine(ds.dims, GCN) as e:  # default mode on a LOW-degree graph with locality: needs an explicit tile=1
+        e.load_partition(ds.image)
         assert e.tile_info(FORWARD)["n_tiles"] == 0
+
+
+def test_default_mode_stages_a_high_degree_graph_with_locality(oracle):
+    """Default options on the community-structured high-degree graph: the plan is kept (coverage >= 50 %), the
+    per-launch slab choice runs (96-float slabs at F = 602, 64-float slabs at F = 128) and the epoch matches."""
+    ds = Community(**HIGH)
+    with engine_for(ds, {}) as e:
+        info = e.tile_info(FORWARD)
+        assert info["n_tiles"] > 0 and info["coverage"] >= 0.5, info
+        check_aggregations(oracle, ds, e)
+        orc = OracleGCN(oracle, [ds.graph], ds.dims)
+        orc.load_features(ds.feats, ds.onehot)
+        want = orc.epoch()
+        st = e.epoch()
+        assert rel_err(e.get_tensor(0, "h"), orc.saved[0][0]["h"]) < TOL
+        for l in range(2):
+            assert rel_err(e.get_weight_grad(l), orc.dW[0][l]) < TOL, l
+        assert st["acc_sum"] == want["acc"][0]
