@@ -216,17 +216,61 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_epochs(graph, dims, x_loc, onehot, steps: int, warmup: int):
-    """The reference's CPU graph-server + local-apply path (the oracle port, oracle/oracle.cpp driven by
-    oracle/driver.py exactly as SURVEY.md §3.1 lays the epoch out) timed on this box's host cores: FULL
-    synchronous epochs over every destination row, the epoch's own h / grad tensors, Adam included.
+def cpu_reference_epochs(graph, dims, x_loc, onehot, steps: int, warmup: int, image=None):
+    """The reference's CPU graph-server + local-apply path timed on this box's host cores: FULL synchronous
+    epochs over every destination row, the epoch's own h / grad tensors, Adam included.
+
+    kind "reference": the reference's OWN object code -- Engine::aggregateGCN and CPUComm::NNCompute from
+    gcn_ops.cpp / CPU_comm.cpp compiled in place (oracle/_ref/librefengine.so, oracle/ref_engine.cpp), built
+    -O3 -march=native -fopenmp -D_CPU_ENABLED_ like its CPU backend, OpenBLAS sgemm; Adam by the oracle's port of
+    AdamOptimizer (bit-identical to the compiled one, tests/test_oracle.py).  kind "port" (the library is not
+    there): oracle/oracle.cpp driven by oracle/driver.py exactly as SURVEY.md §3.1 lays the epoch out.
     Returns per-step times and the aggregation-only share."""
     from oracle.driver import OracleGCN
-    from oracle.pyoracle import Oracle
+    from oracle.pyoracle import Oracle, RefEngine
 
     o = Oracle()
     cores = os.cpu_count() or 1
     o.set_threads(cores)
+    if image is not None and RefEngine.available():
+        L = len(dims) - 1
+        eng = RefEngine(image, dims)
+        eng.set_threads(cores)
+        eng.tensor(0, "x")[:] = x_loc
+        eng.tensor(L - 1, "lab")[:] = onehot
+        W = [o.xavier(dims[l], dims[l + 1]) for l in range(L)]
+        adam = o.adam(0.01, list(dims))
+        agg_s = [0.0]
+
+        def epoch():
+            for l in range(L):
+                eng.set_weights(l, W[l])
+            t_agg = 0.0
+            for l in range(L):
+                t = time.perf_counter()
+                eng.aggregate(l, 0)
+                t_agg += time.perf_counter() - t
+                eng.apply_vertex(l, 0)
+            for l in range(L - 1, 0, -1):
+                t = time.perf_counter()
+                eng.aggregate(l, 1)
+                t_agg += time.perf_counter() - t
+                eng.apply_vertex(l, 1)
+            for l in range(L - 1, -1, -1):  # the weight server receives the last layer's update first
+                adam.update(l, W[l], eng.update(l))
+            agg_s[0] += t_agg
+
+        for _ in range(warmup):
+            epoch()
+        agg_s[0] = 0.0
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            epoch()
+            times.append(time.perf_counter() - t0)
+        acc, loss = eng.stats()
+        adam.close()
+        return dict(cores=cores, times=times, aggregation_s=agg_s[0], loss=loss, acc=acc, kind="reference")
     orc = OracleGCN(o, [graph], list(dims))
     orc.saved[0][0]["x"][:] = x_loc
     orc.saved[0][len(dims) - 2]["lab"][:] = onehot
@@ -247,12 +291,14 @@ def cpu_reference_epochs(graph, dims, x_loc, onehot, steps: int, warmup: int):
         t0 = time.perf_counter()
         orc.epoch()
         times.append(time.perf_counter() - t0)
-    return dict(cores=cores, times=times, aggregation_s=agg_s[0], loss=orc.loss[0], acc=orc.acc[0])
+    return dict(cores=cores, times=times, aggregation_s=agg_s[0], loss=orc.loss[0], acc=orc.acc[0], kind="port")
 
 
-def cpu_baseline_block(r, n_spmm, E, steps, what):
+def cpu_baseline_block(r, n_spmm, E, steps):
     tot = sum(r["times"])
-    return {"value": n_spmm * E * steps / tot, "unit": UNIT, "cores": r["cores"], "kind": "port",
+    what = ("the reference's own gcn_ops.cpp / CPU_comm.cpp object code (oracle/_ref/librefengine.so) on all host cores"
+            if r["kind"] == "reference" else "oracle port of the reference's CPU path on all host cores")
+    return {"value": n_spmm * E * steps / tot, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
             "sample": "%d full synchronous epochs (%s; every destination row, the epoch's own tensors, Adam "
                       "included) after the warm-up" % (steps, what),
             "ms_per_step": 1e3 * tot / steps, "aggregation_share": r["aggregation_s"] / tot}
@@ -358,6 +404,7 @@ def measure(args, ctx: Ctx, arm: dict, want_e2e: bool = True) -> dict:
         k, v = kv.split("=", 1)
         eng.set_option(k, v)
     eng.load_partition(wl.image)
+    keep_image = wl.image if (world == 1 and rank == 0) else None  # the cpu_baseline leg hands it to the reference's Graph::init
     wl.image = None
     sched = [eng.apply_first(l) for l in range(L)] if gnn == "GCN" else [False] * L
     in_name = "x" if gnn == "GCN" else "h"
@@ -541,7 +588,8 @@ def measure(args, ctx: Ctx, arm: dict, want_e2e: bool = True) -> dict:
         value=n_spmm * E_global * args.steps / (ms_total * 1e-3), launches=int(launches), clocks=clk,
         per_layer=per_layer, agg_ms=agg_ms, agg_width=agg_width, agg_list=[n for n, _, _ in agg_list], exchanges=xch,
         e2e=e2e, invariants=inv, loss_sum=res["loss_sum"], acc_sum=res["acc_sum"], fma_peak=fma_peak, peak=peak,
-        peak_src=peak_src, build_s=wl.build_s, graph=graph, pins=(pin_x, pin_l), ship_x_ghosts=ship_x_ghosts)
+        peak_src=peak_src, build_s=wl.build_s, graph=graph, pins=(pin_x, pin_l), ship_x_ghosts=ship_x_ghosts,
+        image=keep_image, tile=eng.tile_info(FORWARD) if hasattr(eng, "tile_info") else None)
     eng.close()
     return out
 
@@ -564,7 +612,7 @@ def arm_summary(m: dict, world: int) -> dict:
          "value": m["value"], "unit": UNIT, "ms_per_step": m["ms_per_step"],
          "aggregations_counted_per_step": m["n_spmm"], "per_layer": m["per_layer"], "exchanges": m["exchanges"],
          "invariants": m["invariants"], "gpu_launches": m["launches"], "loss_sum": m["loss_sum"], "acc_sum": m["acc_sum"],
-         "clocks": m["clocks"], "build_seconds": m["build_s"]}
+         "clocks": m["clocks"], "build_seconds": m["build_s"], "staged_kernel": m.get("tile")}
     if m["e2e"]:
         s["e2e"] = m["e2e"]
     return s
@@ -766,18 +814,19 @@ def main():
             return 0
         # product-free: the graph arrays come from oracle/np_loader.py (numpy), nothing of dorylus_b200's
         # native library is loaded in this process
-        from oracle.np_loader import single_partition_graph
+        from oracle.np_loader import graph_bin_image, single_partition_graph
 
         spec = synth.CONFIGS[args.workload]
         src, dst = synth.generate_edges(spec)
         n_edges = int(src.size)
         graph = single_partition_graph(src, dst, spec.num_vertices)
+        image = graph_bin_image(graph)  # what Graph::init of the reference reads
         del src, dst
         feats = synth.generate_features(spec.num_vertices, spec.dims[0], spec.seed + 1, dense=True)
         onehot = formats.one_hot(synth.generate_labels(spec.num_vertices, spec.dims[-1], spec.seed + 2), spec.dims[-1])
-        r = cpu_reference_epochs(graph, spec.dims, feats, onehot, args.steps, args.warmup)
+        r = cpu_reference_epochs(graph, spec.dims, feats, onehot, args.steps, args.warmup, image=image)
         n_spmm = 2 * (len(spec.dims) - 1) - 1
-        cb = cpu_baseline_block(r, n_spmm, n_edges, args.steps, "oracle port of the reference's CPU path on all host cores")
+        cb = cpu_baseline_block(r, n_spmm, n_edges, args.steps)
         out = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -818,9 +867,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.gnn == "GCN":
         pin_x, pin_l = m["pins"]
-        r = cpu_reference_epochs(graph, dims, pin_x.numpy(), pin_l.numpy(), steps=args.cpu_steps, warmup=1)
-        cpu = cpu_baseline_block(r, n_spmm, E_global, args.cpu_steps, "oracle port on all host cores")
+        r = cpu_reference_epochs(graph, dims, pin_x.numpy(), pin_l.numpy(), steps=args.cpu_steps, warmup=1, image=m["image"])
+        cpu = cpu_baseline_block(r, n_spmm, E_global, args.cpu_steps)
     m["pins"] = None
+    m["image"] = None
 
     extras = {}
     if not args.no_arms and not args.apply_first and args.gnn == "GCN" and \

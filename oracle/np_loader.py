@@ -48,3 +48,21 @@ def single_partition_graph(src: np.ndarray, dst: np.ndarray, num_vertices: int) 
         dst_ghost_lvid=empty, num_nodes=1, fwd_send=[empty], bwd_send=[empty], col_ptrs=col_ptrs,
         row_idxs=row_idxs, fwd_vals=fwd_vals.astype(np.float32), row_ptrs=row_ptrs, col_idxs=col_idxs,
         bwd_vals=bwd_vals.astype(np.float32))
+
+
+def graph_bin_image(g: PartitionGraph) -> bytes:
+    """graph.<id>.bin of a SINGLE-partition graph (RawGraph::dump, graph/graph.cpp:200-273): counts, localToGlobal,
+    vtxDataVec, (no ghost pairs), numNodes, empty send lists, CSC {cols, nnz, values, columnPtrs, rowIdxs}, CSR
+    likewise.  What Graph::init reads back -- the reference-engine library (oracle/ref_engine.cpp) loads it."""
+    assert g.num_nodes == 1 and g.src_ghost_cnt == 0 and g.dst_ghost_cnt == 0
+    V = g.local_vtx_cnt
+    parts = [np.array([V, g.global_vtx_cnt, 0, 0], "<u4").tobytes(),
+             np.array([g.local_in_edge_cnt, g.local_out_edge_cnt, g.global_edge_cnt], "<u8").tobytes(),
+             g.local_to_global.astype("<u4").tobytes(), g.norms.astype("<f4").tobytes(),
+             np.array([1], "<u4").tobytes(),            # numNodes
+             np.array([0], "<u4").tobytes(),            # forwardLocalVtxDsts[0]: empty
+             np.array([0], "<u4").tobytes()]            # backwardLocalVtxDsts[0]: empty
+    for ptrs, idxs, vals in ((g.col_ptrs, g.row_idxs, g.fwd_vals), (g.row_ptrs, g.col_idxs, g.bwd_vals)):
+        parts += [np.array([V], "<u4").tobytes(), np.array([idxs.size], "<u8").tobytes(), vals.astype("<f4").tobytes(),
+                  ptrs.astype("<u8").tobytes(), idxs.astype("<u4").tobytes()]
+    return b"".join(parts)

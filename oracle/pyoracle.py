@@ -377,3 +377,86 @@ class Ref:
         out = np.zeros(max(nnz, 1), np.float32)
         self.lib.ref_funcs_gat_expand_dot(_f(m), _f(v), _q(ptrs), C.c_uint(V), C.c_uint(F), C.c_uint(nnz), _f(out))
         return out[:nnz]
+
+
+class RefEngine:
+    """The reference's OWN object code for the hot path (oracle/_ref/librefengine.so: gcn_ops.cpp and
+    CPU_comm.cpp compiled in place, see oracle/ref_engine.cpp): Engine::preallocateGCN / aggregateGCN and
+    CPUComm::NNCompute (vtxNNForwardGCN / vtxNNBackwardGCN) on one partition, driven chunk by chunk.
+    Tensors are numpy views of the reference's own allocations (savedNNTensors[layer][name]).
+
+    The weight server is an in-process stand-in: `set_weights` installs what getWeightMatrix hands out,
+    `update(layer)` is what sendWeightUpdate received.  No exchange (single partition, or ghost blocks filled
+    by the caller through `tensor(layer, "fg" | "bg")`)."""
+
+    def __init__(self, graph_image, dims):
+        import tempfile
+
+        path = _build.build_ref_engine()
+        if path is None or not os.path.exists(path):
+            raise FileNotFoundError("oracle/_ref/librefengine.so unavailable (no /root/reference, no prebuilt)")
+        self.lib = L = C.CDLL(path)
+        L.refeng_create.restype = C.c_void_p
+        L.refeng_tensor.restype = _f32p
+        self.dims = [int(d) for d in dims]
+        self.L = len(self.dims) - 1
+        self._tmp = tempfile.TemporaryDirectory()
+        gpath = os.path.join(self._tmp.name, "graph.0.bin")
+        with open(gpath, "wb") as f:
+            f.write(bytes(graph_image) if not isinstance(graph_image, np.ndarray) else graph_image.tobytes())
+        wpath = os.path.join(self._tmp.name, "weightservers")
+        with open(wpath, "w") as f:
+            f.write("127.0.0.1\n")
+        arr = (C.c_uint * len(self.dims))(*self.dims)
+        self.h = C.c_void_p(L.refeng_create(gpath.encode(), arr, C.c_uint(self.L), wpath.encode()))
+
+    @staticmethod
+    def available() -> bool:
+        try:
+            p = _build.build_ref_engine()
+            return p is not None and os.path.exists(p)
+        except Exception:
+            return False
+
+    def set_threads(self, n: int):
+        self.lib.refeng_set_threads(int(n))
+
+    def tensor(self, layer: int, name: str) -> np.ndarray:
+        r, c = C.c_uint(), C.c_uint()
+        p = self.lib.refeng_tensor(self.h, C.c_uint(layer), name.encode(), C.byref(r), C.byref(c))
+        if not p:
+            raise KeyError("savedNNTensors[%d][%r]" % (layer, name))
+        return np.ctypeslib.as_array(p, shape=(int(r.value), int(c.value)))
+
+    def set_weights(self, layer: int, w: np.ndarray):
+        w = _c32(w)
+        assert w.shape == (self.dims[layer], self.dims[layer + 1])
+        self.lib.refeng_set_weights(self.h, C.c_uint(layer), _f(w))
+
+    def update(self, layer: int) -> np.ndarray:
+        dw = np.zeros((self.dims[layer], self.dims[layer + 1]), np.float32)
+        if self.lib.refeng_get_update(self.h, C.c_uint(layer), _f(dw)) != 0:
+            raise RuntimeError("no weight update was sent for layer %d yet" % layer)
+        return dw
+
+    def stats(self):
+        a, l = C.c_float(), C.c_float()
+        self.lib.refeng_stats(self.h, C.byref(a), C.byref(l))
+        return float(a.value), float(l.value)
+
+    def aggregate(self, layer: int, dir: int, low: int = 0, up=None):
+        up = self.tensor(0, "x").shape[0] if up is None else up
+        self.lib.refeng_aggregate(self.h, C.c_uint(layer), int(dir), C.c_uint(low), C.c_uint(up))
+
+    def apply_vertex(self, layer: int, dir: int):
+        self.lib.refeng_apply_vertex(self.h, C.c_uint(layer), int(dir))
+
+    def epoch_gcn(self):
+        """One synchronous single-partition GCN epoch in the reference's operator order:
+        GA -> AV forward per layer, then GA -> AV backward; weights are NOT stepped (the caller owns Adam)."""
+        for l in range(self.L):
+            self.aggregate(l, 0)
+            self.apply_vertex(l, 0)
+        for l in range(self.L - 1, 0, -1):
+            self.aggregate(l, 1)
+            self.apply_vertex(l, 1)

@@ -68,7 +68,7 @@ def golden():
     import numpy as np
 
     d = os.path.join(ROOT, "tests", "golden")
-    return {n: np.load(os.path.join(d, n + ".npz")) for n in ("xavier", "masks", "reference_runs", "weight_dump", "numpy_gnn", "funcs_ops", "input_tools")}
+    return {n: np.load(os.path.join(d, n + ".npz")) for n in ("xavier", "masks", "reference_runs", "weight_dump", "numpy_gnn", "funcs_ops", "input_tools", "ref_engine")}
 
 
 @pytest.fixture()

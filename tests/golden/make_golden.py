@@ -262,12 +262,38 @@ def input_tools_fixture():
     np.savez_compressed(os.path.join(HERE, "input_tools.npz"), **out)
 
 
+def ref_engine_fixture():
+    """One synchronous GCN epoch on the reference's OWN object code (Engine::aggregateGCN, CPUComm::NNCompute:
+    oracle/_ref/librefengine.so, built from gcn_ops.cpp / CPU_comm.cpp in place by oracle/build.py) on a small
+    graph with the Reddit widths, Xavier weights (seed 8888): every tensor of the path, both weight updates and the
+    validation statistics.  tests/test_oracle.py holds the oracle port bit-identical to it."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import random_dataset
+    from oracle.pyoracle import Oracle, RefEngine
+
+    dims = [602, 128, 41]
+    ds = random_dataset(V=300, E_und=2400, dims=dims, seed=77)
+    o = Oracle()
+    ref = RefEngine(ds.images[0], dims)
+    ref.tensor(0, "x")[:] = ds.feats
+    ref.tensor(1, "lab")[:] = ds.onehot
+    for l in range(2):
+        ref.set_weights(l, o.xavier(dims[l], dims[l + 1]))
+    ref.epoch_gcn()
+    acc, loss = ref.stats()
+    np.savez_compressed(os.path.join(HERE, "ref_engine.npz"), V=ds.V, dims=np.array(dims), src=ds.src, dst=ds.dst,
+                        feats=ds.feats, labels=ds.labels, ah0=ref.tensor(0, "ah"), z0=ref.tensor(0, "z"), h0=ref.tensor(0, "h"),
+                        ah1=ref.tensor(1, "ah"), grad1=ref.tensor(1, "grad"), aTg0=ref.tensor(0, "aTg"), dW0=ref.update(0),
+                        dW1=ref.update(1), acc=acc, loss=loss)
+
+
 if __name__ == "__main__":
     input_tools_fixture()
     funcs_fixture()
     xavier_fixture()
     weight_dump_fixture()
     numpy_gnn_fixture()
+    ref_engine_fixture()
     mask_fixture()
     ref_fixture()
     for f in sorted(os.listdir(HERE)):

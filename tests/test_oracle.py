@@ -407,3 +407,95 @@ def test_sync_weight_update_matches_reference_weight_tensor(oracle, ref):
             L.ref_wt_destroy(h)
         L.ref_adam_destroy(radam)
         oadam.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# The oracle port against the reference's OWN object code for the hot path: Engine::aggregateGCN
+# (gcn_ops.cpp:130-191) and CPUComm::NNCompute -> vtxNNForwardGCN / vtxNNBackwardGCN with every helper
+# (CPU_comm.cpp:98-159, 265-297, 424-471), compiled in place into oracle/_ref/librefengine.so
+# (oracle/ref_engine.cpp, oracle/build.py: build_ref_engine).  This pins what SURVEY.md 8c had to leave
+# "pinned by our oracle only": the aggregation's summation order, getTrainStat and the loss scale.
+def _ref_engine_case(oracle, V, E_und, dims, seed, epochs):
+    import numpy as np
+    from helpers import random_dataset
+    from oracle.driver import OracleGCN
+    from oracle.pyoracle import RefEngine
+
+    ds = random_dataset(V=V, E_und=E_und, dims=dims, seed=seed)
+    L = len(dims) - 1
+    orc = OracleGCN(oracle, ds.graphs, dims)
+    orc.load_features(ds.feats, ds.onehot)
+    ref = RefEngine(ds.images[0], dims)
+    ref.tensor(0, "x")[:] = ds.feats
+    ref.tensor(L - 1, "lab")[:] = ds.onehot
+    out = []
+    for ep in range(epochs):
+        for l in range(L):
+            ref.set_weights(l, orc.W[l])  # this epoch's weights, as the weight server would hand them out
+        want = orc.epoch()               # (steps Adam at its end)
+        ref.epoch_gcn()
+        t = orc.saved[0]
+        got = {}
+        for l in range(L):
+            got["ah%d" % l] = (ref.tensor(l, "ah").copy(), t[l]["ah"].copy())
+            if l < L - 1:
+                got["z%d" % l] = (ref.tensor(l, "z").copy(), t[l]["z"].copy())
+                got["h%d" % l] = (ref.tensor(l, "h").copy(), t[l]["h"].copy())
+                got["aTg%d" % l] = (ref.tensor(l, "aTg").copy(), t[l]["aTg"].copy())
+            if l > 0:
+                got["grad%d" % l] = (ref.tensor(l, "grad").copy(), t[l]["grad"].copy())
+            got["dW%d" % l] = (ref.update(l), orc.dW[0][l].copy())
+        out.append((got, ref.stats(), (want["acc"][0], want["loss"][0])))
+    return out
+
+
+@pytest.mark.parametrize("shape", [dict(V=600, E_und=7200, dims=[602, 128, 41]), dict(V=2708, E_und=5278, dims=[1433, 16, 7]),
+                                   dict(V=2000, E_und=9000, dims=[100, 64, 64, 25]), dict(V=1800, E_und=6000, dims=[16, 48, 51])],
+                         ids=lambda s: "x".join(map(str, s["dims"])))
+def test_oracle_equals_reference_engine_object_code(oracle, shape):
+    from oracle.pyoracle import RefEngine
+
+    if not RefEngine.available():
+        pytest.skip("oracle/_ref/librefengine.so not available (no /root/reference and no prebuilt library)")
+    for got, stats, want_stats in _ref_engine_case(oracle, seed=21, epochs=2, **shape):
+        for name, (a, b) in got.items():
+            assert np.array_equal(a, b), name  # the port is bit-identical to the reference's own code
+        assert stats == want_stats
+
+
+def test_reference_engine_honours_chunk_bounds(oracle):
+    """Engine::aggregateGCN on a sub-range chunk [lowBound, upBound) (Lambda-style chunking) against the port."""
+    from helpers import random_dataset
+    from oracle.pyoracle import RefEngine
+
+    if not RefEngine.available():
+        pytest.skip("oracle/_ref/librefengine.so not available")
+    ds = random_dataset(V=500, E_und=4000, dims=[24, 8, 5], seed=9)
+    g = ds.graphs[0]
+    ref = RefEngine(ds.images[0], ds.dims)
+    ref.tensor(0, "x")[:] = ds.feats
+    ref.tensor(0, "ah")[:] = -7.0
+    ref.aggregate(0, 0, 100, 333)
+    want = np.full((500, 24), -7.0, np.float32)
+    oracle.aggregate_gcn(g.col_ptrs, g.row_idxs, g.fwd_vals, g.norms, ds.feats, None, 100, 333, out=want)
+    assert np.array_equal(ref.tensor(0, "ah"), want)
+
+
+def test_oracle_equals_reference_engine_golden(oracle, golden):
+    """The same comparison against tests/golden/ref_engine.npz -- outputs of the reference's own object code
+    recorded by tests/golden/make_golden.py, for boxes where neither /root/reference nor the prebuilt library is."""
+    from oracle.driver import OracleGCN
+    from dorylus_b200 import engine as dengine
+    from dorylus_b200 import formats
+
+    g = golden["ref_engine"]
+    V, dims = int(g["V"]), [int(x) for x in g["dims"]]
+    image = dengine.preprocess_edges(g["src"], g["dst"], np.zeros(V, np.int32), V, 0, 1)
+    orc = OracleGCN(oracle, [formats.parse_graph_bin(image)], dims)
+    orc.load_features(g["feats"], formats.one_hot(g["labels"], dims[-1]))
+    want = orc.epoch()
+    t = orc.saved[0]
+    for name in ("ah0", "z0", "h0", "ah1", "grad1", "aTg0", "dW0", "dW1"):
+        mine = orc.dW[0][int(name[-1])] if name.startswith("dW") else t[int(name[-1])][name[:-1]]
+        assert np.array_equal(mine, g[name]), name
+    assert (want["acc"][0], want["loss"][0]) == (float(g["acc"]), float(g["loss"]))
