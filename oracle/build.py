@@ -111,6 +111,8 @@ def build_ref(force: bool = False) -> str | None:
 # -O3 -march=native -fopenmp -D_CPU_ENABLED_ (CMakeLists.txt:7,23).
 REF_ENGINE_SOURCES = [
     "src/graph-server/engine/ops/gcn_ops.cpp",
+    "src/graph-server/engine/ops/gat_ops.cpp",
+    "src/graph-server/engine/ops/tensors.cpp",
     "src/graph-server/commmanager/CPU_comm.cpp",
     "src/common/matrix.cpp",
     "src/common/utils.cpp",

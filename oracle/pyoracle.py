@@ -389,7 +389,7 @@ class RefEngine:
     `update(layer)` is what sendWeightUpdate received.  No exchange (single partition, or ghost blocks filled
     by the caller through `tensor(layer, "fg" | "bg")`)."""
 
-    def __init__(self, graph_image, dims):
+    def __init__(self, graph_image, dims, gat: bool = False):
         import tempfile
 
         path = _build.build_ref_engine()
@@ -408,7 +408,8 @@ class RefEngine:
         with open(wpath, "w") as f:
             f.write("127.0.0.1\n")
         arr = (C.c_uint * len(self.dims))(*self.dims)
-        self.h = C.c_void_p(L.refeng_create(gpath.encode(), arr, C.c_uint(self.L), wpath.encode()))
+        self.gat = gat
+        self.h = C.c_void_p(L.refeng_create(gpath.encode(), arr, C.c_uint(self.L), wpath.encode(), int(gat)))
 
     @staticmethod
     def available() -> bool:
@@ -450,6 +451,32 @@ class RefEngine:
 
     def apply_vertex(self, layer: int, dir: int):
         self.lib.refeng_apply_vertex(self.h, C.c_uint(layer), int(dir))
+
+    # ---- GAT (the reference's chunk.layer convention: feature layer + 1 for everything but ApplyVertex forward)
+    def set_a(self, layer: int, a: np.ndarray):
+        a = _c32(a).reshape(-1)
+        assert a.size == self.dims[layer + 1]
+        self.lib.refeng_set_a(self.h, C.c_uint(layer), _f(a))
+
+    def a_update(self, layer: int) -> np.ndarray:
+        da = np.zeros(self.dims[layer + 1], np.float32)
+        if self.lib.refeng_get_a_update(self.h, C.c_uint(layer), _f(da)) != 0:
+            raise RuntimeError("no a_i update was sent for layer %d yet" % layer)
+        return da
+
+    def gat_forward(self, l: int):
+        """AV -> (SC) -> AE -> GA (-> predict on the last layer) for feature layer l."""
+        self.lib.refeng_gat_op(self.h, 1, C.c_uint(l), 0)
+        self.lib.refeng_gat_op(self.h, 2, C.c_uint(l + 1), 0)
+        self.lib.refeng_gat_op(self.h, 0, C.c_uint(l + 1), 0)
+        if l + 1 == self.L:
+            self.lib.refeng_gat_op(self.h, 3, C.c_uint(l + 1), 0)
+
+    def gat_backward(self, l: int):
+        """(SC) -> AE -> GA -> AV backward for feature layer l."""
+        self.lib.refeng_gat_op(self.h, 2, C.c_uint(l + 1), 1)
+        self.lib.refeng_gat_op(self.h, 0, C.c_uint(l + 1), 1)
+        self.lib.refeng_gat_op(self.h, 1, C.c_uint(l + 1), 1)
 
     def epoch_gcn(self):
         """One synchronous single-partition GCN epoch in the reference's operator order:

@@ -1,7 +1,9 @@
 // TEST INFRASTRUCTURE ONLY.  The reference's own object code for the hot path, callable from Python:
 //
 //   Engine::preallocateGCN / aggregateGCN      src/graph-server/engine/ops/gcn_ops.cpp   (compiled in place)
-//   CPUComm::NNCompute -> vtxNNForwardGCN / vtxNNBackwardGCN and every helper they use
+//   Engine::preallocateGAT / aggregateGAT / predictGAT / applyVertexGAT / applyEdgeGAT
+//                                              src/graph-server/engine/ops/gat_ops.cpp   (compiled in place)
+//   CPUComm::NNCompute -> vtxNNForwardGCN / vtxNNBackwardGCN, vtxNN*GAT / edgNN*GAT and every helper they use
 //   (activate, softmax, getTrainStat, maskout, hadamardSub, activateDerivative)
 //                                              src/graph-server/commmanager/CPU_comm.cpp (compiled in place)
 //   Graph::init, Matrix::dot                   graph/graph.cpp, common/matrix.cpp        (compiled in place)
@@ -31,7 +33,7 @@
 // ------------------------------------------------------------------ in-process weight endpoint
 namespace {
 struct Endpoint {
-    std::vector<std::vector<float>> w, dw;
+    std::vector<std::vector<float>> w, dw, a, da;  // "w" and (GAT) "a_i" per layer, and what was sent back
     std::vector<unsigned> rows, cols;
     float acc = 0.f, loss = 0.f;
     unsigned updates = 0;
@@ -47,8 +49,10 @@ MessageService::MessageService(unsigned wPort_, unsigned nodeId_, unsigned numLa
 void MessageService::setUpWeightSocket(char *) {}
 void MessageService::prefetchWeightsMatrix() {  // message_service.cpp:188-222 without the wire
     epoch++;
-    for (unsigned j = 0; j < numLayers && j < g_ep.w.size(); ++j)
+    for (unsigned j = 0; j < numLayers && j < g_ep.w.size(); ++j) {
         weights[j] = Matrix(g_ep.rows[j], g_ep.cols[j], g_ep.w[j].data());
+        if (j < g_ep.a.size() && !g_ep.a[j].empty()) as[j] = Matrix(g_ep.cols[j], 1, g_ep.a[j].data());
+    }
 }
 Matrix MessageService::getWeightMatrix(unsigned layer) { return weights.at(layer); }
 void MessageService::sendWeightUpdate(Matrix &matrix, unsigned layer) {  // :148-162: the sender owns and frees it
@@ -57,7 +61,10 @@ void MessageService::sendWeightUpdate(Matrix &matrix, unsigned layer) {  // :148
     deleteMatrix(matrix);
 }
 Matrix MessageService::getaMatrix(unsigned layer) { return as.at(layer); }
-void MessageService::sendaUpdate(Matrix &matrix, unsigned) { deleteMatrix(matrix); }
+void MessageService::sendaUpdate(Matrix &matrix, unsigned layer) {
+    g_ep.da.at(layer).assign(matrix.getData(), matrix.getData() + matrix.getNumElemts());
+    deleteMatrix(matrix);
+}
 void MessageService::sendAccloss(float acc, float loss, unsigned) {
     g_ep.acc = acc;
     g_ep.loss = loss;
@@ -121,6 +128,21 @@ Chunk Engine::incLayerGCN(const Chunk &chunk) {
     return nChunk;
 }
 
+// engine/utils.cpp:734-748
+Chunk Engine::incLayerGAT(const Chunk &chunk) {
+    Chunk nChunk = chunk;
+    if (nChunk.dir == PROP_TYPE::FORWARD) {
+        nChunk.layer++;
+    } else if (nChunk.layer == 0) {
+        nChunk.dir = PROP_TYPE::FORWARD;
+        nChunk.vertex = true;
+        nChunk.epoch++;
+    } else {
+        nChunk.layer--;
+    }
+    return nChunk;
+}
+
 // ------------------------------------------------------------------ C interface for oracle/pyoracle.py
 namespace {
 struct RefEngine {
@@ -133,11 +155,11 @@ extern "C" {
 
 // graph_file: a graph.<id>.bin on disk (Graph::init reads it); dims[0..n_layers]; ws_file: a text file with one
 // address line (CPUComm's constructor reads the weight-server list, CPU_comm.cpp:244-263).
-void *refeng_create(const char *graph_file, const unsigned *dims, unsigned n_layers, const char *ws_file) {
+void *refeng_create(const char *graph_file, const unsigned *dims, unsigned n_layers, const char *ws_file, int gat) {
     RefEngine *r = new RefEngine();
     Engine &e = r->eng;
     e.graph.init(std::string(graph_file));
-    e.gnn_type = GNN::GCN;
+    e.gnn_type = gat ? GNN::GAT : GNN::GCN;
     e.numLayers = n_layers;
     e.layerConfig.assign(dims, dims + n_layers + 1);
     e.nodeId = 0;
@@ -149,10 +171,24 @@ void *refeng_create(const char *graph_file, const unsigned *dims, unsigned n_lay
     e.localVerticesLabels = new FeatType[(size_t)e.getFeatDim(n_layers) * e.graph.localVtxCnt]();
     e.savedNNTensors.resize(n_layers);   // engine.cpp:113-114
     e.savedEdgeTensors.resize(n_layers);
-    e.preallocateGCN();                  // the reference's own allocation + pointer tables
+    if (gat) {
+        e.preallocateGAT();
+        // quirk Q11: the reference accumulates the backward aggregation into "aTg" as operator new[] left it
+        // (gat_ops.cpp:103-104,221-241); like the oracle, start from zero
+        for (unsigned l = 0; l < n_layers; ++l) {
+            Matrix &m = e.savedNNTensors[l]["aTg"];
+            std::memset(m.getData(), 0, m.getDataSize());
+        }
+    } else {
+        e.preallocateGCN();              // the reference's own allocation + pointer tables
+    }
     g_ep = Endpoint();
     g_ep.w.resize(n_layers);
     g_ep.dw.resize(n_layers);
+    g_ep.a.resize(n_layers);
+    g_ep.da.resize(n_layers);
+    if (gat)
+        for (unsigned l = 0; l < n_layers; ++l) g_ep.a[l].assign(dims[l + 1], 0.f);
     g_ep.rows.assign(dims, dims + n_layers);
     g_ep.cols.assign(dims + 1, dims + n_layers + 1);
     for (unsigned l = 0; l < n_layers; ++l) g_ep.w[l].assign((size_t)dims[l] * dims[l + 1], 0.f);
@@ -177,6 +213,24 @@ int refeng_get_update(void *, unsigned layer, float *dw) {
     if (g_ep.dw.at(layer).empty()) return -1;
     std::memcpy(dw, g_ep.dw[layer].data(), g_ep.dw[layer].size() * sizeof(float));
     return 0;
+}
+void refeng_set_a(void *, unsigned layer, const float *a) {
+    std::memcpy(g_ep.a.at(layer).data(), a, g_ep.a[layer].size() * sizeof(float));
+}
+int refeng_get_a_update(void *, unsigned layer, float *da) {
+    if (g_ep.da.at(layer).empty()) return -1;
+    std::memcpy(da, g_ep.da[layer].data(), g_ep.da[layer].size() * sizeof(float));
+    return 0;
+}
+// The GAT operators of the reference on a whole-partition chunk with chunk.layer = `layer`:
+// op 0 aggregateGAT, 1 applyVertexGAT, 2 applyEdgeGAT, 3 predictGAT (gat_ops.cpp:173-265,267-275,437-440)
+void refeng_gat_op(void *h, int op, unsigned layer, int dir) {
+    Engine &e = static_cast<RefEngine *>(h)->eng;
+    Chunk c{0, e.nodeId, 0, e.graph.localVtxCnt, layer, dir == 0 ? PROP_TYPE::FORWARD : PROP_TYPE::BACKWARD, 1, op != 2};
+    if (op == 0) e.aggregateGAT(c);
+    else if (op == 1) e.applyVertexGAT(c);
+    else if (op == 2) e.applyEdgeGAT(c);
+    else e.predictGAT(c);
 }
 void refeng_stats(void *, float *acc, float *loss) {
     *acc = g_ep.acc;

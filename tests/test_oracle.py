@@ -499,3 +499,46 @@ def test_oracle_equals_reference_engine_golden(oracle, golden):
         mine = orc.dW[0][int(name[-1])] if name.startswith("dW") else t[int(name[-1])][name[:-1]]
         assert np.array_equal(mine, g[name]), name
     assert (want["acc"][0], want["loss"][0]) == (float(g["acc"]), float(g["loss"]))
+
+
+@pytest.mark.parametrize("shape", [dict(V=300, E_und=3000, dims=[24, 12, 5]), dict(V=600, E_und=14000, dims=[602, 128, 41])],
+                         ids=lambda s: "x".join(map(str, s["dims"])))
+def test_oracle_gat_equals_reference_engine_object_code(oracle, shape):
+    """GAT (BASELINE configs[2]): Engine::aggregateGAT / predictGAT / applyVertexGAT / applyEdgeGAT of gat_ops.cpp and
+    CPUComm's vtxNN*GAT / edgNN*GAT, the reference's own object code, against the port -- bit for bit on every
+    tensor of both layers, forward and backward, with the reference's quirks in force: predictGAT reads "az" (Q9),
+    "A" aliases forwardAdj.values (Q12).  Two things the reference leaves undefined are excluded and said so:
+    * "da": CPUComm::reduce() accumulates into memory operator new[] left uninitialised (Q11, CPU_comm.cpp:366-382);
+    * predictGAT's `#pragma omp parallel` WITHOUT `for` (gat_ops.cpp:258-263) makes every OpenMP thread subtract the
+      labels: with T threads grad = softmax - (up to T) * lab, racily.  The library runs it with one thread here;
+      the port (and the engine) implement softmax - lab."""
+    from helpers import random_dataset
+    from oracle.driver import OracleGAT
+    from oracle.pyoracle import RefEngine
+
+    if not RefEngine.available():
+        pytest.skip("oracle/_ref/librefengine.so not available")
+    dims = shape["dims"]
+    ds = random_dataset(seed=71, **shape)  # E >= V * C: the "az" quirk reads V x C floats of the E x 1 score vector
+    orc = OracleGAT(oracle, ds.graphs, dims, predict_from="az")
+    orc.load_features(ds.feats, ds.onehot)
+    orc.epoch()
+    ref = RefEngine(ds.images[0], dims, gat=True)
+    ref.set_threads(1)
+    ref.tensor(0, "h")[:] = ds.feats
+    ref.tensor(1, "lab")[:] = ds.onehot
+    for l in range(2):
+        ref.set_weights(l, orc.W[l])
+        ref.set_a(l, orc.a[l])
+    for l in range(2):
+        ref.gat_forward(l)
+    for l in (1, 0):
+        ref.gat_backward(l)
+    t = orc.saved[0]
+    for l in range(2):
+        for n in ("z", "ah", "grad", "aTg"):
+            assert np.array_equal(ref.tensor(l, n), t[l][n]), (l, n)
+        for n in ("az", "dA"):
+            assert np.array_equal(ref.tensor(l, n).reshape(-1), t[l][n]), (l, n)
+        assert np.array_equal(ref.update(l), orc.dW[0][l]), (l, "dW")
+    assert np.array_equal(ref.tensor(1, "A").reshape(-1), orc.A[0])
