@@ -3,14 +3,10 @@ against the REFERENCE-order oracle: z / h of every hidden layer, dL/dh, the weig
 validation statistics and the weights after Adam, for one partition, for mixed per-layer choices and
 for two partitions on one GPU with the exchange done by the test; plus the GAT source windows.
 
-Status: written in a session whose GPU budget was spent.  The engine's host logic of these paths has
-been run end to end on the CPU (tests/test_hostcheck_engine.py: the product's engine object against
-scalar statements of the kernels, same oracle comparisons); on the GPU they compose kernels the
-verified suites already exercise, plus one element-wise tanh.  The file sorts last so that a surprise
-here cannot mask those suites under -x.  Only the 2-GPU C++ driver test stays behind
-DORY_TEST_UNVERIFIED=1: its host logic has run as separate processes on the emulated runtime too, but
-NCCL itself and the CUDA-IPC handles of the peer-memory exchange cannot be emulated, and a hang between
-two ranks is the one failure a test run does not survive."""
+Status (round 2): everything here has run on B200s -- the single-GPU cases in every driver run since round 1,
+the 2-GPU C++ driver test (host/run_onnode.sh: NCCL and the CUDA-IPC handles of the peer-memory exchange between
+two real processes) in round 2.  The file still sorts last so that a surprise here cannot mask the other suites
+under -x."""
 import os
 
 import numpy as np
@@ -174,8 +170,6 @@ def test_gat_source_windows_match_oracle(oracle, nb):
             assert rel_err(e.get_weight_grad(l), orc.dW[0][l]) < TOL
 
 
-@pytest.mark.skipif(os.environ.get("DORY_TEST_UNVERIFIED") != "1",
-                    reason="multi-partition C++ driver not yet run on hardware (set DORY_TEST_UNVERIFIED=1)")
 @pytest.mark.parametrize("extra", [[], ["--exchange", "nccl"], ["--apply-first", "1"]], ids=["p2p", "nccl", "apply-first"])
 def test_cpp_driver_two_partitions_match_oracle(oracle, extra):
     """host/run_onnode.sh: one dorylus_b200_run process per GPU, the plan from the partition images,
