@@ -502,9 +502,10 @@ def measure(args, ctx: Ctx, arm: dict, want_e2e: bool = True) -> dict:
             eng.event_record(5)
             eng.sync()
             rows = graph.src_ghost_cnt if d == FORWARD else graph.dst_ghost_cnt
-            pitch = width if width <= 16 else (width + 31) // 32 * 32
+            # the peer-memory store kernel ships the data columns of a row (whole float4s); the NCCL path its pitch
+            moved = (width + 3) // 4 * 4 if args.exchange == "p2p" else (width if width <= 16 else (width + 31) // 32 * 32)
             xch[name] = dict(ms=eng.event_elapsed_ms(4, 5) / 3, rows_in=rows, width=width,
-                             bytes_in=rows * pitch * 4)
+                             bytes_in=rows * moved * 4)
 
     # ---- end to end through the public API: H2D of the step's inputs + epoch + D2H of the result
     e2e = None
