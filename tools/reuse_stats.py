@@ -22,6 +22,22 @@ sys.path.insert(0, ROOT)
 from dorylus_b200 import synth  # noqa: E402
 
 
+def rmat_edges(n_und: int, scale: int, seed: int, a=0.57, b=0.19, c=0.19):
+    """R-MAT: every edge picks one quadrant per bit level (a: top-left, b: top-right, c: bottom-left, d: the rest)."""
+    rng = np.random.default_rng(seed)
+    u = np.zeros(n_und, np.int64)
+    v = np.zeros(n_und, np.int64)
+    for _ in range(scale):
+        r = rng.random(n_und, dtype=np.float32)
+        u = (u << 1) | (r >= a + b)                        # bottom half: c or d
+        v = (v << 1) | (((r >= a) & (r < a + b)) | (r >= a + b + c))  # right half: b or d
+    keep = u != v
+    lo, hi = np.minimum(u[keep], v[keep]), np.maximum(u[keep], v[keep])
+    key = np.unique(lo * (1 << scale) + hi)
+    lo, hi = (key >> scale).astype(np.uint32), (key & ((1 << scale) - 1)).astype(np.uint32)
+    return np.concatenate([lo, hi]), np.concatenate([hi, lo]), n_und
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="reddit")
@@ -29,11 +45,20 @@ def main():
     ap.add_argument("--locality", type=float, default=None)
     ap.add_argument("--communities", type=int, default=None)
     ap.add_argument("--out", default="")
+    ap.add_argument("--rmat", action="store_true",
+                    help="the generator SURVEY.md 8d names instead of synth.py's: R-MAT (a, b, c = .57, .19, .19) over 2^18 "
+                         "vertices, the workload's edge count drawn, symmetrised, duplicates and self loops removed")
     args = ap.parse_args()
     spec = synth.CONFIGS[args.workload]
     if args.locality is not None:
         spec = dataclasses.replace(spec, locality=args.locality, communities=args.communities or 41)
-    src, dst = synth.generate_edges(spec)
+    if args.rmat:
+        src, dst, drawn = rmat_edges(spec.num_edges // 2, 18, seed=11)
+        spec = dataclasses.replace(spec, name=spec.name + "-rmat", num_vertices=1 << 18)
+        print("R-MAT: %d undirected edges drawn, %d distinct after de-duplication (%.1f %% kept)"
+              % (drawn, src.size // 2, 100.0 * (src.size // 2) / drawn), file=sys.stderr)
+    else:
+        src, dst = synth.generate_edges(spec)
     V, E = spec.num_vertices, src.size
     deg = np.bincount(dst, minlength=V)
     if spec.locality > 0:
