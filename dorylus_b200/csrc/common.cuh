@@ -153,6 +153,7 @@ int launch_softmax_ce(const SoftmaxCEArgs &a, cudaStream_t s);
 // The same, fused behind the logits product A[V x K] . W[K x ld] (a.z is not read); 0 = shape does not qualify.
 int launch_gemm_softmax_ce(const float *A, uint32_t lda, const float *W, uint32_t ldw, uint64_t K, const SoftmaxCEArgs &a,
                            cudaStream_t s);
+int launch_softmax_stats(const SoftmaxCEArgs &a, cudaStream_t s);  // the reduction alone (after launch_gemm_tc_softmax)
 
 // Adam step on one weight matrix (AdamOptimizer.cpp:36-48); lr_t is computed on the host.
 int launch_adam(float *w, const float *grad, float *m, float *v, size_t n, float lr_t, float beta1,

@@ -645,6 +645,12 @@ int launch_gemm_softmax_ce(const float *A, uint32_t lda, const float *W, uint32_
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
+// stats = sums of the per-row validation statistics a fused last-layer kernel left in a.rowstat
+int launch_softmax_stats(const SoftmaxCEArgs &a, cudaStream_t s) {
+    stat_reduce_kernel<<<1, 1024, 0, s>>>(a.rowstat, a.V, a.valEnd - a.trainEnd, a.stats);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 int launch_adam(float *w, const float *grad, float *m, float *v, size_t n, float lr_t, float beta1,
                 float beta2, float eps, cudaStream_t s) {
     if (n == 0) return 0;

@@ -160,7 +160,11 @@ struct dory_engine {
     uint32_t tile_edges = 4096;   // low-degree mode: edges per tile (their ids / weights are staged too)
     int tile_pipe = 1;            // low-degree mode: persistent CTAs with a two-stage TMA pipeline
     int tn_small = 1;             // option "tn_small": narrow-M fp32 kernel for dW of layers with input width <= 64
-    int fuse_softmax = 1;         // option "fuse_softmax": last-layer logits + soft-max / maskout in one kernel (C <= 64)
+    int fuse_softmax = 1;         // option "fuse_softmax": last-layer logits + soft-max / maskout in one kernel (C <= 64);
+                                  // 1 = on tcgen05 when the shape qualifies, else fp32 SIMT; 2 = the SIMT kernel only
+    int tc_small = 1;             // option "tc_small": the small-tile tcgen05 kernel (several CTAs per SM) for that product, for
+                                  // Z = A.W with K <= 128, N <= 64 and for grad = G.W^T; 0 = the round-1 kernels
+    int tc_stages = 0;            // option "tc_stages": its shared-memory stages per CTA (0 = choose)
     // apply-first schedule (DORY_FLAG_APPLY_FIRST, include/dorylus_b200.h): af[l] != 0 -> layer l runs
     // A_hat . (in . W); decided in dory_load_partition from the flag / the "apply_first_mask" option
     std::vector<uint8_t> af;
@@ -945,7 +949,7 @@ bool use_tensor_cores(const dory_engine *e) { return e->tensor_cores && !(e->cfg
 int gemm_nn(dory_engine *e, const DevMat &A, const WeightSet &W, const DevMat &C, const DevMat *C2) {
     if (use_tensor_cores(e)) {
         int n = launch_gemm_tc(A.p, A.ld, A.rows, W.w.as<float>(), W.ld, W.prows, C.p, C2 ? C2->p : nullptr, C.ld,
-                               C2 ? EPI_TANH : EPI_NONE, e->stream);
+                               C2 ? EPI_TANH : EPI_NONE, e->stream, e->tc_small ? e->tc_stages : -1);
         if (n > 0) {
             e->stats.kernel_launches += n;
             return DORY_OK;
@@ -964,6 +968,14 @@ int gemm_nn(dory_engine *e, const DevMat &A, const WeightSet &W, const DevMat &C
 
 // C = G . W^T   (G: V x Fout, W: Fin x Fout -> C: V x Fin)
 int gemm_nt(dory_engine *e, const float *G, uint32_t ldg, uint64_t rows, const WeightSet &W, const DevMat &C) {
+    if (use_tensor_cores(e) && e->tc_small) {
+        const int n = launch_gemm_nt_tc(G, ldg, rows, W.w.as<float>(), W.ld, W.prows, C.p, C.ld, e->tc_stages, e->stream);
+        if (n > 0) {
+            e->stats.kernel_launches += n;
+            return DORY_OK;
+        }
+        if (n < 0) return fail(e, DORY_ECUDA, "tcgen05 GEMM (G . W^T) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     GemmArgs g{};
     g.A = G; g.lda = ldg; g.B = W.w.as<float>(); g.ldb = W.ld; g.C = C.p; g.ldc = C.ld;
     g.M = rows; g.N = C.ld; g.K = W.ld;
@@ -1047,7 +1059,16 @@ int vtx_forward_gcn(dory_engine *e, uint32_t layer) {
     bool fused = false;
     if (e->fuse_softmax) {  // logits + soft-max in one kernel when a row's classes fit one tile (C <= 64)
         SoftmaxCEArgs sa = softmax_args(e, nullptr, lab, d.p);
-        const int n = launch_gemm_softmax_ce(ah.p, ah.ld, W.w.as<float>(), W.ld, ah.ld, sa, e->stream);
+        int n = 0;
+        if (use_tensor_cores(e) && e->tc_small && e->fuse_softmax != 2) {  // tcgen05 logits, thread-per-row epilogue out of TMEM
+            n = launch_gemm_tc_softmax(ah.p, ah.ld, W.w.as<float>(), W.ld, W.prows, sa, e->tc_stages, e->stream);
+            if (n < 0) return fail(e, DORY_ECUDA, "tcgen05 soft-max GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            if (n > 0) {
+                e->stats.kernel_launches += n;
+                n = launch_softmax_stats(sa, e->stream);
+            }
+        }
+        if (n == 0) n = launch_gemm_softmax_ce(ah.p, ah.ld, W.w.as<float>(), W.ld, ah.ld, sa, e->stream);
         LAUNCHED(n);
         if (n > 0) {
             fused = true;
@@ -1522,7 +1543,11 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
     } else if (std::strcmp(key, "tn_small") == 0) {
         e->tn_small = v != 0;
     } else if (std::strcmp(key, "fuse_softmax") == 0) {
-        e->fuse_softmax = v != 0;
+        e->fuse_softmax = (int)v;
+    } else if (std::strcmp(key, "tc_stages") == 0) {
+        e->tc_stages = (int)v;
+    } else if (std::strcmp(key, "tc_small") == 0) {
+        e->tc_small = v != 0;
     } else if (std::strcmp(key, "tensor_cores") == 0) {
         e->tensor_cores = v != 0;
     } else if (std::strcmp(key, "spmm_unroll") == 0) {

@@ -288,6 +288,242 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 }
 
+// ------------------------------------------------------------------ last layer: logits + soft-max, skinny K
+//
+// The last ApplyVertex of a GCN is [V x K] . [K x C] with K <= 128 and C <= 64 followed by a row soft-max
+// (CPU_comm.cpp:98-121, 276-297, 448-471).  gemm_tc_kernel above holds 3-4 stages of 48-64 KB: one CTA per
+// SM, and with one or two K blocks per tile a CTA is all latency (launch, TMA, split, MMA, epilogue, one
+// after the other: 4.5 us per 128-row tile on the 8.2 M-row Friendster partition).  Here a CTA takes only
+// `nst` <= 2 stages (BN = 64: 48 KB each) so that 2-4 CTAs share an SM and cover each other's latencies,
+// and the epilogue is the whole of softmax_ce_kernel: a TMEM lane is an output row, so tcgen05.ld hands every
+// thread the C logits of ONE vertex -- the soft-max, both arg-maxes, the validation statistics, the maskout
+// (quirk Q6) and d = (P - Y) / scale need no shuffle and the logits never reach HBM.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Soft-max, validation statistics, maskout and d = (P - Y) / scale of ONE vertex row whose logits are in v
+// (softmax_ce_kernel of dense.cu, sequential over the classes): CPU_comm.cpp:108-121, 276-297, 448-471.
+template <int BN>
+__device__ __forceinline__ void softmax_ce_row(float (&v)[BN], uint64_t row, const SoftmaxCEArgs &a) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < BN; ++j)
+        if ((uint32_t)j < a.C) mx = fmaxf(mx, v[j]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < BN; ++j) {
+        v[j] = (uint32_t)j < a.C ? expf(v[j] - mx) : 0.f;
+        sum += v[j];
+    }
+    const float denom = 1e-20f + sum;  // CPU_comm.cpp:285-290
+    const uint64_t maskBeg = (uint64_t)a.trainEnd * a.C;
+    float pbest = -INFINITY, lbest = -INFINITY, lab_at_pbest = 0.f, p_at_lbest = 1.f;
+    const float4 *lab4 = reinterpret_cast<const float4 *>(a.lab + row * a.ld);
+    float4 *d4 = reinterpret_cast<float4 *>(a.d + row * a.ld);
+    float4 *pred4 = a.pred ? reinterpret_cast<float4 *>(a.pred + row * a.ld) : nullptr;
+#pragma unroll
+    for (int j4 = 0; j4 < BN / 4; ++j4) {
+        const float4 l4 = lab4[j4];
+        const float lb[4] = {l4.x, l4.y, l4.z, l4.w};
+        float d[4], pr[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t c = 4 * j4 + k;
+            float p = v[c] / denom;
+            pr[k] = p;
+            d[k] = 0.f;
+            if (c < a.C) {
+                // first maximum wins, like the reference's argmax helper
+                if (p > pbest) pbest = p, lab_at_pbest = lb[k];
+                if (lb[k] > lbest) lbest = lb[k], p_at_lbest = p;
+                const uint64_t flat = row * a.C + c;  // index in the reference's dense V x C array
+                const bool masked =
+                    a.strictMask ? (row >= a.trainEnd) : (flat >= maskBeg && flat < maskBeg + a.maskFloats);
+                if (masked) p = lb[k];  // maskout, then hadamardSub and the scale (CPU_comm.cpp:118-121, 464-471)
+                d[k] = (p - lb[k]) / a.denom;
+            }
+        }
+        d4[j4] = make_float4(d[0], d[1], d[2], d[3]);
+        if (pred4) pred4[j4] = make_float4(pr[0], pr[1], pr[2], pr[3]);
+    }
+    if (row >= a.trainEnd && row < a.valEnd) {  // getTrainStat over the validation slice (CPU_comm.cpp:448-462)
+        a.rowstat[row - a.trainEnd] = lab_at_pbest;
+        a.rowstat[(size_t)a.V + (row - a.trainEnd)] = -logf(p_at_lbest);
+    }
+}
+
+// SOFTMAX = false: the same pipeline with the plain epilogue of gemm_tc_kernel (C, and C2 = tanh(C) for EPI_TANH)
+// -- the skinny products of the Amazon / Friendster widths (K <= 128, N <= 64) and grad = G . W^T.
+struct SmallOut {
+    float *C, *C2;
+    uint32_t ldc;
+    int epilogue;
+};
+
+template <int BN, bool SOFTMAX>
+__global__ void __launch_bounds__(kThreads, (SOFTMAX && BN == 64) ? 3 : 4)
+gemm_tc_small_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBhi,
+                     const __grid_constant__ CUtensorMap mapBlo, uint32_t nkb, uint32_t nst, uint64_t M, const SmallOut o,
+                     const SoftmaxCEArgs a) {
+    using L = SmemLayout<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // [base, base + 1024): barriers and the TMEM slot; stages follow (1024 B aligned for the 128 B swizzle)
+    constexpr int kMaxStages = 4;
+    auto stage_off = [&](uint32_t s) { return 1024u + s * L::kStageBytes; };
+    auto stage_a_hi = [&](uint32_t s) { return base + stage_off(s); };
+    auto stage_a_lo = [&](uint32_t s) { return base + stage_off(s) + L::kABytes; };
+    auto stage_b_hi = [&](uint32_t s) { return base + stage_off(s) + 2 * L::kABytes; };
+    auto stage_b_lo = [&](uint32_t s) { return base + stage_off(s) + 2 * L::kABytes + L::kBBytes; };
+    auto bar_full = [&](uint32_t s) { return base + 8 * s; };
+    auto bar_conv = [&](uint32_t s) { return base + 8 * (kMaxStages + s); };
+    auto bar_empty = [&](uint32_t s) { return base + 8 * (2 * kMaxStages + s); };
+    const uint32_t bar_done = base + 8 * (3 * kMaxStages);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen_base + 8 * (3 * kMaxStages + 1));
+
+    const uint64_t m0 = (uint64_t)blockIdx.x * BM;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapBhi);
+        tma_prefetch_desc(&mapBlo);
+        for (uint32_t s = 0; s < nst; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_conv(s), kConvThreads);
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(2 * BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (SOFTMAX && warp >= 2) {  // the label row of this thread's vertex is needed only in the epilogue: start it now
+        const uint64_t row = m0 + (uint64_t)(warp & 3) * 32 + lane;
+        if (row < M) {
+            const float *lp = a.lab + row * a.ld;
+            prefetch_l2(lp);
+            if (BN > 32) prefetch_l2(lp + 32);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+                const uint32_t s = kb % nst, ph = (kb / nst) & 1;
+                mbar_wait(bar_empty(s), ph ^ 1);
+                mbar_expect_tx(bar_full(s), L::kTxBytes);
+                tma_load_2d(stage_a_hi(s), &mapA, kb * BK, (int)m0, bar_full(s));
+                tma_load_2d(stage_b_hi(s), &mapBhi, kb * BK, 0, bar_full(s));
+                tma_load_2d(stage_b_lo(s), &mapBlo, kb * BK, 0, bar_full(s));
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc_tf32<BN>();
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+            const uint32_t s = kb % nst, ph = (kb / nst) & 1;
+            mbar_wait(bar_full(s), ph);
+            mbar_wait(bar_conv(s), ph);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint32_t koff = k * UMMA_K * 4;
+                    const uint64_t a_hi = umma_desc_sw128(stage_a_hi(s) + koff);
+                    const uint64_t a_lo = umma_desc_sw128(stage_a_lo(s) + koff);
+                    const uint64_t b_hi = umma_desc_sw128(stage_b_hi(s) + koff);
+                    const uint64_t b_lo = umma_desc_sw128(stage_b_lo(s) + koff);
+                    const uint32_t acc = (kb | (uint32_t)k) ? 1u : 0u;
+                    tc_mma_tf32(tmem, a_hi, b_hi, idesc, acc);
+                    tc_mma_tf32(tmem + BN, a_hi, b_lo, idesc, acc);
+                    tc_mma_tf32(tmem + BN, a_lo, b_hi, idesc, 1u);
+                }
+                tc_commit(bar_empty(s));
+                if (kb + 1 == nkb) tc_commit(bar_done);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int t = threadIdx.x - 64;
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+            const uint32_t s = kb % nst, ph = (kb / nst) & 1;
+            mbar_wait(bar_full(s), ph);
+            float4 *hi = reinterpret_cast<float4 *>(gen_base + stage_off(s));
+            float4 *lo = reinterpret_cast<float4 *>(gen_base + stage_off(s) + L::kABytes);
+#pragma unroll
+            for (int i = 0; i < (BM * BK / 4) / kConvThreads; ++i) {
+                const int idx = t + i * kConvThreads;
+                const float4 v = hi[idx];
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                l.x = v.x - h.x;
+                l.y = v.y - h.y;
+                l.z = v.z - h.z;
+                l.w = v.w - h.w;
+                hi[idx] = h;
+                lo[idx] = l;
+            }
+            fence_proxy_async();
+            mbar_arrive(bar_conv(s));
+        }
+        // ---- epilogue: thread = vertex row (TMEM lane quarter of this warp)
+        mbar_wait(bar_done, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const uint64_t row = m0 + (uint64_t)q * 32 + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        if constexpr (!SOFTMAX) {
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                float d0[32], d1[32];
+                tc_ld_32x32(lane_base + c * 32, d0);
+                tc_ld_32x32(lane_base + BN + c * 32, d1);
+                tc_wait_ld();
+                if (row < M) {
+                    float4 *out = reinterpret_cast<float4 *>(o.C + row * o.ldc + c * 32);
+                    float4 *out2 = reinterpret_cast<float4 *>(o.C2 + row * o.ldc + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 z = make_float4(d0[4 * j] + d1[4 * j], d0[4 * j + 1] + d1[4 * j + 1],
+                                                     d0[4 * j + 2] + d1[4 * j + 2], d0[4 * j + 3] + d1[4 * j + 3]);
+                        out[j] = z;
+                        if (o.epilogue == EPI_TANH) out2[j] = make_float4(tanhf(z.x), tanhf(z.y), tanhf(z.z), tanhf(z.w));
+                    }
+                }
+            }
+        }
+        if constexpr (SOFTMAX) {
+            float v[BN];
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                float d0[32], d1[32];
+                tc_ld_32x32(lane_base + c * 32, d0);
+                tc_ld_32x32(lane_base + BN + c * 32, d1);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[c * 32 + j] = d0[j] + d1[j];
+            }
+            if (row < M) softmax_ce_row<BN>(v, row, a);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN) : "memory");
+    }
+}
+
 // Wt_hi[n][k], Wt_lo[n][k] (K-major, [BN x Kpad]) from W[k][n] ([Kpad x ldw]); rows n >= ldw are zero.
 __global__ void split_transpose_kernel(const float *__restrict__ W, uint32_t ldw, uint32_t Kpad, uint32_t BN,
                                        float *__restrict__ hi, float *__restrict__ lo) {
@@ -606,7 +842,91 @@ int launch_bn(const float *A, uint32_t lda, uint64_t M, const float *W, uint32_t
     return 2;
 }
 
+// W_hi / W_lo of a weight matrix used UNtransposed: grad = G . W^T contracts over W's columns, so W [prows x ld]
+// row-major already is the K-major [N x K] operand.
+__global__ void split_kernel(const float *__restrict__ W, size_t n, float *__restrict__ hi, float *__restrict__ lo) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float w = W[i];
+    const float h = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+    hi[i] = h;
+    lo[i] = w - h;
+}
+
+// transposed = false: B operand from W^T (Z = A . W, W [Kpad x ldw], BN = ldw); true: from W itself
+// (C = A . W^T, W [BN x Kpad] with pitch Kpad).
+template <int BN, bool SOFTMAX>
+int launch_small(const float *A, uint32_t lda, uint64_t M, const float *W, uint32_t ldw, uint32_t Kpad, bool transposed,
+                 const SmallOut &o, const SoftmaxCEArgs &a, int stages, cudaStream_t s) {
+    using L = SmemLayout<BN>;
+    Cache &c = cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto wkey = std::make_tuple(W, transposed ? (ldw | 0x80000000u) : ldw, Kpad);
+    auto wit = c.weights.find(wkey);
+    if (wit == c.weights.end()) {
+        WeightSplit ws;
+        const size_t bytes = (size_t)BN * Kpad * 4;
+        if (cudaMalloc(&ws.hi, bytes) != cudaSuccess || cudaMalloc(&ws.lo, bytes) != cudaSuccess) return -1;
+        if (!make_map(&ws.mapHi, ws.hi, BN, Kpad, Kpad, BN) || !make_map(&ws.mapLo, ws.lo, BN, Kpad, Kpad, BN)) return 0;
+        wit = c.weights.emplace(wkey, ws).first;
+    }
+    auto akey = std::make_tuple(A, lda, M | ((uint64_t)Kpad << 40));  // the map's extent along K is part of it
+    auto ait = c.amaps.find(akey);
+    if (ait == c.amaps.end()) {
+        CUtensorMap m;
+        if (!make_map(&m, A, M, Kpad, lda, BM)) return 0;
+        ait = c.amaps.emplace(akey, m).first;
+    }
+    const uint32_t nkb = Kpad / BK;
+    // one stage per CTA (three to four CTAs per SM) unless the K loop is long enough to want its own ring
+    const uint32_t nst = stages > 0 ? std::min<uint32_t>((uint32_t)stages, std::min<uint32_t>(nkb, 4)) : (nkb <= 2 ? 1u : 2u);
+    const uint32_t smem = 1024 + 1024 + nst * L::kStageBytes;
+    static uint32_t granted = 0;
+    if (smem > granted) {
+        if (cudaFuncSetAttribute(gemm_tc_small_kernel<BN, SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+            return -1;
+        granted = smem;
+    }
+    // weights change every epoch (Adam): re-split them on every call
+    if (transposed) {
+        const size_t n = (size_t)BN * Kpad;
+        split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(W, n, wit->second.hi, wit->second.lo);
+    } else {
+        dim3 sg((Kpad + 127) / 128, BN);
+        split_transpose_kernel<<<sg, 128, 0, s>>>(W, ldw, Kpad, BN, wit->second.hi, wit->second.lo);
+    }
+    const unsigned grid = (unsigned)((M + BM - 1) / BM);
+    gemm_tc_small_kernel<BN, SOFTMAX><<<grid, kThreads, smem, s>>>(ait->second, wit->second.mapHi, wit->second.mapLo, nkb, nst,
+                                                                   M, o, a);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return 2;
+}
+
 }  // namespace
+
+int launch_gemm_tc_softmax(const float *A, uint32_t lda, const float *W, uint32_t ldw, uint32_t Kpad, const SoftmaxCEArgs &a,
+                           int stages, cudaStream_t s) {
+    // Supported: K a multiple of the 32-float swizzle span, the label / logit pitch exactly 32 or 64 (one row's
+    // classes in one accumulator tile).  Anything else takes the fp32 path (launch_gemm_softmax_ce, dense.cu).
+    if (Kpad % BK != 0 || Kpad == 0 || lda < Kpad || a.ld != ldw || a.C > a.ld || a.V == 0) return 0;
+    const SmallOut none{nullptr, nullptr, 0, EPI_NONE};
+    if (ldw == 64) return launch_small<64, true>(A, lda, a.V, W, ldw, Kpad, false, none, a, stages, s);
+    if (ldw == 32) return launch_small<32, true>(A, lda, a.V, W, ldw, Kpad, false, none, a, stages, s);
+    return 0;
+}
+
+int launch_gemm_nt_tc(const float *G, uint32_t ldg, uint64_t M, const float *W, uint32_t ldw, uint32_t prows, float *C,
+                      uint32_t ldc, int stages, cudaStream_t s) {
+    // C[M x prows] = G[M x ldw] . W^T with W [prows x ldw]: the contraction runs over W's pitch (<= 128: the K
+    // loop of the small kernel), the output pitch is W's padded row count (32 or 64).
+    if (ldw % BK != 0 || ldw == 0 || ldw > 128 || ldg != ldw || ldc != prows || M == 0) return 0;
+    const SmallOut o{C, C, ldc, EPI_NONE};
+    const SoftmaxCEArgs none{};
+    if (prows == 64) return launch_small<64, false>(G, ldg, M, W, ldw, ldw, true, o, none, stages, s);
+    if (prows == 32) return launch_small<32, false>(G, ldg, M, W, ldw, ldw, true, o, none, stages, s);
+    return 0;
+}
 
 namespace {
 
@@ -669,10 +989,16 @@ int launch_gemm_tn_tc(const float *A, uint32_t lda, uint32_t Mpad, const float *
 }
 
 int launch_gemm_tc(const float *A, uint32_t lda, uint64_t M, const float *W, uint32_t ldw, uint32_t Kpad, float *C,
-                   float *C2, uint32_t ldc, int epilogue, cudaStream_t s) {
+                   float *C2, uint32_t ldc, int epilogue, cudaStream_t s, int small_stages) {
     // Supported: K a multiple of the 32-float swizzle span, N (padded) exactly 64 or 128, and the
     // output pitch equal to N.  Anything else takes the fp32 SIMT path (dense.cu).
     if (Kpad % BK != 0 || Kpad == 0 || lda < Kpad || ldc != ldw || M == 0) return 0;
+    if (Kpad / BK <= 4 && (ldw == 64 || ldw == 32) && small_stages >= 0) {  // skinny: several CTAs per SM instead of a deep ring
+        const SmallOut o{C, C2 ? C2 : C, ldc, C2 ? epilogue : EPI_NONE};
+        const SoftmaxCEArgs none{};
+        return ldw == 64 ? launch_small<64, false>(A, lda, M, W, ldw, Kpad, false, o, none, small_stages, s)
+                         : launch_small<32, false>(A, lda, M, W, ldw, Kpad, false, o, none, small_stages, s);
+    }
     if (ldw == 128) return launch_bn<128>(A, lda, M, W, ldw, Kpad, C, C2, ldc, epilogue, s);
     if (ldw == 64) return launch_bn<64>(A, lda, M, W, ldw, Kpad, C, C2, ldc, epilogue, s);
     return 0;

@@ -91,6 +91,7 @@ int launch_tanh_forward(const float *z, float *h, uint64_t n, cudaStream_t) {
 
 // round 2: the fused logits + soft-max kernel is not emulated ("shape does not qualify" -> GEMM, then the statement below)
 int launch_gemm_softmax_ce(const float *, uint32_t, const float *, uint32_t, uint64_t, const SoftmaxCEArgs &, cudaStream_t) { return 0; }
+int launch_softmax_stats(const SoftmaxCEArgs &, cudaStream_t) { return 0; }
 
 int launch_softmax_ce(const SoftmaxCEArgs &a, cudaStream_t) {
     float acc = 0.f, loss = 0.f;
@@ -163,8 +164,10 @@ size_t tile_edge_smem_bytes(uint64_t, uint32_t) { return 0; }
 
 
 // ------------------------------------------------------------------ tcgen05 paths: "shape not supported"
+int launch_gemm_nt_tc(const float *, uint32_t, uint64_t, const float *, uint32_t, uint32_t, float *, uint32_t, int, cudaStream_t) { return 0; }
+int launch_gemm_tc_softmax(const float *, uint32_t, const float *, uint32_t, uint32_t, const SoftmaxCEArgs &, int, cudaStream_t) { return 0; }
 int launch_gemm_tc(const float *, uint32_t, uint64_t, const float *, uint32_t, uint32_t, float *, float *, uint32_t, int,
-                   cudaStream_t) {
+                   cudaStream_t, int) {
     return 0;
 }
 int launch_gemm_tn_tc(const float *, uint32_t, uint32_t, const float *, uint32_t, uint64_t, float *, uint32_t, float *,

@@ -17,8 +17,9 @@ def _engine(ds, tc):
     return e
 
 
-@pytest.mark.parametrize("dims,V", [([602, 128, 41], 3000), ([128, 64, 64, 25], 1111), ([96, 128, 7], 257)],
-                         ids=["reddit", "amazon", "odd"])
+@pytest.mark.parametrize("dims,V", [([602, 128, 41], 3000), ([128, 64, 64, 25], 1111), ([96, 128, 7], 257),
+                                    ([100, 64, 64, 25], 4099), ([64, 32, 5], 777), ([32, 20, 5], 130)],
+                         ids=["reddit", "amazon", "odd", "amazon-100", "n32", "k32-n32"])
 def test_forward_apply_tensor_core_path(dims, V):
     ds = random_dataset(V=V, E_und=4 * V, dims=dims, seed=91)
     rng = np.random.default_rng(5)
@@ -83,3 +84,46 @@ def test_epochs_with_tensor_cores_match_oracle(oracle):
                 assert rel_err(e.get_weight_grad(l), orc.dW[0][l]) < 1e-5
                 e.set_weights(l, orc.W[l])
             assert st["acc_sum"] == want["acc"][0]
+
+
+@pytest.mark.parametrize("dims,V", [([602, 128, 41], 5003), ([100, 64, 64, 25], 4099), ([16, 48, 51], 6001),
+                                    ([96, 128, 64], 130), ([32, 32, 17], 127)],
+                         ids=["reddit", "amazon", "friendster", "64-classes", "one-tile"])
+def test_last_layer_softmax_on_tensor_cores(dims, V):
+    """Last ApplyVertex (logits, soft-max, validation statistics, maskout, d, d.W^T, AH^T.d): the tcgen05
+    kernel whose epilogue reads one vertex row per thread out of TMEM (gemm_tc_softmax_kernel, 1 / 2 / 4
+    stages per CTA) against the separate fp32 GEMM + soft-max kernels and the fused fp32 kernel."""
+    L = len(dims) - 1
+    ds = random_dataset(V=V, E_und=2 * V, dims=dims, seed=94)
+    rng = np.random.default_rng(7)
+    ah = rng.standard_normal((V, dims[L - 1])).astype(np.float32)
+    out = {}
+    variants = {"separate": dict(tensor_cores=0, fuse_softmax=0), "fused-simt": dict(fuse_softmax=2),
+                "tc": dict(), "tc-1": dict(tc_stages=1), "tc-2": dict(tc_stages=2), "tc-4": dict(tc_stages=4),
+                "round-1 tc": dict(tc_small=0)}
+    for name, opts in variants.items():
+        e = Engine(ds.dims, GCN)
+        for k, v in opts.items():
+            e.set_option(k, v)
+        e.load_partition(ds.images[0])
+        e.set_tensor(L - 1, "lab", ds.onehot)
+        e.init_weights()
+        with e:
+            e.set_tensor(L - 1, "ah", ah)
+            before = e.stats()["kernel_launches"]
+            e.applyVertexGCN(e.whole_chunk(L - 1, FORWARD))
+            st = e.stats()
+            out[name] = (e.get_tensor(L - 1, "grad"), e.get_weight_grad(L - 1), st["acc_sum"], st["loss_sum"],
+                         st["kernel_launches"] - before)
+    ref = out["separate"]
+    assert np.abs(ref[0]).max() > 0 and np.abs(ref[1]).max() > 0
+    for name, got in out.items():
+        assert rel_err(got[0], ref[0]) < 1e-5, name
+        assert rel_err(got[1], ref[1]) < 1e-5, name
+        assert got[2] == ref[2], name
+        assert abs(got[3] - ref[3]) <= 1e-5 * abs(ref[3]), name
+    # the tensor-core variants really took the tcgen05 kernel: weight split + GEMM/soft-max + statistics,
+    # against GEMM + soft-max + statistics (+ the split when the separate GEMM is on tensor cores too)
+    print({k: v[4] for k, v in out.items()})
+    nt_tc = 16 < dims[L - 1] <= 64 and 16 < dims[L] <= 128  # grad = d . W^T on the small-tile kernel: one more launch (the split)
+    assert out["tc"][4] == out["round-1 tc"][4] + 1 + (1 if nt_tc else 0)
