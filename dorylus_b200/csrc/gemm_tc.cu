@@ -298,12 +298,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // and the epilogue is the whole of softmax_ce_kernel: a TMEM lane is an output row, so tcgen05.ld hands every
 // thread the C logits of ONE vertex -- the soft-max, both arg-maxes, the validation statistics, the maskout
 // (quirk Q6) and d = (P - Y) / scale need no shuffle and the logits never reach HBM.
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // Soft-max, validation statistics, maskout and d = (P - Y) / scale of ONE vertex row whose logits are in v
 // (softmax_ce_kernel of dense.cu, sequential over the classes): CPU_comm.cpp:108-121, 276-297, 448-471.
-template <int BN>
-__device__ __forceinline__ void softmax_ce_row(float (&v)[BN], uint64_t row, const SoftmaxCEArgs &a) {
+// The label row is read from, and d written to, the thread's row of the warp's staging slab in shared memory
+// (`wrow`, chunk j at wrow[swz(j)]): the slab is filled and drained with coalesced global accesses.
+template <int BN, class Swz>
+__device__ __forceinline__ void softmax_ce_row(float (&v)[BN], uint64_t row, const SoftmaxCEArgs &a, float4 *wrow, Swz swz) {
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < BN; ++j)
@@ -314,35 +314,42 @@ __device__ __forceinline__ void softmax_ce_row(float (&v)[BN], uint64_t row, con
         v[j] = (uint32_t)j < a.C ? expf(v[j] - mx) : 0.f;
         sum += v[j];
     }
-    const float denom = 1e-20f + sum;  // CPU_comm.cpp:285-290
-    const uint64_t maskBeg = (uint64_t)a.trainEnd * a.C;
+    // One reciprocal per row instead of a division per class (the row's 2 x C divisions were most of this
+    // epilogue's instructions): P and d differ from the divided form by at most one rounding.
+    const float rdenom = 1.f / (1e-20f + sum);  // CPU_comm.cpp:285-290
+    const float rscale = 1.f / a.denom;
+    // maskout (quirk Q6): the classes [clo, chi) of this row lie in the overwritten range of the dense V x C array
+    uint32_t clo = 0, chi = 0;
+    if (a.strictMask) {
+        if (row >= a.trainEnd) chi = a.C;
+    } else {
+        const uint64_t f0 = row * a.C, mb = (uint64_t)a.trainEnd * a.C, me = mb + a.maskFloats;
+        if (f0 + a.C > mb && f0 < me) {
+            clo = mb > f0 ? (uint32_t)(mb - f0) : 0u;
+            chi = me - f0 < a.C ? (uint32_t)(me - f0) : a.C;
+        }
+    }
     float pbest = -INFINITY, lbest = -INFINITY, lab_at_pbest = 0.f, p_at_lbest = 1.f;
-    const float4 *lab4 = reinterpret_cast<const float4 *>(a.lab + row * a.ld);
-    float4 *d4 = reinterpret_cast<float4 *>(a.d + row * a.ld);
     float4 *pred4 = a.pred ? reinterpret_cast<float4 *>(a.pred + row * a.ld) : nullptr;
 #pragma unroll
     for (int j4 = 0; j4 < BN / 4; ++j4) {
-        const float4 l4 = lab4[j4];
+        const float4 l4 = wrow[swz(j4)];
         const float lb[4] = {l4.x, l4.y, l4.z, l4.w};
         float d[4], pr[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t c = 4 * j4 + k;
-            float p = v[c] / denom;
+            const float p = v[c] * rdenom;
             pr[k] = p;
-            d[k] = 0.f;
-            if (c < a.C) {
-                // first maximum wins, like the reference's argmax helper
-                if (p > pbest) pbest = p, lab_at_pbest = lb[k];
-                if (lb[k] > lbest) lbest = lb[k], p_at_lbest = p;
-                const uint64_t flat = row * a.C + c;  // index in the reference's dense V x C array
-                const bool masked =
-                    a.strictMask ? (row >= a.trainEnd) : (flat >= maskBeg && flat < maskBeg + a.maskFloats);
-                if (masked) p = lb[k];  // maskout, then hadamardSub and the scale (CPU_comm.cpp:118-121, 464-471)
-                d[k] = (p - lb[k]) / a.denom;
-            }
+            // first maximum wins, like the reference's argmax helper (classes >= C hold p = 0 and label 0: the
+            // strict comparisons never pick them unless the row has no positive entry at all, where class 0 won already)
+            if (c < a.C && p > pbest) pbest = p, lab_at_pbest = lb[k];
+            if (c < a.C && lb[k] > lbest) lbest = lb[k], p_at_lbest = p;
+            // maskout, then hadamardSub and the scale (CPU_comm.cpp:118-121, 464-471); padding columns stay zero
+            const bool keep = c < a.C && !(c >= clo && c < chi);
+            d[k] = keep ? (p - lb[k]) * rscale : 0.f;
         }
-        d4[j4] = make_float4(d[0], d[1], d[2], d[3]);
+        wrow[swz(j4)] = make_float4(d[0], d[1], d[2], d[3]);
         if (pred4) pred4[j4] = make_float4(pr[0], pr[1], pr[2], pr[3]);
     }
     if (row >= a.trainEnd && row < a.valEnd) {  // getTrainStat over the validation slice (CPU_comm.cpp:448-462)
@@ -401,12 +408,24 @@ gemm_tc_small_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (SOFTMAX && warp >= 2) {  // the label row of this thread's vertex is needed only in the epilogue: start it now
-        const uint64_t row = m0 + (uint64_t)(warp & 3) * 32 + lane;
-        if (row < M) {
-            const float *lp = a.lab + row * a.ld;
-            prefetch_l2(lp);
-            if (BN > 32) prefetch_l2(lp + 32);
+    // Epilogue traffic goes through a staging slab in shared memory (the A buffers of stage 0, dead once the
+    // accumulators are final): a thread owns a ROW of the tile (TMEM lane), but a warp instruction that touches 32
+    // rows 128-256 B apart costs the L1 one tag cycle per row.  One warp instruction here covers RPI whole rows
+    // (lane -> row i*RPI + lane / CPR, 16-byte chunk lane % CPR); in the slab chunk c of row r sits at
+    // r*CPR + (c ^ r) & 7 (within its group of 8), conflict-free for both the row-per-thread and the coalesced view.
+    constexpr int CPR = BN / 4, RPI = 32 / CPR, NIT = 32 / RPI;
+    const int q = warp & 3;  // TMEM lane quarter of this warp = its 32-row slab of the tile
+    const int crow = lane / CPR, cchunk = lane % CPR;
+    auto swz = [](int r, int c) { return r * CPR + ((c & ~7) | ((c ^ r) & 7)); };
+    float4 labr[SOFTMAX ? NIT : 1];
+    if constexpr (SOFTMAX) {
+        if (warp >= 2) {  // the labels are needed only in the epilogue: fetch them now, behind the TMA / MMA latency
+            const float4 *lab4 = reinterpret_cast<const float4 *>(a.lab);
+#pragma unroll
+            for (int i = 0; i < NIT; ++i) {
+                const uint64_t row = m0 + (uint64_t)q * 32 + i * RPI + crow;
+                labr[i] = row < M ? lab4[row * CPR + cchunk] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
     }
     tc_fence_before();
@@ -479,30 +498,15 @@ gemm_tc_small_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         // ---- epilogue: thread = vertex row (TMEM lane quarter of this warp)
         mbar_wait(bar_done, 0);
         tc_fence_after();
-        const int q = warp & 3;
         const uint64_t row = m0 + (uint64_t)q * 32 + lane;
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-        if constexpr (!SOFTMAX) {
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                float d0[32], d1[32];
-                tc_ld_32x32(lane_base + c * 32, d0);
-                tc_ld_32x32(lane_base + BN + c * 32, d1);
-                tc_wait_ld();
-                if (row < M) {
-                    float4 *out = reinterpret_cast<float4 *>(o.C + row * o.ldc + c * 32);
-                    float4 *out2 = reinterpret_cast<float4 *>(o.C2 + row * o.ldc + c * 32);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 z = make_float4(d0[4 * j] + d1[4 * j], d0[4 * j + 1] + d1[4 * j + 1],
-                                                     d0[4 * j + 2] + d1[4 * j + 2], d0[4 * j + 3] + d1[4 * j + 3]);
-                        out[j] = z;
-                        if (o.epilogue == EPI_TANH) out2[j] = make_float4(tanhf(z.x), tanhf(z.y), tanhf(z.z), tanhf(z.w));
-                    }
-                }
-            }
-        }
+        float4 *wbuf = reinterpret_cast<float4 *>(gen_base + stage_off(0)) + q * 32 * CPR;  // this warp's slab
+        float4 *wrow = wbuf + lane * CPR;
+        auto swz_mine = [&](int c) { return (c & ~7) | ((c ^ lane) & 7); };
         if constexpr (SOFTMAX) {
+#pragma unroll
+            for (int i = 0; i < NIT; ++i) wbuf[swz(i * RPI + crow, cchunk)] = labr[i];
+            __syncwarp();
             float v[BN];
 #pragma unroll
             for (int c = 0; c < BN / 32; ++c) {
@@ -513,7 +517,36 @@ gemm_tc_small_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[c * 32 + j] = d0[j] + d1[j];
             }
-            if (row < M) softmax_ce_row<BN>(v, row, a);
+            if (row < M) softmax_ce_row<BN>(v, row, a, wrow, swz_mine);
+            __syncwarp();
+            float4 *d4 = reinterpret_cast<float4 *>(a.d);
+#pragma unroll
+            for (int i = 0; i < NIT; ++i) {
+                const uint64_t r = m0 + (uint64_t)q * 32 + i * RPI + crow;
+                if (r < M) d4[r * CPR + cchunk] = wbuf[swz(i * RPI + crow, cchunk)];
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                float d0[32], d1[32];
+                tc_ld_32x32(lane_base + c * 32, d0);
+                tc_ld_32x32(lane_base + BN + c * 32, d1);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    wrow[swz_mine(c * 8 + j)] = make_float4(d0[4 * j] + d1[4 * j], d0[4 * j + 1] + d1[4 * j + 1],
+                                                            d0[4 * j + 2] + d1[4 * j + 2], d0[4 * j + 3] + d1[4 * j + 3]);
+            }
+            __syncwarp();
+            float4 *c4 = reinterpret_cast<float4 *>(o.C), *t4 = reinterpret_cast<float4 *>(o.C2);
+#pragma unroll
+            for (int i = 0; i < NIT; ++i) {
+                const uint64_t r = m0 + (uint64_t)q * 32 + i * RPI + crow;
+                if (r >= M) continue;
+                const float4 z = wbuf[swz(i * RPI + crow, cchunk)];
+                c4[r * CPR + cchunk] = z;  // the output pitch is BN
+                if (o.epilogue == EPI_TANH) t4[r * CPR + cchunk] = make_float4(tanhf(z.x), tanhf(z.y), tanhf(z.z), tanhf(z.w));
+            }
         }
     }
     tc_fence_before();
