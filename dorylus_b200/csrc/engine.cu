@@ -986,10 +986,12 @@ int gemm_nt(dory_engine *e, const float *G, uint32_t ldg, uint64_t rows, const W
 
 // dW = A^T . G   (A: V x Fin, G: V x Fout -> dW: Fin x Fout), deterministic split over vertices
 int gemm_tn(dory_engine *e, const DevMat &A, const float *G, uint32_t ldg, WeightSet &W, float *out) {
-    // input width <= 64: the narrow fp32 kernel (dense.cu: gemm_tn_small_kernel); the tcgen05 kernel's 128-row M
-    // tile and TMA pipeline are sized for wide layers (Friendster's 64 x 64 gradient over 8.2 M vertices: 2.7 ms)
-    // (measured, profiles/round2_dense_skinny.md: 64-wide at 1.2 M vertices the tcgen05 kernel is the faster one)
-    const bool narrow = e->tn_small && (W.prows <= 32 || (W.prows <= 64 && A.rows > (4u << 20)));
+    // input width <= 32 (Friendster's 16): the narrow fp32 kernel (dense.cu: gemm_tn_small_kernel) -- the tcgen05
+    // kernel needs a multiple of 32 input columns and its 128-row M tile would be three quarters padding.  From 64
+    // columns on the tcgen05 kernel wins at every vertex count measured with CUDA events in the operator's own
+    // sequence (profiles/round2_dense_skinny.md: 8.2 M x 64 x 64 -- 1.3 ms against 2.1 ms; the 2.7 ms of an earlier
+    // cold ncu pass had put the rule at 4 M vertices).
+    const bool narrow = e->tn_small && W.prows <= 32;
     if (use_tensor_cores(e) && !narrow) {
         int n = launch_gemm_tn_tc(A.p, A.ld, W.prows, G, ldg, A.rows, out, W.ld, e->gemm_ws.as<float>(),
                                   e->gemm_ws.bytes / 4, e->stream);

@@ -18,7 +18,7 @@ from helpers import random_dataset  # noqa: E402
 
 VARIANTS = {"separate": dict(fuse_softmax=0), "separate-simt": dict(tensor_cores=0, fuse_softmax=0),
             "fused-simt": dict(fuse_softmax=2), "tc": dict(), "tc-1": dict(tc_stages=1), "tc-2": dict(tc_stages=2),
-            "tc-4": dict(tc_stages=4)}
+            "tc-4": dict(tc_stages=4), "tc+tn-tc": dict(tn_small=0), "round-1 tc": dict(tc_small=0)}
 
 
 def main():
@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--rows", type=int, default=2_000_000)
     ap.add_argument("--dims", default="16,48,51")
     ap.add_argument("--reps", type=int, default=10)
-    ap.add_argument("--variants", default=",".join(VARIANTS))
+    ap.add_argument("--variants", default="separate,fused-simt,tc,tc-2")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     dims = [int(x) for x in args.dims.split(",")]
