@@ -172,7 +172,15 @@ int dory_sync(dory_engine *e);
  *   "tile_team"             high-degree graphs: rows with at least this many edges are walked by the whole CTA.
  *   "fuse_softmax"          1 (default): the last layer's logits product and its soft-max / statistics / maskout /
  *                           gradient scale run as one kernel when the classes fit one 64-wide tile (the logits
- *                           never go to HBM); 0: GEMM, then softmax_ce_kernel.
+ *                           never go to HBM) -- on tcgen05 with a thread-per-row epilogue out of TMEM when the
+ *                           shape qualifies (K a multiple of 32, class pitch 32 or 64), else on the fp32 kernel;
+ *                           2: the fp32 kernel only; 0: GEMM, then softmax_ce_kernel.
+ *   "tc_small"              1 (default): the small-tile tcgen05 kernel (several CTAs per SM) for that product, for
+ *                           Z = A.W with K <= 128 and N = 32 / 64, and for grad = G.W^T; 0: the deep-ring tcgen05
+ *                           kernel / fp32 kernels of round 1.
+ *   "tc_stages"             shared-memory stages per CTA of the small-tile kernel (0 = choose: 1 up to two K
+ *                           blocks, else 2).
+ *   "tn_small"              1 (default): narrow-M fp32 kernel for dW of layers whose input width is <= 32.
  *   "apply_first_mask"      bit l = 1: layer l runs apply-first (overrides the width rule of
  *                           DORY_FLAG_APPLY_FIRST; GCN only; set before dory_load_partition). */
 int dory_set_option(dory_engine *e, const char *key, const char *value);
