@@ -219,7 +219,8 @@ def main():
                              ms_per_rank=[float("%.4f" % x) for x in per_rank[:, i]]) for i, (name, _, _) in enumerate(ops)],
                    epoch_ms_with_events=float(vmax[n_ops]), epoch_ms=float(vmax[n_ops + 1]),
                    scatter_L1_fwd_ms={k: float(vmax[n_ops + 2 + i]) for i, k in enumerate(sc)},
-                   sustained_epoch_ms=float(vmax[-1]), sustained_epochs=args.sustain, gpu_clocks_sustained=clk)
+                   sustained_epoch_ms=None if emu else float(vmax[-1]), sustained_epochs=0 if emu else args.sustain,
+                   gpu_clocks_sustained=clk)
         print(json.dumps(out), flush=True)
         for o in out["ops"]:
             print("  %-22s %8.3f ms  (min over ranks %8.3f)  %s" % (o["op"], o["ms_max"], o["ms_min"], o["ms_per_rank"]),
@@ -228,7 +229,8 @@ def main():
               file=sys.stderr)
         for k, v in out["scatter_L1_fwd_ms"].items():
             print("  scatter L1 fwd [%s]: %.3f ms" % (k, v), file=sys.stderr)
-        print("  sustained (%d epochs): %.3f ms/epoch; clocks %s" % (args.sustain, out["sustained_epoch_ms"], clk), file=sys.stderr)
+        if not emu:  # an emulated partition has no peers to run whole epochs with
+            print("  sustained (%d epochs): %.3f ms/epoch; clocks %s" % (args.sustain, out["sustained_epoch_ms"], clk), file=sys.stderr)
         if args.out:
             os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
             with open(args.out, "w") as f:
