@@ -123,6 +123,7 @@ struct GemmArgs {
     int epilogue;
     float *ws;         // split-K workspace (transA only)
     size_t ws_floats;  // capacity of ws
+    const float *Bh;   // narrow transA kernel only (M <= 64, ws set): B is read as B (*) (1 - Bh^2), Bh with B's pitch
 };
 int launch_gemm(const GemmArgs &g, cudaStream_t s);
 

@@ -26,8 +26,8 @@ constexpr int kGemmThreads = (BM / TM) * (BN / TN);  // 256
 template <int BMs>
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_tn_small_kernel(const float *__restrict__ A, uint32_t lda, const float *__restrict__ B, uint32_t ldb,
-                     float *__restrict__ C, uint32_t ldc, uint64_t M, uint32_t N, uint64_t K, uint64_t kchunk,
-                     size_t split_stride) {
+                     const float *__restrict__ Bh, float *__restrict__ C, uint32_t ldc, uint64_t M, uint32_t N, uint64_t K,
+                     uint64_t kchunk, size_t split_stride) {
     constexpr int TMs = BMs / 16;
     constexpr int BKs = 32;  // deeper k tile: the tile is small, the barrier cost per k step is not
     __shared__ __align__(16) float As[BKs][BMs + 4];
@@ -62,7 +62,14 @@ gemm_tn_small_kernel(const float *__restrict__ A, uint32_t lda, const float *__r
             const uint64_t k = k0 + kk;
             const uint32_t n = n0 + n4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k < kend && n < N) v = *reinterpret_cast<const float4 *>(B + k * ldb + n);
+            if (k < kend && n < N) {
+                v = *reinterpret_cast<const float4 *>(B + k * ldb + n);
+                if (Bh) {  // B = aTg (*) (1 - h^2) formed on the way in (tanh_backward_kernel's statement)
+                    const float4 t = *reinterpret_cast<const float4 *>(Bh + k * ldb + n);
+                    v = make_float4(v.x * (1.f - t.x * t.x), v.y * (1.f - t.y * t.y), v.z * (1.f - t.z * t.z),
+                                    v.w * (1.f - t.w * t.w));
+                }
+            }
             *reinterpret_cast<float4 *>(&Bs[kk][n4]) = v;
         }
         __syncthreads();
@@ -559,15 +566,17 @@ int launch_gemm(const GemmArgs &g, cudaStream_t s) {
         nsplit = (int)((g.K + kchunk - 1) / kchunk);
         grid.z = nsplit;
         float *out = nsplit > 1 ? g.ws : g.C;
-        if (bms == 16) gemm_tn_small_kernel<16><<<grid, kGemmThreads, 0, s>>>(g.A, g.lda, g.B, g.ldb, out, g.ldc, g.M, g.N, g.K, kchunk, cfloats);
-        else if (bms == 32) gemm_tn_small_kernel<32><<<grid, kGemmThreads, 0, s>>>(g.A, g.lda, g.B, g.ldb, out, g.ldc, g.M, g.N, g.K, kchunk, cfloats);
-        else gemm_tn_small_kernel<64><<<grid, kGemmThreads, 0, s>>>(g.A, g.lda, g.B, g.ldb, out, g.ldc, g.M, g.N, g.K, kchunk, cfloats);
+        if (bms == 16) gemm_tn_small_kernel<16><<<grid, kGemmThreads, 0, s>>>(g.A, g.lda, g.B, g.ldb, g.Bh, out, g.ldc, g.M, g.N, g.K, kchunk, cfloats);
+        else if (bms == 32) gemm_tn_small_kernel<32><<<grid, kGemmThreads, 0, s>>>(g.A, g.lda, g.B, g.ldb, g.Bh, out, g.ldc, g.M, g.N, g.K, kchunk, cfloats);
+        else gemm_tn_small_kernel<64><<<grid, kGemmThreads, 0, s>>>(g.A, g.lda, g.B, g.ldb, g.Bh, out, g.ldc, g.M, g.N, g.K, kchunk, cfloats);
         ++launches;
         if (nsplit > 1) {
             const size_t n4 = cfloats / 4;
             splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(g.ws, g.C, n4, n4, nsplit);
             ++launches;
         }
+    } else if (g.Bh) {
+        return -1;  // the fused tanh' operand exists in the narrow kernel only (the caller checks the shape)
     } else if (g.transA) {
         // split the vertex dimension so that ~4 CTAs per SM are in flight (chunks of >= 256 vertices:
         // one eighth of the Reddit shape got 15 CTAs for its 128 x 41 product with 2048-vertex chunks,

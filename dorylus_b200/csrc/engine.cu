@@ -162,6 +162,8 @@ struct dory_engine {
     int tn_small = 1;             // option "tn_small": narrow-M fp32 kernel for dW of layers with input width <= 64
     int fuse_softmax = 1;         // option "fuse_softmax": last-layer logits + soft-max / maskout in one kernel (C <= 64);
                                   // 1 = on tcgen05 when the shape qualifies, else fp32 SIMT; 2 = the SIMT kernel only
+    int fuse_tanh_bwd = 1;        // option "fuse_tanh_bwd": layer-0 backward with an input width <= 32: tanh' applied inside the
+                                  // narrow dW kernel's operand load instead of a pass of its own
     int tc_small = 1;             // option "tc_small": the small-tile tcgen05 kernel (several CTAs per SM) for that product, for
                                   // Z = A.W with K <= 128, N <= 64 and for grad = G.W^T; 0 = the round-1 kernels
     int tc_stages = 0;            // option "tc_stages": its shared-memory stages per CTA (0 = choose)
@@ -985,13 +987,20 @@ int gemm_nt(dory_engine *e, const float *G, uint32_t ldg, uint64_t rows, const W
 }
 
 // dW = A^T . G   (A: V x Fin, G: V x Fout -> dW: Fin x Fout), deterministic split over vertices
-int gemm_tn(dory_engine *e, const DevMat &A, const float *G, uint32_t ldg, WeightSet &W, float *out) {
+// Gh != null (narrow kernel only, see tn_fusable): G is read as G (*) (1 - Gh^2), i.e. tanh' is applied on the way in.
+bool tn_fusable(const dory_engine *e, const WeightSet &W) {
+    return e->fuse_tanh_bwd && e->tn_small && W.prows <= 32 && e->gemm_ws.p != nullptr;
+}
+
+int gemm_tn(dory_engine *e, const DevMat &A, const float *G, uint32_t ldg, WeightSet &W, float *out,
+            const float *Gh = nullptr) {
     // input width <= 32 (Friendster's 16): the narrow fp32 kernel (dense.cu: gemm_tn_small_kernel) -- the tcgen05
     // kernel needs a multiple of 32 input columns and its 128-row M tile would be three quarters padding.  From 64
     // columns on the tcgen05 kernel wins at every vertex count measured with CUDA events in the operator's own
     // sequence (profiles/round2_dense_skinny.md: 8.2 M x 64 x 64 -- 1.3 ms against 2.1 ms; the 2.7 ms of an earlier
     // cold ncu pass had put the rule at 4 M vertices).
     const bool narrow = e->tn_small && W.prows <= 32;
+    if (Gh && !tn_fusable(e, W)) return fail(e, DORY_EINVAL, "internal: fused tanh' operand outside the narrow dW kernel");
     if (use_tensor_cores(e) && !narrow) {
         int n = launch_gemm_tn_tc(A.p, A.ld, W.prows, G, ldg, A.rows, out, W.ld, e->gemm_ws.as<float>(),
                                   e->gemm_ws.bytes / 4, e->stream);
@@ -1006,6 +1015,7 @@ int gemm_tn(dory_engine *e, const DevMat &A, const float *G, uint32_t ldg, Weigh
     g.M = W.prows; g.N = W.ld; g.K = A.rows;
     g.transA = true; g.transB = false; g.epilogue = EPI_NONE;
     g.ws = e->gemm_ws.as<float>(); g.ws_floats = e->gemm_ws.bytes / 4;
+    g.Bh = Gh;
     LAUNCHED(launch_gemm(g, e->stream));
     return DORY_OK;
 }
@@ -1101,6 +1111,9 @@ int vtx_backward_gcn(dory_engine *e, uint32_t layer) {
     }
     const DevMat &ah = *find_tensor(e, layer, "ah");
     WeightSet &W = e->W[layer];
+    // layer 0 wants dW only (no gradient flows further down): with a narrow input the dW kernel forms
+    // g = aTg (*) (1 - h^2) while loading it, and the pass that writes g (and its re-read) disappears
+    if (layer == 0 && tn_fusable(e, W)) return gemm_tn(e, ah, aTg.p, aTg.ld, W, W.dw.as<float>(), h.p);
     float *g = e->scratchA.as<float>();
     LAUNCHED(launch_tanh_backward(aTg.p, h.p, g, (uint64_t)e->V * aTg.ld, e->stream));
     int rc = gemm_tn(e, ah, g, aTg.ld, W, W.dw.as<float>());
@@ -1548,6 +1561,8 @@ int dory_set_option(dory_engine *e, const char *key, const char *value) {
         e->fuse_softmax = (int)v;
     } else if (std::strcmp(key, "tc_stages") == 0) {
         e->tc_stages = (int)v;
+    } else if (std::strcmp(key, "fuse_tanh_bwd") == 0) {
+        e->fuse_tanh_bwd = v != 0;
     } else if (std::strcmp(key, "tc_small") == 0) {
         e->tc_small = v != 0;
     } else if (std::strcmp(key, "tensor_cores") == 0) {

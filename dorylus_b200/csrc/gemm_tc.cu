@@ -894,7 +894,10 @@ int launch_small(const float *A, uint32_t lda, uint64_t M, const float *W, uint3
     using L = SmemLayout<BN>;
     Cache &c = cache();
     std::lock_guard<std::mutex> lock(c.mu);
-    auto wkey = std::make_tuple(W, transposed ? (ldw | 0x80000000u) : ldw, Kpad);
+    // the split copies are [BN x Kpad]: BN is W's pitch for the transposed copy, but W's padded ROW count for the
+    // untransposed one, which the pitch does not determine -- it is part of the key (engines created one after the
+    // other in a process get the same addresses back from the allocator)
+    auto wkey = std::make_tuple(W, transposed ? (ldw | ((uint32_t)BN << 8) | 0x80000000u) : ldw, Kpad);
     auto wit = c.weights.find(wkey);
     if (wit == c.weights.end()) {
         WeightSplit ws;

@@ -181,6 +181,8 @@ int dory_sync(dory_engine *e);
  *   "tc_stages"             shared-memory stages per CTA of the small-tile kernel (0 = choose: 1 up to two K
  *                           blocks, else 2).
  *   "tn_small"              1 (default): narrow-M fp32 kernel for dW of layers whose input width is <= 32.
+ *   "fuse_tanh_bwd"         1 (default): layer-0 backward with an input width <= 32 applies tanh' inside that kernel's
+ *                           operand load instead of in a pass of its own (layer 0 needs dW only).
  *   "apply_first_mask"      bit l = 1: layer l runs apply-first (overrides the width rule of
  *                           DORY_FLAG_APPLY_FIRST; GCN only; set before dory_load_partition). */
 int dory_set_option(dory_engine *e, const char *key, const char *value);

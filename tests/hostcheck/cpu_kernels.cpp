@@ -70,7 +70,8 @@ int launch_gemm(const GemmArgs &g, cudaStream_t) {
             double s = 0.0;  // any summation order is within the 1e-5 bar; double keeps this side exact
             for (uint64_t k = 0; k < g.K; ++k) {
                 const float av = g.transA ? g.A[k * g.lda + m] : g.A[m * g.lda + k];
-                const float bv = g.transB ? g.B[(size_t)n * g.ldb + k] : g.B[k * g.ldb + n];
+                float bv = g.transB ? g.B[(size_t)n * g.ldb + k] : g.B[k * g.ldb + n];
+                if (g.Bh) bv = bv * (1.f - g.Bh[k * g.ldb + n] * g.Bh[k * g.ldb + n]);  // fused tanh' operand (transA, !transB)
                 s += (double)av * bv;
             }
             g.C[m * g.ldc + n] = (float)s;

@@ -16,7 +16,9 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from dorylus_b200.engine import FORWARD, GCN, Engine  # noqa: E402
 from helpers import random_dataset  # noqa: E402
 
-VARIANTS = {"separate": dict(fuse_softmax=0), "separate-simt": dict(tensor_cores=0, fuse_softmax=0),
+# --op bwd0: ApplyVertex backward of layer 0 (tanh', dW = ah0^T . g) instead
+VARIANTS = {"fused-bwd0": dict(), "separate-bwd0": dict(fuse_tanh_bwd=0),
+            "separate": dict(fuse_softmax=0), "separate-simt": dict(tensor_cores=0, fuse_softmax=0),
             "fused-simt": dict(fuse_softmax=2), "tc": dict(), "tc-1": dict(tc_stages=1), "tc-2": dict(tc_stages=2),
             "tc-4": dict(tc_stages=4), "tc+tn-tc": dict(tn_small=0), "round-1 tc": dict(tc_small=0)}
 
@@ -28,7 +30,10 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--variants", default="separate,fused-simt,tc,tc-2")
     ap.add_argument("--out", default="")
+    ap.add_argument("--op", default="last", choices=["last", "bwd0"])
     args = ap.parse_args()
+    if args.op == "bwd0":
+        return bwd0(args)
     dims = [int(x) for x in args.dims.split(",")]
     L = len(dims) - 1
     V = args.rows
@@ -65,6 +70,44 @@ def main():
     if args.out:
         with open(args.out, "w") as f:
             json.dump(res, f, indent=1)
+
+
+def bwd0(args):
+    from dorylus_b200.engine import BACKWARD
+
+    dims = [int(x) for x in args.dims.split(",")]
+    V = args.rows
+    ds = random_dataset(V=V, E_und=V // 2, dims=dims, seed=3)
+    rng = np.random.default_rng(1)
+    ah = rng.standard_normal((V, dims[0]), dtype=np.float32)
+    aTg = rng.standard_normal((V, dims[1]), dtype=np.float32)
+    h = np.tanh(rng.standard_normal((V, dims[1]), dtype=np.float32))
+    first = None
+    for name in ("separate-bwd0", "fused-bwd0"):
+        e = Engine(ds.dims, GCN)
+        for k, v in VARIANTS[name].items():
+            e.set_option(k, v)
+        e.load_partition(ds.images[0])
+        e.set_tensor(len(dims) - 2, "lab", ds.onehot)
+        e.init_weights()
+        with e:
+            e.set_tensor(0, "ah", ah)
+            e.set_tensor(0, "aTg", aTg)
+            e.set_tensor(0, "h", h)
+            ch = e.whole_chunk(1, BACKWARD)
+            for _ in range(3):
+                e.applyVertexGCN(ch)
+            e.sync()
+            e.event_record(0)
+            for _ in range(args.reps):
+                e.applyVertexGCN(ch)
+            e.event_record(1)
+            e.sync()
+            ms = e.event_elapsed_ms(0, 1) / args.reps
+            dw = e.get_weight_grad(0)
+            if first is None:
+                first = dw
+            print(name, "%.3f ms" % ms, "dW err vs separate %.2e" % float(np.abs(dw - first).max() / np.abs(first).max()), flush=True)
 
 
 if __name__ == "__main__":
